@@ -1,0 +1,86 @@
+/*
+ * mettagrid_b200.h -- C ABI of the B200-native batched MettaGrid step.
+ *
+ * Drop-in boundary for the reference's pybind class `MettaGrid`
+ * (/root/reference/cpp/bindings/mettagrid_c.hpp:58-320, bound in mettagrid_py.cpp:251-312): one handle
+ * owns N independent environments that all run the same compiled game program
+ * (include/mg_program.h).  Plain pointers and sizes only; every entry point returns 0 on success or
+ * a negative MG_E_* code, with text available from mg_last_error().
+ *
+ * Buffers follow the reference's set_buffers contract (mettagrid_py.cpp:253-266,
+ * mettagrid_c.cpp:1165-1184): the CALLER owns them, the library aliases them and re-runs
+ * _init_buffers.  Layouts are the reference's with a leading env dimension:
+ *   observations uint8 [N][A][T][3], terminals/truncations bool(uint8) [N][A], rewards float [N][A],
+ *   actions / vibe_actions int32 [N][A].
+ */
+#ifndef METTAGRID_B200_H_
+#define METTAGRID_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mg_handle mg_handle;
+
+#define MG_OK 0
+#define MG_E_INVALID -1     /* bad argument / bad program */
+#define MG_E_CUDA -2        /* CUDA runtime error */
+#define MG_E_UNSUPPORTED -3 /* program needs a feature this build does not run on the GPU */
+#define MG_E_ENV -4         /* an environment raised an error (see mg_poll_errors) */
+
+/* replaces MettaGrid::MettaGrid(GameConfig, map, seed) -- mettagrid_c.cpp:42-191.
+ * program      : compiled game program (mettagrid_b200.compiler), nwords int32 words (host)
+ * init_cells   : host int16 [num_envs][H][W], template index per cell, -1 = empty
+ * init_gstats  : host float [num_envs][S_G] initial game stats ("objects.<cell>" counts) or NULL
+ * seeds        : host uint32 [num_envs], one std::mt19937 seed per environment
+ * device       : CUDA device ordinal */
+int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t* init_cells, const float* init_gstats,
+              const uint32_t* seeds, int device, mg_handle** out);
+void mg_destroy(mg_handle* h);
+const char* mg_last_error(const mg_handle* h); /* h may be NULL: error of the last failed mg_create */
+
+/* replaces MettaGrid::set_buffers -- mettagrid_c.cpp:1165-1184.  DEVICE pointers.  Runs
+ * _init_buffers (initial observations) on `stream` (a cudaStream_t, may be NULL). */
+int mg_set_buffers(mg_handle* h, void* observations, void* terminals, void* truncations, void* rewards,
+                   const void* actions, const void* vibe_actions, void* stream);
+
+/* replaces MettaGrid::step -- mettagrid_c.cpp:1186-1205.  Asynchronous on `stream`. */
+int mg_step(mg_handle* h, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies actions in, steps, copies results out,
+ * synchronises.  Any output pointer may be NULL. */
+int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actions, uint8_t* observations,
+                 float* rewards, uint8_t* terminals, uint8_t* truncations);
+
+/* reset = rebuild from the stored initial state, like constructing a new MettaGrid with the same
+ * map and seed (envs/mettagrid_puffer_env.py:225-228).  env_mask: DEVICE uint8 [num_envs] or NULL
+ * for all.  new_seeds: host uint32 [num_envs] or NULL to keep the seeds. */
+int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, void* stream);
+
+/* first environment with a pending error: token-budget overflow (mettagrid_c.cpp:364-375) etc.
+ * Returns MG_OK when none, MG_E_ENV otherwise.  code = MGERR_* bits, info = agent | attempted<<16. */
+int mg_poll_errors(mg_handle* h, int* env, int* code, int* info);
+
+/* introspection (mettagrid_py.cpp:161-239); all outputs are HOST buffers */
+int mg_get_episode_rewards(mg_handle* h, float* out /*[N][A]*/);
+int mg_get_action_success(mg_handle* h, uint8_t* out /*[N][A]*/);
+int mg_get_current_steps(mg_handle* h, int32_t* out /*[N]*/);
+int mg_get_agent_stats(mg_handle* h, int env, float* values /*[A][S_A]*/, uint8_t* touched /*[A][S_A]*/);
+int mg_get_game_stats(mg_handle* h, int env, float* values /*[S_G]*/, uint8_t* touched /*[S_G]*/);
+/* one row of (8 + 2R) int32 per live object in id order:
+ * id, type_id, r, c, vibe, agent (-1), tag word 0, #present resources, inv[R], order[R] (-1 padded) */
+int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows);
+
+/* sizes */
+int mg_num_envs(const mg_handle* h);
+int mg_num_agents(const mg_handle* h);
+int mg_num_tokens(const mg_handle* h);
+size_t mg_state_bytes(const mg_handle* h); /* HBM held by the handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METTAGRID_B200_H_ */

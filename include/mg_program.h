@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #define MG_MAGIC 0x4D47B200
-#define MG_VERSION 3
+#define MG_VERSION 4
 
 /* ---- header word indices ------------------------------------------------------------ */
 enum {
@@ -129,7 +129,10 @@ enum {
 #define MG_ACTION_WORDS 4 /* kind, arg, priority, is_vibe */
 enum { MGA_NOOP = 0, MGA_MOVE = 1, MGA_CHANGE_VIBE = 2 };
 
-#define MG_MOVEH_WORDS 3 /* handler id, max_range, accepts_empty (actions/move.hpp:26-40) */
+#define MG_MOVEH_WORDS 4 /* handler id, max_range, accepts_empty (actions/move.hpp:26-40), builtin */
+/* builtin: the two handlers the reference always appends (action_handler_factory.cpp:33-45) are
+   also emitted as ordinary handlers; the marker lets an engine take a table-free fast path. */
+enum { MGMB_GENERIC = 0, MGMB_RELOCATE = 1, MGMB_USE_TARGET = 2 };
 
 /* ---- handlers (handler/handler.cpp:76-103, multi_handler.cpp:8-21) -------------------- */
 #define MG_HANDLER_WORDS 5 /* kind, a, b, c, d */

@@ -1,0 +1,63 @@
+"""Build the CUDA extension in-tree: ``mettagrid_b200/libmettagrid_b200.so`` (sm_100a only)."""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libmettagrid_b200.so"
+SOURCES = ["mg_kernels.cu", "mg_capi.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",  # the reference's float math is unfused mul/add
+    "-Xcompiler", "-fPIC",
+]  # fmt: skip
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((PKG.parent / "include").glob("*.h"))
+    return LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps)
+
+
+def build_native(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    nvcc = _nvcc()
+    objs = []
+    build_dir = PKG / "build"
+    build_dir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = build_dir / (Path(src).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    for cmd, p in procs:
+        out, _ = p.communicate(timeout=1200)
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{out}")
+    subprocess.check_call([nvcc, "-shared", "-o", str(LIB), *objs])
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

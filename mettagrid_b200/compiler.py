@@ -703,17 +703,17 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
                 max_range = f.radius if f.radius > 0 else 1
             if ft == "target_loc_empty":
                 accepts_empty = 1
-        move_chain.append([hid, int(max_range), accepts_empty])
+        move_chain.append([hid, int(max_range), accepts_empty, K["MGMB_GENERIC"]])
     f0, fn = b._place_filters([[K["MGF_TARGET_LOC_EMPTY"], 0, 0, 0, 0, 0]])
     m0 = len(b.mutations)
     b.mutations.append([K["MGM_RELOCATE"], 0, 0, 0, 0, 0, 0, 0])
     b.handlers.append([K["MGHK_SIMPLE"], f0, fn, m0, 1])
-    move_chain.append([len(b.handlers) - 1, 1, 1])
+    move_chain.append([len(b.handlers) - 1, 1, 1, K["MGMB_RELOCATE"]])
     f0, fn = b._place_filters([[K["MGF_TARGET_IS_USABLE"], 0, 0, 0, 0, 0]])
     m0 = len(b.mutations)
     b.mutations.append([K["MGM_USE_TARGET"], 0, 0, 0, 0, 0, 0, 0])
     b.handlers.append([K["MGHK_SIMPLE"], f0, fn, m0, 1])
-    move_chain.append([len(b.handlers) - 1, 1, 0])
+    move_chain.append([len(b.handlers) - 1, 1, 0, K["MGMB_USE_TARGET"]])
 
     # ---- templates --------------------------------------------------------------------------------
     templates: list[list[int]] = []
@@ -967,6 +967,8 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     body: list[int] = []
 
     def section(key: str, rows, width: int | None = None):
+        while (K["MGH_HEADER_WORDS"] + len(body)) % 4:  # sections start 16-byte aligned (int4 loads)
+            body.append(0)
         hdr[H[key]] = K["MGH_HEADER_WORDS"] + len(body)
         for row in rows:
             if width is not None and len(row) != width:

@@ -1,0 +1,381 @@
+// mg_capi.cu -- the C ABI (include/mettagrid_b200.h): host-side handle, memory, launches.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mettagrid_b200.h"
+#include "mg_state.h"
+
+size_t mg_smem_bytes(const MgDev& d);
+cudaError_t mg_configure_kernels(const MgDev& d);
+cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st);
+cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st);
+cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
+
+struct mg_handle {
+  MgDev d;
+  int device = 0;
+  std::vector<int32_t> program;
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  std::string err;
+  bool buffers_set = false;
+  // device-side staging for mg_step_host
+  int32_t* h_act = nullptr;
+  int32_t* h_vact = nullptr;
+  uint8_t* h_obs = nullptr;
+  float* h_rew = nullptr;
+  uint8_t* h_term = nullptr;
+  uint8_t* h_trunc = nullptr;
+  uint32_t* seeds_dev = nullptr;
+  cudaStream_t own_stream = nullptr;
+};
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return MG_E_CUDA;                                                                            \
+    }                                                                                              \
+  } while (0)
+
+template <class T>
+static int dev_alloc(mg_handle* h, T** p, size_t count) {
+  size_t bytes = (count ? count : 1) * sizeof(T);
+  bytes = (bytes + 255) & ~(size_t)255;
+  CK(cudaMalloc((void**)p, bytes));
+  CK(cudaMemset(*p, 0, bytes));
+  h->allocs.push_back(*p);
+  h->bytes += bytes;
+  return MG_OK;
+}
+
+// engine capabilities: anything else in the program is refused loudly rather than mis-simulated
+static const char* unsupported_reason(const int32_t* P) {
+  if (P[MGH_NUM_EVENTS_SCHED] > 0) return "events";
+  if (P[MGH_NUM_TERRITORIES] > 0 || P[MGH_FEAT_AOE_MASK] != 0) return "territories / aoe_mask";
+  if (P[MGH_NUM_MQ] > 0) return "materialized queries";
+  if (P[MGH_MAX_AOE_SOURCES] > 0) return "AOE sources";
+  const int32_t* q = P + P[MGS_QUERIES];
+  (void)q;
+  int nq = (P[MGS_TEMPLATES] - P[MGS_QUERIES]) / MG_QUERY_WORDS;
+  if (nq > 0) return "queries";
+  int nm = (P[MGS_VALUES] - P[MGS_MUTATIONS]) / MG_MUTATION_WORDS;
+  const int32_t* m = P + P[MGS_MUTATIONS];
+  for (int i = 0; i < nm; i++) {
+    int op = m[i * MG_MUTATION_WORDS];
+    if (op == MGM_SPAWN_OBJECT || op == MGM_RAYCAST_SPAWN) return "spawn mutations";
+    if (op == MGM_ADD_TAG || op == MGM_REMOVE_TAG || op == MGM_REMOVE_TAGS_PREFIX) return "tag mutations";
+    if (op == MGM_RESOURCE_TRANSFER && m[i * MG_MUTATION_WORDS + 5]) return "remove_source_when_empty";
+  }
+  return nullptr;
+}
+
+extern "C" {
+
+int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t* init_cells, const float* init_gstats,
+              const uint32_t* seeds, int device, mg_handle** out) {
+  if (!out) return MG_E_INVALID;
+  *out = nullptr;
+  if (!program || nwords < (size_t)MGH_HEADER_WORDS || (uint32_t)program[MGH_MAGIC] != MG_MAGIC ||
+      program[MGH_VERSION] != MG_VERSION || (size_t)program[MGH_TOTAL_WORDS] != nwords) {
+    g_create_error = "mg_create: not a compiled game program of this version";
+    return MG_E_INVALID;
+  }
+  if (num_envs <= 0 || !init_cells || !seeds) {
+    g_create_error = "mg_create: num_envs, init_cells and seeds are required";
+    return MG_E_INVALID;
+  }
+  if (const char* why = unsupported_reason(program)) {
+    g_create_error = std::string("mg_create: program uses ") + why + ", which this build does not run on the GPU";
+    return MG_E_UNSUPPORTED;
+  }
+  mg_handle* h = new mg_handle();
+  auto fail = [&](int code) {
+    g_create_error = h->err;
+    mg_destroy(h);
+    return code;
+  };
+  h->device = device;
+  h->program.assign(program, program + nwords);
+  const int32_t* P = program;
+  MgDev& d = h->d;
+  memset(&d, 0, sizeof d);
+  d.num_envs = num_envs;
+  d.H = P[MGH_H], d.W = P[MGH_W], d.HW = d.H * d.W, d.HWp = (d.HW + 7) & ~7;
+  d.A = P[MGH_NUM_AGENTS], d.T = P[MGH_NUM_TOKENS], d.R = P[MGH_NUM_RESOURCES], d.TW = P[MGH_TAG_WORDS];
+  d.OS = P[MGH_OBJ_STRIDE], d.AS = P[MGH_AGENT_STRIDE], d.SA = P[MGH_NUM_AGENT_STATS], d.SAW = (d.SA + 31) / 32;
+  d.SG = P[MGH_NUM_GAME_STATS], d.SGW = (d.SG + 31) / 32, d.CW = P[MGH_COVER_WORDS], d.maxobj = P[MGH_MAX_OBJECTS];
+  d.NOFF = P[MGH_NUM_OFFSETS], d.B = P[MGH_TOKEN_BASE], d.ND = P[MGH_INV_DIGITS], d.NTERR = P[MGH_NUM_TERRITORIES];
+  if (d.R > 13 || d.maxobj > 65535 || d.A > 4096) {
+    h->err = "mg_create: program exceeds engine limits (R<=13, objects<=65535, agents<=4096)";
+    return fail(MG_E_INVALID);
+  }
+  int rc;
+#define TRY(x) \
+  if ((rc = (x)) != MG_OK) return fail(rc)
+  if (cudaSetDevice(device) != cudaSuccess) {
+    h->err = "mg_create: cudaSetDevice failed (no CUDA device?)";
+    return fail(MG_E_CUDA);
+  }
+  const size_t N = (size_t)num_envs;
+  int32_t* Pd;
+  int16_t* ic;
+  float* ig = nullptr;
+  float* lt;
+  TRY(dev_alloc(h, &Pd, nwords));
+  TRY(dev_alloc(h, &ic, N * d.HW));
+  if (init_gstats) TRY(dev_alloc(h, &ig, N * d.SG));
+  TRY(dev_alloc(h, &h->seeds_dev, N));
+  TRY(dev_alloc(h, &d.cells, N * d.HWp));
+  TRY(dev_alloc(h, &d.objs, N * d.maxobj * d.OS));
+  TRY(dev_alloc(h, &d.agents, N * d.A * d.AS));
+  TRY(dev_alloc(h, &d.astats, N * d.A * d.SA));
+  TRY(dev_alloc(h, &d.atouched, N * d.A * d.SAW));
+  TRY(dev_alloc(h, &d.gstats, N * d.SG));
+  TRY(dev_alloc(h, &d.gtouched, N * d.SGW));
+  TRY(dev_alloc(h, &d.cover, N * d.A * d.CW));
+  TRY(dev_alloc(h, &d.rng, N * MG_RNG_WORDS));
+  TRY(dev_alloc(h, &d.env, N * MGEV_WORDS));
+  TRY(dev_alloc(h, &d.success, N * d.A));
+  TRY(dev_alloc(h, &lt, 65536));
+  {
+    // logf through the HOST libm, the same function the reference calls (core/game_value.cpp:91)
+    std::vector<float> tab(65536);
+    for (int k = 0; k < 65536; k++) tab[k] = logf((float)k + 1.0f);
+    if (cudaMemcpy(lt, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      h->err = "mg_create: upload failed";
+      return fail(MG_E_CUDA);
+    }
+  }
+  if (cudaMemcpy(Pd, program, nwords * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ic, init_cells, N * d.HW * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->seeds_dev, seeds, N * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      (ig && cudaMemcpy(ig, init_gstats, N * d.SG * 4, cudaMemcpyHostToDevice) != cudaSuccess)) {
+    h->err = "mg_create: upload failed";
+    return fail(MG_E_CUDA);
+  }
+  d.P = Pd, d.init_cells = ic, d.init_gstats = ig, d.seeds = h->seeds_dev, d.logtab = lt;
+  cudaError_t e = mg_configure_kernels(d);
+  if (e != cudaSuccess) {
+    h->err = std::string("mg_create: kernel configuration failed: ") + cudaGetErrorString(e) +
+             " (shared memory per CTA = " + std::to_string(mg_smem_bytes(d)) + " bytes)";
+    return fail(MG_E_CUDA);
+  }
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    h->err = "mg_create: stream creation failed";
+    return fail(MG_E_CUDA);
+  }
+  e = mg_launch_reset(d, nullptr, h->own_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+  if (e != cudaSuccess) {
+    h->err = std::string("mg_create: reset kernel failed: ") + cudaGetErrorString(e);
+    return fail(MG_E_CUDA);
+  }
+#undef TRY
+  *out = h;
+  return MG_OK;
+}
+
+void mg_destroy(mg_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+const char* mg_last_error(const mg_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mg_set_buffers(mg_handle* h, void* observations, void* terminals, void* truncations, void* rewards,
+                   const void* actions, const void* vibe_actions, void* stream) {
+  if (!h) return MG_E_INVALID;
+  if (!observations || !terminals || !truncations || !rewards || !actions || !vibe_actions) {
+    h->err = "mg_set_buffers: all six buffers are required";
+    return MG_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  MgDev& d = h->d;
+  d.obs = (uint8_t*)observations, d.terminals = (uint8_t*)terminals, d.truncations = (uint8_t*)truncations;
+  d.rewards = (float*)rewards, d.actions = (const int32_t*)actions, d.vibe_actions = (const int32_t*)vibe_actions;
+  h->buffers_set = true;
+  CK(mg_launch_init_buffers(d, nullptr, (cudaStream_t)stream));
+  return MG_OK;
+}
+
+int mg_step(mg_handle* h, void* stream) {
+  if (!h) return MG_E_INVALID;
+  if (!h->buffers_set) {
+    h->err = "mg_step: call mg_set_buffers first";
+    return MG_E_INVALID;
+  }
+  CK(mg_launch_step(h->d, (cudaStream_t)stream));
+  return MG_OK;
+}
+
+int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actions, uint8_t* observations,
+                 float* rewards, uint8_t* terminals, uint8_t* truncations) {
+  if (!h || !actions) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  MgDev& d = h->d;
+  const size_t NA = (size_t)d.num_envs * d.A;
+  if (!h->h_act) {  // first use: device-side buffers owned by the handle
+    int rc;
+    if ((rc = dev_alloc(h, &h->h_act, NA)) || (rc = dev_alloc(h, &h->h_vact, NA)) ||
+        (rc = dev_alloc(h, &h->h_obs, NA * d.T * 3)) || (rc = dev_alloc(h, &h->h_rew, NA)) ||
+        (rc = dev_alloc(h, &h->h_term, NA)) || (rc = dev_alloc(h, &h->h_trunc, NA)))
+      return rc;
+    rc = mg_set_buffers(h, h->h_obs, h->h_term, h->h_trunc, h->h_rew, h->h_act, h->h_vact, h->own_stream);
+    if (rc) return rc;
+  }
+  cudaStream_t st = h->own_stream;
+  CK(cudaMemcpyAsync(h->h_act, actions, NA * 4, cudaMemcpyHostToDevice, st));
+  if (vibe_actions)
+    CK(cudaMemcpyAsync(h->h_vact, vibe_actions, NA * 4, cudaMemcpyHostToDevice, st));
+  else
+    CK(cudaMemsetAsync(h->h_vact, 0, NA * 4, st));
+  // the handle may have been pointed at caller buffers since; step on the staging set
+  MgDev run = d;
+  run.obs = h->h_obs, run.terminals = h->h_term, run.truncations = h->h_trunc, run.rewards = h->h_rew;
+  run.actions = h->h_act, run.vibe_actions = h->h_vact;
+  CK(mg_launch_step(run, st));
+  if (observations) CK(cudaMemcpyAsync(observations, h->h_obs, NA * d.T * 3, cudaMemcpyDeviceToHost, st));
+  if (rewards) CK(cudaMemcpyAsync(rewards, h->h_rew, NA * 4, cudaMemcpyDeviceToHost, st));
+  if (terminals) CK(cudaMemcpyAsync(terminals, h->h_term, NA, cudaMemcpyDeviceToHost, st));
+  if (truncations) CK(cudaMemcpyAsync(truncations, h->h_trunc, NA, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MG_OK;
+}
+
+int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, void* stream) {
+  if (!h) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (new_seeds) CK(cudaMemcpyAsync(h->seeds_dev, new_seeds, (size_t)h->d.num_envs * 4, cudaMemcpyHostToDevice, st));
+  CK(mg_launch_reset(h->d, env_mask, st));
+  if (h->buffers_set) CK(mg_launch_init_buffers(h->d, env_mask, st));
+  return MG_OK;
+}
+
+int mg_poll_errors(mg_handle* h, int* env, int* code, int* info) {
+  if (!h) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  std::vector<int32_t> e((size_t)h->d.num_envs * MGEV_WORDS);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(e.data(), h->d.env, e.size() * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < h->d.num_envs; i++)
+    if (e[(size_t)i * MGEV_WORDS + MGEV_ERROR]) {
+      if (env) *env = i;
+      if (code) *code = e[(size_t)i * MGEV_WORDS + MGEV_ERROR];
+      if (info) *info = e[(size_t)i * MGEV_WORDS + MGEV_ERR_INFO];
+      h->err = "environment " + std::to_string(i) + " raised error bits " +
+               std::to_string(e[(size_t)i * MGEV_WORDS + MGEV_ERROR]);
+      return MG_E_ENV;
+    }
+  return MG_OK;
+}
+
+int mg_get_episode_rewards(mg_handle* h, float* out) {
+  if (!h || !out) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const MgDev& d = h->d;
+  std::vector<uint32_t> ag((size_t)d.num_envs * d.A * d.AS);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(ag.data(), d.agents, ag.size() * 4, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < (size_t)d.num_envs * d.A; i++) memcpy(&out[i], &ag[i * d.AS + MGAG_EPISODE_REWARD], 4);
+  return MG_OK;
+}
+
+int mg_get_action_success(mg_handle* h, uint8_t* out) {
+  if (!h || !out) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, h->d.success, (size_t)h->d.num_envs * h->d.A, cudaMemcpyDeviceToHost));
+  return MG_OK;
+}
+
+int mg_get_current_steps(mg_handle* h, int32_t* out) {
+  if (!h || !out) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  std::vector<int32_t> e((size_t)h->d.num_envs * MGEV_WORDS);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(e.data(), h->d.env, e.size() * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < h->d.num_envs; i++) out[i] = e[(size_t)i * MGEV_WORDS + MGEV_STEP];
+  return MG_OK;
+}
+
+int mg_get_agent_stats(mg_handle* h, int env, float* values, uint8_t* touched) {
+  if (!h || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const MgDev& d = h->d;
+  CK(cudaDeviceSynchronize());
+  if (values) CK(cudaMemcpy(values, d.astats + (size_t)env * d.A * d.SA, (size_t)d.A * d.SA * 4, cudaMemcpyDeviceToHost));
+  if (touched) {
+    std::vector<uint32_t> t((size_t)d.A * d.SAW);
+    CK(cudaMemcpy(t.data(), d.atouched + (size_t)env * d.A * d.SAW, t.size() * 4, cudaMemcpyDeviceToHost));
+    for (int a = 0; a < d.A; a++)
+      for (int i = 0; i < d.SA; i++) touched[a * d.SA + i] = (t[a * d.SAW + (i >> 5)] >> (i & 31)) & 1;
+  }
+  return MG_OK;
+}
+
+int mg_get_game_stats(mg_handle* h, int env, float* values, uint8_t* touched) {
+  if (!h || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const MgDev& d = h->d;
+  CK(cudaDeviceSynchronize());
+  if (values) CK(cudaMemcpy(values, d.gstats + (size_t)env * d.SG, (size_t)d.SG * 4, cudaMemcpyDeviceToHost));
+  if (touched) {
+    std::vector<uint32_t> t(d.SGW);
+    CK(cudaMemcpy(t.data(), d.gtouched + (size_t)env * d.SGW, t.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < d.SG; i++) touched[i] = (t[i >> 5] >> (i & 31)) & 1;
+  }
+  return MG_OK;
+}
+
+int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
+  if (!h || !out || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const MgDev& d = h->d;
+  CK(cudaDeviceSynchronize());
+  int32_t E[MGEV_WORDS];
+  CK(cudaMemcpy(E, d.env + (size_t)env * MGEV_WORDS, sizeof E, cudaMemcpyDeviceToHost));
+  int nobj = E[MGEV_NEXT_OBJ];
+  std::vector<uint32_t> objs((size_t)nobj * d.OS);
+  CK(cudaMemcpy(objs.data(), d.objs + (size_t)env * d.maxobj * d.OS, objs.size() * 4, cudaMemcpyDeviceToHost));
+  const int32_t* P = h->program.data();
+  int n = 0, stride = 8 + 2 * d.R;
+  for (int s = 1; s < nobj && n < max_rows; s++) {
+    const uint32_t* o = &objs[(size_t)s * d.OS];
+    int flags = o[MGO_META] >> 24;
+    if (!(flags & MGOF_ALIVE)) continue;
+    int32_t* row = out + (size_t)n * stride;
+    int t = o[MGO_META] & 0xffff;
+    row[0] = (int32_t)o[MGO_ID];
+    row[1] = P[P[MGS_TEMPLATES] + t * MG_TEMPLATE_WORDS + MGT_TYPE_ID];
+    row[2] = o[MGO_LOC] >> 16, row[3] = o[MGO_LOC] & 0xffff, row[4] = (o[MGO_META] >> 16) & 0xff;
+    row[5] = (int32_t)o[MGO_AGENT], row[6] = (int32_t)o[MGO_TAGS];
+    uint64_t ord = (uint64_t)o[MGO_INVORD_LO] | ((uint64_t)o[MGO_INVORD_HI] << 32);
+    int cnt = (int)(ord >> 60);
+    row[7] = cnt;
+    const uint16_t* inv = (const uint16_t*)(o + MGO_TAGS + d.TW);
+    for (int i = 0; i < d.R; i++) row[8 + i] = inv[i];
+    for (int i = 0; i < d.R; i++) row[8 + d.R + i] = i < cnt ? (int)((ord >> (4 * i)) & 15) : -1;
+    n++;
+  }
+  return n;
+}
+
+int mg_num_envs(const mg_handle* h) { return h ? h->d.num_envs : 0; }
+int mg_num_agents(const mg_handle* h) { return h ? h->d.A : 0; }
+int mg_num_tokens(const mg_handle* h) { return h ? h->d.T : 0; }
+size_t mg_state_bytes(const mg_handle* h) { return h ? h->bytes : 0; }
+
+}  // extern "C"

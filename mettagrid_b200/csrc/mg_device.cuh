@@ -1,0 +1,661 @@
+// mg_device.cuh -- per-environment device state view and the handler interpreter.
+//
+// One WARP owns one environment for a whole tick.  The reference's
+// conflict semantics are sequential per env (bindings/mettagrid_c.cpp:958-999), so everything
+// that mutates shared env state runs on lane 0 ("serial" functions below); per-agent and
+// per-cell work fans out over the 32 lanes.  Nothing here is shared with oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+
+#include "mg_state.h"
+
+// Per-warp view of one environment.
+struct Wv {
+  const int32_t* P;
+  const int32_t* hdr;  // shared-memory copy of the header
+  uint16_t* cells;     // shared-memory staged grid
+  uint16_t* cells_g;
+  uint32_t* objs;
+  uint32_t* agents;
+  float* astats;
+  uint32_t* atouched;
+  float* gstats;
+  uint32_t* gtouched;
+  uint32_t* cover;
+  uint32_t* rng;
+  int32_t* E;
+  const float* logtab;
+  uint32_t step;
+  int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND;
+  // rng window (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0
+  int* rs;
+  uint32_t* rand;
+};
+
+// handler/handler_context.hpp:34-55
+struct Ctx {
+  int actor, target, source;
+  int distance, tr, tc, move_dir;
+  bool skip_trigger, failed;
+};
+__device__ __forceinline__ Ctx make_ctx() {
+  Ctx c;
+  c.actor = c.target = c.source = 0;
+  c.distance = c.tr = c.tc = c.move_dir = 0;
+  c.skip_trigger = c.failed = false;
+  return c;
+}
+
+// ---- program access -------------------------------------------------------------------------
+__device__ __forceinline__ int pg(const Wv& w, int i) { return __ldg(w.P + i); }
+__device__ __forceinline__ const int32_t* sec(const Wv& w, int k) { return w.P + w.hdr[k]; }
+__device__ __forceinline__ const int32_t* pool(const Wv& w, int off) { return w.P + w.hdr[MGS_POOL] + off; }
+__device__ __forceinline__ const int32_t* tmpl(const Wv& w, int t) { return sec(w, MGS_TEMPLATES) + t * MG_TEMPLATE_WORDS; }
+
+// ---- object records ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t* objp(const Wv& w, int s) { return w.objs + (size_t)s * w.OS; }
+__device__ __forceinline__ int o_r(const uint32_t* o) { return (int)(o[MGO_LOC] >> 16); }
+__device__ __forceinline__ int o_c(const uint32_t* o) { return (int)(o[MGO_LOC] & 0xffffu); }
+__device__ __forceinline__ int o_tmpl(const uint32_t* o) { return (int)(o[MGO_META] & 0xffffu); }
+__device__ __forceinline__ int o_vibe(const uint32_t* o) { return (int)((o[MGO_META] >> 16) & 0xffu); }
+__device__ __forceinline__ int o_flags(const uint32_t* o) { return (int)(o[MGO_META] >> 24); }
+__device__ __forceinline__ bool o_is_agent(const uint32_t* o) { return (o_flags(o) & MGOF_AGENT) != 0; }
+__device__ __forceinline__ int o_agent(const uint32_t* o) { return (int)o[MGO_AGENT]; }
+__device__ __forceinline__ void o_set_vibe(uint32_t* o, int v) { o[MGO_META] = (o[MGO_META] & 0xff00ffffu) | ((uint32_t)(v & 0xff) << 16); }
+__device__ __forceinline__ uint16_t* o_inv(const Wv& w, uint32_t* o) { return (uint16_t*)(o + MGO_TAGS + w.TW); }
+__device__ __forceinline__ bool o_has_tag(const uint32_t* o, int t) { return (o[MGO_TAGS + (t >> 5)] >> (t & 31)) & 1u; }
+
+// inventory iteration order: packed 4-bit ids, most recently inserted first
+__device__ __forceinline__ uint64_t o_order(const uint32_t* o) { return (uint64_t)o[MGO_INVORD_LO] | ((uint64_t)o[MGO_INVORD_HI] << 32); }
+__device__ __forceinline__ void o_set_order(uint32_t* o, uint64_t v) {
+  o[MGO_INVORD_LO] = (uint32_t)v;
+  o[MGO_INVORD_HI] = (uint32_t)(v >> 32);
+}
+__device__ __forceinline__ int ord_count(uint64_t v) { return (int)(v >> 60); }
+__device__ __forceinline__ int ord_item(uint64_t v, int i) { return (int)((v >> (4 * i)) & 15u); }
+__device__ __forceinline__ uint64_t ord_push_front(uint64_t v, int item) {
+  uint64_t n = (uint64_t)(ord_count(v) + 1);
+  uint64_t body = (v & 0x0fffffffffffffffull) << 4 | (uint64_t)item;
+  return (body & 0x0fffffffffffffffull) | (n << 60);
+}
+__device__ __forceinline__ uint64_t ord_erase(uint64_t v, int item) {
+  int n = ord_count(v);
+  uint64_t body = v & 0x0fffffffffffffffull;
+  for (int i = 0; i < n; i++)
+    if (ord_item(body, i) == item) {
+      uint64_t low = body & ((1ull << (4 * i)) - 1);
+      uint64_t high = (body >> (4 * (i + 1))) << (4 * i);
+      return (low | high) | ((uint64_t)(n - 1) << 60);
+    }
+  return v;
+}
+
+// ---- stats (systems/stats_tracker.hpp:57-98); lane-exclusive per (agent) or serial ----------
+__device__ __forceinline__ void astat_touch(const Wv& w, int a, int id) { w.atouched[a * w.SAW + (id >> 5)] |= 1u << (id & 31); }
+__device__ __forceinline__ void astat_add(const Wv& w, int a, int id, float v) {
+  w.astats[a * w.SA + id] = __fadd_rn(w.astats[a * w.SA + id], v);
+  astat_touch(w, a, id);
+}
+__device__ __forceinline__ void astat_set(const Wv& w, int a, int id, float v) {
+  w.astats[a * w.SA + id] = v;
+  astat_touch(w, a, id);
+}
+__device__ __forceinline__ void gstat_touch(const Wv& w, int id) { w.gtouched[id >> 5] |= 1u << (id & 31); }
+__device__ __forceinline__ void gstat_add(const Wv& w, int id, float v) {
+  w.gstats[id] = __fadd_rn(w.gstats[id], v);
+  gstat_touch(w, id);
+}
+
+__device__ __forceinline__ void set_error(const Wv& w, int code, int info) {
+  if (!(w.E[MGEV_ERROR] & code)) w.E[MGEV_ERR_INFO] = info;
+  w.E[MGEV_ERROR] |= code;
+}
+
+// ---- MT19937.  Outputs are identical to std::mt19937: the generator is advanced
+// one element at a time instead of 624 at once, which yields the same stream. -----------------
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+  uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// all lanes: precompute the next <=32 outputs without committing them.
+// rand[0..32) = tempered outputs, rand[32..64) = the new state words they came from.
+__device__ __forceinline__ void rng_window_fill(Wv& w, int lane) {
+  int idx0 = w.E[MGEV_RNG_IDX];
+  if (idx0 >= MG_RNG_WORDS) idx0 = 0;
+  int count = min(MG_RNG_WINDOW, MG_RNG_WORDS - idx0);
+  if (lane < count) {
+    int i = idx0 + lane;
+    int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
+    int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
+    uint32_t nw = mt_twist(w.rng[i], w.rng[i1], w.rng[i2]);
+    w.rand[lane] = mt_temper(nw);
+    w.rand[MG_RNG_WINDOW + lane] = nw;
+  }
+  if (lane == 0) {
+    w.rs[0] = 0;
+    w.rs[1] = count;
+    w.rs[2] = 0;
+    w.rs[3] = idx0;
+  }
+}
+// all lanes: commit what the serial code consumed from the window
+__device__ __forceinline__ void rng_window_commit(Wv& w, int lane) {
+  if (w.rs[2]) return;  // direct mode already committed
+  int used = w.rs[0];
+  if (lane < used) w.rng[w.rs[3] + lane] = w.rand[MG_RNG_WINDOW + lane];
+  if (lane == 0 && used > 0) w.E[MGEV_RNG_IDX] = w.rs[3] + used;
+}
+// serial: next raw 32-bit output
+__device__ __noinline__ uint32_t rng_next_slow(Wv& w, const uint32_t* pending /*smem new words*/) {
+  if (!w.rs[2]) {  // leave window mode: commit the whole window, continue directly on global state
+    int count = w.rs[1];
+    for (int k = 0; k < count; k++) w.rng[w.rs[3] + k] = pending[k];
+    w.E[MGEV_RNG_IDX] = w.rs[3] + count;
+    w.rs[2] = 1;
+  }
+  int i = w.E[MGEV_RNG_IDX];
+  if (i >= MG_RNG_WORDS) i = 0;
+  int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
+  int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
+  uint32_t nw = mt_twist(w.rng[i], w.rng[i1], w.rng[i2]);
+  w.rng[i] = nw;
+  w.E[MGEV_RNG_IDX] = i + 1;
+  return mt_temper(nw);
+}
+__device__ __forceinline__ uint32_t rng_next(Wv& w) {
+  int pos = w.rs[0];
+  if (!w.rs[2] && pos < w.rs[1]) {
+    w.rs[0] = pos + 1;
+    return w.rand[pos];
+  }
+  return rng_next_slow(w, w.rand + MG_RNG_WINDOW);
+}
+// Lemire multiply-shift with rejection (bits/uniform_int_dist.h:252-282)
+__device__ __forceinline__ uint32_t rng_below(Wv& w, uint32_t range) {
+  uint64_t prod = (uint64_t)rng_next(w) * range;
+  uint32_t low = (uint32_t)prod;
+  if (low < range) {
+    uint32_t thr = (0u - range) % range;
+    while (low < thr) {
+      prod = (uint64_t)rng_next(w) * range;
+      low = (uint32_t)prod;
+    }
+  }
+  return (uint32_t)(prod >> 32);
+}
+// libstdc++ std::shuffle (bits/stl_algo.h:3719-3805): two swap positions per draw
+template <class T>
+__device__ __forceinline__ void rng_shuffle(Wv& w, T* v, int n) {
+  if (n < 2) return;
+  int i = 1;
+  if ((n & 1) == 0) {
+    int j = (int)rng_below(w, 2);
+    T t = v[i];
+    v[i] = v[j];
+    v[j] = t;
+    i++;
+  }
+  while (i < n) {
+    uint32_t sr = (uint32_t)i + 1;
+    uint32_t x = rng_below(w, sr * (sr + 1));
+    int p0 = (int)(x / (sr + 1)), p1 = (int)(x % (sr + 1));
+    T t = v[i];
+    v[i] = v[p0];
+    v[p0] = t;
+    i++;
+    t = v[i];
+    v[i] = v[p1];
+    v[p1] = t;
+    i++;
+  }
+}
+
+// ---- inventory (objects/inventory.cpp:38-173, inventory.hpp:26-40) -----------------------------
+__device__ __forceinline__ int limit_of(const Wv& w, const uint32_t* o, int item) { return __ldg(pool(w, __ldg(tmpl(w, o_tmpl(o)) + MGT_LIMIT_OF)) + item); }
+__device__ __forceinline__ bool is_modifier(const Wv& w, const uint32_t* o, int item) { return (__ldg(tmpl(w, o_tmpl(o)) + MGT_MODIFIER_MASK) >> item) & 1; }
+__device__ __forceinline__ int effective_limit(const Wv& w, uint32_t* o, int lim) {
+  const int32_t* L = sec(w, MGS_LIMITS) + lim * MG_LIMIT_WORDS;
+  const uint16_t* inv = o_inv(w, o);
+  const int32_t* m = pool(w, __ldg(L + 2));
+  int nm = __ldg(L + 3), sum = 0;
+  for (int i = 0; i < nm; i++) sum += (int)inv[__ldg(m + 2 * i)] * __ldg(m + 2 * i + 1);
+  int eff = min(__ldg(L + 1), max(__ldg(L + 0), sum));
+  return min(max(eff, 0), 65535);
+}
+__device__ __forceinline__ int limit_amount(const Wv& w, uint32_t* o, int lim) {
+  const int32_t* L = sec(w, MGS_LIMITS) + lim * MG_LIMIT_WORDS;
+  const uint16_t* inv = o_inv(w, o);
+  const int32_t* mem = pool(w, __ldg(L + 4));
+  int n = __ldg(L + 5);
+  uint32_t s = 0;
+  for (int i = 0; i < n; i++) s += inv[__ldg(mem + i)];
+  return (int)(s & 0xffffu);  // SharedInventoryLimit::amount is a uint16 running sum
+}
+// objects/agent.cpp:106-121
+__device__ __forceinline__ void on_inventory_change(const Wv& w, uint32_t* o, int item, int delta) {
+  if (!o_is_agent(o) || o_agent(o) < 0) return;
+  int a = o_agent(o);
+  const int32_t* rs = sec(w, MGS_RES_STATS) + item * 4;
+  if (delta > 0)
+    astat_add(w, a, __ldg(rs + 0), (float)delta);
+  else
+    astat_add(w, a, __ldg(rs + 1), (float)(-delta));
+  int amount = o_inv(w, o)[item];
+  astat_set(w, a, __ldg(rs + 2), (float)amount);
+  if (amount == 0 && delta < 0 && item == w.hdr[MGH_HP_RESOURCE]) astat_add(w, a, w.hdr[MGH_ST_DEATH], 1.0f);
+}
+template <int D>
+__device__ __noinline__ int inv_update(const Wv& w, uint32_t* o, int item, int attempted, bool ignore_limits = false, bool notify = true);
+template <int D>
+__device__ __noinline__ void enforce_all_limits(const Wv& w, uint32_t* o) {
+  const int32_t* t = tmpl(w, o_tmpl(o));
+  const int32_t* lo = pool(w, __ldg(t + MGT_LIMIT_ORDER));
+  int nl = __ldg(t + MGT_LIMIT_ORDER_N);
+  for (int i = 0; i < nl; i++) {
+    int lim = __ldg(lo + i);
+    int excess = limit_amount(w, o, lim) - effective_limit(w, o, lim);
+    if (excess <= 0) continue;
+    const int32_t* L = sec(w, MGS_LIMITS) + lim * MG_LIMIT_WORDS;
+    const int32_t* mem = pool(w, __ldg(L + 4));
+    int n = __ldg(L + 5);
+    for (int k = 0; k < n; k++) {
+      int it = __ldg(mem + k);
+      int drop = min((int)o_inv(w, o)[it], excess);
+      if (drop > 0) {
+        if constexpr (D > 0)
+          inv_update<D - 1>(w, o, it, -drop);
+        else
+          set_error(w, MGERR_UNSUPPORTED, 1);
+        excess = limit_amount(w, o, lim) - effective_limit(w, o, lim);
+      }
+      if (excess <= 0) break;
+    }
+  }
+}
+template <int D>
+__device__ __noinline__ int inv_update(const Wv& w, uint32_t* o, int item, int attempted, bool ignore_limits, bool notify) {
+  uint16_t* inv = o_inv(w, o);
+  int initial = inv[item];
+  int na = initial + attempted;
+  int mx = 65535;
+  int lim = limit_of(w, o, item);
+  if (!ignore_limits && lim >= 0) {
+    int others = limit_amount(w, o, lim) - initial;
+    if (others < 0) others = 0;
+    int mi = effective_limit(w, o, lim) - others;
+    mx = mi < 0 ? 0 : (mi & 0xffff);
+  }
+  int clamped = min(max(na, 0), mx);
+  if (clamped == 0) {
+    if (initial != 0) o_set_order(o, ord_erase(o_order(o), item));
+  } else if (initial == 0) {
+    o_set_order(o, ord_push_front(o_order(o), item));
+  }
+  inv[item] = (uint16_t)clamped;
+  int d = clamped - initial;
+  if (notify && d != 0) on_inventory_change(w, o, item, d);
+  if (d < 0 && is_modifier(w, o, item)) enforce_all_limits<D>(w, o);
+  return d;
+}
+__device__ __forceinline__ int free_space(const Wv& w, uint32_t* o, int item) {
+  int lim = limit_of(w, o, item);
+  if (lim < 0) return 65535 - (int)o_inv(w, o)[item];
+  int used = limit_amount(w, o, lim), eff = effective_limit(w, o, lim);
+  return eff > used ? eff - used : 0;
+}
+// objects/has_inventory.cpp:76-108
+__device__ __noinline__ int transfer(const Wv& w, uint32_t* src, uint32_t* dst, int item, int delta) {
+  if (delta <= 0) return 0;
+  int give = min((int)o_inv(w, src)[item], delta);
+  int amount = min(give, free_space(w, dst, item));
+  inv_update<2>(w, src, item, -amount);
+  inv_update<2>(w, dst, item, amount);
+  return amount;
+}
+
+// ---- grid (core/grid.hpp:31-130) -----------------------------------------------------------------
+__device__ __forceinline__ bool valid_loc(const Wv& w, int r, int c) { return r >= 0 && c >= 0 && r < w.H && c < w.W; }
+__device__ __forceinline__ void set_cell(const Wv& w, int r, int c, int s) {
+  w.cells[r * w.W + c] = (uint16_t)s;
+  w.cells_g[r * w.W + c] = (uint16_t)s;  // write-through: the staged copy is never flushed
+}
+__device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
+  if (!valid_loc(w, r, c) || w.cells[r * w.W + c] != 0) return false;
+  uint32_t* o = objp(w, s);
+  set_cell(w, r, c, s);
+  set_cell(w, o_r(o), o_c(o), 0);
+  o[MGO_LOC] = ((uint32_t)r << 16) | (uint32_t)c;
+  return true;
+}
+
+// ---- game values (core/game_value.cpp:14-148) -----------------------------------------------------
+__device__ __forceinline__ float host_logf_plus1(const Wv& w, float term) {
+  // std::log(term + 1.0f) through the host-libm table when term is an integer in range
+  float x = __fadd_rn(term, 1.0f);
+  float k = x - 1.0f;
+  if (x >= 1.0f && x <= 65536.0f && truncf(x) == x) return __ldg(w.logtab + (int)x - 1);
+  (void)k;
+  return (float)log((double)x);  // non-integer argument: correctly rounded double log (<= 1 ulp vs glibc)
+}
+template <int D>
+__device__ __noinline__ float eval_value(const Wv& w, int node, int entity) {
+  const int32_t* v = sec(w, MGS_VALUES) + node * MG_VALUE_WORDS;
+  int op = __ldg(v), scope = __ldg(v + 1), a = __ldg(v + 2), b = __ldg(v + 3);
+  switch (op) {
+    case MGV_INVENTORY:
+      if (entity) return (float)o_inv(w, objp(w, entity))[a];
+      if (scope == MGSC_GAME) {
+        int id = __ldg(sec(w, MGS_RES_GSTATS) + a);
+        gstat_touch(w, id);
+        return w.gstats[id];
+      }
+      return 0.0f;
+    case MGV_STAT:
+      if (scope == MGSC_GAME) {
+        gstat_touch(w, a);
+        return w.gstats[a];
+      }
+      if (entity) {
+        const uint32_t* o = objp(w, entity);
+        if (o_is_agent(o) && o_agent(o) >= 0) {
+          astat_touch(w, o_agent(o), a);
+          return w.astats[o_agent(o) * w.SA + a];
+        }
+      }
+      return 0.0f;
+    case MGV_CONST:
+      return __int_as_float(a);
+    case MGV_SUM: {
+      if constexpr (D > 0) {
+        float total = 0.0f;
+        const int32_t* kids = pool(w, a);
+        int woff = __ldg(v + 4), lg = __ldg(v + 5);
+        for (int i = 0; i < b; i++) {
+          float term = eval_value<D - 1>(w, __ldg(kids + i), entity);
+          if (lg) term = host_logf_plus1(w, term);
+          if (woff >= 0) term = __fmul_rn(term, __int_as_float(__ldg(pool(w, woff) + i)));
+          total = __fadd_rn(total, term);
+        }
+        return total;
+      }
+      break;
+    }
+    case MGV_RATIO: {
+      if constexpr (D > 0) {
+        float num = eval_value<D - 1>(w, a, entity), den = eval_value<D - 1>(w, b, entity);
+        return den > 0.0f ? __fdiv_rn(num, den) : num;
+      }
+      break;
+    }
+    case MGV_MAX:
+    case MGV_MIN: {
+      if constexpr (D > 0) {
+        if (b == 0) return 0.0f;
+        const int32_t* kids = pool(w, a);
+        float best = op == MGV_MAX ? -3.402823466e+38f : 3.402823466e+38f;
+        for (int i = 0; i < b; i++) {
+          float x = eval_value<D - 1>(w, __ldg(kids + i), entity);
+          // std::max(a, b) = (a < b) ? b : a ; std::min(a, b) = (b < a) ? b : a
+          if (op == MGV_MAX)
+            best = (best < x) ? x : best;
+          else
+            best = (x < best) ? x : best;
+        }
+        return best;
+      }
+      break;
+    }
+    default:
+      break;
+  }
+  set_error(w, MGERR_UNSUPPORTED, 2);  // queries inside values / nesting too deep
+  return 0.0f;
+}
+__device__ __forceinline__ int resolve_entity(const Ctx& c, int e) { return e == MGE_ACTOR ? c.actor : e == MGE_TARGET ? c.target : c.source; }
+
+// ---- filters (handler/filters/*.hpp) -------------------------------------------------------------
+template <int D>
+__device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx) {
+  const int32_t* f = sec(w, MGS_FILTERS) + fi * MG_FILTER_WORDS;
+  int op = __ldg(f), a = __ldg(f + 2), b = __ldg(f + 3);
+  int e = resolve_entity(ctx, __ldg(f + 1));
+  switch (op) {
+    case MGF_VIBE:
+      return e && o_vibe(objp(w, e)) == a;
+    case MGF_RESOURCE:
+      return e && (int)o_inv(w, objp(w, e))[a] >= b;
+    case MGF_SHARED_TAG_PREFIX: {
+      if (!ctx.actor || !ctx.target) return false;
+      const uint32_t *x = objp(w, ctx.actor), *y = objp(w, ctx.target);
+      const int32_t* m = pool(w, a);
+      for (int k = 0; k < w.TW; k++)
+        if (x[MGO_TAGS + k] & y[MGO_TAGS + k] & (uint32_t)__ldg(m + k)) return true;
+      return false;
+    }
+    case MGF_TAG_PREFIX: {
+      if (!e) return false;
+      const uint32_t* x = objp(w, e);
+      const int32_t* m = pool(w, a);
+      for (int k = 0; k < w.TW; k++)
+        if (x[MGO_TAGS + k] & (uint32_t)__ldg(m + k)) return true;
+      return false;
+    }
+    case MGF_GAME_VALUE:
+      return eval_value<4>(w, a, e) >= eval_value<4>(w, b, e);
+    case MGF_NEG:
+      if constexpr (D > 0) {
+        for (int i = 0; i < b; i++)
+          if (!filter_pass<D - 1>(w, a + i, ctx)) return true;
+        return false;
+      }
+      break;
+    case MGF_OR:
+      if constexpr (D > 0) {
+        for (int i = 0; i < b; i++)
+          if (filter_pass<D - 1>(w, a + i, ctx)) return true;
+        return false;
+      }
+      break;
+    case MGF_MAX_DISTANCE: {  // max_distance_filter.hpp:31-63 (binary form)
+      if (!e) return false;
+      if (a < 0) {
+        int ref = ctx.source ? ctx.source : ctx.actor;
+        if (!ref) return false;
+        if (b == 0) return true;
+        const uint32_t *x = objp(w, e), *y = objp(w, ref);
+        long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
+        return dr * dr + dc * dc <= (long long)b * b;
+      }
+      break;  // unary (query) form: not in this kernel yet
+    }
+    case MGF_TARGET_LOC_EMPTY:
+      return ctx.target == 0;
+    case MGF_TARGET_IS_USABLE:
+      return ctx.target != 0;
+    case MGF_PERIODIC:
+      if (w.step < (uint32_t)b) return false;
+      return (w.step - (uint32_t)b) % (uint32_t)a == 0;
+    default:
+      break;
+  }
+  set_error(w, MGERR_UNSUPPORTED, 3);
+  return false;
+}
+template <int D>
+__device__ __forceinline__ bool filters_pass(const Wv& w, int f0, int n, const Ctx& ctx) {
+  for (int i = 0; i < n; i++)
+    if (!filter_pass<D>(w, f0 + i, ctx)) return false;
+  return true;
+}
+
+// ---- mutations + handlers (handler/mutations/*.hpp, handler.cpp:76-103, multi_handler.cpp:8-21) ---
+template <int D>
+__device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx);
+
+template <int D>
+__device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
+  const int32_t* m = sec(w, MGS_MUTATIONS) + mi * MG_MUTATION_WORDS;
+  int op = __ldg(m), a = __ldg(m + 3), b = __ldg(m + 4), c = __ldg(m + 5), d = __ldg(m + 6);
+  int e1 = resolve_entity(ctx, __ldg(m + 1)), e2 = resolve_entity(ctx, __ldg(m + 2));
+  switch (op) {
+    case MGM_RESOURCE_DELTA:
+      if (e1) inv_update<2>(w, objp(w, e1), a, b);
+      return;
+    case MGM_RESOURCE_TRANSFER: {
+      if (!e1 || !e2) return;
+      uint32_t* src = objp(w, e1);
+      int amount = b < 0 ? (int)o_inv(w, src)[a] : b;
+      int moved = transfer(w, src, objp(w, e2), a, amount);
+      if (moved > 0 && o_is_agent(src) && o_agent(src) >= 0) astat_add(w, o_agent(src), __ldg(sec(w, MGS_RES_STATS) + a * 4 + 3), (float)moved);
+      if (c) set_error(w, MGERR_UNSUPPORTED, 4);  // remove_source_when_empty
+      return;
+    }
+    case MGM_CLEAR_INVENTORY: {
+      if (!e1) return;
+      uint32_t* o = objp(w, e1);
+      if (b == 0) {
+        uint64_t ord = o_order(o);
+        int n = ord_count(ord);
+        for (int i = 0; i < n; i++) {
+          int it = ord_item(ord, i);
+          inv_update<2>(w, o, it, -(int)o_inv(w, o)[it]);
+        }
+      } else {
+        const int32_t* ids = pool(w, a);
+        for (int i = 0; i < b; i++) {
+          int it = __ldg(ids + i);
+          inv_update<2>(w, o, it, -(int)o_inv(w, o)[it]);
+        }
+      }
+      return;
+    }
+    case MGM_ATTACK: {
+      if (!ctx.actor || !ctx.target) return;
+      int weapon = o_inv(w, objp(w, ctx.actor))[a], armor = o_inv(w, objp(w, ctx.target))[b];
+      int dmg = max(0, weapon * d / 100 - armor);
+      if (dmg > 0) inv_update<2>(w, objp(w, ctx.target), c, -dmg);
+      return;
+    }
+    case MGM_STATS: {
+      int ent = c ? ctx.actor : ctx.target;
+      float v = eval_value<4>(w, d, ent);
+      if (b == 0) {
+        w.gstats[a] = v;
+        gstat_touch(w, a);
+      } else if (ent) {
+        const uint32_t* o = objp(w, ent);
+        if (o_is_agent(o) && o_agent(o) >= 0) astat_set(w, o_agent(o), a, v);
+      }
+      return;
+    }
+    case MGM_GAME_VALUE: {
+      float delta = eval_value<4>(w, b, e1);
+      const int32_t* v = sec(w, MGS_VALUES) + a * MG_VALUE_WORDS;
+      int vop = __ldg(v), vscope = __ldg(v + 1), va = __ldg(v + 2);
+      if (vop == MGV_INVENTORY) {
+        if (e1)
+          inv_update<2>(w, objp(w, e1), va, (int)delta);
+        else if (vscope == MGSC_GAME)
+          gstat_add(w, __ldg(sec(w, MGS_RES_GSTATS) + va), delta);
+      } else if (vop == MGV_STAT) {
+        if (vscope == MGSC_GAME) {
+          gstat_add(w, va, delta);
+        } else if (e1) {
+          const uint32_t* o = objp(w, e1);
+          if (o_is_agent(o) && o_agent(o) >= 0) astat_add(w, o_agent(o), va, delta);
+        }
+      }
+      return;
+    }
+    case MGM_RELOCATE:
+      if (ctx.actor && o_is_agent(objp(w, ctx.actor))) move_object(w, ctx.actor, ctx.tr, ctx.tc);
+      return;
+    case MGM_SWAP: {  // swap_mutation.hpp:15-22, core/grid.hpp:78-92
+      if (!ctx.actor || !ctx.target) return;
+      uint32_t *x = objp(w, ctx.actor), *y = objp(w, ctx.target);
+      if (!o_is_agent(x) || !o_is_agent(y)) return;
+      uint32_t lx = x[MGO_LOC], ly = y[MGO_LOC];
+      set_cell(w, (int)(lx >> 16), (int)(lx & 0xffff), ctx.target);
+      set_cell(w, (int)(ly >> 16), (int)(ly & 0xffff), ctx.actor);
+      x[MGO_LOC] = ly;
+      y[MGO_LOC] = lx;
+      if (o_agent(x) >= 0) astat_add(w, o_agent(x), w.hdr[MGH_ST_ACTIONS_SWAP], 1.0f);
+      return;
+    }
+    case MGM_USE_TARGET: {  // use_target_mutation.hpp:17-30
+      if (!ctx.target || !ctx.actor || !o_is_agent(objp(w, ctx.actor))) {
+        ctx.failed = true;
+        return;
+      }
+      if constexpr (D > 0) {
+        int h = __ldg(tmpl(w, o_tmpl(objp(w, ctx.target))) + MGT_ON_USE);
+        bool ok = false;
+        if (h >= 0) {
+          Ctx u = ctx;
+          ok = handler_apply<D - 1>(w, h, u);
+        }
+        if (!ok) {
+          ctx.failed = true;
+          return;
+        }
+        int after = __ldg(tmpl(w, o_tmpl(objp(w, ctx.actor))) + MGT_ON_AFTER_USE);
+        if (after >= 0) handler_apply<D - 1>(w, after, ctx);  // shares ctx (objects/agent.cpp:73-77)
+        return;
+      }
+      break;
+    }
+    case MGM_CHANGE_VIBE:
+      if (e1) o_set_vibe(objp(w, e1), a);
+      return;
+    case MGM_PUSH_OBJECT: {  // push_object_mutation.hpp:27-57
+      if (!ctx.actor || !ctx.target) {
+        ctx.failed = true;
+        return;
+      }
+      const uint32_t *x = objp(w, ctx.actor), *t = objp(w, ctx.target);
+      int dr = min(max(o_r(t) - o_r(x), -1), 1), dc = min(max(o_c(t) - o_c(x), -1), 1);
+      if (!move_object(w, ctx.target, o_r(t) + dr, o_c(t) + dc)) ctx.failed = true;
+      return;
+    }
+    default:
+      break;
+  }
+  set_error(w, MGERR_UNSUPPORTED, 5 | (op << 8));
+}
+
+template <int D>
+__device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx) {
+  const int32_t* hd = sec(w, MGS_HANDLERS) + h * MG_HANDLER_WORDS;
+  int kind = __ldg(hd), a = __ldg(hd + 1), b = __ldg(hd + 2);
+  if (kind == MGHK_SIMPLE) {
+    if (!filters_pass<3>(w, a, b, ctx)) return false;
+    int m0 = __ldg(hd + 3), mn = __ldg(hd + 4);
+    ctx.failed = false;
+    for (int i = 0; i < mn; i++) {
+      mutate<D>(w, m0 + i, ctx);
+      if (ctx.failed) return false;
+    }
+    return true;
+  }
+  if constexpr (D > 0) {
+    bool any = false;
+    const int32_t* kids = pool(w, a);
+    for (int i = 0; i < b; i++)
+      if (handler_apply<D - 1>(w, __ldg(kids + i), ctx)) {
+        any = true;
+        if (kind == MGHK_FIRST_MATCH) return true;
+      }
+    return any;
+  }
+  set_error(w, MGERR_UNSUPPORTED, 6);
+  return false;
+}

@@ -1,0 +1,768 @@
+// mg_kernels.cu -- sm_100a kernels for the batched MettaGrid tick.
+//
+//   k_reset        : build per-env state from the template map (the reference's constructor,
+//                    bindings/mettagrid_c.cpp:42-191,200-269)
+//   k_init_buffers : _init_buffers (:294-319): clear flags, reset coverage, initial observations
+//   k_step         : MettaGrid::_step (:921-1102), all 15 phases fused in one launch
+//
+// Mapping: one warp = one environment; MG_WARPS_PER_CTA envs per CTA.  The
+// env's grid is staged in shared memory, each agent's observation is composed in shared memory and
+// streamed to HBM with 16-byte stores.
+#include "mg_device.cuh"
+
+namespace {
+
+struct Smem {
+  int32_t* hdr;
+  uint32_t* offs;
+  // per warp
+  uint16_t* cells;
+  uint8_t* stage;
+  int* rs;
+  uint32_t* rand;
+  uint32_t* a_slot;   // agent -> object slot
+  uint32_t* a_loc;    // location after the action phase (observer position)
+  uint32_t* a_step;   // location at the start of the tick (_prev_agent_locations)
+  int32_t* a_act;     // primary-stream action index
+  int32_t* a_vact;    // vibe-stream action index
+  uint32_t* a_res;    // MGR_* bits recorded by the serial action loop
+  uint32_t* a_locp;   // location right after the primary-stream action
+  uint32_t* a_locv;   // location right after the vibe-stream action
+  int32_t* a_exec;    // executed action (last successful)
+  uint16_t* a_order;  // shuffled agent order
+};
+#define MG_AGENT_WORD_ARRAYS 9
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// bytes of dynamic shared memory per warp / per CTA (must match carve())
+__host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {
+  size_t n = 0;
+  n += align16((size_t)HWp * 2);
+  n += align16((size_t)3 * T + 32);
+  n += align16(4 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
+  n += align16((size_t)A * 4) * MG_AGENT_WORD_ARRAYS;
+  n += align16((size_t)A * 2);
+  return n;
+}
+__host__ __device__ inline size_t smem_per_cta(int NOFF) { return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4); }
+
+__device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int warp, Smem& s) {
+  s.hdr = (int32_t*)base;
+  base += align16(MGH_HEADER_WORDS * 4);
+  s.offs = (uint32_t*)base;
+  base += align16((size_t)d.NOFF * 4);
+  base += (size_t)warp * smem_per_warp(d.HWp, d.T, d.A);
+  s.cells = (uint16_t*)base;
+  base += align16((size_t)d.HWp * 2);
+  s.stage = base;
+  base += align16((size_t)3 * d.T + 32);
+  s.rs = (int*)base;
+  s.rand = (uint32_t*)(base + 4 * sizeof(int));
+  base += align16(4 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
+  size_t aw = align16((size_t)d.A * 4);
+  s.a_slot = (uint32_t*)base, base += aw;
+  s.a_loc = (uint32_t*)base, base += aw;
+  s.a_step = (uint32_t*)base, base += aw;
+  s.a_act = (int32_t*)base, base += aw;
+  s.a_vact = (int32_t*)base, base += aw;
+  s.a_res = (uint32_t*)base, base += aw;
+  s.a_locp = (uint32_t*)base, base += aw;
+  s.a_locv = (uint32_t*)base, base += aw;
+  s.a_exec = (int32_t*)base, base += aw;
+  s.a_order = (uint16_t*)base;
+}
+
+// CTA prologue: header + packed observation offsets into shared memory
+__device__ __forceinline__ void load_cta_tables(const MgDev& d, Smem& s) {
+  for (int i = threadIdx.x; i < MGH_HEADER_WORDS; i += blockDim.x) s.hdr[i] = __ldg(d.P + i);
+  __syncthreads();
+  const int32_t* offs = d.P + s.hdr[MGS_OFFSETS];
+  int rr = s.hdr[MGH_OBS_H] >> 1, cr = s.hdr[MGH_OBS_W] >> 1;
+  for (int i = threadIdx.x; i < d.NOFF; i += blockDim.x) {
+    int dr = __ldg(offs + 2 * i), dc = __ldg(offs + 2 * i + 1);
+    uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));  // systems/packed_coordinate.hpp:50-56
+    s.offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env, Wv& w) {
+  w.P = d.P;
+  w.hdr = s.hdr;
+  w.cells = s.cells;
+  w.cells_g = d.cells + (size_t)env * d.HWp;
+  w.objs = d.objs + (size_t)env * d.maxobj * d.OS;
+  w.agents = d.agents + (size_t)env * d.A * d.AS;
+  w.astats = d.astats + (size_t)env * d.A * d.SA;
+  w.atouched = d.atouched + (size_t)env * d.A * d.SAW;
+  w.gstats = d.gstats + (size_t)env * d.SG;
+  w.gtouched = d.gtouched + (size_t)env * d.SGW;
+  w.cover = d.cover + (size_t)env * d.A * d.CW;
+  w.rng = d.rng + (size_t)env * MG_RNG_WORDS;
+  w.E = d.env + (size_t)env * MGEV_WORDS;
+  w.logtab = d.logtab;
+  w.H = d.H, w.W = d.W, w.A = d.A, w.R = d.R, w.TW = d.TW, w.OS = d.OS, w.AS = d.AS;
+  w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND;
+  w.rs = s.rs;
+  w.rand = s.rand;
+  w.step = (uint32_t)w.E[MGEV_STEP];
+}
+
+__device__ __forceinline__ void stage_cells(const MgDev& d, const Wv& w, int lane) {
+  const uint4* src = (const uint4*)w.cells_g;
+  uint4* dst = (uint4*)w.cells;
+  for (int i = lane; i < d.HWp / 8; i += 32) dst[i] = src[i];
+  __syncwarp();
+}
+
+// ---- shared-memory helpers for the observation stage --------------------------------------------
+__device__ __forceinline__ void fill_ff(uint8_t* p, int n, int lane) {
+  if (n <= 0) return;
+  int head = (int)((16u - ((uint32_t)(uintptr_t)p & 15u)) & 15u);
+  if (head > n) head = n;
+  if (lane < head) p[lane] = 0xFF;
+  int body = (n - head) >> 4;
+  uint4* p4 = (uint4*)(p + head);
+  const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  for (int i = lane; i < body; i += 32) p4[i] = ff;
+  int done = head + (body << 4);
+  if (lane < n - done) p[done + lane] = 0xFF;
+}
+// stage and destination share the same 16-byte phase, so the body moves as aligned 16-byte vectors
+__device__ __forceinline__ void flush_obs(const uint8_t* src, uint8_t* g, int n, int lane) {
+  int head = (int)((16u - ((uint32_t)(uintptr_t)g & 15u)) & 15u);
+  if (head > n) head = n;
+  if (lane < head) g[lane] = src[lane];
+  int body = (n - head) >> 4;
+  const uint4* s4 = (const uint4*)(src + head);
+  uint4* g4 = (uint4*)(g + head);
+  for (int i = lane; i < body; i += 32) __stcs(g4 + i, s4[i]);
+  int done = head + (body << 4);
+  if (lane < n - done) g[done + lane] = src[done + lane];
+}
+
+__device__ __forceinline__ int num_digits(uint32_t v, uint32_t B, int ND) {
+  int n = 1;
+  v /= B;
+  while (v > 0 && n < ND) {
+    v /= B;
+    n++;
+  }
+  return n;
+}
+
+// tokens an object contributes (core/grid_object.cpp:178-203, objects/agent.cpp:142-154)
+__device__ __forceinline__ int count_tokens(const Wv& w, uint32_t* o) {
+  int n = 0;
+  for (int k = 0; k < w.TW; k++) n += __popc(o[MGO_TAGS + k]);
+  n += o_vibe(o) != 0;
+  int fl = o_flags(o);
+  if (fl & MGOF_OBS_INV) {
+    uint64_t ord = o_order(o);
+    int cnt = ord_count(ord);
+    const uint16_t* inv = o_inv(w, o);
+    if (w.B == 256) {
+      for (int i = 0; i < cnt; i++) n += 1 + (inv[ord_item(ord, i)] >= 256);
+    } else {
+      for (int i = 0; i < cnt; i++) n += num_digits(inv[ord_item(ord, i)], (uint32_t)w.B, w.ND);
+    }
+  }
+  if (fl & MGOF_AGENT) n += 2;
+  return n;
+}
+__device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc, int feat, int val) {
+  if (pos < T) {
+    out[pos * 3 + 0] = (uint8_t)loc;
+    out[pos * 3 + 1] = (uint8_t)feat;
+    out[pos * 3 + 2] = (uint8_t)val;
+  }
+}
+__device__ __forceinline__ void write_tokens(const Wv& w, uint32_t* o, uint8_t* out, int pos, int loc) {
+  const int T = w.T;
+  const int ftag = w.hdr[MGH_FEAT_TAG];
+  for (int k = 0; k < w.TW; k++) {
+    uint32_t m = o[MGO_TAGS + k];
+    while (m) {
+      int b = __ffs(m) - 1;
+      put_token(out, T, pos++, loc, ftag, k * 32 + b);
+      m &= m - 1;
+    }
+  }
+  int vibe = o_vibe(o);
+  if (vibe) put_token(out, T, pos++, loc, w.hdr[MGH_FEAT_VIBE], vibe);
+  int fl = o_flags(o);
+  if (fl & MGOF_OBS_INV) {
+    uint64_t ord = o_order(o);
+    int cnt = ord_count(ord);
+    const uint16_t* inv = o_inv(w, o);
+    const int32_t* feats = sec(w, MGS_INV_FEATS);
+    for (int i = 0; i < cnt; i++) {
+      int it = ord_item(ord, i);
+      uint32_t amt = inv[it];
+      int p = 0;
+      do {
+        put_token(out, T, pos++, loc, __ldg(feats + it * w.ND + p), (int)(amt % (uint32_t)w.B));
+        amt /= (uint32_t)w.B;
+        p++;
+      } while (amt > 0 && p < w.ND);
+    }
+  }
+  if (fl & MGOF_AGENT) {
+    int ai = o_agent(o);
+    put_token(out, T, pos++, loc, w.hdr[MGH_FEAT_GROUP], __ldg(tmpl(w, o_tmpl(o)) + MGT_GROUP));
+    put_token(out, T, pos++, loc, w.hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
+  }
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
+  int x = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int y = __shfl_up_sync(MG_FULL, x, off);
+    if (lane >= off) x += y;
+  }
+  total = __shfl_sync(MG_FULL, x, 31);
+  return x - v;
+}
+
+// One agent's observation, composed by the whole warp (bindings/mettagrid_c.cpp:665-824).
+// Returns the number of tokens attempted; `tok` accumulates the env's token stats.
+__device__ int observe_agent(const MgDev& d, const Wv& w, const Smem& s, int env, int a, int action, uint32_t steploc,
+                             int lane) {
+  const int T = w.T;
+  uint8_t* g = d.obs + ((size_t)env * d.A + a) * (size_t)(3 * T);
+  uint8_t* out = s.stage + ((uint32_t)(uintptr_t)g & 15u);
+  const uint32_t loc0 = s.a_loc[a];
+  const int r0 = (int)(loc0 >> 16), c0 = (int)(loc0 & 0xffffu);
+  const int flags = w.hdr[MGH_GLOBAL_FLAGS];
+  uint32_t* ag = w.agents + a * w.AS;
+
+  // ---- global tokens (:700-742), one candidate per lane, compacted in order
+  int feat = 0, val = 0, have = 0;
+  if (lane == 0 && (flags & MGG_EPISODE_PCT)) {
+    int ms = w.hdr[MGH_MAX_STEPS];
+    have = 1, feat = w.hdr[MGH_FEAT_EPISODE_PCT];
+    if (ms > 0) val = w.step >= (uint32_t)ms ? 255 : (int)((256u * w.step / (uint32_t)ms) & 0xffu);
+  } else if (lane == 1 && (flags & MGG_LAST_ACTION)) {
+    have = 1, feat = w.hdr[MGH_FEAT_LAST_ACTION], val = action & 0xff;
+  } else if (lane == 2 && (flags & MGG_LAST_ACTION_MOVE) && w.hdr[MGH_FEAT_LAST_ACTION_MOVE] != 0) {
+    have = 1, feat = w.hdr[MGH_FEAT_LAST_ACTION_MOVE], val = loc0 != steploc;
+  } else if (lane == 3 && (flags & MGG_LAST_REWARD)) {
+    // rewards are zeroed before and written after the observation pass (:937-938,1062,1070): always 0
+    have = 1, feat = w.hdr[MGH_FEAT_LAST_REWARD], val = 0;
+  } else if ((lane == 4 || lane == 5) && (flags & MGG_LOCAL_POSITION)) {
+    uint32_t sp = ag[MGAG_SPAWN];
+    int dd = lane == 4 ? c0 - (int)(sp & 0xffffu) : (int)(sp >> 16) - r0;
+    if (dd != 0) {
+      have = 1;
+      val = min(abs(dd), 255);
+      feat = lane == 4 ? (dd > 0 ? w.hdr[MGH_FEAT_LP_EAST] : w.hdr[MGH_FEAT_LP_WEST])
+                       : (dd > 0 ? w.hdr[MGH_FEAT_LP_NORTH] : w.hdr[MGH_FEAT_LP_SOUTH]);
+    }
+  }
+  int total;
+  int pre = warp_excl_scan(have, lane, total);
+  if (have) put_token(out, T, pre, 0xFE, feat, val);
+  int base = total;
+
+  // ---- configured global game values (:1207-1238), serial
+  int nov = w.hdr[MGH_NUM_OBS_VALUES];
+  if (nov > 0) {
+    if (lane == 0) {
+      const int32_t* ov = sec(w, MGS_OBS_VALUES);
+      int me = (int)s.a_slot[a];
+      for (int i = 0; i < nov; i++) {
+        uint32_t enc = (uint32_t)eval_value<4>(w, __ldg(ov + 2 * i + 1), me);
+        int f = __ldg(ov + 2 * i);
+        put_token(out, T, base++, 0xFE, f, (int)(enc % (uint32_t)w.B));
+        enc /= (uint32_t)w.B;
+        while (enc > 0) {
+          f++;
+          put_token(out, T, base++, 0xFE, f, (int)(enc % (uint32_t)w.B));
+          enc /= (uint32_t)w.B;
+        }
+      }
+    }
+    base = __shfl_sync(MG_FULL, base, 0);
+  }
+
+  // ---- window cells in Manhattan order, 32 per pass (:756-811)
+  uint32_t stale_sum = 0;
+  for (int k0 = 0; k0 < d.NOFF; k0 += 32) {
+    int k = k0 + lane;
+    int n = 0, loc = 0;
+    uint32_t* o = nullptr;
+    if (k < d.NOFF) {
+      uint32_t pk = s.offs[k];
+      int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
+      loc = (int)(pk >> 8);
+      if (r >= 0 && c >= 0 && r < w.H && c < w.W) {
+        int slot = w.cells[r * w.W + c];
+        if (slot) {
+          o = objp(w, slot);
+          uint32_t vis = o[MGO_VISITED];
+          if (vis < w.step) {  // cell staleness (:787-796): agents are visited in index order
+            stale_sum += w.step - vis;
+            o[MGO_VISITED] = w.step;
+          }
+          n = count_tokens(w, o);
+        }
+      }
+    }
+    int tot;
+    int p = warp_excl_scan(n, lane, tot);
+    if (n && base + p < T) write_tokens(w, o, out, base + p, loc);
+    base += tot;
+  }
+  stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
+  if (lane == 0 && stale_sum) astat_add(w, a, w.hdr[MGH_ST_CELL_VISITED], (float)stale_sum);
+
+  // ---- pad with 0xFF and stream out
+  __syncwarp();
+  int written = min(base, T);
+  fill_ff(out + written * 3, (T - written) * 3, lane);
+  __syncwarp();
+  flush_obs(out, g, 3 * T, lane);
+  __syncwarp();
+  return base;
+}
+
+// all agents' observations + token stats (:826-912, :640-642)
+__device__ void observe_all(const MgDev& d, const Wv& w, const Smem& s, int env, int lane, bool initial) {
+  for (int a = 0; a < w.A; a++) {
+    int action = initial ? 0 : s.a_exec[a];
+    int attempted = observe_agent(d, w, s, env, a, action, s.a_step[a], lane);
+    if (lane == 0) {
+      if (attempted > w.T) {  // hard error in the reference (:364-375)
+        set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
+      } else {  // one float add per agent, in agent order, like the reference (:659-661)
+        gstat_add(w, w.hdr[MGH_GST_TOKENS_WRITTEN], (float)attempted);
+        gstat_add(w, w.hdr[MGH_GST_TOKENS_DROPPED], 0.0f);
+        gstat_add(w, w.hdr[MGH_GST_TOKENS_FREE], (float)(w.T - attempted));
+      }
+    }
+  }
+}
+
+
+// =================================================================================================
+// k_reset: the constructor.  Objects get ids 1.. in row-major map order, agents get ids in
+// encounter order (bindings/mettagrid_c.cpp:222-267); each lane builds the object of one cell.
+// =================================================================================================
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Smem s;
+  carve(d, smem_raw, warp, s);
+  load_cta_tables(d, s);
+  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  if (env >= d.num_envs) return;
+  if (mask && !mask[env]) return;
+  Wv w;
+  bind_env(d, s, env, w);
+
+  for (int i = lane; i < d.HWp; i += 32) w.cells_g[i] = 0;
+  for (int i = lane; i < d.A * d.SA; i += 32) w.astats[i] = 0.0f;
+  for (int i = lane; i < d.A * d.SAW; i += 32) w.atouched[i] = 0;
+  for (int i = lane; i < d.A * d.CW; i += 32) w.cover[i] = 0;
+  for (int i = lane; i < d.A; i += 32) d.success[(size_t)env * d.A + i] = 0;
+  for (int i = lane; i < d.SGW; i += 32) w.gtouched[i] = 0;
+  __syncwarp();
+  for (int i = lane; i < d.SG; i += 32) {
+    float v = d.init_gstats ? d.init_gstats[(size_t)env * d.SG + i] : 0.0f;
+    w.gstats[i] = v;
+    if (v != 0.0f) atomicOr(&w.gtouched[i >> 5], 1u << (i & 31));
+  }
+  if (lane == 0) {
+    for (int i = 0; i < MGEV_WORDS; i++) w.E[i] = 0;
+    w.E[MGEV_RNG_IDX] = MG_RNG_WORDS;
+    // std::mt19937(seed) (bits/random.tcc seed())
+    uint32_t x = d.seeds[env];
+    w.rng[0] = x;
+    for (int i = 1; i < MG_RNG_WORDS; i++) {
+      x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+      w.rng[i] = x;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {  // stat keys the constructor creates (:134-136)
+    atomicOr(&w.gtouched[w.hdr[MGH_GST_TOKENS_WRITTEN] >> 5], 1u << (w.hdr[MGH_GST_TOKENS_WRITTEN] & 31));
+    atomicOr(&w.gtouched[w.hdr[MGH_GST_TOKENS_DROPPED] >> 5], 1u << (w.hdr[MGH_GST_TOKENS_DROPPED] & 31));
+    atomicOr(&w.gtouched[w.hdr[MGH_GST_TOKENS_FREE] >> 5], 1u << (w.hdr[MGH_GST_TOKENS_FREE] & 31));
+  }
+
+  const int16_t* init = d.init_cells + (size_t)env * d.HW;
+  int nobj = 0, nagent = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (int base = 0; base < d.HW; base += 32) {
+    int i = base + lane;
+    int t = i < d.HW ? (int)init[i] : -1;
+    int kind = -1;
+    const int32_t* tp = nullptr;
+    if (t >= 0) {
+      tp = tmpl(w, t);
+      kind = __ldg(tp + MGT_KIND);
+    }
+    uint32_t m = __ballot_sync(MG_FULL, t >= 0), ma = __ballot_sync(MG_FULL, kind == 1);
+    if (t >= 0) {
+      int slot = nobj + __popc(m & lt) + 1;
+      int aidx = kind == 1 ? nagent + __popc(ma & lt) : -1;
+      int r = i / d.W, c = i - r * d.W;
+      if (slot >= d.maxobj || aidx >= d.A) {
+        set_error(w, MGERR_POOL_EXHAUSTED, slot);
+      } else {
+        uint32_t* o = objp(w, slot);
+        for (int k = 0; k < d.OS; k++) o[k] = 0;
+        int flags = MGOF_ALIVE | MGOF_OBS_INV | (kind == 1 ? MGOF_AGENT : 0) | (kind == 0 ? MGOF_WALL : 0);
+        o[MGO_LOC] = ((uint32_t)r << 16) | (uint32_t)c;
+        o[MGO_META] = (uint32_t)t | ((uint32_t)(__ldg(tp + MGT_VIBE) & 0xff) << 16) | ((uint32_t)flags << 24);
+        o[MGO_AGENT] = (uint32_t)aidx;
+        o[MGO_ID] = (uint32_t)slot;
+        const int32_t* tg = pool(w, __ldg(tp + MGT_TAGS));
+        for (int k = 0; k < d.TW; k++) o[MGO_TAGS + k] = (uint32_t)__ldg(tg + k);
+        // initial inventory, stored in emission order; inserting back to front reproduces it
+        const int32_t* iv = pool(w, __ldg(tp + MGT_INIT_INV));
+        int ni = __ldg(tp + MGT_INIT_INV_N);
+        for (int k = ni - 1; k >= 0; k--) inv_update<0>(w, o, __ldg(iv + 2 * k), __ldg(iv + 2 * k + 1), true, false);
+        w.cells_g[i] = (uint16_t)slot;
+        if (kind == 1) {
+          uint32_t* ag = w.agents + aidx * d.AS;
+          for (int k = 0; k < d.AS; k++) ag[k] = 0;
+          ag[MGAG_OBJ] = (uint32_t)slot;
+          ag[MGAG_SPAWN] = o[MGO_LOC];
+          ag[MGAG_PREV_LOC] = o[MGO_LOC];
+          ag[MGAG_STEP_LOC] = o[MGO_LOC];
+          // populate_initial_inventory sets "<res>.amount" for every configured item (agent.cpp:79-84)
+          for (int k = 0; k < ni; k++)
+            astat_set(w, aidx, __ldg(sec(w, MGS_RES_STATS) + __ldg(iv + 2 * k) * 4 + 2), (float)__ldg(iv + 2 * k + 1));
+          // init_reward: a top-level StatValue entry creates its key (core/game_value.cpp:40-47)
+          const int32_t* rw = pool(w, __ldg(tp + MGT_REWARDS));
+          int nr = __ldg(tp + MGT_REWARDS_N);
+          for (int k = 0; k < nr; k++) {
+            const int32_t* v = sec(w, MGS_VALUES) + __ldg(rw + 2 * k) * MG_VALUE_WORDS;
+            if (__ldg(v) == MGV_STAT) {
+              if (__ldg(v + 1) == MGSC_GAME)
+                atomicOr(&w.gtouched[__ldg(v + 2) >> 5], 1u << (__ldg(v + 2) & 31));
+              else
+                astat_touch(w, aidx, __ldg(v + 2));
+            }
+          }
+        }
+      }
+    }
+    nobj += __popc(m);
+    nagent += __popc(ma);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    w.E[MGEV_NEXT_OBJ] = nobj + 1;
+    w.E[MGEV_NEXT_ID] = nobj + 1;
+    if (nagent != d.A) set_error(w, MGERR_POOL_EXHAUSTED, -nagent - 1);
+  }
+}
+
+// load per-agent slot/location into shared memory (all lanes)
+__device__ __forceinline__ void load_agents(const Wv& w, const Smem& s, int lane) {
+  for (int a = lane; a < w.A; a += 32) {
+    uint32_t slot = w.agents[a * w.AS + MGAG_OBJ];
+    s.a_slot[a] = slot;
+    uint32_t loc = objp(w, (int)slot)[MGO_LOC];
+    s.a_loc[a] = loc;
+    s.a_step[a] = loc;
+  }
+  __syncwarp();
+}
+
+// =================================================================================================
+// k_init_buffers: _init_buffers (bindings/mettagrid_c.cpp:294-319) + Agent::init via set_buffers
+// =================================================================================================
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d, const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Smem s;
+  carve(d, smem_raw, warp, s);
+  load_cta_tables(d, s);
+  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  if (env >= d.num_envs) return;
+  if (mask && !mask[env]) return;
+  Wv w;
+  bind_env(d, s, env, w);
+  stage_cells(d, w, lane);
+  load_agents(w, s, lane);
+  for (int a = lane; a < w.A; a += 32) {
+    // reset_coverage_tracking (objects/agent.cpp:41-47)
+    uint32_t* cv = w.cover + a * d.CW;
+    for (int k = 0; k < d.CW; k++) cv[k] = 0;
+    uint32_t loc = s.a_loc[a];
+    int cell = (int)(loc >> 16) * w.W + (int)(loc & 0xffffu);
+    cv[cell >> 5] = 1u << (cell & 31);
+    uint32_t* ag = w.agents + a * w.AS;
+    ag[MGAG_UNIQUE] = 1;
+    ag[MGAG_MAX_DIST] = 0;
+    ag[MGAG_EPISODE_REWARD] = 0;
+    astat_set(w, a, w.hdr[MGH_ST_UNIQUE_VISITED], 1.0f);
+    astat_set(w, a, w.hdr[MGH_ST_MAX_DIST], 0.0f);
+    size_t gi = (size_t)env * d.A + a;
+    d.terminals[gi] = 0;
+    d.truncations[gi] = 0;
+    d.rewards[gi] = 0.0f;
+  }
+  __syncwarp();
+  observe_all(d, w, s, env, lane, true);
+}
+
+// =================================================================================================
+// k_step: one tick for every environment
+// =================================================================================================
+#define MGR_ACTED_P 1u
+#define MGR_OK_P 2u
+#define MGR_ACTED_V 4u
+#define MGR_OK_V 8u
+#define MGR_KIND_P_SHIFT 4
+#define MGR_KIND_V_SHIFT 6
+
+// actions/move.hpp:81-115 + change_vibe.hpp:48-57 + noop.hpp:21-23 (serial)
+__device__ bool do_action(const Wv& w, int slot, int kind, int arg) {
+  if (kind == MGA_NOOP) return true;
+  uint32_t* o = objp(w, slot);
+  if (kind == MGA_CHANGE_VIBE) {
+    o_set_vibe(o, arg);
+    return true;
+  }
+  // actions/orientation.hpp:28-48
+  const int dr = (arg == 0 || arg == 4 || arg == 5) ? -1 : (arg == 1 || arg == 6 || arg == 7) ? 1 : 0;
+  const int dc = (arg == 2 || arg == 4 || arg == 6) ? -1 : (arg == 3 || arg == 5 || arg == 7) ? 1 : 0;
+  const int32_t* chain = sec(w, MGS_MOVE_CHAIN);
+  const int nh = w.hdr[MGH_NUM_MOVE_HANDLERS];
+  for (int k = 0; k < nh; k++) {
+    const int4 mh = __ldg((const int4*)(chain + k * MG_MOVEH_WORDS));  // handler, range, accepts_empty, builtin
+    for (int i = 1; i <= mh.y; i++) {
+      int tr = o_r(o) + dr * i, tc = o_c(o) + dc * i;
+      if (!valid_loc(w, tr, tc)) break;
+      int t = w.cells[tr * w.W + tc];
+      if (!t && !mh.z) continue;
+      if (mh.w == MGMB_RELOCATE) {  // [TargetLocEmpty -> Relocate]
+        if (t == 0 && move_object(w, slot, tr, tc)) return true;
+        break;
+      }
+      if (mh.w == MGMB_USE_TARGET && __ldg(tmpl(w, o_tmpl(objp(w, t))) + MGT_ON_USE) < 0) break;  // onUse -> false
+      Ctx ctx = make_ctx();
+      ctx.actor = slot;
+      ctx.target = t;
+      ctx.tr = tr;
+      ctx.tc = tc;
+      ctx.distance = i;
+      ctx.move_dir = arg;
+      if (handler_apply<3>(w, mh.x, ctx)) return true;
+      break;
+    }
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_step(MgDev d) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Smem s;
+  carve(d, smem_raw, warp, s);
+  load_cta_tables(d, s);
+  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  if (env >= d.num_envs) return;
+  Wv w;
+  bind_env(d, s, env, w);
+  w.step += 1;  // :951
+  const int A = w.A;
+  const size_t g0 = (size_t)env * A;
+
+  // phase 1-2: stage state, read actions (:929-944; the obs buffer is rewritten whole below)
+  stage_cells(d, w, lane);
+  load_agents(w, s, lane);
+  for (int a = lane; a < A; a += 32) {
+    s.a_act[a] = d.actions[g0 + a];
+    s.a_vact[a] = d.vibe_actions[g0 + a];
+    s.a_res[a] = 0;
+    s.a_exec[a] = 0;
+    s.a_order[a] = (uint16_t)a;
+  }
+  rng_window_fill(w, lane);
+  __syncwarp();
+
+  // phase 4-5: shuffled, sequential action resolution (:958-999)
+  if (lane == 0) {
+    rng_shuffle(w, s.a_order, A);
+    const int NA = w.hdr[MGH_NUM_ACTIONS];
+    const int32_t* acts = sec(w, MGS_ACTIONS);
+    const int maxp = w.hdr[MGH_MAX_PRIORITY];
+    for (int off = 0; off <= maxp; off++) {
+      const int prio = maxp - off;
+      for (int stream = 0; stream < 2; stream++)
+        for (int i = 0; i < A; i++) {
+          const int a = s.a_order[i];
+          const int idx = stream ? s.a_vact[a] : s.a_act[a];
+          if (idx < 0 || idx >= NA) continue;  // invalid indices are accounted per agent below
+          const int4 act = __ldg((const int4*)(acts + idx * MG_ACTION_WORDS));  // kind, arg, priority, is_vibe
+          if (act.w != stream || act.z != prio) continue;
+          const int slot = (int)s.a_slot[a];
+          bool ok = do_action(w, slot, act.x, act.y);
+          uint32_t loc = objp(w, slot)[MGO_LOC];
+          if (stream == 0) {
+            s.a_res[a] |= MGR_ACTED_P | (ok ? MGR_OK_P : 0u) | ((uint32_t)act.x << MGR_KIND_P_SHIFT);
+            s.a_locp[a] = loc;
+          } else {
+            s.a_res[a] |= MGR_ACTED_V | (ok ? MGR_OK_V : 0u) | ((uint32_t)act.x << MGR_KIND_V_SHIFT);
+            s.a_locv[a] = loc;
+          }
+          if (ok) s.a_exec[a] = idx;
+        }
+    }
+  }
+  __syncwarp();
+
+  // per-agent bookkeeping of handle_action (actions/action_handler.hpp:78-105), one lane per agent.
+  // It only touches the acting agent's own counters, so it is order-independent across agents.
+  {
+    const int NA = w.hdr[MGH_NUM_ACTIONS];
+    const int npass = w.hdr[MGH_MAX_PRIORITY] + 1;
+    for (int a = lane; a < A; a += 32) {
+      uint32_t* ag = w.agents + a * w.AS;
+      uint32_t prev = ag[MGAG_PREV_LOC], swm = ag[MGAG_SWM];
+      const uint32_t res = s.a_res[a];
+      const int ia = s.a_act[a], iv = s.a_vact[a];
+      const bool inv_p = ia < 0 || ia >= NA, inv_v = iv < 0 || iv >= NA;
+      bool success = false;
+      for (int stream = 0; stream < 2; stream++) {
+        const bool acted = res & (stream ? MGR_ACTED_V : MGR_ACTED_P);
+        const bool ok = res & (stream ? MGR_OK_V : MGR_OK_P);
+        if ((stream ? inv_v : inv_p)) {  // _handle_invalid_action, once per priority pass
+          astat_add(w, a, w.hdr[MGH_ST_INVALID_INDEX], (float)npass);
+          success = false;
+        }
+        if (!acted) continue;
+        const uint32_t loc = stream ? s.a_locv[a] : s.a_locp[a];
+        if (loc == prev) {
+          swm += 1;
+          if ((float)swm > w.astats[a * w.SA + w.hdr[MGH_ST_MAX_SWM]]) astat_set(w, a, w.hdr[MGH_ST_MAX_SWM], (float)swm);
+        } else {
+          swm = 0;
+        }
+        prev = loc;
+        const int kind = (res >> (stream ? MGR_KIND_V_SHIFT : MGR_KIND_P_SHIFT)) & 3;
+        if (ok) {
+          astat_add(w, a, w.hdr[MGH_ST_NOOP_SUCCESS + 2 * kind], 1.0f);
+          success = true;
+        } else {
+          astat_add(w, a, w.hdr[MGH_ST_NOOP_FAILED + 2 * kind], 1.0f);
+          astat_add(w, a, w.hdr[MGH_ST_ACTION_FAILED], 1.0f);
+        }
+      }
+      ag[MGAG_PREV_LOC] = prev;
+      ag[MGAG_SWM] = swm;
+      d.success[g0 + a] = success;
+    }
+  }
+  __syncwarp();
+
+  // phases 6-11 (events, on_tick, AOE, territory, game on_tick): serial
+  if (lane == 0) {
+    for (int a = 0; a < A; a++) {  // agent on_tick (:1019-1024)
+      const int slot = (int)s.a_slot[a];
+      const int h = __ldg(tmpl(w, o_tmpl(objp(w, slot))) + MGT_ON_TICK);
+      if (h >= 0) {
+        Ctx c = make_ctx();
+        c.actor = c.target = slot;
+        handler_apply<3>(w, h, c);
+      }
+    }
+    const int gh = w.hdr[MGH_GAME_ON_TICK];
+    if (gh >= 0) {
+      Ctx c = make_ctx();
+      handler_apply<3>(w, gh, c);
+    }
+  }
+  __syncwarp();
+
+  // phase 12: coverage (objects/agent.cpp:49-57), one lane per agent
+  for (int a = lane; a < A; a += 32) {
+    uint32_t* ag = w.agents + a * w.AS;
+    const uint32_t loc = objp(w, (int)s.a_slot[a])[MGO_LOC];
+    s.a_loc[a] = loc;
+    const int r = (int)(loc >> 16), c = (int)(loc & 0xffffu);
+    const int cell = r * w.W + c;
+    uint32_t* cv = w.cover + a * d.CW + (cell >> 5);
+    const uint32_t bit = 1u << (cell & 31);
+    uint32_t unique = ag[MGAG_UNIQUE];
+    if (!(*cv & bit)) {
+      *cv |= bit;
+      ag[MGAG_UNIQUE] = ++unique;
+    }
+    astat_set(w, a, w.hdr[MGH_ST_UNIQUE_VISITED], (float)unique);
+    const uint32_t sp = ag[MGAG_SPAWN];
+    const uint32_t dist = (uint32_t)(abs((int)(sp >> 16) - r) + abs(c - (int)(sp & 0xffffu)));
+    const uint32_t md = max(ag[MGAG_MAX_DIST], dist);
+    ag[MGAG_MAX_DIST] = md;
+    astat_set(w, a, w.hdr[MGH_ST_MAX_DIST], (float)md);
+  }
+  __syncwarp();
+
+  // phase 13: observations
+  observe_all(d, w, s, env, lane, false);
+
+  // phase 14-15: rewards (systems/reward.hpp:56-77), episode rewards, truncation (:1070-1096)
+  const int ms = w.hdr[MGH_MAX_STEPS];
+  const bool done = ms > 0 && w.step >= (uint32_t)ms;
+  for (int a = lane; a < A; a += 32) {
+    uint32_t* ag = w.agents + a * w.AS;
+    const int slot = (int)s.a_slot[a];
+    const int32_t* tp = tmpl(w, o_tmpl(objp(w, slot)));
+    const int nr = __ldg(tp + MGT_REWARDS_N);
+    float reward = 0.0f;
+    if (nr > 0) {
+      const int32_t* rw = pool(w, __ldg(tp + MGT_REWARDS));
+      float total = 0.0f;
+      for (int i = 0; i < nr; i++) {
+        const float v = eval_value<4>(w, __ldg(rw + 2 * i), slot);
+        const float prevv = __uint_as_float(ag[MGAG_REWARD_PREV + i]);
+        total = __ldg(rw + 2 * i + 1) ? __fadd_rn(total, v) : __fadd_rn(total, __fsub_rn(v, prevv));
+        ag[MGAG_REWARD_PREV + i] = __float_as_uint(v);
+      }
+      if (total != 0.0f) reward = __fadd_rn(0.0f, total);
+    }
+    d.rewards[g0 + a] = reward;
+    ag[MGAG_EPISODE_REWARD] = __float_as_uint(__fadd_rn(__uint_as_float(ag[MGAG_EPISODE_REWARD]), reward));
+    if (done) {
+      if (w.hdr[MGH_EPISODE_TRUNCATES])
+        d.truncations[g0 + a] = 1;
+      else
+        d.terminals[g0 + a] = 1;
+    }
+  }
+  rng_window_commit(w, lane);
+  if (lane == 0) w.E[MGEV_STEP] = (int32_t)w.step;
+}
+
+}  // namespace
+
+// ---- host-side launchers (used by mg_capi.cu) --------------------------------------------------
+size_t mg_smem_bytes(const MgDev& d) { return smem_per_cta(d.NOFF) + (size_t)MG_WARPS_PER_CTA * smem_per_warp(d.HWp, d.T, d.A); }
+
+cudaError_t mg_configure_kernels(const MgDev& d) {
+  size_t bytes = mg_smem_bytes(d);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_init_buffers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+static inline int mg_grid(const MgDev& d) { return (d.num_envs + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
+cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
+  k_reset<<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask);
+  return cudaGetLastError();
+}
+cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
+  k_init_buffers<<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask);
+  return cudaGetLastError();
+}
+cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st) {
+  k_step<<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
+  return cudaGetLastError();
+}

@@ -1,0 +1,40 @@
+// mg_state.h -- device-state descriptor shared by the kernels and the C-ABI host code.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/mg_program.h"
+
+#define MG_FULL 0xffffffffu
+#define MG_WARPS_PER_CTA 4
+#define MG_RNG_WINDOW 32
+
+// Everything a kernel needs, passed by value.
+struct MgDev {
+  const int32_t* P;  // compiled program (global, read-only)
+  int num_envs;
+  int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
+  // persistent state
+  const int16_t* init_cells;  // [N][HW] template per cell
+  const float* init_gstats;   // [N][SG]
+  const uint32_t* seeds;      // [N]
+  uint16_t* cells;            // [N][HWp] object slot per cell (0 = empty)
+  uint32_t* objs;             // [N][maxobj][OS]
+  uint32_t* agents;           // [N][A][AS]
+  float* astats;              // [N][A][SA]
+  uint32_t* atouched;         // [N][A][SAW]
+  float* gstats;              // [N][SG]
+  uint32_t* gtouched;         // [N][SGW]
+  uint32_t* cover;            // [N][A][CW]
+  uint32_t* rng;              // [N][624]
+  int32_t* env;               // [N][MGEV_WORDS]
+  uint8_t* success;           // [N][A]
+  const float* logtab;        // logf(k + 1), k in [0, 65536), from the host libm
+  // caller-owned buffers (aliased like the reference's numpy arrays)
+  uint8_t* obs;               // [N][A][T][3]
+  uint8_t* terminals;         // [N][A]
+  uint8_t* truncations;       // [N][A]
+  float* rewards;             // [N][A]
+  const int32_t* actions;     // [N][A]
+  const int32_t* vibe_actions;// [N][A]
+};
+
