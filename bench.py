@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MettaGrid step (BASELINE.json metric: agent-steps/s including observations).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E] [--agents A]
+
+Workload (config.workload): BASELINE.json configs[1] ("C2") -- the reference benchmark game
+(benchmarks/test_mettagrid_env_benchmark.py:21-29: 20x20 RandomMapBuilder map, 16 agents, 13x13
+observation window, 100 tokens, noop + 4-way move + 152 vibes, max_steps=0) batched to 4096 envs per
+GPU, env e using map seed 42+e and env seed 42+e, "effective" random actions.
+
+A step = one tick of every env.  `value` is measured with all inputs resident in HBM (CUDA events
+around mg_step only, L2 flushed between timed steps); `e2e` is the same tick through the C ABI's
+host-buffer entry point (mg_step_host: pinned host actions in, observations/rewards/flags out).
+
+`--impl reference` times the UNMODIFIED reference C++ step (oracle/_ref, built from /root/reference
+by oracle/Makefile.ref) on the host cores: one worker process per core, each stepping its own share
+of a bounded sample of the same workload.  The only places this file touches oracle/ are that arm
+and the `cpu_baseline` leg.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "agent_steps_per_sec_incl_obs"
+UNIT = "agent-steps/s"
+ALGO_BYTES_PER_AGENT_STEP = 550.0  # C1/C2 (T=100, 20x20, R=10, A=16)
+
+
+def make_cfg(agents: int):
+    from tests import cases
+
+    return cases.benchmark_config(agents)
+
+
+def gen_actions(num_actions: int, num_primary: int, steps: int, envs: int, agents: int, seed: int):
+    """'effective' sampling: primary uniform over non-vibe actions, vibe change with p = 0.1"""
+    rng = np.random.RandomState(seed)
+    prim = rng.randint(0, num_primary, size=(steps, envs, agents)).astype(np.int32)
+    vibe = np.zeros_like(prim)
+    m = rng.rand(steps, envs, agents) < 0.1
+    vibe[m] = rng.randint(num_primary, num_actions, size=int(m.sum()))
+    return prim, vibe
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference C++ env on host cores
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(rank: int, agents: int, envs: int, env0: int, steps: int, warmup: int, barrier, out_q):
+    try:
+        os.sched_setaffinity(0, {rank % os.cpu_count()})
+    except Exception:
+        pass
+    sys.path.insert(0, str(ROOT))
+    from mettagrid_b200.mapgen import random_map
+    from oracle.ref_driver import RefEnv
+
+    cfg = make_cfg(agents)
+    sims = []
+    for e in range(envs):
+        grid = random_map(cfg.game.map_builder, seed=42 + env0 + e)
+        sims.append(RefEnv(cfg, grid, 42 + env0 + e))
+    names_n = 5 + 152
+    prim, vibe = gen_actions(names_n, 5, 64, envs, agents, 1000 + rank)
+    for t in range(warmup):
+        for e, s in enumerate(sims):
+            s.step(prim[t % 64, e], vibe[t % 64, e])
+    barrier.wait()
+    t0 = time.perf_counter()
+    for t in range(steps):
+        for e, s in enumerate(sims):
+            s.step(prim[t % 64, e], vibe[t % 64, e])
+    dt = time.perf_counter() - t0
+    barrier.wait()
+    out_q.put((rank, dt))
+
+
+def run_reference(agents: int, steps: int, warmup: int, envs_per_worker: int):
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    P = os.cpu_count() or 1
+    barrier = ctx.Barrier(P)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ref_worker, args=(r, agents, envs_per_worker, r * envs_per_worker, steps, warmup, barrier, q))
+             for r in range(P)]  # fmt: skip
+    for p in procs:
+        p.start()
+    times = [q.get()[1] for _ in procs]
+    for p in procs:
+        p.join()
+    dt = max(times)
+    total = P * envs_per_worker * agents * steps
+    return {"value": total / dt, "ms_per_step": dt / steps * 1e3, "cores": P, "envs": P * envs_per_worker, "seconds": dt}
+
+
+def reference_available() -> bool:
+    from oracle import reference
+
+    return reference.so_path() is not None
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")  # fmt: skip
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}  # fmt: skip
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from mettagrid_b200.sim import BatchedSimulation
+
+    envs, A = args.envs, args.agents
+    cfg = make_cfg(A)
+    env0 = rank * envs
+    sim = BatchedSimulation(cfg, envs, seeds=[42 + env0 + e for e in range(envs)],
+                            map_seeds=[42 + env0 + e for e in range(envs)], device=local_rank)  # fmt: skip
+    P = sim.program
+    num_actions = len(P.action_names)
+    num_primary = sum(1 for n in P.action_names if not n.startswith("change_vibe_"))
+    POOL = 16
+    prim_h, vibe_h = gen_actions(num_actions, num_primary, POOL, envs, A, 7 + rank)
+    prim = torch.from_numpy(prim_h).cuda()
+    vibe = torch.from_numpy(vibe_h).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    def one_step(i):
+        sim.actions.copy_(prim[i % POOL])
+        sim.vibe_actions.copy_(vibe[i % POOL])
+
+    for i in range(warmup):
+        one_step(i)
+        sim.step()
+    torch.cuda.synchronize()
+    sim.check_errors()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        one_step(warmup + i)  # inputs resident in HBM before the timed region of this step
+        flush.fill_(i & 0xFF)  # evict L2 between timed iterations
+        ev[i][0].record()
+        sim.step()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = steps  # one k_step launch per tick
+    clocks = sampler.stop()
+
+    # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region
+    NA = envs * A
+    h_prim = torch.from_numpy(prim_h[0].copy()).pin_memory()
+    h_vibe = torch.from_numpy(vibe_h[0].copy()).pin_memory()
+    h_obs = torch.empty((envs, A, P.num_tokens, 3), dtype=torch.uint8).pin_memory()
+    h_rew = torch.empty((envs, A), dtype=torch.float32).pin_memory()
+    h_term = torch.empty((envs, A), dtype=torch.uint8).pin_memory()
+    h_trunc = torch.empty((envs, A), dtype=torch.uint8).pin_memory()
+    hs = lambda t: t.numpy()  # noqa: E731
+    for i in range(3):
+        sim.step_host(hs(h_prim), hs(h_vibe), hs(h_obs), hs(h_rew), hs(h_term), hs(h_trunc))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        h_prim.copy_(torch.from_numpy(prim_h[i % POOL]))  # next step's host inputs (host memcpy, part of e2e)
+        h_vibe.copy_(torch.from_numpy(vibe_h[i % POOL]))
+        sim.step_host(hs(h_prim), hs(h_vibe), hs(h_obs), hs(h_rew), hs(h_term), hs(h_trunc))
+    e2e_s = time.perf_counter() - t0
+    e2e_sum = float(h_rew.sum()) + float(h_obs[0, 0, 0, 0])  # consume the result on the host
+    sim.check_errors()
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # the one collective the path has: episode-stat reduction over NVLink (envs/stats_tracker.py:40-45)
+        av, _, _, _ = sim.stats_arrays(0)
+        st = torch.from_numpy(av.sum(0)).cuda()
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    agent_steps = world * envs * A * steps
+    value = agent_steps / (total_ms * 1e-3)
+    e2e_value = agent_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured"
+        else:
+            peak, peak_src = 6650.0, "fallback"
+        per_launch_ms = total_ms / steps
+        achieved = ALGO_BYTES_PER_AGENT_STEP * envs * A / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            traffic = json.loads(tpath.read_text()).get("k_step_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
+            "config": {"workload": f"C2: reference benchmark game 20x20, {A} agents/env, {envs} envs/GPU, 13x13 obs, 100 tokens",
+                       "envs_per_gpu": envs, "agents_per_env": A, "actions": "primary uniform over 5, vibe p=0.1",
+                       "l2": "flushed between timed steps (256 MB fill)", "obs_write_GBps": value * 3 * P.num_tokens / 1e9},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * NA * 4,
+                    "d2h_bytes_per_step": NA * (3 * P.num_tokens + 4 + 1 + 1), "check": e2e_sum},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_step", "peak_source": peak_src,
+                         "algorithmic_bytes_per_agent_step": ALGO_BYTES_PER_AGENT_STEP},
+        }  # fmt: skip
+        if world == 1 and not args.no_cpu_baseline and reference_available():
+            sim.close()
+            cb = run_reference(A, steps=args.cpu_steps, warmup=50, envs_per_worker=args.cpu_envs_per_worker)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "reference",
+                                    "sample": f"{cb['envs']} envs x {args.cpu_steps} steps of the same game, one process per core "
+                                              f"({cb['seconds']:.1f} s)"}  # fmt: skip
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--agents", type=int, default=16)
+    ap.add_argument("--cpu-steps", type=int, default=40000)
+    ap.add_argument("--cpu-envs-per-worker", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        if rank != 0:
+            return
+        if not reference_available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (make -f oracle/Makefile.ref)"}))
+            return
+        # one "step" = one tick of the bounded sample (cores x envs_per_worker envs)
+        cb = run_reference(args.agents, steps=max(args.steps, 1) * 30, warmup=max(args.warmup, 3) * 10,
+                           envs_per_worker=args.cpu_envs_per_worker)  # fmt: skip
+        line = {
+            "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
+            "config": {"workload": f"C2 sample: reference benchmark game 20x20, {args.agents} agents/env, {cb['envs']} envs on "
+                                   f"{cb['cores']} host cores (reference C++ step, one process per core)",
+                       "ticks_per_step": 30},
+            "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "reference",
+                             "sample": f"{cb['envs']} envs x {max(args.steps, 1) * 30} ticks"},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }  # fmt: skip
+        print(json.dumps(line))
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

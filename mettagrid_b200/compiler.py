@@ -109,6 +109,33 @@ def observation_offsets(obs_h: int, obs_w: int) -> list[tuple[int, int]]:
     return out
 
 
+_FAST_BKT = [2, 2, 2, 3, 5, 5, 7, 7, 11, 11, 11, 11, 13, 13]
+_PRIMES = [17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73, 79, 83, 89, 97, 103, 109, 113, 127, 137, 139, 149,
+           157, 167, 179, 193, 199, 211, 227, 241, 257, 277, 293, 313, 337, 359, 383, 409, 439, 467, 503, 541]  # fmt: skip
+
+
+def pybind_dict_order(keys: list[int]) -> list[int]:
+    """Iteration order of the ``std::unordered_map<uint8_t, ...>`` pybind11 builds from a Python dict
+    whose keys arrive in ``keys`` order (refined).
+
+    pybind11's map_caster reserves ``len(dict)`` first, so the table has ``next_bkt(n)`` buckets
+    (libstdc++ hashtable_c++0x.cc: 2,2,2,3,5,5,7,7,11,11,11,11,13,13 for n < 14, else the next
+    prime) and keys collide modulo that count.  libstdc++ links a new node at the global list head
+    when its bucket is empty, otherwise at the head of its bucket's chain (hashtable.h
+    _M_insert_bucket_begin).  Verified against the reference: initial inventory
+    {hp:0, weapon:1, armor:2, mobility:3, energy:5} iterates as 3,2,1,5,0."""
+    n = len(keys)
+    if n == 0:
+        return []
+    nb = _FAST_BKT[n] if n < len(_FAST_BKT) else next(p for p in _PRIMES if p >= n)
+    order: list[int] = []
+    for k in keys:
+        b = k % nb
+        pos = next((i for i, x in enumerate(order) if x % nb == b), None)
+        order.insert(0 if pos is None else pos, k)
+    return order
+
+
 def _digits_needed(max_value: int, base: int) -> int:
     # systems/observation_encoder.hpp:71-85
     n, v = 0, max_value
@@ -610,6 +637,12 @@ class _Builder:
         self.handlers.append([kind, self.plist(kids), len(kids), 0, 0])
         return len(self.handlers) - 1
 
+    def initial_inventory(self, amounts: dict[int, int]) -> list[tuple[int, int]]:
+        """(resource, amount) pairs in token EMISSION order.  The C++ side iterates the pybind-built
+        config map and inserts each entry at the front of the (collision-free, 13-bucket) inventory
+        map (objects/agent.cpp:79-84), so emission order is that iteration order reversed."""
+        return [(k, amounts[k]) for k in reversed(pybind_dict_order(list(amounts.keys())))]
+
     # -- inventory limits -----------------------------------------------------------------------
     def limit_tables(self, limit_defs: list[tuple[list[int], int, int, dict[int, int]]]):
         """limit_defs in definition order -> (limit_of[R], enforce order, _limits iteration order, modifier mask).
@@ -800,7 +833,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         for idx, a in enumerate(members):
             t = common_template(a, 1, agent_limit_defs(a))
             t[K["MGT_GROUP"]] = gid
-            init = [(b.rid[k], int(v)) for k, v in a.inventory.initial.items()]
+            init = b.initial_inventory({b.rid[k]: int(v) for k, v in a.inventory.initial.items()})
             t[K["MGT_INIT_INV"]], t[K["MGT_INIT_INV_N"]] = b.plist(x for p in init for x in p), len(init)
             rew = []
             for ar in a.rewards.values():  # :671-676
@@ -849,7 +882,8 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
             for rname in inv.initial:
                 if rname not in configured and rname in b.rid:
                     defs.append(([b.rid[rname]], inv.default_limit, 65535, {}))
-            init = [(b.rid[k], int(v)) for k, v in inv.initial.items() if k in b.rid and int(v) > 0]
+            init = b.initial_inventory({b.rid[k]: int(v) for k, v in inv.initial.items() if k in b.rid})
+            init = [p for p in init if p[1] > 0]  # grid_object_factory.cpp:83-87
         t = common_template(oc, 0 if is_wall else 2, defs)
         t[K["MGT_INIT_INV"]], t[K["MGT_INIT_INV_N"]] = b.plist(x for p in init for x in p), len(init)
         if init or defs:

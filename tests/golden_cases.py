@@ -1,0 +1,90 @@
+"""Registry of golden cases: name -> (config builder taking a class namespace, map builder, seed, steps,
+action sampling).  The fixtures under tests/golden/*.npz are produced from these by
+tests/golden/make_golden.py running the REAL reference (its own Python lowering + C++ step)."""
+
+from __future__ import annotations
+
+import hashlib
+import json
+
+import numpy as np
+
+from tests import cases
+
+
+def _bench(ns, agents, **kw):
+    return ns.MettaGridConfig(
+        game=ns.GameConfig(
+            num_agents=agents,
+            obs=ns.ObsConfig(num_tokens=kw.get("num_tokens", 100)),
+            max_steps=kw.get("max_steps", 0),
+            actions=ns.ActionsConfig(noop=ns.NoopActionConfig(), move=ns.MoveActionConfig()),
+        )
+    )
+
+
+def _bench_map(agents, seed):
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+
+    return random_map(RandomMapConfig(agents=agents, width=20, height=20, seed=seed))
+
+
+def _walled(ns, agents, **kw):
+    return ns.MettaGridConfig(
+        game=ns.GameConfig(
+            num_agents=agents,
+            obs=ns.ObsConfig(width=7, height=9, num_tokens=150, global_obs=ns.GlobalObsConfig(local_position=True, last_action_move=True)),
+            max_steps=kw.get("max_steps", 60),
+            episode_truncates=kw.get("truncates", True),
+            actions=ns.ActionsConfig(noop=ns.NoopActionConfig(), move=ns.MoveActionConfig(allowed_directions=list(cases.EIGHT_WAY))),
+            objects={"wall": ns.WallConfig()},
+        )
+    )
+
+
+def _walled_map(agents, seed):
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+
+    return random_map(RandomMapConfig(agents=agents, width=14, height=10, seed=seed, border_width=1, objects={"wall": 15}))
+
+
+CASES = {
+    # name: (cfg builder(ns), map builder(), env seed, steps, p_vibe, p_invalid)
+    "c1_a1": (lambda ns: _bench(ns, 1), lambda: _bench_map(1, 42), 42, 300, 0.1, 0.0),
+    "c1_a4": (lambda ns: _bench(ns, 4), lambda: _bench_map(4, 42), 42, 1000, 0.0, 0.0),
+    "c1_a16": (lambda ns: _bench(ns, 16), lambda: _bench_map(16, 42), 42, 400, 0.1, 0.0),
+    "c1_a5_invalid": (lambda ns: _bench(ns, 5), lambda: _bench_map(5, 7), 9, 300, 0.4, 0.1),
+    "walled_8way": (lambda ns: _walled(ns, 6), lambda: _walled_map(6, 3), 5, 90, 0.1, 0.02),
+    "combat_3v3": (lambda ns: cases.combat_config(ns, 3), lambda: cases.combat_map(3, seed=1), 1, 500, 0.3, 0.0),
+    "combat_4v4_base16": (lambda ns: cases.combat_config(ns, 4, token_value_base=16, max_steps=250),
+                          lambda: cases.combat_map(4, seed=5), 5, 300, 0.3, 0.01),  # fmt: skip
+}
+
+
+def case_actions(name, prog):
+    _, _, seed, steps, p_vibe, p_inv = CASES[name]
+    A = prog.num_agents
+    nprim = sum(1 for n in prog.action_names if not n.startswith("change_vibe_"))
+    if name == "c1_a4":  # the SURVEY 8(c) known-answer run
+        return np.random.RandomState(42).randint(0, 5, size=(1000, 4)).astype(np.int32), np.zeros((1000, 4), np.int32)
+    return cases.random_actions(np.random.RandomState(seed), steps, (A,), nprim, len(prog.action_names), p_vibe, p_inv)
+
+
+def step_digest(obs, rewards, success) -> bytes:
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(obs).tobytes())
+    h.update(np.ascontiguousarray(rewards, dtype=np.float32).tobytes())
+    h.update(np.ascontiguousarray(success).astype(np.uint8).tobytes())
+    return h.digest()
+
+
+def clean_stats(stats: dict) -> dict:
+    """Drop the per-value 'action.invalid_index.<N>' keys (not tracked by the engines; the total is)."""
+    out = {"game": dict(stats["game"]), "agent": []}
+    for a in stats["agent"]:
+        out["agent"].append({k: v for k, v in a.items() if not k.startswith("action.invalid_index.")})
+    return out
+
+
+def stats_json(stats: dict) -> str:
+    return json.dumps(clean_stats(stats), sort_keys=True)

@@ -80,3 +80,32 @@ def test_local_position_and_last_action_move():
 def test_many_envs_c2_shape():
     # the C2 shape at reduced env count; every env checked at a stride of steps
     _run_pair(cases.benchmark_config(16), num_envs=64, steps=64, check_every=8)
+
+
+@pytest.mark.parametrize("base", [256, 10])
+def test_combat_handlers_inventory_rewards(base):
+    """C3-style game: handler chains, inventory limits with modifiers, on_use/on_tick, rewards (logf)."""
+    from mettagrid_b200.sim import BatchedSimulation
+    from oracle.oracle import OracleEnv
+
+    cfg = cases.combat_config(None, 4, token_value_base=base, max_steps=150)
+    maps = [cases.combat_map(4, seed=s) for s in range(12)]
+    sim = BatchedSimulation(cfg, 12, seeds=100, maps=maps)
+    P = sim.program
+    oracles = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(12)]
+    prim, vibe = cases.random_actions(np.random.RandomState(3), 200, (12, 8), 9, len(P.action_names), 0.3, 0.01)
+    for t in range(200):
+        sim.step(prim[t], vibe[t])
+        for e, o in enumerate(oracles):
+            o.step(prim[t, e], vibe[t, e])
+        if t % 5 == 0 or t == 199:
+            torch.cuda.synchronize()
+            obs, rew = sim.observations.cpu().numpy(), sim.rewards.cpu().numpy()
+            for e, o in enumerate(oracles):
+                assert np.array_equal(obs[e], o.observations()), f"obs differ: step {t} env {e}"
+                assert np.array_equal(rew[e].view(np.uint32), o.rewards().view(np.uint32)), f"rewards differ: step {t} env {e}"
+    sim.check_errors()
+    for e, o in enumerate(oracles):
+        assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
+        assert np.array_equal(sim.dump_objects(e), o.dump_objects()), f"object state differs in env {e}"
+    sim.close()
