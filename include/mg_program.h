@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #define MG_MAGIC 0x4D47B200
-#define MG_VERSION 4
+#define MG_VERSION 5
 
 /* ---- header word indices ------------------------------------------------------------ */
 enum {
@@ -55,6 +55,7 @@ enum {
   MGH_FEAT_LAST_ACTION_MOVE,  /* 0 = disabled */
   MGH_NUM_ACTIONS,
   MGH_MAX_PRIORITY,
+  MGH_PRIORITY_MASK,   /* bit p set when some action has priority p */
   MGH_NUM_AGENT_STATS, /* S_A */
   MGH_NUM_GAME_STATS,  /* S_G */
   MGH_MAX_OBJECTS,     /* object pool capacity per env (slot 0 unused) */

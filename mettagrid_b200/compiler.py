@@ -974,6 +974,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         ("MGH_FEAT_AGENT_ID", fid["agent_id"]), ("MGH_FEAT_AOE_MASK", fid.get("aoe_mask", 0)),
         ("MGH_FEAT_LAST_ACTION_MOVE", fid.get("last_action_move", 0)),
         ("MGH_NUM_ACTIONS", len(actions)), ("MGH_MAX_PRIORITY", max_priority),
+        ("MGH_PRIORITY_MASK", sum(1 << p for p in {a[2] for a in actions})),
         ("MGH_NUM_TEMPLATES", len(templates)), ("MGH_OBJ_STRIDE", obj_stride), ("MGH_AGENT_STRIDE", agent_stride),
         ("MGH_COVER_WORDS", (n_cells + 31) // 32), ("MGH_MAX_REWARDS", max_rewards),
         ("MGH_HP_RESOURCE", b.rid.get("hp", -1)),

@@ -28,7 +28,8 @@ struct Wv {
   int32_t* E;
   const float* logtab;
   uint32_t step;
-  int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND;
+  int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW;
+  uint8_t* obs;  // this env's observation rows [A][T][3]
   // rng window (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0
   int* rs;
   uint32_t* rand;

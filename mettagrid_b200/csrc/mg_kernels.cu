@@ -30,8 +30,11 @@ struct Smem {
   uint32_t* a_locv;   // location right after the vibe-stream action
   int32_t* a_exec;    // executed action (last successful)
   uint16_t* a_order;  // shuffled agent order
+  Wv* wv;             // this warp's env view, kept in shared memory
+  Smem* self;         // shared-memory copy of this struct
 };
 #define MG_AGENT_WORD_ARRAYS 9
+#define MG_MIN_CTAS_PER_SM 8  // 64 registers per thread -> 32 resident warps per SM
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -43,6 +46,7 @@ __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {
   n += align16(4 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
   n += align16((size_t)A * 4) * MG_AGENT_WORD_ARRAYS;
   n += align16((size_t)A * 2);
+  n += align16(sizeof(Wv)) + align16(sizeof(Smem));
   return n;
 }
 __host__ __device__ inline size_t smem_per_cta(int NOFF) { return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4); }
@@ -70,7 +74,9 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   s.a_locp = (uint32_t*)base, base += aw;
   s.a_locv = (uint32_t*)base, base += aw;
   s.a_exec = (int32_t*)base, base += aw;
-  s.a_order = (uint16_t*)base;
+  s.a_order = (uint16_t*)base, base += align16((size_t)d.A * 2);
+  s.wv = (Wv*)base, base += align16(sizeof(Wv));
+  s.self = (Smem*)base;
 }
 
 // CTA prologue: header + packed observation offsets into shared memory
@@ -103,10 +109,20 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.E = d.env + (size_t)env * MGEV_WORDS;
   w.logtab = d.logtab;
   w.H = d.H, w.W = d.W, w.A = d.A, w.R = d.R, w.TW = d.TW, w.OS = d.OS, w.AS = d.AS;
-  w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND;
+  w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND, w.NOFF = d.NOFF, w.CW = d.CW;
+  w.obs = d.obs + (size_t)env * d.A * (size_t)(3 * d.T);
   w.rs = s.rs;
   w.rand = s.rand;
   w.step = (uint32_t)w.E[MGEV_STEP];
+}
+
+// Publish the per-warp view structs to shared memory so that they cost no registers / local memory.
+__device__ __forceinline__ void publish_warp(const MgDev& d, const Smem& s, int env, int lane) {
+  if (lane == 0) {
+    *s.self = s;
+    bind_env(d, s, env, *s.wv);
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void stage_cells(const MgDev& d, const Wv& w, int lane) {
@@ -228,15 +244,22 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 
 // One agent's observation, composed by the whole warp (bindings/mettagrid_c.cpp:665-824).
 // Returns the number of tokens attempted; `tok` accumulates the env's token stats.
-__device__ int observe_agent(const MgDev& d, const Wv& w, const Smem& s, int env, int a, int action, uint32_t steploc,
-                             int lane) {
+__device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int action, uint32_t steploc, int lane) {
   const int T = w.T;
-  uint8_t* g = d.obs + ((size_t)env * d.A + a) * (size_t)(3 * T);
+  uint8_t* g = w.obs + (size_t)a * (size_t)(3 * T);
   uint8_t* out = s.stage + ((uint32_t)(uintptr_t)g & 15u);
   const uint32_t loc0 = s.a_loc[a];
   const int r0 = (int)(loc0 >> 16), c0 = (int)(loc0 & 0xffffu);
   const int flags = w.hdr[MGH_GLOBAL_FLAGS];
   uint32_t* ag = w.agents + a * w.AS;
+
+  // the stage starts as all 0xFF (EmptyTokenByte, :940-942); tokens overwrite its head
+  {
+    uint4* st4 = (uint4*)s.stage;
+    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int i = lane; i < (3 * T + 32 + 15) / 16; i += 32) st4[i] = ff;
+    __syncwarp();
+  }
 
   // ---- global tokens (:700-742), one candidate per lane, compacted in order
   int feat = 0, val = 0, have = 0;
@@ -289,11 +312,11 @@ __device__ int observe_agent(const MgDev& d, const Wv& w, const Smem& s, int env
 
   // ---- window cells in Manhattan order, 32 per pass (:756-811)
   uint32_t stale_sum = 0;
-  for (int k0 = 0; k0 < d.NOFF; k0 += 32) {
+  for (int k0 = 0; k0 < w.NOFF; k0 += 32) {
     int k = k0 + lane;
     int n = 0, loc = 0;
     uint32_t* o = nullptr;
-    if (k < d.NOFF) {
+    if (k < w.NOFF) {
       uint32_t pk = s.offs[k];
       int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
       loc = (int)(pk >> 8);
@@ -310,6 +333,7 @@ __device__ int observe_agent(const MgDev& d, const Wv& w, const Smem& s, int env
         }
       }
     }
+    if (__ballot_sync(MG_FULL, n != 0) == 0) continue;  // nothing visible in these 32 cells
     int tot;
     int p = warp_excl_scan(n, lane, tot);
     if (n && base + p < T) write_tokens(w, o, out, base + p, loc);
@@ -318,10 +342,7 @@ __device__ int observe_agent(const MgDev& d, const Wv& w, const Smem& s, int env
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
   if (lane == 0 && stale_sum) astat_add(w, a, w.hdr[MGH_ST_CELL_VISITED], (float)stale_sum);
 
-  // ---- pad with 0xFF and stream out
-  __syncwarp();
-  int written = min(base, T);
-  fill_ff(out + written * 3, (T - written) * 3, lane);
+  // ---- stream out
   __syncwarp();
   flush_obs(out, g, 3 * T, lane);
   __syncwarp();
@@ -329,10 +350,10 @@ __device__ int observe_agent(const MgDev& d, const Wv& w, const Smem& s, int env
 }
 
 // all agents' observations + token stats (:826-912, :640-642)
-__device__ void observe_all(const MgDev& d, const Wv& w, const Smem& s, int env, int lane, bool initial) {
+__device__ void observe_all(const Wv& w, const Smem& s, int lane, bool initial) {
   for (int a = 0; a < w.A; a++) {
     int action = initial ? 0 : s.a_exec[a];
-    int attempted = observe_agent(d, w, s, env, a, action, s.a_step[a], lane);
+    int attempted = observe_agent(w, s, a, action, s.a_step[a], lane);
     if (lane == 0) {
       if (attempted > w.T) {  // hard error in the reference (:364-375)
         set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
@@ -353,14 +374,19 @@ __device__ void observe_all(const MgDev& d, const Wv& w, const Smem& s, int env,
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Smem s;
-  carve(d, smem_raw, warp, s);
-  load_cta_tables(d, s);
+  {
+    Smem cta;
+    carve(d, smem_raw, warp, cta);
+    load_cta_tables(d, cta);
+  }
   const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
   if (mask && !mask[env]) return;
-  Wv w;
-  bind_env(d, s, env, w);
+  Smem s0;
+  carve(d, smem_raw, warp, s0);
+  publish_warp(d, s0, env, lane);
+  const Smem& s = *s0.self;
+  Wv& w = *s0.wv;
 
   for (int i = lane; i < d.HWp; i += 32) w.cells_g[i] = 0;
   for (int i = lane; i < d.A * d.SA; i += 32) w.astats[i] = 0.0f;
@@ -480,14 +506,19 @@ __device__ __forceinline__ void load_agents(const Wv& w, const Smem& s, int lane
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d, const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Smem s;
-  carve(d, smem_raw, warp, s);
-  load_cta_tables(d, s);
+  {
+    Smem cta;
+    carve(d, smem_raw, warp, cta);
+    load_cta_tables(d, cta);
+  }
   const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
   if (mask && !mask[env]) return;
-  Wv w;
-  bind_env(d, s, env, w);
+  Smem s0;
+  carve(d, smem_raw, warp, s0);
+  publish_warp(d, s0, env, lane);
+  const Smem& s = *s0.self;
+  Wv& w = *s0.wv;
   stage_cells(d, w, lane);
   load_agents(w, s, lane);
   for (int a = lane; a < w.A; a += 32) {
@@ -509,7 +540,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
     d.rewards[gi] = 0.0f;
   }
   __syncwarp();
-  observe_all(d, w, s, env, lane, true);
+  observe_all(w, s, lane, true);
 }
 
 // =================================================================================================
@@ -523,7 +554,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
 #define MGR_KIND_V_SHIFT 6
 
 // actions/move.hpp:81-115 + change_vibe.hpp:48-57 + noop.hpp:21-23 (serial)
-__device__ bool do_action(const Wv& w, int slot, int kind, int arg) {
+__device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg) {
   if (kind == MGA_NOOP) return true;
   uint32_t* o = objp(w, slot);
   if (kind == MGA_CHANGE_VIBE) {
@@ -561,17 +592,23 @@ __device__ bool do_action(const Wv& w, int slot, int kind, int arg) {
   return false;
 }
 
-__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_step(MgDev d) {
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_step(MgDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  Smem s;
-  carve(d, smem_raw, warp, s);
-  load_cta_tables(d, s);
+  {
+    Smem cta;
+    carve(d, smem_raw, warp, cta);
+    load_cta_tables(d, cta);
+  }
   const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
-  Wv w;
-  bind_env(d, s, env, w);
-  w.step += 1;  // :951
+  Smem s0;
+  carve(d, smem_raw, warp, s0);
+  publish_warp(d, s0, env, lane);
+  const Smem& s = *s0.self;
+  Wv& w = *s0.wv;
+  if (lane == 0) w.step += 1;  // :951
+  __syncwarp();
   const int A = w.A;
   const size_t g0 = (size_t)env * A;
 
@@ -594,8 +631,10 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_step(MgDev d) {
     const int NA = w.hdr[MGH_NUM_ACTIONS];
     const int32_t* acts = sec(w, MGS_ACTIONS);
     const int maxp = w.hdr[MGH_MAX_PRIORITY];
+    const int pmask = w.hdr[MGH_PRIORITY_MASK];
     for (int off = 0; off <= maxp; off++) {
       const int prio = maxp - off;
+      if (!((pmask >> prio) & 1)) continue;  // no action has this priority: the pass only re-reports invalid indices
       for (int stream = 0; stream < 2; stream++)
         for (int i = 0; i < A; i++) {
           const int a = s.a_order[i];
@@ -706,7 +745,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_step(MgDev d) {
   __syncwarp();
 
   // phase 13: observations
-  observe_all(d, w, s, env, lane, false);
+  observe_all(w, s, lane, false);
 
   // phase 14-15: rewards (systems/reward.hpp:56-77), episode rewards, truncation (:1070-1096)
   const int ms = w.hdr[MGH_MAX_STEPS];
@@ -751,7 +790,12 @@ cudaError_t mg_configure_kernels(const MgDev& d) {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_init_buffers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+  // leave room for MG_MIN_CTAS_PER_SM CTAs' shared memory; the rest of the 256 KB stays L1
+  int want_kb = (int)((bytes + 1024) * MG_MIN_CTAS_PER_SM / 1024) + 8;
+  int pct = want_kb * 100 / 228 + 1;
+  if (pct > 100) pct = 100;
+  return cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 static inline int mg_grid(const MgDev& d) { return (d.num_envs + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
 cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
