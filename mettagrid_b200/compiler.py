@@ -892,14 +892,6 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         templates.append(t)
         template_names.append(oc.map_name)
 
-    # spawn references: map key lookup; unknown type -> mutation fails at run time (-1)
-    for ref_i, (_mi, otype) in enumerate(b._spawn_refs):
-        code = -(2 + ref_i)
-        tmpl = cell_to_template.get(otype, -1)
-        for m in b.mutations:
-            if m[0] in (K["MGM_SPAWN_OBJECT"], K["MGM_RAYCAST_SPAWN"]) and m[3] == code:
-                m[3] = tmpl
-
     # ---- territories, events, materialized queries, obs values, game on_tick ---------------------
     territories = []
     for name, tc in g.territories.items():
@@ -931,6 +923,14 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     if obs_values:
         b.features.add("game_value")
     game_on_tick = b.any_handler(g.on_tick)
+
+    # spawn references: map key lookup; unknown type -> mutation fails at run time (-1)
+    for ref_i, (_mi, otype) in enumerate(b._spawn_refs):
+        code = -(2 + ref_i)
+        tmpl = cell_to_template.get(otype, -1)
+        for m in b.mutations:
+            if m[0] in (K["MGM_SPAWN_OBJECT"], K["MGM_RAYCAST_SPAWN"]) and m[3] == code:
+                m[3] = tmpl
 
     # ---- header -------------------------------------------------------------------------------------
     gobs = g.obs.global_obs

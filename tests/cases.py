@@ -165,3 +165,130 @@ def combat_map(agents_per_team: int = 3, width: int = 13, height: int = 11, seed
     return random_map(RandomMapConfig(width=width, height=height, border_width=1, seed=seed,
                                       agents={"red": agents_per_team, "blue": agents_per_team},
                                       objects={"wall": 8, "chest": 3, "altar": 2}))  # fmt: skip
+
+
+# --------------------------------------------------------------------------------------------------
+# C4-style "world" game: fixed AOEs (tick mutations + presence deltas), one mobile agent aura, a 2-team
+# territory with on_enter / presence / on_exit handlers and aoe_mask observation tokens, periodic events
+# with max_targets (RNG shuffle), tag queries (isNear, QueryCountValue reward, query-inventory mutation),
+# tag add/remove with an on_tag_remove handler, spawn and remove-when-empty, on_tick regeneration.
+# --------------------------------------------------------------------------------------------------
+WORLD_RESOURCES = ["hp", "energy", "ore", "gem", "shield"]
+
+
+def world_config(ns=None, agents_per_team: int = 3, num_tokens: int = 200, max_steps: int = 0, spawn: bool = True,
+                 aoe_mask: bool = True):  # fmt: skip
+    if ns is None:
+        ns = C
+    H, A = ns.Handler, ns.EntityTarget
+    vibes = [ns.Vibe("", n) for n in ["default", "swords", "shield"]]
+
+    def team_agent(team: int, tag: str, aura: bool):
+        aoes = {}
+        if aura:  # mobile aura: allies nearby gain a shield point while inside, lose it when they leave
+            aoes["aura"] = ns.AOEConfig(radius=2, is_static=False, filters=[ns.sharedTagPrefix("team:")],
+                                        presence_deltas={"shield": 1})  # fmt: skip
+        return ns.AgentConfig(
+            team_id=team,
+            tags=[tag],
+            aoes=aoes,
+            inventory=ns.InventoryConfig(
+                default_limit=30,
+                initial={"hp": 10, "energy": 4},
+                limits={"hp": ns.ResourceLimitsConfig(base=12, resources=["hp"])},
+            ),
+            rewards={
+                "gems": ns.inventoryReward("gem", weight=1.0),
+                "marked": ns.reward(ns.num("state:marked"), weight=0.125, per_tick=True),
+            },
+            on_tick=H(name="regen", filters=[ns.PeriodicFilter(period=4)], mutations=[ns.updateTarget({"energy": 1})]),
+        )
+
+    healer = ns.GridObjectConfig(  # fixed AOE: heals agents in radius 2 each tick, +1 energy while present
+        name="healer",
+        aoes={"heal": ns.AOEConfig(radius=2, filters=[ns.isA("agent")], mutations=[ns.updateTarget({"hp": 1})],
+                                   presence_deltas={"energy": 1})},  # fmt: skip
+    )
+    spikes = ns.GridObjectConfig(  # fixed AOE radius 3 that hurts only the other team; two deltas net out per tick
+        name="spikes",
+        tags=["team:red"],
+        aoes={"hurt": ns.AOEConfig(radius=3, filters=[ns.isA("agent"), ns.isNot(ns.sharedTagPrefix("team:"))],
+                                   mutations=[ns.updateTarget({"hp": -2}), ns.updateTarget({"hp": 1, "energy": -1})])},  # fmt: skip
+    )
+    beacon_red = ns.GridObjectConfig(name="beacon_red", tags=["team:red"],
+                                     territory_controls=[ns.TerritoryControlConfig(territory="land", strength=8, decay=2)])  # fmt: skip
+    beacon_blue = ns.GridObjectConfig(name="beacon_blue", tags=["team:blue"],
+                                      territory_controls=[ns.TerritoryControlConfig(territory="land", strength=6, decay=1)])  # fmt: skip
+    mine = ns.GridObjectConfig(  # crates of ore that vanish when emptied; using one marks the agent
+        name="mine",
+        inventory=ns.InventoryConfig(initial={"ore": 3}),
+        on_use_handler=H(name="dig", filters=[ns.targetHas({"ore": 1})],
+                         mutations=[ns.withdraw({"ore": 1}, remove_when_empty=True), ns.addTag("state:marked", target=A.ACTOR)]),  # fmt: skip
+    )
+    vault = ns.GridObjectConfig(
+        name="vault",
+        inventory=ns.InventoryConfig(initial={"gem": 2}),
+        on_use_handler=ns.firstMatch([
+            H(name="trade", filters=[ns.actorHas({"ore": 2}), ns.isNear(ns.typeTag("healer"), radius=6)],
+              mutations=[ns.updateActor({"ore": -2, "gem": 1}), ns.removeTag("state:marked", target=A.ACTOR)]),
+            H(name="peek", filters=[ns.actorHasTag("state:marked")], mutations=[ns.logStat("vault.peeks")]),
+        ]),  # fmt: skip
+    )
+    objects = {"wall": ns.WallConfig(), "healer": healer, "spikes": spikes, "beacon_red": beacon_red,
+               "beacon_blue": beacon_blue, "mine": mine, "vault": vault}  # fmt: skip
+    events = {
+        "storm": ns.EventConfig(  # hits 2 random agents every 7 ticks
+            name="storm", target_query=ns.query(ns.typeTag("agent")), timesteps=ns.periodic(3, 7, 400), max_targets=2,
+            mutations=[ns.updateTarget({"hp": -1}), ns.logStat("storm.hits")],
+        ),
+        "amnesty": ns.EventConfig(  # clears the marked tag from everyone marked, else (fallback) refills the vaults
+            name="amnesty", target_query=ns.query("state:marked"), timesteps=ns.periodic(10, 15, 400), fallback="refill",
+            mutations=[ns.removeTag("state:marked")],
+        ),
+        "refill": ns.EventConfig(
+            name="refill", target_query=ns.query(ns.typeTag("vault"), [ns.isNot(ns.targetHas({"gem": 3}))]), timesteps=[],
+            mutations=[ns.updateTarget({"gem": 1})],
+        ),
+    }  # fmt: skip
+    if spawn:
+        objects["sprout"] = ns.GridObjectConfig(name="sprout", inventory=ns.InventoryConfig(initial={"ore": 1}),
+                                                on_use_handler=H(name="pick", mutations=[ns.withdraw({"ore": 1}, remove_when_empty=True)]))  # fmt: skip
+        events["growth"] = ns.EventConfig(  # a sprout grows on a healer's north side now and then
+            name="growth", target_query=ns.query(ns.typeTag("healer")), timesteps=ns.periodic(5, 11, 400), max_targets=1,
+            mutations=[ns.RaycastSpawnMutation(object_type="sprout", directions=["north", "east"], max_range=2, blocker=[ns.isA("wall")])],
+        )  # fmt: skip
+    agents = [team_agent(0, "team:red", i == 0) for i in range(agents_per_team)] + \
+             [team_agent(1, "team:blue", False) for _ in range(agents_per_team)]  # fmt: skip
+    on_marked_removed = H(name="unmark", mutations=[ns.updateTarget({"energy": 2})])
+    for a in agents:
+        a.on_tag_remove = {"state:": on_marked_removed}
+    game = ns.GameConfig(
+        resource_names=list(WORLD_RESOURCES),
+        num_agents=2 * agents_per_team,
+        max_steps=max_steps,
+        obs=ns.ObsConfig(width=11, height=11, num_tokens=num_tokens, aoe_mask=aoe_mask,
+                         global_obs=ns.GlobalObsConfig(obs={"marked": ns.num("state:marked")})),
+        agents=agents,
+        actions=ns.ActionsConfig(noop=ns.NoopActionConfig(), move=ns.MoveActionConfig(allowed_directions=list(EIGHT_WAY)),
+                                 change_vibe=ns.ChangeVibeActionConfig(vibes=vibes)),
+        objects=objects,
+        tags=["state:marked"],
+        territories={"land": ns.TerritoryConfig(
+            tag_prefix="team:",
+            on_enter={"enter": H(filters=[ns.sharedTagPrefix("team:")], mutations=[ns.updateTarget({"shield": 2})])},
+            on_exit={"exit": H(filters=[ns.sharedTagPrefix("team:")], mutations=[ns.updateTarget({"shield": -2})])},
+            presence={"tax": H(filters=[ns.isNot(ns.sharedTagPrefix("team:")), ns.PeriodicFilter(period=3)],
+                               mutations=[ns.updateTarget({"energy": -1})])},
+        )},
+        events=events,
+    )  # fmt: skip
+    return ns.MettaGridConfig(game=game)
+
+
+def world_map(agents_per_team: int = 3, width: int = 18, height: int = 14, seed: int = 0) -> np.ndarray:
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+
+    return random_map(RandomMapConfig(width=width, height=height, border_width=1, seed=seed,
+                                      agents={"red": agents_per_team, "blue": agents_per_team},
+                                      objects={"wall": 10, "healer": 2, "spikes": 2, "beacon_red": 2, "beacon_blue": 2,
+                                               "mine": 3, "vault": 2}))  # fmt: skip

@@ -47,6 +47,16 @@ def test_combat_fresh_seeds(reference_pkg, seed):
     _compare(cases.combat_config(ns, 3), cases.combat_config(None, 3), grid, seed, 400)
 
 
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_world_fresh_seeds(reference_pkg, seed):
+    """AOE, territory + aoe_mask, events with max_targets, queries, tags, spawn, remove-when-empty."""
+    from tests import refns
+
+    ns = refns.reference_namespace()
+    grid = cases.world_map(3, seed=seed)
+    _compare(cases.world_config(ns, 3), cases.world_config(None, 3), grid, seed, 350, p_vibe=0.2, p_invalid=0.0)
+
+
 @pytest.mark.parametrize("agents", [1, 2, 8, 16])
 def test_benchmark_fresh_seeds(reference_pkg, agents):
     from mettagrid_b200 import config as C
