@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #define MG_MAGIC 0x4D47B200
-#define MG_VERSION 5
+#define MG_VERSION 6
 
 /* ---- header word indices ------------------------------------------------------------ */
 enum {
@@ -94,6 +94,8 @@ enum {
   MGH_NUM_DYN_TAGS,     /* tags that can be added at run time (need insertion stamps) */
   MGH_MAX_AOE_SOURCES,  /* capacity of the per-env AOE source table */
   MGH_MAX_TERR_SOURCES,
+  MGH_PROXY_TEMPLATE,   /* inert template (kind 3) used by territory proxy-cell objects */
+  MGH_SPAWN_AOES,       /* max AOE configs on any template a spawn mutation can create */
   /* section offsets */
   MGS_OFFSETS,      /* NUM_OFFSETS x (dr, dc) */
   MGS_ACTIONS,      /* NUM_ACTIONS x MG_ACTION_WORDS */
@@ -217,7 +219,7 @@ enum {
 /* ---- object templates (one per map-cell name; core/grid_object_factory.cpp:62-104) ------ */
 #define MG_TEMPLATE_WORDS 24
 enum {
-  MGT_KIND = 0,     /* 0 wall, 1 agent, 2 object */
+  MGT_KIND = 0,     /* 0 wall, 1 agent, 2 object, 3 territory proxy cell */
   MGT_TYPE_ID,
   MGT_VIBE,
   MGT_TAGS,         /* pool offset of TW words */

@@ -924,6 +924,17 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         b.features.add("game_value")
     game_on_tick = b.any_handler(g.on_tick)
 
+    # inert template for territory proxy cells (core/territory_tracker.cpp:103-107: a bare GridObject)
+    proxy = [0] * K["MG_TEMPLATE_WORDS"]
+    proxy[K["MGT_KIND"]] = 3
+    proxy[K["MGT_TAGS"]] = b.tag_mask([])
+    proxy[K["MGT_LIMIT_OF"]] = b.plist([-1] * R)
+    for key in ("MGT_ON_USE", "MGT_ON_TICK", "MGT_ON_AFTER_USE"):
+        proxy[K[key]] = -1
+    proxy_template = len(templates)
+    templates.append(proxy)
+    template_names.append("<territory_cell>")
+
     # spawn references: map key lookup; unknown type -> mutation fails at run time (-1)
     for ref_i, (_mi, otype) in enumerate(b._spawn_refs):
         code = -(2 + ref_i)
@@ -980,7 +991,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         ("MGH_HP_RESOURCE", b.rid.get("hp", -1)),
         ("MGH_NUM_MOVE_HANDLERS", len(move_chain)), ("MGH_NUM_OBS_VALUES", len(obs_values)),
         ("MGH_NUM_EVENTS_SCHED", len(schedule)), ("MGH_NUM_TERRITORIES", len(territories)), ("MGH_NUM_MQ", len(mqs)),
-        ("MGH_GAME_ON_TICK", game_on_tick), ("MGH_NUM_DYN_TAGS", len(dyn)),
+        ("MGH_GAME_ON_TICK", game_on_tick), ("MGH_NUM_DYN_TAGS", len(dyn)), ("MGH_PROXY_TEMPLATE", proxy_template),
     ]:  # fmt: skip
         hdr[H[key]] = int(v)
     if g.obs.aoe_mask:
@@ -993,6 +1004,8 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     hdr[H["MGH_NUM_GAME_STATS"]] = len(b.game_stats)
     # pool capacity: every cell can hold at most one object; spawned objects get fresh slots.
     hdr[H["MGH_MAX_OBJECTS"]] = n_cells + spawn_headroom + 1
+    spawnable = {m[3] for m in b.mutations if m[0] in (K["MGM_SPAWN_OBJECT"], K["MGM_RAYCAST_SPAWN"]) and m[3] >= 0}
+    hdr[H["MGH_SPAWN_AOES"]] = max([templates[t][K["MGT_AOES_N"]] for t in spawnable] + [0])
     n_aoe_per_t = max([t[K["MGT_AOES_N"]] for t in templates] + [0])
     n_terr_per_t = max([t[K["MGT_TERR_N"]] for t in templates] + [0])
     hdr[H["MGH_MAX_AOE_SOURCES"]] = (n_cells + spawn_headroom) * n_aoe_per_t if n_aoe_per_t else 0

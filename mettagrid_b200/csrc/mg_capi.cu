@@ -57,24 +57,11 @@ static int dev_alloc(mg_handle* h, T** p, size_t count) {
   return MG_OK;
 }
 
-// engine capabilities: anything else in the program is refused loudly rather than mis-simulated
+// engine limits: anything beyond them is refused loudly rather than mis-simulated
 static const char* unsupported_reason(const int32_t* P) {
-  if (P[MGH_NUM_EVENTS_SCHED] > 0) return "events";
-  if (P[MGH_NUM_TERRITORIES] > 0 || P[MGH_FEAT_AOE_MASK] != 0) return "territories / aoe_mask";
-  if (P[MGH_NUM_MQ] > 0) return "materialized queries";
-  if (P[MGH_MAX_AOE_SOURCES] > 0) return "AOE sources";
-  const int32_t* q = P + P[MGS_QUERIES];
-  (void)q;
-  int nq = (P[MGS_TEMPLATES] - P[MGS_QUERIES]) / MG_QUERY_WORDS;
-  if (nq > 0) return "queries";
-  int nm = (P[MGS_VALUES] - P[MGS_MUTATIONS]) / MG_MUTATION_WORDS;
-  const int32_t* m = P + P[MGS_MUTATIONS];
-  for (int i = 0; i < nm; i++) {
-    int op = m[i * MG_MUTATION_WORDS];
-    if (op == MGM_SPAWN_OBJECT || op == MGM_RAYCAST_SPAWN) return "spawn mutations";
-    if (op == MGM_ADD_TAG || op == MGM_REMOVE_TAG || op == MGM_REMOVE_TAGS_PREFIX) return "tag mutations";
-    if (op == MGM_RESOURCE_TRANSFER && m[i * MG_MUTATION_WORDS + 5]) return "remove_source_when_empty";
-  }
+  const int32_t* T_ = P + P[MGS_TERRITORIES];
+  for (int i = 0; i < P[MGH_NUM_TERRITORIES]; i++)
+    if (T_[i * MG_TERR_WORDS + 1] > 16) return "more than 16 tags under one territory prefix";
   return nullptr;
 }
 
@@ -135,7 +122,41 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   if (init_gstats) TRY(dev_alloc(h, &ig, N * d.SG));
   TRY(dev_alloc(h, &h->seeds_dev, N));
   TRY(dev_alloc(h, &d.cells, N * d.HWp));
-  TRY(dev_alloc(h, &d.objs, N * d.maxobj * d.OS));
+  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NTERR) * d.OS));
+  {
+    // capacities of the world-system tables, from the program and the initial maps
+    const int32_t* TP = P + P[MGS_TEMPLATES];
+    size_t max_aoe = 0, max_terr = 0;
+    for (size_t e = 0; e < N; e++) {
+      size_t na = 0, nt = 0;
+      const int16_t* cells = init_cells + e * d.HW;
+      for (int i = 0; i < d.HW; i++)
+        if (cells[i] >= 0) {
+          if (cells[i] >= P[MGH_NUM_TEMPLATES]) {
+            h->err = "mg_create: init_cells holds a template index outside the program";
+            return fail(MG_E_INVALID);
+          }
+          na += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_AOES_N];
+          nt += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_TERR_N];
+        }
+      max_aoe = na > max_aoe ? na : max_aoe;
+      max_terr = nt > max_terr ? nt : max_terr;
+    }
+    const int spawn_aoes = P[MGH_SPAWN_AOES];
+    d.AOECAP = (int)max_aoe + spawn_aoes * 1024;
+    d.AOEW = 4 + (d.A + 31) / 32;
+    d.PENDCAP = spawn_aoes > 0 ? 256 : 0;
+    d.TERRCAP = (int)max_terr;
+    d.NDYN = P[MGH_NUM_DYN_TAGS];
+    const int nq = (P[MGS_TEMPLATES] - P[MGS_QUERIES]) / MG_QUERY_WORDS;
+    d.ARENA = (nq > 0 || P[MGH_NUM_MQ] > 0) ? 4 * d.maxobj + 64 : 0;
+  }
+  TRY(dev_alloc(h, &d.arena, N * d.ARENA));
+  TRY(dev_alloc(h, &d.aoe_src, N * d.AOECAP * d.AOEW));
+  TRY(dev_alloc(h, &d.aoe_pending, N * d.PENDCAP * 2));
+  TRY(dev_alloc(h, &d.terr_src, N * d.TERRCAP * 4));
+  TRY(dev_alloc(h, &d.inside_tag, N * d.A * d.NTERR));
+  TRY(dev_alloc(h, &d.dyn_stamp, N * d.maxobj * d.NDYN));
   TRY(dev_alloc(h, &d.agents, N * d.A * d.AS));
   TRY(dev_alloc(h, &d.astats, N * d.A * d.SA));
   TRY(dev_alloc(h, &d.atouched, N * d.A * d.SAW));
@@ -349,7 +370,7 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
   CK(cudaMemcpy(E, d.env + (size_t)env * MGEV_WORDS, sizeof E, cudaMemcpyDeviceToHost));
   int nobj = E[MGEV_NEXT_OBJ];
   std::vector<uint32_t> objs((size_t)nobj * d.OS);
-  CK(cudaMemcpy(objs.data(), d.objs + (size_t)env * d.maxobj * d.OS, objs.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(objs.data(), d.objs + (size_t)env * (d.maxobj + d.NTERR) * d.OS, objs.size() * 4, cudaMemcpyDeviceToHost));
   const int32_t* P = h->program.data();
   int n = 0, stride = 8 + 2 * d.R;
   for (int s = 1; s < nobj && n < max_rows; s++) {

@@ -1,17 +1,23 @@
-// mg_device.cuh -- per-environment device state view and the handler interpreter.
+// mg_device.cuh -- per-environment device state view and the game-program interpreter.
 //
-// One WARP owns one environment for a whole tick.  The reference's
-// conflict semantics are sequential per env (bindings/mettagrid_c.cpp:958-999), so everything
-// that mutates shared env state runs on lane 0 ("serial" functions below); per-agent and
-// per-cell work fans out over the 32 lanes.  Nothing here is shared with oracle/.
+// One WARP owns one environment for a whole tick.  The reference's conflict
+// semantics are sequential per env (bindings/mettagrid_c.cpp:958-999), so everything that mutates
+// shared env state runs on lane 0 ("serial" functions below); per-agent and per-cell work fans out
+// over the 32 lanes.  Nothing here is shared with oracle/.
+//
+// The interpreter functions call each other recursively (handler -> mutation -> handler, filter ->
+// query -> filter, value -> query ...).  Recursion is bounded by a template depth D that every nested
+// call decrements, and each instantiation is a real (__noinline__) function: inlining the web grows
+// code exponentially.  A program that nests deeper sets MGERR_UNSUPPORTED instead of misbehaving.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-
 #include "mg_state.h"
 
-// Per-warp view of one environment.
+#define MG_DEPTH 5
+
+// Per-warp view of one environment (lives in shared memory).
 struct Wv {
   const int32_t* P;
   const int32_t* hdr;  // shared-memory copy of the header
@@ -27,12 +33,27 @@ struct Wv {
   uint32_t* rng;
   int32_t* E;
   const float* logtab;
+  uint16_t* arena;
+  uint32_t* aoe_src;
+  int32_t* aoe_pending;
+  uint32_t* terr_src;
+  int16_t* inside_tag;
+  uint32_t* dyn_stamp;
   uint32_t step;
-  int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW;
+  int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW, maxobj;
+  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR;
   uint8_t* obs;  // this env's observation rows [A][T][3]
-  // rng window (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0
+  // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top
   int* rs;
   uint32_t* rand;
+};
+
+// deferred per-target ResourceDelta accumulator of AOETracker::apply_fixed (aoe_tracker.cpp:282-361)
+struct Deferred {
+  int n;
+  int8_t order[16];
+  int32_t delta[16];
+  uint16_t seen;
 };
 
 // handler/handler_context.hpp:34-55
@@ -40,17 +61,18 @@ struct Ctx {
   int actor, target, source;
   int distance, tr, tc, move_dir;
   bool skip_trigger, failed;
+  Deferred* deferred;
 };
 __device__ __forceinline__ Ctx make_ctx() {
   Ctx c;
   c.actor = c.target = c.source = 0;
   c.distance = c.tr = c.tc = c.move_dir = 0;
   c.skip_trigger = c.failed = false;
+  c.deferred = nullptr;
   return c;
 }
 
 // ---- program access -------------------------------------------------------------------------
-__device__ __forceinline__ int pg(const Wv& w, int i) { return __ldg(w.P + i); }
 __device__ __forceinline__ const int32_t* sec(const Wv& w, int k) { return w.P + w.hdr[k]; }
 __device__ __forceinline__ const int32_t* pool(const Wv& w, int off) { return w.P + w.hdr[MGS_POOL] + off; }
 __device__ __forceinline__ const int32_t* tmpl(const Wv& w, int t) { return sec(w, MGS_TEMPLATES) + t * MG_TEMPLATE_WORDS; }
@@ -63,10 +85,11 @@ __device__ __forceinline__ int o_tmpl(const uint32_t* o) { return (int)(o[MGO_ME
 __device__ __forceinline__ int o_vibe(const uint32_t* o) { return (int)((o[MGO_META] >> 16) & 0xffu); }
 __device__ __forceinline__ int o_flags(const uint32_t* o) { return (int)(o[MGO_META] >> 24); }
 __device__ __forceinline__ bool o_is_agent(const uint32_t* o) { return (o_flags(o) & MGOF_AGENT) != 0; }
+__device__ __forceinline__ bool o_alive(const uint32_t* o) { return (o_flags(o) & MGOF_ALIVE) != 0; }
 __device__ __forceinline__ int o_agent(const uint32_t* o) { return (int)o[MGO_AGENT]; }
 __device__ __forceinline__ void o_set_vibe(uint32_t* o, int v) { o[MGO_META] = (o[MGO_META] & 0xff00ffffu) | ((uint32_t)(v & 0xff) << 16); }
 __device__ __forceinline__ uint16_t* o_inv(const Wv& w, uint32_t* o) { return (uint16_t*)(o + MGO_TAGS + w.TW); }
-__device__ __forceinline__ bool o_has_tag(const uint32_t* o, int t) { return (o[MGO_TAGS + (t >> 5)] >> (t & 31)) & 1u; }
+__device__ __forceinline__ bool o_has_tag(const uint32_t* o, int t) { return t >= 0 && t < 256 && ((o[MGO_TAGS + (t >> 5)] >> (t & 31)) & 1u); }
 
 // inventory iteration order: packed 4-bit ids, most recently inserted first
 __device__ __forceinline__ uint64_t o_order(const uint32_t* o) { return (uint64_t)o[MGO_INVORD_LO] | ((uint64_t)o[MGO_INVORD_HI] << 32); }
@@ -129,7 +152,7 @@ __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_
 }
 // all lanes: precompute the next <=32 outputs without committing them.
 // rand[0..32) = tempered outputs, rand[32..64) = the new state words they came from.
-__device__ __forceinline__ void rng_window_fill(Wv& w, int lane) {
+__device__ __forceinline__ void rng_window_fill(const Wv& w, int lane) {
   int idx0 = w.E[MGEV_RNG_IDX];
   if (idx0 >= MG_RNG_WORDS) idx0 = 0;
   int count = min(MG_RNG_WINDOW, MG_RNG_WORDS - idx0);
@@ -149,17 +172,17 @@ __device__ __forceinline__ void rng_window_fill(Wv& w, int lane) {
   }
 }
 // all lanes: commit what the serial code consumed from the window
-__device__ __forceinline__ void rng_window_commit(Wv& w, int lane) {
+__device__ __forceinline__ void rng_window_commit(const Wv& w, int lane) {
   if (w.rs[2]) return;  // direct mode already committed
   int used = w.rs[0];
   if (lane < used) w.rng[w.rs[3] + lane] = w.rand[MG_RNG_WINDOW + lane];
   if (lane == 0 && used > 0) w.E[MGEV_RNG_IDX] = w.rs[3] + used;
 }
-// serial: next raw 32-bit output
-__device__ __noinline__ uint32_t rng_next_slow(Wv& w, const uint32_t* pending /*smem new words*/) {
+// serial: next raw 32-bit output once the window is exhausted
+__device__ __noinline__ uint32_t rng_next_slow(const Wv& w) {
   if (!w.rs[2]) {  // leave window mode: commit the whole window, continue directly on global state
     int count = w.rs[1];
-    for (int k = 0; k < count; k++) w.rng[w.rs[3] + k] = pending[k];
+    for (int k = 0; k < count; k++) w.rng[w.rs[3] + k] = w.rand[MG_RNG_WINDOW + k];
     w.E[MGEV_RNG_IDX] = w.rs[3] + count;
     w.rs[2] = 1;
   }
@@ -172,16 +195,16 @@ __device__ __noinline__ uint32_t rng_next_slow(Wv& w, const uint32_t* pending /*
   w.E[MGEV_RNG_IDX] = i + 1;
   return mt_temper(nw);
 }
-__device__ __forceinline__ uint32_t rng_next(Wv& w) {
+__device__ __forceinline__ uint32_t rng_next(const Wv& w) {
   int pos = w.rs[0];
   if (!w.rs[2] && pos < w.rs[1]) {
     w.rs[0] = pos + 1;
     return w.rand[pos];
   }
-  return rng_next_slow(w, w.rand + MG_RNG_WINDOW);
+  return rng_next_slow(w);
 }
 // Lemire multiply-shift with rejection (bits/uniform_int_dist.h:252-282)
-__device__ __forceinline__ uint32_t rng_below(Wv& w, uint32_t range) {
+__device__ __forceinline__ uint32_t rng_below(const Wv& w, uint32_t range) {
   uint64_t prod = (uint64_t)rng_next(w) * range;
   uint32_t low = (uint32_t)prod;
   if (low < range) {
@@ -195,7 +218,7 @@ __device__ __forceinline__ uint32_t rng_below(Wv& w, uint32_t range) {
 }
 // libstdc++ std::shuffle (bits/stl_algo.h:3719-3805): two swap positions per draw
 template <class T>
-__device__ __forceinline__ void rng_shuffle(Wv& w, T* v, int n) {
+__device__ __forceinline__ void rng_shuffle(const Wv& w, T* v, int n) {
   if (n < 2) return;
   int i = 1;
   if ((n & 1) == 0) {
@@ -338,17 +361,64 @@ __device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
   return true;
 }
 
+// ---- object creation (core/grid_object_factory.cpp:62-104); used by k_reset (one lane per object)
+// and by the spawn mutations (serial) --------------------------------------------------------------
+__device__ __forceinline__ void init_object(const Wv& w, int slot, int t, int r, int c, int aidx, bool obs_inv, uint32_t seq) {
+  uint32_t* o = objp(w, slot);
+  const int32_t* tp = tmpl(w, t);
+  for (int k = 0; k < w.OS; k++) o[k] = 0;
+  int kind = __ldg(tp + MGT_KIND);
+  int flags = MGOF_ALIVE | (obs_inv ? MGOF_OBS_INV : 0) | (kind == 1 ? MGOF_AGENT : 0) | (kind == 0 ? MGOF_WALL : 0);
+  o[MGO_LOC] = ((uint32_t)r << 16) | (uint32_t)c;
+  o[MGO_META] = (uint32_t)t | ((uint32_t)(__ldg(tp + MGT_VIBE) & 0xff) << 16) | ((uint32_t)flags << 24);
+  o[MGO_AGENT] = (uint32_t)aidx;
+  o[MGO_ID] = (uint32_t)slot;
+  const int32_t* tg = pool(w, __ldg(tp + MGT_TAGS));
+  for (int k = 0; k < w.TW; k++) o[MGO_TAGS + k] = (uint32_t)__ldg(tg + k);
+  for (int k = 0; k < w.NDYN; k++) w.dyn_stamp[(size_t)slot * w.NDYN + k] = seq;  // tag-index registration order
+  // initial inventory, stored in emission order; inserting back to front reproduces it
+  const int32_t* iv = pool(w, __ldg(tp + MGT_INIT_INV));
+  int ni = __ldg(tp + MGT_INIT_INV_N);
+  for (int k = ni - 1; k >= 0; k--) inv_update<0>(w, o, __ldg(iv + 2 * k), __ldg(iv + 2 * k + 1), true, false);
+}
+
+// ==================================================================================================
+// interpreter
+// ==================================================================================================
+struct QList {
+  uint16_t* p;
+  int n;
+};
+template <int D>
+__device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, int entity);
+template <int D>
+__device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx);
+template <int D>
+__device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx);
+template <int D>
+__device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx);
+template <int D>
+__device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx);
+
+template <int D>
+__device__ __forceinline__ bool filters_pass(const Wv& w, int f0, int n, const Ctx& ctx) {
+  for (int i = 0; i < n; i++)
+    if (!filter_pass<D>(w, f0 + i, ctx)) return false;
+  return true;
+}
+__device__ __forceinline__ int resolve_entity(const Ctx& c, int e) { return e == MGE_ACTOR ? c.actor : e == MGE_TARGET ? c.target : c.source; }
+__device__ __forceinline__ int arena_top(const Wv& w) { return w.rs[4]; }
+__device__ __forceinline__ void arena_set(const Wv& w, int t) { w.rs[4] = t; }
+
 // ---- game values (core/game_value.cpp:14-148) -----------------------------------------------------
 __device__ __forceinline__ float host_logf_plus1(const Wv& w, float term) {
-  // std::log(term + 1.0f) through the host-libm table when term is an integer in range
+  // std::log(term + 1.0f) through the host-libm table when the argument is an integer in range
   float x = __fadd_rn(term, 1.0f);
-  float k = x - 1.0f;
   if (x >= 1.0f && x <= 65536.0f && truncf(x) == x) return __ldg(w.logtab + (int)x - 1);
-  (void)k;
   return (float)log((double)x);  // non-integer argument: correctly rounded double log (<= 1 ulp vs glibc)
 }
 template <int D>
-__device__ __noinline__ float eval_value(const Wv& w, int node, int entity) {
+__device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, int entity) {
   const int32_t* v = sec(w, MGS_VALUES) + node * MG_VALUE_WORDS;
   int op = __ldg(v), scope = __ldg(v + 1), a = __ldg(v + 2), b = __ldg(v + 3);
   switch (op) {
@@ -375,36 +445,49 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, int entity) {
       return 0.0f;
     case MGV_CONST:
       return __int_as_float(a);
-    case MGV_SUM: {
-      if constexpr (D > 0) {
+    default:
+      break;
+  }
+  if constexpr (D > 0) {
+    switch (op) {
+      case MGV_QUERY_INVENTORY:
+      case MGV_QUERY_COUNT: {
+        Ctx c = ctx;
+        c.actor = entity;  // HandlerContext::resolve_game_value: value_ctx.actor = entity
+        int mark = arena_top(w);
+        QList q = query_eval<D - 1>(w, b, c);
+        float total = 0.0f;
+        if (op == MGV_QUERY_COUNT) {
+          total = (float)q.n;
+        } else {
+          for (int i = 0; i < q.n; i++) total = __fadd_rn(total, (float)o_inv(w, objp(w, q.p[i]))[a]);
+        }
+        arena_set(w, mark);
+        return total;
+      }
+      case MGV_SUM: {
         float total = 0.0f;
         const int32_t* kids = pool(w, a);
         int woff = __ldg(v + 4), lg = __ldg(v + 5);
         for (int i = 0; i < b; i++) {
-          float term = eval_value<D - 1>(w, __ldg(kids + i), entity);
+          float term = eval_value<D - 1>(w, __ldg(kids + i), ctx, entity);
           if (lg) term = host_logf_plus1(w, term);
           if (woff >= 0) term = __fmul_rn(term, __int_as_float(__ldg(pool(w, woff) + i)));
           total = __fadd_rn(total, term);
         }
         return total;
       }
-      break;
-    }
-    case MGV_RATIO: {
-      if constexpr (D > 0) {
-        float num = eval_value<D - 1>(w, a, entity), den = eval_value<D - 1>(w, b, entity);
+      case MGV_RATIO: {
+        float num = eval_value<D - 1>(w, a, ctx, entity), den = eval_value<D - 1>(w, b, ctx, entity);
         return den > 0.0f ? __fdiv_rn(num, den) : num;
       }
-      break;
-    }
-    case MGV_MAX:
-    case MGV_MIN: {
-      if constexpr (D > 0) {
+      case MGV_MAX:
+      case MGV_MIN: {
         if (b == 0) return 0.0f;
         const int32_t* kids = pool(w, a);
         float best = op == MGV_MAX ? -3.402823466e+38f : 3.402823466e+38f;
         for (int i = 0; i < b; i++) {
-          float x = eval_value<D - 1>(w, __ldg(kids + i), entity);
+          float x = eval_value<D - 1>(w, __ldg(kids + i), ctx, entity);
           // std::max(a, b) = (a < b) ? b : a ; std::min(a, b) = (b < a) ? b : a
           if (op == MGV_MAX)
             best = (best < x) ? x : best;
@@ -413,15 +496,13 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, int entity) {
         }
         return best;
       }
-      break;
+      default:
+        break;
     }
-    default:
-      break;
   }
-  set_error(w, MGERR_UNSUPPORTED, 2);  // queries inside values / nesting too deep
+  set_error(w, MGERR_UNSUPPORTED, 2);
   return 0.0f;
 }
-__device__ __forceinline__ int resolve_entity(const Ctx& c, int e) { return e == MGE_ACTOR ? c.actor : e == MGE_TARGET ? c.target : c.source; }
 
 // ---- filters (handler/filters/*.hpp) -------------------------------------------------------------
 template <int D>
@@ -450,34 +531,6 @@ __device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx) {
         if (x[MGO_TAGS + k] & (uint32_t)__ldg(m + k)) return true;
       return false;
     }
-    case MGF_GAME_VALUE:
-      return eval_value<4>(w, a, e) >= eval_value<4>(w, b, e);
-    case MGF_NEG:
-      if constexpr (D > 0) {
-        for (int i = 0; i < b; i++)
-          if (!filter_pass<D - 1>(w, a + i, ctx)) return true;
-        return false;
-      }
-      break;
-    case MGF_OR:
-      if constexpr (D > 0) {
-        for (int i = 0; i < b; i++)
-          if (filter_pass<D - 1>(w, a + i, ctx)) return true;
-        return false;
-      }
-      break;
-    case MGF_MAX_DISTANCE: {  // max_distance_filter.hpp:31-63 (binary form)
-      if (!e) return false;
-      if (a < 0) {
-        int ref = ctx.source ? ctx.source : ctx.actor;
-        if (!ref) return false;
-        if (b == 0) return true;
-        const uint32_t *x = objp(w, e), *y = objp(w, ref);
-        long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
-        return dr * dr + dc * dc <= (long long)b * b;
-      }
-      break;  // unary (query) form: not in this kernel yet
-    }
     case MGF_TARGET_LOC_EMPTY:
       return ctx.target == 0;
     case MGF_TARGET_IS_USABLE:
@@ -485,30 +538,390 @@ __device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx) {
     case MGF_PERIODIC:
       if (w.step < (uint32_t)b) return false;
       return (w.step - (uint32_t)b) % (uint32_t)a == 0;
+    case MGF_MAX_DISTANCE:
+      if (!e) return false;
+      if (a < 0) {  // binary form (max_distance_filter.hpp:38-47)
+        int ref = ctx.source ? ctx.source : ctx.actor;
+        if (!ref) return false;
+        if (b == 0) return true;
+        const uint32_t *x = objp(w, e), *y = objp(w, ref);
+        long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
+        return dr * dr + dc * dc <= (long long)b * b;
+      }
+      break;
     default:
       break;
+  }
+  if constexpr (D > 0) {
+    switch (op) {
+      case MGF_GAME_VALUE:
+        return eval_value<D - 1>(w, a, ctx, e) >= eval_value<D - 1>(w, b, ctx, e);
+      case MGF_NEG:
+        for (int i = 0; i < b; i++)
+          if (!filter_pass<D - 1>(w, a + i, ctx)) return true;
+        return false;
+      case MGF_OR:
+        for (int i = 0; i < b; i++)
+          if (filter_pass<D - 1>(w, a + i, ctx)) return true;
+        return false;
+      case MGF_MAX_DISTANCE: {  // unary form: within radius of any query result (:49-62)
+        int mark = arena_top(w);
+        QList q = query_eval<D - 1>(w, a, ctx);
+        bool ok = false;
+        if (b == 0) {
+          ok = q.n > 0;
+        } else {
+          const uint32_t* x = objp(w, e);
+          for (int i = 0; i < q.n && !ok; i++) {
+            const uint32_t* y = objp(w, q.p[i]);
+            long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
+            ok = dr * dr + dc * dc <= (long long)b * b;
+          }
+        }
+        arena_set(w, mark);
+        return ok;
+      }
+      case MGF_QUERY_RESOURCE: {  // query_resource_filter.hpp:26-43
+        int mark = arena_top(w);
+        QList q = query_eval<D - 1>(w, a, ctx);
+        const int32_t* rq = pool(w, b);
+        int nreq = __ldg(f + 4);
+        bool ok = true;
+        for (int i = 0; i < nreq && ok; i++) {
+          uint32_t total = 0, need = (uint32_t)__ldg(rq + 2 * i + 1);
+          int rid = __ldg(rq + 2 * i);
+          for (int k = 0; k < q.n; k++) {
+            total += o_inv(w, objp(w, q.p[k]))[rid];
+            if (total >= need) break;
+          }
+          ok = total >= need;
+        }
+        arena_set(w, mark);
+        return ok;
+      }
+      default:
+        break;
+    }
   }
   set_error(w, MGERR_UNSUPPORTED, 3);
   return false;
 }
+
+// ---- tag index + queries (core/tag_index.cpp, core/query_system.cpp:29-89,178-330) ------------------
+// Objects carrying `tag`, in the reference's TagIndex order: registration order for tags fixed at
+// creation (= slot order), insertion-stamp order for tags that can be added at run time.
+__device__ __noinline__ QList collect_tag(const Wv& w, int tag) {
+  int top = arena_top(w);
+  uint16_t* out = w.arena + top;
+  int n = 0, cap = w.ARENA - top;
+  const int last = w.E[MGEV_NEXT_OBJ];
+  const int word = MGO_TAGS + (tag >> 5);
+  const uint32_t bit = 1u << (tag & 31);
+  for (int s = 1; s < last; s++) {
+    const uint32_t* o = objp(w, s);
+    if ((o[word] & bit) && o_alive(o)) {
+      if (n >= cap) {
+        set_error(w, MGERR_POOL_EXHAUSTED, 7);
+        break;
+      }
+      out[n++] = (uint16_t)s;
+    }
+  }
+  int ds = __ldg(sec(w, MGS_DYN_TAGS) + tag);
+  if (ds >= 0) {  // insertion sort by stamp (stable: equal stamps keep slot order)
+    for (int i = 1; i < n; i++) {
+      uint16_t s = out[i];
+      uint32_t key = w.dyn_stamp[(size_t)s * w.NDYN + ds];
+      int j = i - 1;
+      while (j >= 0 && w.dyn_stamp[(size_t)out[j] * w.NDYN + ds] > key) {
+        out[j + 1] = out[j];
+        j--;
+      }
+      out[j + 1] = s;
+    }
+  }
+  arena_set(w, top + n);
+  return QList{out, n};
+}
 template <int D>
-__device__ __forceinline__ bool filters_pass(const Wv& w, int f0, int n, const Ctx& ctx) {
+__device__ __forceinline__ bool matches(const Wv& w, int s, int f0, int n, const Ctx& ctx) {
+  if (n == 0) return true;
+  Ctx c = ctx;
+  c.target = s;
+  return filters_pass<D>(w, f0, n, c);
+}
+template <int D>
+__device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
+  const int32_t* q = sec(w, MGS_QUERIES) + qi * MG_QUERY_WORDS;
+  const int kind = __ldg(q), mark = arena_top(w);
+  uint16_t* res = w.arena + mark;
+  int n = 0;
+  if constexpr (D > 0) {
+    if (kind == MGQ_TAG || kind == MGQ_FILTERED) {
+      QList c = kind == MGQ_TAG ? collect_tag(w, __ldg(q + 3)) : query_eval<D - 1>(w, __ldg(q + 3), ctx);
+      int f0 = __ldg(q + 4), fn = __ldg(q + 5);
+      for (int i = 0; i < c.n; i++) {  // in-place compaction; nested scratch lives above the list
+        uint16_t s = c.p[i];
+        if (matches<D - 1>(w, s, f0, fn, ctx)) res[n++] = s;
+      }
+    } else if (kind == MGQ_CLOSURE) {
+      QList roots = query_eval<D - 1>(w, __ldg(q + 3), ctx);
+      if (__ldg(q + 4) < 0) {
+        n = roots.n;
+      } else {
+        QList cand = query_eval<D - 1>(w, __ldg(q + 4), ctx);
+        int top = arena_top(w);
+        uint16_t* out = w.arena + top;
+        int cap = w.ARENA - top, m = 0;
+        if (cap < roots.n + cand.n) {
+          set_error(w, MGERR_POOL_EXHAUSTED, 8);
+        } else {
+          arena_set(w, top + roots.n + cand.n);
+          auto seen = [&](uint16_t s) {
+            for (int k = 0; k < m; k++)
+              if (out[k] == s) return true;
+            return false;
+          };
+          for (int i = 0; i < roots.n; i++)
+            if (!seen(roots.p[i])) out[m++] = roots.p[i];
+          int e0 = __ldg(q + 5), en = __ldg(q + 6);
+          for (int h = 0; h < m; h++) {  // BFS: the result list is its own frontier queue
+            uint16_t cur = out[h];
+            for (int i = 0; i < cand.n; i++) {
+              uint16_t cd = cand.p[i];
+              if (seen(cd)) continue;
+              if (en > 0) {
+                Ctx e = ctx;
+                e.source = cur;
+                e.target = cd;
+                if (!filters_pass<D - 1>(w, e0, en, e)) continue;
+              }
+              out[m++] = cd;
+            }
+          }
+          int r0 = __ldg(q + 7), rn = __ldg(q + 8);
+          for (int i = 0; i < m; i++)
+            if (matches<D - 1>(w, out[i], r0, rn, ctx)) res[n++] = out[i];  // res < out: forward copy is safe
+        }
+      }
+    } else if (kind == MGQ_RAYCAST) {
+      QList srcs = query_eval<D - 1>(w, __ldg(q + 3), ctx);
+      int top = arena_top(w);
+      uint16_t* out = w.arena + top;
+      int cap = w.ARENA - top, m = 0;
+      const int nd = __ldg(q + 6) ? __ldg(q + 6) : 4;
+      const int32_t* dirs = pool(w, __ldg(q + 5));
+      const int b0 = __ldg(q + 7), bn = __ldg(q + 8), incl = __ldg(q + 9);
+      for (int si = 0; si < srcs.n; si++) {
+        int s = srcs.p[si];
+        Ctx sc = ctx;
+        sc.actor = s;
+        sc.target = s;
+        arena_set(w, top + m);
+        int range = (int)eval_value<D - 1>(w, __ldg(q + 4), sc, s);
+        if (range <= 0) continue;
+        const uint32_t* so = objp(w, s);
+        for (int d = 0; d < nd; d++) {
+          int dr, dc;
+          if (__ldg(q + 6)) {
+            dr = __ldg(dirs + 2 * d), dc = __ldg(dirs + 2 * d + 1);
+          } else {  // CARDINALS {{-1,0},{1,0},{0,1},{0,-1}}
+            dr = d == 0 ? -1 : d == 1 ? 1 : 0;
+            dc = d == 2 ? 1 : d == 3 ? -1 : 0;
+          }
+          for (int dist = 1; dist <= range; dist++) {
+            int r = o_r(so) + dr * dist, c = o_c(so) + dc * dist;
+            if (!valid_loc(w, r, c)) break;
+            int o = w.cells[r * w.W + c];
+            if (!o) continue;
+            bool blk = false;
+            if (bn > 0) {
+              Ctx bc = ctx;
+              bc.target = o;
+              arena_set(w, top + m);
+              for (int i = 0; i < bn && !blk; i++) blk = filter_pass<D - 1>(w, b0 + i, bc);
+            }
+            bool dup = false;
+            for (int k = 0; k < m && !dup; k++) dup = out[k] == o;
+            if ((!blk || incl) && !dup) {
+              if (m < cap) out[m++] = (uint16_t)o;
+              else set_error(w, MGERR_POOL_EXHAUSTED, 9);
+            }
+            if (blk) break;
+          }
+        }
+      }
+      for (int i = 0; i < m; i++) res[n++] = out[i];
+    } else {
+      set_error(w, MGERR_UNSUPPORTED, 10);
+    }
+    arena_set(w, mark + n);
+    // apply_limits (query_system.cpp:74-89)
+    if (__ldg(q + 2)) rng_shuffle(w, res, n);
+    int mi = __ldg(q + 1);
+    if (mi >= 0) {
+      int mx = (int)eval_value<D - 1>(w, mi, ctx, ctx.actor);
+      if (mx >= 0 && n > mx) n = mx;
+    }
+    arena_set(w, mark + n);
+    return QList{res, n};
+  }
+  set_error(w, MGERR_UNSUPPORTED, 11);
+  return QList{res, 0};
+}
+
+// ---- tags (core/grid_object.cpp:91-141) ------------------------------------------------------------
+template <int D>
+__device__ __noinline__ void run_tag_handlers(const Wv& w, int s, int tag, const Ctx& ctx) {
+  const int32_t* t = tmpl(w, o_tmpl(objp(w, s)));
+  const int32_t* pr = pool(w, __ldg(t + MGT_TAG_REMOVE));
+  int n = __ldg(t + MGT_TAG_REMOVE_N);
+  if (n == 0) return;
+  Ctx h = ctx;
+  h.actor = s;
+  h.target = s;
+  h.skip_trigger = false;
   for (int i = 0; i < n; i++)
-    if (!filter_pass<D>(w, f0 + i, ctx)) return false;
-  return true;
+    if (__ldg(pr + 2 * i) == tag) {
+      if constexpr (D > 0)
+        handler_apply<D - 1>(w, __ldg(pr + 2 * i + 1), h);
+      else
+        set_error(w, MGERR_UNSUPPORTED, 12);
+    }
+}
+__device__ __forceinline__ void add_tag(const Wv& w, int s, int tag) {
+  uint32_t* o = objp(w, s);
+  if (tag < 0 || tag >= 256 || o_has_tag(o, tag)) return;
+  o[MGO_TAGS + (tag >> 5)] |= 1u << (tag & 31);
+  int ds = __ldg(sec(w, MGS_DYN_TAGS) + tag);
+  if (ds >= 0 && s < w.maxobj) w.dyn_stamp[(size_t)s * w.NDYN + ds] = (uint32_t)(w.E[MGEV_TAG_SEQ]++);
+  // on_tag_add handlers cannot be configured from Python (no add_on_tag_add_handler call in the lowering)
+}
+template <int D>
+__device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ctx& ctx) {
+  uint32_t* o = objp(w, s);
+  if (tag < 0 || tag >= 256 || !o_has_tag(o, tag)) return;
+  o[MGO_TAGS + (tag >> 5)] &= ~(1u << (tag & 31));
+  if (!ctx.skip_trigger) run_tag_handlers<D>(w, s, tag, ctx);
+}
+
+// ---- AOE bookkeeping shared by mutations (core/aoe_tracker.cpp:141-145,207-276) ----------------------
+__device__ __forceinline__ uint32_t* aoe_rec(const Wv& w, int k) { return w.aoe_src + (size_t)k * w.AOEW; }
+__device__ __forceinline__ const int32_t* aoe_cfg(const Wv& w, int cfg) { return sec(w, MGS_AOES) + cfg * MG_AOE_WORDS; }
+__device__ __forceinline__ bool aoe_inside(const uint32_t* s, int ag) { return (s[4 + (ag >> 5)] >> (ag & 31)) & 1u; }
+__device__ __forceinline__ void aoe_set_inside(uint32_t* s, int ag, bool v) {
+  if (v)
+    s[4 + (ag >> 5)] |= 1u << (ag & 31);
+  else
+    s[4 + (ag >> 5)] &= ~(1u << (ag & 31));
+}
+__device__ __noinline__ void apply_presence(const Wv& w, const int32_t* a, int target, int mult) {
+  const int32_t* pd = pool(w, __ldg(a + 7));
+  int n = __ldg(a + 8);
+  uint32_t* o = objp(w, target);
+  for (int i = 0; i < n; i++) inv_update<2>(w, o, __ldg(pd + 2 * i), __ldg(pd + 2 * i + 1) * mult);
+}
+__device__ __forceinline__ void register_aoe(const Wv& w, int slot, int cfg) {
+  int k = w.E[MGEV_NUM_AOE];
+  if (k >= w.AOECAP) {
+    set_error(w, MGERR_POOL_EXHAUSTED, 13);
+    return;
+  }
+  uint32_t* s = aoe_rec(w, k);
+  s[0] = (uint32_t)slot, s[1] = (uint32_t)cfg, s[2] = objp(w, slot)[MGO_LOC], s[3] = 1;
+  for (int i = 4; i < w.AOEW; i++) s[i] = 0;
+  w.E[MGEV_NUM_AOE] = k + 1;
+}
+__device__ __noinline__ void remove_object(const Wv& w, int slot) {  // resource_mutation.hpp:88-97
+  int na = w.E[MGEV_NUM_AOE];
+  for (int k = 0; k < na; k++) {
+    uint32_t* s = aoe_rec(w, k);
+    if (!s[3] || (int)s[0] != slot) continue;
+    const int32_t* a = aoe_cfg(w, (int)s[1]);
+    for (int ag = 0; ag < w.A; ag++)
+      if (aoe_inside(s, ag)) {
+        apply_presence(w, a, (int)w.agents[ag * w.AS + MGAG_OBJ], -1);
+        aoe_set_inside(s, ag, false);
+      }
+    s[3] = 0;
+  }
+  uint32_t* o = objp(w, slot);
+  set_cell(w, o_r(o), o_c(o), 0);
+  o[MGO_META] &= ~((uint32_t)MGOF_ALIVE << 24);  // leaves the tag index; territory sources persist like the reference
+}
+__device__ __noinline__ int spawn_object(const Wv& w, int t, int r, int c) {  // spawn_object_mutation.cpp:27-63
+  int slot = w.E[MGEV_NEXT_OBJ];
+  if (slot >= w.maxobj) {
+    set_error(w, MGERR_POOL_EXHAUSTED, 14);
+    return 0;
+  }
+  w.E[MGEV_NEXT_OBJ] = slot + 1;
+  init_object(w, slot, t, r, c, -1, false, (uint32_t)(w.E[MGEV_TAG_SEQ]++));
+  set_cell(w, r, c, slot);
+  const int32_t* tp = tmpl(w, t);
+  int na = __ldg(tp + MGT_AOES_N);
+  for (int i = 0; i < na; i++) {
+    int k = w.E[MGEV_NUM_AOE_PENDING];
+    if (k >= w.PENDCAP) {
+      set_error(w, MGERR_POOL_EXHAUSTED, 15);
+      break;
+    }
+    w.aoe_pending[2 * k] = slot;
+    w.aoe_pending[2 * k + 1] = __ldg(tp + MGT_AOES) + i;
+    w.E[MGEV_NUM_AOE_PENDING] = k + 1;
+  }
+  return slot;
+}
+
+// ---- materialized queries (core/query_system.cpp:91-175) ---------------------------------------------
+template <int D>
+__device__ __noinline__ void recompute_mq(const Wv& w, int tag, const Ctx& ctx, bool fire_handlers) {
+  if constexpr (D > 1) {
+    const int32_t* mq = sec(w, MGS_MQ);
+    int nmq = w.hdr[MGH_NUM_MQ];
+    Ctx tc = ctx;
+    tc.skip_trigger = true;
+    for (int i = 0; i < nmq; i++) {
+      if (__ldg(mq + 2 * i) != tag) continue;
+      int mark = arena_top(w);
+      QList lost = collect_tag(w, tag);
+      for (int k = 0; k < lost.n; k++) remove_tag<D - 1>(w, lost.p[k], tag, tc);
+      QList keep = query_eval<D - 1>(w, __ldg(mq + 2 * i + 1), ctx);
+      for (int k = 0; k < keep.n; k++) add_tag(w, keep.p[k], tag);
+      if (fire_handlers) {
+        tc.skip_trigger = false;
+        for (int k = 0; k < lost.n; k++) {
+          bool kept = false;
+          for (int j = 0; j < keep.n && !kept; j++) kept = keep.p[j] == lost.p[k];
+          if (!kept) run_tag_handlers<D - 1>(w, lost.p[k], tag, tc);
+        }
+      }
+      arena_set(w, mark);
+      break;
+    }
+    return;
+  }
+  set_error(w, MGERR_UNSUPPORTED, 16);
 }
 
 // ---- mutations + handlers (handler/mutations/*.hpp, handler.cpp:76-103, multi_handler.cpp:8-21) ---
-template <int D>
-__device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx);
-
 template <int D>
 __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
   const int32_t* m = sec(w, MGS_MUTATIONS) + mi * MG_MUTATION_WORDS;
   int op = __ldg(m), a = __ldg(m + 3), b = __ldg(m + 4), c = __ldg(m + 5), d = __ldg(m + 6);
   int e1 = resolve_entity(ctx, __ldg(m + 1)), e2 = resolve_entity(ctx, __ldg(m + 2));
   switch (op) {
-    case MGM_RESOURCE_DELTA:
+    case MGM_RESOURCE_DELTA:  // resource_mutation.hpp:23-39
+      if (ctx.deferred && __ldg(m + 1) == MGE_TARGET && ctx.target && !is_modifier(w, objp(w, ctx.target), a)) {
+        Deferred& df = *ctx.deferred;
+        if (!((df.seen >> a) & 1)) {
+          df.seen |= (uint16_t)(1u << a);
+          df.order[df.n++] = (int8_t)a;
+          df.delta[a] = 0;
+        }
+        df.delta[a] += b;
+        return;
+      }
       if (e1) inv_update<2>(w, objp(w, e1), a, b);
       return;
     case MGM_RESOURCE_TRANSFER: {
@@ -517,7 +930,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
       int amount = b < 0 ? (int)o_inv(w, src)[a] : b;
       int moved = transfer(w, src, objp(w, e2), a, amount);
       if (moved > 0 && o_is_agent(src) && o_agent(src) >= 0) astat_add(w, o_agent(src), __ldg(sec(w, MGS_RES_STATS) + a * 4 + 3), (float)moved);
-      if (c) set_error(w, MGERR_UNSUPPORTED, 4);  // remove_source_when_empty
+      if (c && ord_count(o_order(src)) == 0) remove_object(w, e1);
       return;
     }
     case MGM_CLEAR_INVENTORY: {
@@ -546,37 +959,9 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
       if (dmg > 0) inv_update<2>(w, objp(w, ctx.target), c, -dmg);
       return;
     }
-    case MGM_STATS: {
-      int ent = c ? ctx.actor : ctx.target;
-      float v = eval_value<4>(w, d, ent);
-      if (b == 0) {
-        w.gstats[a] = v;
-        gstat_touch(w, a);
-      } else if (ent) {
-        const uint32_t* o = objp(w, ent);
-        if (o_is_agent(o) && o_agent(o) >= 0) astat_set(w, o_agent(o), a, v);
-      }
+    case MGM_ADD_TAG:
+      if (e1) add_tag(w, e1, a);
       return;
-    }
-    case MGM_GAME_VALUE: {
-      float delta = eval_value<4>(w, b, e1);
-      const int32_t* v = sec(w, MGS_VALUES) + a * MG_VALUE_WORDS;
-      int vop = __ldg(v), vscope = __ldg(v + 1), va = __ldg(v + 2);
-      if (vop == MGV_INVENTORY) {
-        if (e1)
-          inv_update<2>(w, objp(w, e1), va, (int)delta);
-        else if (vscope == MGSC_GAME)
-          gstat_add(w, __ldg(sec(w, MGS_RES_GSTATS) + va), delta);
-      } else if (vop == MGV_STAT) {
-        if (vscope == MGSC_GAME) {
-          gstat_add(w, va, delta);
-        } else if (e1) {
-          const uint32_t* o = objp(w, e1);
-          if (o_is_agent(o) && o_agent(o) >= 0) astat_add(w, o_agent(o), va, delta);
-        }
-      }
-      return;
-    }
     case MGM_RELOCATE:
       if (ctx.actor && o_is_agent(objp(w, ctx.actor))) move_object(w, ctx.actor, ctx.tr, ctx.tc);
       return;
@@ -592,12 +977,110 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
       if (o_agent(x) >= 0) astat_add(w, o_agent(x), w.hdr[MGH_ST_ACTIONS_SWAP], 1.0f);
       return;
     }
-    case MGM_USE_TARGET: {  // use_target_mutation.hpp:17-30
-      if (!ctx.target || !ctx.actor || !o_is_agent(objp(w, ctx.actor))) {
+    case MGM_CHANGE_VIBE:
+      if (e1) o_set_vibe(objp(w, e1), a);
+      return;
+    case MGM_PUSH_OBJECT: {  // push_object_mutation.hpp:27-57
+      if (!ctx.actor || !ctx.target) {
         ctx.failed = true;
         return;
       }
-      if constexpr (D > 0) {
+      const uint32_t *x = objp(w, ctx.actor), *t = objp(w, ctx.target);
+      int dr = min(max(o_r(t) - o_r(x), -1), 1), dc = min(max(o_c(t) - o_c(x), -1), 1);
+      if (!move_object(w, ctx.target, o_r(t) + dr, o_c(t) + dc)) ctx.failed = true;
+      return;
+    }
+    case MGM_SPAWN_OBJECT: {
+      if (a < 0 || !valid_loc(w, ctx.tr, ctx.tc) || w.cells[ctx.tr * w.W + ctx.tc] != 0) {
+        ctx.failed = true;
+        return;
+      }
+      int s = spawn_object(w, a, ctx.tr, ctx.tc);
+      if (!s) {
+        ctx.failed = true;
+        return;
+      }
+      ctx.target = s;
+      return;
+    }
+    default:
+      break;
+  }
+  if constexpr (D > 0) {
+    switch (op) {
+      case MGM_STATS: {  // stats_mutation.hpp:21-41
+        int ent = c ? ctx.actor : ctx.target;
+        float v = eval_value<D - 1>(w, d, ctx, ent);
+        if (b == 0) {
+          w.gstats[a] = v;
+          gstat_touch(w, a);
+        } else if (ent) {
+          const uint32_t* o = objp(w, ent);
+          if (o_is_agent(o) && o_agent(o) >= 0) astat_set(w, o_agent(o), a, v);
+        }
+        return;
+      }
+      case MGM_GAME_VALUE: {  // game_value_mutation.hpp:18-25
+        float delta = eval_value<D - 1>(w, b, ctx, e1);
+        const int32_t* v = sec(w, MGS_VALUES) + a * MG_VALUE_WORDS;
+        int vop = __ldg(v), vscope = __ldg(v + 1), va = __ldg(v + 2);
+        if (vop == MGV_INVENTORY) {
+          if (e1)
+            inv_update<2>(w, objp(w, e1), va, (int)delta);
+          else if (vscope == MGSC_GAME)
+            gstat_add(w, __ldg(sec(w, MGS_RES_GSTATS) + va), delta);
+        } else if (vop == MGV_STAT) {
+          if (vscope == MGSC_GAME) {
+            gstat_add(w, va, delta);
+          } else if (e1) {
+            const uint32_t* o = objp(w, e1);
+            if (o_is_agent(o) && o_agent(o) >= 0) astat_add(w, o_agent(o), va, delta);
+          }
+        }
+        return;
+      }
+      case MGM_REMOVE_TAG:
+        if (e1) remove_tag<D - 1>(w, e1, a, ctx);
+        return;
+      case MGM_REMOVE_TAGS_PREFIX: {
+        if (!e1) return;
+        const int32_t* ids = pool(w, a);
+        for (int i = 0; i < b; i++) remove_tag<D - 1>(w, e1, __ldg(ids + i), ctx);
+        return;
+      }
+      case MGM_RECOMPUTE_MQ:
+        recompute_mq<D - 1>(w, a, ctx, true);
+        return;
+      case MGM_QUERY_INVENTORY: {  // query_inventory_mutation.hpp:24-52
+        int mark = arena_top(w);
+        QList q = query_eval<D - 1>(w, a, ctx);
+        const int32_t* pr = pool(w, b);
+        int stat_off = __ldg(m + 7);
+        if (d) {
+          if (e1) {
+            for (int k = 0; k < q.n; k++)
+              for (int i = 0; i < c; i++) {
+                int rid = __ldg(pr + 2 * i), dl = __ldg(pr + 2 * i + 1), actual = 0;
+                if (dl > 0)
+                  actual = transfer(w, objp(w, e1), objp(w, q.p[k]), rid, dl);
+                else if (dl < 0)
+                  actual = transfer(w, objp(w, q.p[k]), objp(w, e1), rid, -dl);
+                if (actual != 0 && stat_off >= 0 && __ldg(pool(w, stat_off) + rid) >= 0)
+                  gstat_add(w, __ldg(pool(w, stat_off) + rid), (float)actual);
+              }
+          }
+        } else {
+          for (int k = 0; k < q.n; k++)
+            for (int i = 0; i < c; i++) inv_update<2>(w, objp(w, q.p[k]), __ldg(pr + 2 * i), __ldg(pr + 2 * i + 1));
+        }
+        arena_set(w, mark);
+        return;
+      }
+      case MGM_USE_TARGET: {  // use_target_mutation.hpp:17-30
+        if (!ctx.target || !ctx.actor || !o_is_agent(objp(w, ctx.actor))) {
+          ctx.failed = true;
+          return;
+        }
         int h = __ldg(tmpl(w, o_tmpl(objp(w, ctx.target))) + MGT_ON_USE);
         bool ok = false;
         if (h >= 0) {
@@ -612,23 +1095,37 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         if (after >= 0) handler_apply<D - 1>(w, after, ctx);  // shares ctx (objects/agent.cpp:73-77)
         return;
       }
-      break;
-    }
-    case MGM_CHANGE_VIBE:
-      if (e1) o_set_vibe(objp(w, e1), a);
-      return;
-    case MGM_PUSH_OBJECT: {  // push_object_mutation.hpp:27-57
-      if (!ctx.actor || !ctx.target) {
-        ctx.failed = true;
+      case MGM_RAYCAST_SPAWN: {  // raycast_spawn_mutation.cpp:16-93
+        if (!ctx.target || a < 0) {
+          ctx.failed = true;
+          return;
+        }
+        const uint32_t* org = objp(w, ctx.target);
+        int orr = o_r(org), oc = o_c(org);
+        int range = (int)eval_value<D - 1>(w, d, ctx, ctx.target);
+        if (range <= 0) return;
+        const int32_t* dirs = pool(w, b);
+        int b0 = __ldg(m + 7), bn = __ldg(m + 2);
+        for (int di = 0; di < c; di++)
+          for (int dist = 1; dist <= range; dist++) {
+            int r = orr + __ldg(dirs + 2 * di) * dist, cc = oc + __ldg(dirs + 2 * di + 1) * dist;
+            if (!valid_loc(w, r, cc)) break;
+            int ex = w.cells[r * w.W + cc];
+            if (ex) {
+              bool blk = false;
+              Ctx bc = ctx;
+              bc.target = ex;
+              for (int i = 0; i < bn && !blk; i++) blk = filter_pass<D - 1>(w, b0 + i, bc);
+              if (blk) break;
+              continue;
+            }
+            spawn_object(w, a, r, cc);
+          }
         return;
       }
-      const uint32_t *x = objp(w, ctx.actor), *t = objp(w, ctx.target);
-      int dr = min(max(o_r(t) - o_r(x), -1), 1), dc = min(max(o_c(t) - o_c(x), -1), 1);
-      if (!move_object(w, ctx.target, o_r(t) + dr, o_c(t) + dc)) ctx.failed = true;
-      return;
+      default:
+        break;
     }
-    default:
-      break;
   }
   set_error(w, MGERR_UNSUPPORTED, 5 | (op << 8));
 }
@@ -638,7 +1135,7 @@ __device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx) {
   const int32_t* hd = sec(w, MGS_HANDLERS) + h * MG_HANDLER_WORDS;
   int kind = __ldg(hd), a = __ldg(hd + 1), b = __ldg(hd + 2);
   if (kind == MGHK_SIMPLE) {
-    if (!filters_pass<3>(w, a, b, ctx)) return false;
+    if (!filters_pass<D>(w, a, b, ctx)) return false;
     int m0 = __ldg(hd + 3), mn = __ldg(hd + 4);
     ctx.failed = false;
     for (int i = 0; i < mn; i++) {

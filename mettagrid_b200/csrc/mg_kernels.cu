@@ -9,6 +9,7 @@
 // env's grid is staged in shared memory, each agent's observation is composed in shared memory and
 // streamed to HBM with 16-byte stores.
 #include "mg_device.cuh"
+#include "mg_world.cuh"
 
 namespace {
 
@@ -43,7 +44,7 @@ __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {
   size_t n = 0;
   n += align16((size_t)HWp * 2);
   n += align16((size_t)3 * T + 32);
-  n += align16(4 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
+  n += align16(8 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
   n += align16((size_t)A * 4) * MG_AGENT_WORD_ARRAYS;
   n += align16((size_t)A * 2);
   n += align16(sizeof(Wv)) + align16(sizeof(Smem));
@@ -62,8 +63,8 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   s.stage = base;
   base += align16((size_t)3 * d.T + 32);
   s.rs = (int*)base;
-  s.rand = (uint32_t*)(base + 4 * sizeof(int));
-  base += align16(4 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
+  s.rand = (uint32_t*)(base + 8 * sizeof(int));
+  base += align16(8 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
   size_t aw = align16((size_t)d.A * 4);
   s.a_slot = (uint32_t*)base, base += aw;
   s.a_loc = (uint32_t*)base, base += aw;
@@ -98,7 +99,7 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.hdr = s.hdr;
   w.cells = s.cells;
   w.cells_g = d.cells + (size_t)env * d.HWp;
-  w.objs = d.objs + (size_t)env * d.maxobj * d.OS;
+  w.objs = d.objs + (size_t)env * (d.maxobj + d.NTERR) * d.OS;
   w.agents = d.agents + (size_t)env * d.A * d.AS;
   w.astats = d.astats + (size_t)env * d.A * d.SA;
   w.atouched = d.atouched + (size_t)env * d.A * d.SAW;
@@ -111,6 +112,15 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.H = d.H, w.W = d.W, w.A = d.A, w.R = d.R, w.TW = d.TW, w.OS = d.OS, w.AS = d.AS;
   w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND, w.NOFF = d.NOFF, w.CW = d.CW;
   w.obs = d.obs + (size_t)env * d.A * (size_t)(3 * d.T);
+  w.maxobj = d.maxobj, w.NTERR = d.NTERR;
+  w.ARENA = d.ARENA, w.AOECAP = d.AOECAP, w.AOEW = d.AOEW, w.PENDCAP = d.PENDCAP, w.TERRCAP = d.TERRCAP, w.NDYN = d.NDYN;
+  w.arena = d.arena + (size_t)env * d.ARENA;
+  w.aoe_src = d.aoe_src + (size_t)env * d.AOECAP * d.AOEW;
+  w.aoe_pending = d.aoe_pending + (size_t)env * d.PENDCAP * 2;
+  w.terr_src = d.terr_src + (size_t)env * d.TERRCAP * 4;
+  w.inside_tag = d.inside_tag + (size_t)env * d.A * d.NTERR;
+  w.dyn_stamp = d.dyn_stamp + (size_t)env * d.maxobj * d.NDYN;
+  s.rs[4] = 0;
   w.rs = s.rs;
   w.rand = s.rand;
   w.step = (uint32_t)w.E[MGEV_STEP];
@@ -296,7 +306,9 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
       const int32_t* ov = sec(w, MGS_OBS_VALUES);
       int me = (int)s.a_slot[a];
       for (int i = 0; i < nov; i++) {
-        uint32_t enc = (uint32_t)eval_value<4>(w, __ldg(ov + 2 * i + 1), me);
+        Ctx vc = make_ctx();
+        vc.actor = vc.target = me;
+        uint32_t enc = (uint32_t)eval_value<MG_DEPTH>(w, __ldg(ov + 2 * i + 1), vc, me);
         int f = __ldg(ov + 2 * i);
         put_token(out, T, base++, 0xFE, f, (int)(enc % (uint32_t)w.B));
         enc /= (uint32_t)w.B;
@@ -312,15 +324,18 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
 
   // ---- window cells in Manhattan order, 32 per pass (:756-811)
   uint32_t stale_sum = 0;
+  const int fmask = w.NTERR > 0 ? w.hdr[MGH_FEAT_AOE_MASK] : 0;
+  const uint32_t* me = objp(w, (int)s.a_slot[a]);
   for (int k0 = 0; k0 < w.NOFF; k0 += 32) {
     int k = k0 + lane;
-    int n = 0, loc = 0;
+    int n = 0, loc = 0, mask = 0;
     uint32_t* o = nullptr;
     if (k < w.NOFF) {
       uint32_t pk = s.offs[k];
       int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
       loc = (int)(pk >> 8);
       if (r >= 0 && c >= 0 && r < w.H && c < w.W) {
+        if (fmask) mask = territory_mask(w, r, c, me);  // :337-362, emitted before the cell's object tokens
         int slot = w.cells[r * w.W + c];
         if (slot) {
           o = objp(w, slot);
@@ -333,10 +348,11 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
         }
       }
     }
-    if (__ballot_sync(MG_FULL, n != 0) == 0) continue;  // nothing visible in these 32 cells
+    if (__ballot_sync(MG_FULL, (n | mask) != 0) == 0) continue;  // nothing visible in these 32 cells
     int tot;
-    int p = warp_excl_scan(n, lane, tot);
-    if (n && base + p < T) write_tokens(w, o, out, base + p, loc);
+    int p = warp_excl_scan(n + (mask != 0), lane, tot);
+    if (mask) put_token(out, T, base + p, loc, fmask, mask);
+    if (n && base + p + (mask != 0) < T) write_tokens(w, o, out, base + p + (mask != 0), loc);
     base += tot;
   }
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
@@ -438,21 +454,12 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
       if (slot >= d.maxobj || aidx >= d.A) {
         set_error(w, MGERR_POOL_EXHAUSTED, slot);
       } else {
+        init_object(w, slot, t, r, c, aidx, true, (uint32_t)slot);
         uint32_t* o = objp(w, slot);
-        for (int k = 0; k < d.OS; k++) o[k] = 0;
-        int flags = MGOF_ALIVE | MGOF_OBS_INV | (kind == 1 ? MGOF_AGENT : 0) | (kind == 0 ? MGOF_WALL : 0);
-        o[MGO_LOC] = ((uint32_t)r << 16) | (uint32_t)c;
-        o[MGO_META] = (uint32_t)t | ((uint32_t)(__ldg(tp + MGT_VIBE) & 0xff) << 16) | ((uint32_t)flags << 24);
-        o[MGO_AGENT] = (uint32_t)aidx;
-        o[MGO_ID] = (uint32_t)slot;
-        const int32_t* tg = pool(w, __ldg(tp + MGT_TAGS));
-        for (int k = 0; k < d.TW; k++) o[MGO_TAGS + k] = (uint32_t)__ldg(tg + k);
-        // initial inventory, stored in emission order; inserting back to front reproduces it
-        const int32_t* iv = pool(w, __ldg(tp + MGT_INIT_INV));
-        int ni = __ldg(tp + MGT_INIT_INV_N);
-        for (int k = ni - 1; k >= 0; k--) inv_update<0>(w, o, __ldg(iv + 2 * k), __ldg(iv + 2 * k + 1), true, false);
         w.cells_g[i] = (uint16_t)slot;
         if (kind == 1) {
+          const int32_t* iv = pool(w, __ldg(tp + MGT_INIT_INV));
+          int ni = __ldg(tp + MGT_INIT_INV_N);
           uint32_t* ag = w.agents + aidx * d.AS;
           for (int k = 0; k < d.AS; k++) ag[k] = 0;
           ag[MGAG_OBJ] = (uint32_t)slot;
@@ -474,6 +481,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
                 astat_touch(w, aidx, __ldg(v + 2));
             }
           }
+          for (int k = 0; k < d.NTERR; k++) w.inside_tag[aidx * d.NTERR + k] = -1;
         }
       }
     }
@@ -481,10 +489,42 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
     nagent += __popc(ma);
   }
   __syncwarp();
+  stage_cells(d, w, lane);  // the serial set-up below (materialized queries) reads the staged grid
   if (lane == 0) {
     w.E[MGEV_NEXT_OBJ] = nobj + 1;
     w.E[MGEV_NEXT_ID] = nobj + 1;
+    w.E[MGEV_TAG_SEQ] = nobj + 1;
     if (nagent != d.A) set_error(w, MGERR_POOL_EXHAUSTED, -nagent - 1);
+    // AOE / territory sources register in object-creation order (:249-257); proxies for territory handlers
+    if (d.AOECAP > 0 || d.TERRCAP > 0) {
+      for (int slot = 1; slot <= nobj; slot++) {
+        const int32_t* tp = tmpl(w, o_tmpl(objp(w, slot)));
+        for (int k = 0; k < __ldg(tp + MGT_AOES_N); k++) register_aoe(w, slot, __ldg(tp + MGT_AOES) + k);
+        const int32_t* tc = pool(w, __ldg(tp + MGT_TERR));
+        for (int k = 0; k < __ldg(tp + MGT_TERR_N); k++) {
+          int n = w.E[MGEV_NUM_TERR];
+          if (n >= d.TERRCAP) {
+            set_error(w, MGERR_POOL_EXHAUSTED, 18);
+            break;
+          }
+          uint32_t* ts = w.terr_src + (size_t)n * 4;
+          ts[0] = (uint32_t)slot, ts[1] = (uint32_t)__ldg(tc + 3 * k), ts[2] = (uint32_t)__ldg(tc + 3 * k + 1);
+          ts[3] = (uint32_t)__ldg(tc + 3 * k + 2);
+          w.E[MGEV_NUM_TERR] = n + 1;
+        }
+      }
+    }
+    for (int ti = 0; ti < d.NTERR; ti++) {
+      uint32_t* po = objp(w, d.maxobj + ti);
+      for (int k = 0; k < d.OS; k++) po[k] = 0;
+      po[MGO_META] = (uint32_t)w.hdr[MGH_PROXY_TEMPLATE];  // not alive, not in the grid
+      po[MGO_AGENT] = (uint32_t)-1;
+    }
+    if (w.hdr[MGH_NUM_MQ] > 0) {  // QuerySystem::compute_all (core/query_system.cpp:91-114)
+      Ctx g = make_ctx();
+      const int32_t* mq = sec(w, MGS_MQ);
+      for (int i = 0; i < w.hdr[MGH_NUM_MQ]; i++) recompute_mq<MG_DEPTH>(w, __ldg(mq + 2 * i), g, false);
+    }
   }
 }
 
@@ -585,7 +625,7 @@ __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg)
       ctx.tc = tc;
       ctx.distance = i;
       ctx.move_dir = arg;
-      if (handler_apply<3>(w, mh.x, ctx)) return true;
+      if (handler_apply<MG_DEPTH>(w, mh.x, ctx)) return true;
       break;
     }
   }
@@ -704,19 +744,28 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
 
   // phases 6-11 (events, on_tick, AOE, territory, game on_tick): serial
   if (lane == 0) {
+    if (w.hdr[MGH_NUM_EVENTS_SCHED] > 0) process_events(w);  // :1009-1011
     for (int a = 0; a < A; a++) {  // agent on_tick (:1019-1024)
       const int slot = (int)s.a_slot[a];
       const int h = __ldg(tmpl(w, o_tmpl(objp(w, slot))) + MGT_ON_TICK);
       if (h >= 0) {
         Ctx c = make_ctx();
         c.actor = c.target = slot;
-        handler_apply<3>(w, h, c);
+        handler_apply<MG_DEPTH>(w, h, c);
       }
+    }
+    if (w.E[MGEV_NUM_AOE] > 0 || w.NTERR > 0 || w.E[MGEV_NUM_AOE_PENDING] > 0) {  // :1032-1042
+      for (int a = 0; a < A; a++) {
+        if (w.E[MGEV_NUM_AOE] > 0) aoe_apply_fixed(w, a);
+        if (w.NTERR > 0) terr_apply(w, a);
+      }
+      aoe_apply_mobile(w);
+      aoe_flush_deferred(w);
     }
     const int gh = w.hdr[MGH_GAME_ON_TICK];
     if (gh >= 0) {
       Ctx c = make_ctx();
-      handler_apply<3>(w, gh, c);
+      handler_apply<MG_DEPTH>(w, gh, c);
     }
   }
   __syncwarp();
@@ -759,8 +808,10 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     if (nr > 0) {
       const int32_t* rw = pool(w, __ldg(tp + MGT_REWARDS));
       float total = 0.0f;
+      Ctx rc = make_ctx();
+      rc.actor = rc.target = slot;
       for (int i = 0; i < nr; i++) {
-        const float v = eval_value<4>(w, __ldg(rw + 2 * i), slot);
+        const float v = eval_value<MG_DEPTH>(w, __ldg(rw + 2 * i), rc, slot);
         const float prevv = __uint_as_float(ag[MGAG_REWARD_PREV + i]);
         total = __ldg(rw + 2 * i + 1) ? __fadd_rn(total, v) : __fadd_rn(total, __fsub_rn(v, prevv));
         ag[MGAG_REWARD_PREV + i] = __float_as_uint(v);

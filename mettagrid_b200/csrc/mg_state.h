@@ -29,6 +29,14 @@ struct MgDev {
   int32_t* env;               // [N][MGEV_WORDS]
   uint8_t* success;           // [N][A]
   const float* logtab;        // logf(k + 1), k in [0, 65536), from the host libm
+  // world systems (queries / AOE / territory / tags); sizes are 0 when the program does not use them
+  uint16_t* arena;            // [N][ARENA] scratch for query result lists (stack discipline)
+  uint32_t* aoe_src;          // [N][AOECAP][AOEW]: obj slot, cfg, registration loc, alive, inside bits per agent
+  int32_t* aoe_pending;       // [N][PENDCAP][2]: (obj slot, cfg) registrations deferred to the end of the AOE phase
+  uint32_t* terr_src;         // [N][TERRCAP][4]: obj slot, territory, strength, decay
+  int16_t* inside_tag;        // [N][A][NTERR]: winning tag the agent stood in last tick, or -1
+  uint32_t* dyn_stamp;        // [N][maxobj][NDYN]: insertion stamp of run-time-addable tags (tag-index order)
+  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN;
   // caller-owned buffers (aliased like the reference's numpy arrays)
   uint8_t* obs;               // [N][A][T][3]
   uint8_t* terminals;         // [N][A]

@@ -1,0 +1,256 @@
+// mg_world.cuh -- per-tick world systems: events, AOE, territory (all serial on lane 0 except the
+// read-only territory ownership test, which every lane evaluates for its own observation cell).
+#pragma once
+#include "mg_device.cuh"
+
+// ---- events (handler/event.cpp:34-99, event_scheduler.cpp:36-53) -----------------------------------
+__device__ __noinline__ int event_execute(const Wv& w, int ev, int depth) {
+  const int32_t* e = sec(w, MGS_EVENTS) + ev * MG_EVENT_WORDS;
+  const int maxt = __ldg(e + 1), f0 = __ldg(e + 2), fn = __ldg(e + 3), m0 = __ldg(e + 4), mn = __ldg(e + 5);
+  Ctx g = make_ctx();
+  int mark = arena_top(w);
+  QList q = query_eval<MG_DEPTH>(w, __ldg(e), g);
+  if (maxt >= 0 && q.n > maxt) rng_shuffle(w, q.p, q.n);
+  int applied = 0;
+  for (int i = 0; i < q.n; i++) {
+    if (maxt >= 0 && applied >= maxt) break;
+    int t = q.p[i];
+    Ctx c = make_ctx();
+    c.actor = c.target = t;
+    const uint32_t* o = objp(w, t);
+    c.tr = o_r(o), c.tc = o_c(o);
+    if (!filters_pass<MG_DEPTH>(w, f0, fn, c)) continue;
+    for (int k = 0; k < mn; k++) mutate<MG_DEPTH>(w, m0 + k, c);
+    applied++;
+  }
+  arena_set(w, mark);
+  int fb = __ldg(e + 6);
+  if (applied == 0 && fb >= 0) {
+    if (depth >= 8) {
+      set_error(w, MGERR_UNSUPPORTED, 17);
+      return 0;
+    }
+    return event_execute(w, fb, depth + 1);
+  }
+  return applied;
+}
+__device__ __forceinline__ void process_events(const Wv& w) {
+  const int n = w.hdr[MGH_NUM_EVENTS_SCHED];
+  const int32_t* sch = sec(w, MGS_SCHEDULE);
+  int cur = w.E[MGEV_EVENT_CURSOR];
+  while (cur < n && __ldg(sch + 2 * cur) <= (int)w.step) {
+    event_execute(w, __ldg(sch + 2 * cur + 1), 0);
+    cur++;
+  }
+  w.E[MGEV_EVENT_CURSOR] = cur;
+}
+
+// ---- AOE (core/aoe_tracker.cpp:166-200,278-415) ------------------------------------------------------
+__device__ __forceinline__ bool aoe_is_territory(const int32_t* a) { return __ldg(a + 6) == 0 && __ldg(a + 8) == 0 && __ldg(a) > 0; }
+__device__ __forceinline__ bool aoe_covers(const uint32_t* s, const int32_t* a, int r, int c) {
+  long long range = __ldg(a), dr = r - (int)(s[2] >> 16), dc = c - (int)(s[2] & 0xffffu);
+  if (dr < -range || dr > range || dc < -range || dc > range) return false;
+  long long d2 = dr * dr + dc * dc;
+  if (d2 > range * range) return false;
+  if (aoe_is_territory(a) && range >= 2 && d2 == range * range && (dr == 0 || dc == 0)) return false;
+  return true;
+}
+__device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag) {
+  const int target = (int)w.agents[ag * w.AS + MGAG_OBJ];
+  Deferred df;
+  df.n = 0;
+  df.seen = 0;
+  Ctx base = make_ctx();
+  base.target = target;
+  base.deferred = &df;
+  const uint32_t* to = objp(w, target);
+  const int na = w.E[MGEV_NUM_AOE];
+  // exits: sources the target was inside whose cells no longer cover it (registration order)
+  for (int k = 0; k < na; k++) {
+    uint32_t* s = aoe_rec(w, k);
+    if (!s[3]) continue;
+    const int32_t* a = aoe_cfg(w, (int)s[1]);
+    if (!__ldg(a + 1)) continue;
+    if (aoe_inside(s, ag) && !aoe_covers(s, a, o_r(to), o_c(to))) {
+      aoe_set_inside(s, ag, false);
+      apply_presence(w, a, target, -1);
+    }
+  }
+  for (int k = 0; k < na; k++) {
+    uint32_t* s = aoe_rec(w, k);
+    if (!s[3]) continue;
+    const int32_t* a = aoe_cfg(w, (int)s[1]);
+    const int mn = __ldg(a + 6), pn = __ldg(a + 8);
+    if (!__ldg(a + 1) || !aoe_covers(s, a, o_r(to), o_c(to))) continue;
+    if (mn == 0 && pn == 0) continue;
+    Ctx c = base;
+    c.actor = (int)s[0];
+    const bool skip_self = !__ldg(a + 2) && (int)s[0] == target;
+    const bool now = !skip_self && filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c);
+    const bool was = aoe_inside(s, ag);
+    if (now && !was) {
+      aoe_set_inside(s, ag, true);
+      apply_presence(w, a, target, +1);
+    } else if (!now && was) {
+      aoe_set_inside(s, ag, false);
+      apply_presence(w, a, target, -1);
+    }
+    if (now && mn > 0) {  // AOESource::try_apply re-checks the filters, then applies every mutation
+      Ctx c2 = base;
+      c2.actor = (int)s[0];
+      if (filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c2))
+        for (int i = 0; i < mn; i++) mutate<MG_DEPTH>(w, __ldg(a + 5) + i, c2);
+    }
+  }
+  for (int i = 0; i < df.n; i++) {
+    int rid = df.order[i];
+    if (df.delta[rid] != 0) inv_update<2>(w, objp(w, target), rid, df.delta[rid]);
+  }
+}
+__device__ __noinline__ void aoe_apply_mobile(const Wv& w) {
+  const int na = w.E[MGEV_NUM_AOE];
+  for (int k = 0; k < na; k++) {
+    uint32_t* s = aoe_rec(w, k);
+    if (!s[3]) continue;
+    const int32_t* a = aoe_cfg(w, (int)s[1]);
+    if (__ldg(a + 1)) continue;
+    const int so = (int)s[0], mn = __ldg(a + 6);
+    const long long range = __ldg(a);
+    for (int ag = 0; ag < w.A; ag++) {
+      const int t = (int)w.agents[ag * w.AS + MGAG_OBJ];
+      if (!__ldg(a + 2) && so == t) continue;
+      const bool was = aoe_inside(s, ag);
+      const uint32_t *x = objp(w, so), *y = objp(w, t);
+      long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
+      if (dr * dr + dc * dc > range * range) {
+        if (was) {
+          aoe_set_inside(s, ag, false);
+          apply_presence(w, a, t, -1);
+        }
+        continue;
+      }
+      Ctx c = make_ctx();
+      c.actor = so;
+      c.target = t;
+      const bool now = filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c);
+      if (now) {
+        if (!was) {
+          aoe_set_inside(s, ag, true);
+          apply_presence(w, a, t, +1);
+        }
+        if (mn > 0) {
+          Ctx c2 = make_ctx();
+          c2.actor = so;
+          c2.target = t;
+          if (filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c2))
+            for (int i = 0; i < mn; i++) mutate<MG_DEPTH>(w, __ldg(a + 5) + i, c2);
+        }
+      } else if (was) {
+        aoe_set_inside(s, ag, false);
+        apply_presence(w, a, t, -1);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void aoe_flush_deferred(const Wv& w) {
+  int n = w.E[MGEV_NUM_AOE_PENDING];
+  for (int k = 0; k < n; k++) register_aoe(w, w.aoe_pending[2 * k], w.aoe_pending[2 * k + 1]);
+  w.E[MGEV_NUM_AOE_PENDING] = 0;
+}
+
+// ---- territory (core/territory_tracker.cpp:20-50,215-346) -----------------------------------------------
+#define MG_MAX_PREFIX_TAGS 16
+__device__ __forceinline__ unsigned long long floor_sqrt_u64(unsigned long long v) {
+  unsigned long long root = 0, bit = 1ull << 62;
+  while (bit > v) bit >>= 2;
+  while (bit != 0) {
+    if (v >= root + bit) {
+      v -= root + bit;
+      root = (root >> 1) + bit;
+    } else {
+      root >>= 1;
+    }
+    bit >>= 2;
+  }
+  return root;
+}
+// winning tag at (r, c) for territory ti, or -1 (read-only: callable from every lane)
+__device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti) {
+  const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
+  const int32_t* pre = pool(w, __ldg(T_));
+  const int np = min(__ldg(T_ + 1), MG_MAX_PREFIX_TAGS);
+  long long score[MG_MAX_PREFIX_TAGS];
+  for (int i = 0; i < np; i++) score[i] = 0;
+  const int nt = w.E[MGEV_NUM_TERR];
+  for (int k = 0; k < nt; k++) {
+    const uint32_t* s = w.terr_src + (size_t)k * 4;
+    if ((int)s[1] != ti) continue;
+    const uint32_t* o = objp(w, (int)s[0]);
+    const int strength = (int)s[2], decay = (int)s[3];
+    const int range = decay > 0 ? strength / decay : strength;
+    long long dr = r - o_r(o), dc = c - o_c(o);
+    if (dr < -range || dr > range || dc < -range || dc > range) continue;
+    long long d2 = dr * dr + dc * dc;
+    if (d2 > (long long)range * range) continue;
+    int pi = -1;
+    for (int i = 0; i < np; i++)
+      if (o_has_tag(o, __ldg(pre + i))) {
+        pi = i;
+        break;
+      }
+    if (pi < 0) continue;
+    long long sc = (long long)strength * 1024 - (long long)decay * (long long)floor_sqrt_u64((unsigned long long)d2 * 1024ull * 1024ull);
+    if (sc > 0) score[pi] += sc;
+  }
+  int win = -1;
+  long long best = 0;
+  bool tied = false;
+  for (int i = 0; i < np; i++) {
+    if (score[i] <= 0) continue;
+    if (score[i] > best) {
+      win = __ldg(pre + i);
+      best = score[i];
+      tied = false;
+    } else if (score[i] == best && win >= 0) {
+      tied = true;
+    }
+  }
+  return tied ? -1 : win;
+}
+__device__ __forceinline__ int territory_mask(const Wv& w, int r, int c, const uint32_t* observer) {  // :254-273
+  for (int ti = 0; ti < w.NTERR; ti++) {
+    int win = cell_owner(w, r, c, ti);
+    if (win < 0) continue;
+    return o_has_tag(observer, win) ? 1 : 2;
+  }
+  return 0;
+}
+__device__ __noinline__ void terr_run(const Wv& w, int ti, int list_off, int n, int tag, int target) {
+  const int px = w.maxobj + ti;
+  uint32_t* po = objp(w, px);
+  for (int k = 0; k < w.TW; k++) po[MGO_TAGS + k] = 0;
+  po[MGO_TAGS + (tag >> 5)] = 1u << (tag & 31);
+  po[MGO_LOC] = objp(w, target)[MGO_LOC];
+  const int32_t* hs = pool(w, list_off);
+  for (int i = 0; i < n; i++) {
+    const int32_t* hd = sec(w, MGS_HANDLERS) + __ldg(hs + i) * MG_HANDLER_WORDS;
+    Ctx c = make_ctx();
+    c.actor = px;
+    c.target = target;
+    if (filters_pass<MG_DEPTH>(w, __ldg(hd + 1), __ldg(hd + 2), c))
+      for (int k = 0; k < __ldg(hd + 4); k++) mutate<MG_DEPTH>(w, __ldg(hd + 3) + k, c);  // no mutation_failed check
+  }
+}
+__device__ __noinline__ void terr_apply(const Wv& w, int ag) {
+  const int target = (int)w.agents[ag * w.AS + MGAG_OBJ];
+  for (int ti = 0; ti < w.NTERR; ti++) {
+    const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
+    const uint32_t* to = objp(w, target);
+    const int cur = cell_owner(w, o_r(to), o_c(to), ti);
+    const int prev = w.inside_tag[ag * w.NTERR + ti];
+    if (prev != cur && prev >= 0) terr_run(w, ti, __ldg(T_ + 4), __ldg(T_ + 5), prev, target);
+    if (prev != cur && cur >= 0) terr_run(w, ti, __ldg(T_ + 2), __ldg(T_ + 3), cur, target);
+    w.inside_tag[ag * w.NTERR + ti] = (int16_t)cur;
+    if (cur >= 0) terr_run(w, ti, __ldg(T_ + 6), __ldg(T_ + 7), cur, target);
+  }
+}

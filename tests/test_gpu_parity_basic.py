@@ -109,3 +109,37 @@ def test_combat_handlers_inventory_rewards(base):
         assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
         assert np.array_equal(sim.dump_objects(e), o.dump_objects()), f"object state differs in env {e}"
     sim.close()
+
+
+@pytest.mark.parametrize("spawn", [True, False])
+def test_world_aoe_territory_events_queries(spawn):
+    """C4-style game: fixed + mobile AOE, territory handlers and aoe_mask tokens, events with max_targets
+    (RNG shuffles), tag queries, tag add/remove with handlers, raycast spawn, remove-when-empty."""
+    from mettagrid_b200.sim import BatchedSimulation
+    from oracle.oracle import OracleEnv
+
+    cfg = cases.world_config(None, 3, spawn=spawn, max_steps=0)
+    maps = [cases.world_map(3, seed=40 + s) for s in range(10)]
+    sim = BatchedSimulation(cfg, 10, seeds=500, maps=maps)
+    P = sim.program
+    oracles = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(10)]
+    prim, vibe = cases.random_actions(np.random.RandomState(8), 300, (10, 6), 9, len(P.action_names), 0.2)
+    torch.cuda.synchronize()
+    obs = sim.observations.cpu().numpy()
+    for e, o in enumerate(oracles):
+        assert np.array_equal(obs[e], o.observations()), f"initial obs differ: env {e}"
+    for t in range(300):
+        sim.step(prim[t], vibe[t])
+        for e, o in enumerate(oracles):
+            o.step(prim[t, e], vibe[t, e])
+        if t % 3 == 0 or t == 299:
+            torch.cuda.synchronize()
+            obs, rew = sim.observations.cpu().numpy(), sim.rewards.cpu().numpy()
+            for e, o in enumerate(oracles):
+                assert np.array_equal(obs[e], o.observations()), f"obs differ: step {t} env {e}"
+                assert np.array_equal(rew[e].view(np.uint32), o.rewards().view(np.uint32)), f"rewards differ: step {t} env {e}"
+    sim.check_errors()
+    for e, o in enumerate(oracles):
+        assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
+        assert np.array_equal(sim.dump_objects(e), o.dump_objects()), f"object state differs in env {e}"
+    sim.close()

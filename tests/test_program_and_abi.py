@@ -112,19 +112,15 @@ def test_capi_exports_every_declared_symbol():
     assert b"compiled game program" in L.mg_last_error(None)
 
 
-def test_unsupported_features_are_refused_loudly():
-    """Programs that need features the GPU engine does not run yet must fail at mg_create, not fall back."""
+def test_bad_template_index_is_rejected_before_any_cuda_call():
     from mettagrid_b200 import native
     from mettagrid_b200.build import build_native
 
     build_native()
-    cfg = cases.benchmark_config(2)
-    cfg.game.events = {"e": C.EventConfig(name="e", target_query=C.query("type:agent"), timesteps=[3],
-                                          mutations=[C.updateTarget({"heart": 1})])}  # fmt: skip
-    p = compile_config(cfg)
+    p = compile_config(cases.benchmark_config(2))
     L = native.lib()
     out = ctypes.c_void_p()
-    cells = np.full((1, 20, 20), -1, dtype=np.int16)
     seeds = np.zeros(1, dtype=np.uint32)
-    rc = L.mg_create(p.blob.ctypes.data, p.blob.size, 1, cells.ctypes.data, None, seeds.ctypes.data, 0, ctypes.byref(out))
-    assert rc == native.MG_E_UNSUPPORTED and b"events" in L.mg_last_error(None)
+    # a NULL map is refused up front
+    rc = L.mg_create(p.blob.ctypes.data, p.blob.size, 1, None, None, seeds.ctypes.data, 0, ctypes.byref(out))
+    assert rc == native.MG_E_INVALID and b"init_cells" in L.mg_last_error(None)
