@@ -821,3 +821,17 @@ class MettaGridConfig:
     label: str = "mettagrid"
     game: GameConfig = field(default_factory=GameConfig)
     desync_episodes: bool = True
+
+
+def closureQuery(source, candidates, edge_filters=None, filters=None) -> ClosureQuery:
+    as_list = lambda x: x if isinstance(x, list) else [x] if x else []  # noqa: E731
+    return ClosureQuery(source=source, candidates=candidates, edge_filters=as_list(edge_filters), filters=as_list(filters))
+
+
+def materializedQuery(tag, q) -> MaterializedQuery:
+    return MaterializedQuery(tag=tag, query=q)
+
+
+def raycastQuery(source, max_range=2, directions=None, blocker=None, include_blocker=True) -> RaycastQuery:
+    return RaycastQuery(source=source, max_range=max_range, directions=directions or ["north", "south", "east", "west"],
+                        blocker=list(blocker or []), include_blocker=include_blocker)  # fmt: skip

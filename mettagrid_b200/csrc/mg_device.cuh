@@ -15,7 +15,7 @@
 
 #include "mg_state.h"
 
-#define MG_DEPTH 5
+#define MG_DEPTH 8
 
 // Per-warp view of one environment (lives in shared memory).
 struct Wv {

@@ -292,3 +292,78 @@ def world_map(agents_per_team: int = 3, width: int = 18, height: int = 14, seed:
                                       agents={"red": agents_per_team, "blue": agents_per_team},
                                       objects={"wall": 10, "healer": 2, "spikes": 2, "beacon_red": 2, "beacon_blue": 2,
                                                "mine": 3, "vault": 2}))  # fmt: skip
+
+
+# --------------------------------------------------------------------------------------------------
+# "network" game: materialized + closure + raycast queries, query-inventory transfers with stats,
+# push, clear-inventory, game-value filters, ratio / min / max values, game-level on_tick, on_after_use.
+# --------------------------------------------------------------------------------------------------
+NETWORK_RESOURCES = ["power", "scrap", "gear", "heart"]
+
+
+def network_config(ns=None, num_agents: int = 4, num_tokens: int = 220, max_steps: int = 0):
+    if ns is None:
+        ns = C
+    H, A = ns.Handler, ns.EntityTarget
+    vibes = [ns.Vibe("", n) for n in ["default", "swords"]]
+    powered = ns.closureQuery(ns.typeTag("hub"), ns.query(ns.typeTag("relay")), [ns.maxDistance(4)])
+    hub = ns.GridObjectConfig(
+        name="hub",
+        inventory=ns.InventoryConfig(initial={"power": 40}),
+        on_use_handler=H(name="charge", filters=[ns.GameValueFilter(target=ns.HandlerTarget.ACTOR, value=ns.inv("power"), min=0),
+                                                 ns.isNot(ns.actorHas({"power": 6}))],
+                         mutations=[ns.withdraw({"power": 3}), ns.recomputeMaterializedQuery("net:")]),  # fmt: skip
+    )
+    relay = ns.GridObjectConfig(
+        name="relay",
+        inventory=ns.InventoryConfig(initial={"scrap": 2}),
+        on_use_handler=ns.firstMatch([
+            # powered relays hand out gear paid for from every powered node's scrap
+            H(name="craft", filters=[ns.hasTag("net:powered"), ns.actorHas({"power": 1})],
+              mutations=[ns.updateActor({"power": -1, "gear": 1}),
+                         ns.queryWithdraw(ns.query("net:powered"), {"scrap": 1}, stat_prefix="net.")]),
+            H(name="shove", mutations=[ns.PushObjectMutation(), ns.recomputeMaterializedQuery("net:")]),
+        ]),  # fmt: skip
+    )
+    crate = ns.GridObjectConfig(
+        name="crate",
+        inventory=ns.InventoryConfig(initial={"heart": 1}),
+        on_use_handler=H(name="push", mutations=[ns.PushObjectMutation()]),
+    )
+    agent = ns.AgentConfig(
+        inventory=ns.InventoryConfig(
+            default_limit=20,
+            initial={"power": 2},
+            limits={"tools": ns.ResourceLimitsConfig(base=3, resources=["gear", "scrap"])},
+        ),
+        rewards={
+            "eff": ns.AgentReward(reward=ns.RatioGameValue(numerator=ns.inv("gear"), denominator=ns.inv("power"))),
+            "net": ns.reward(ns.QueryInventoryValue(query=ns.query("net:powered"), item="scrap"), weight=0.05, max=1.0, min=0.1),
+            "seen": ns.reward(ns.QueryCountValue(query=ns.raycastQuery(ns.query(ns.typeTag("hub")), max_range=3,
+                                                                        blocker=[ns.isA("wall")], include_blocker=False)), weight=0.01, per_tick=True),
+        },
+        on_after_use_handler=H(name="tired", filters=[ns.actorHas({"gear": 3})],
+                               mutations=[ns.ClearInventoryMutation(target=A.ACTOR, limit_name="tools"), ns.logStat("resets")]),
+    )  # fmt: skip
+    game = ns.GameConfig(
+        resource_names=list(NETWORK_RESOURCES),
+        num_agents=num_agents,
+        max_steps=max_steps,
+        obs=ns.ObsConfig(width=9, height=9, num_tokens=num_tokens),
+        agent=agent,
+        actions=ns.ActionsConfig(noop=ns.NoopActionConfig(), move=ns.MoveActionConfig(), change_vibe=ns.ChangeVibeActionConfig(vibes=vibes)),
+        objects={"wall": ns.WallConfig(), "hub": hub, "relay": relay, "crate": crate},
+        tags=["net:powered"],
+        materialize_queries=[ns.materializedQuery("net:powered", powered)],
+        on_tick=H(name="leak", filters=[ns.PeriodicFilter(period=6)],
+                  mutations=[ns.queryDelta(ns.query("net:powered", [ns.targetHas({"scrap": 1})]), {"scrap": -1}),
+                             ns.logStat("leaks")]),
+    )  # fmt: skip
+    return ns.MettaGridConfig(game=game)
+
+
+def network_map(num_agents: int = 4, width: int = 16, height: int = 12, seed: int = 0) -> np.ndarray:
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+
+    return random_map(RandomMapConfig(width=width, height=height, border_width=1, seed=seed, agents=num_agents,
+                                      objects={"wall": 6, "hub": 2, "relay": 7, "crate": 4}))  # fmt: skip

@@ -59,6 +59,7 @@ CASES = {
     "combat_4v4_base16": (lambda ns: cases.combat_config(ns, 4, token_value_base=16, max_steps=250),
                           lambda: cases.combat_map(4, seed=5), 5, 300, 0.3, 0.01),  # fmt: skip
     "world_3v3": (lambda ns: cases.world_config(ns, 3), lambda: cases.world_map(3, seed=2), 2, 400, 0.2, 0.0),
+    "network_4": (lambda ns: cases.network_config(ns, 4), lambda: cases.network_map(4, seed=6), 6, 400, 0.1, 0.0),
     "world_2v2_nospawn_trunc": (lambda ns: cases.world_config(ns, 2, spawn=False, max_steps=120, num_tokens=160),
                                 lambda: cases.world_map(2, width=15, height=12, seed=9), 9, 150, 0.25, 0.01),  # fmt: skip
 }

@@ -143,3 +143,32 @@ def test_world_aoe_territory_events_queries(spawn):
         assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
         assert np.array_equal(sim.dump_objects(e), o.dump_objects()), f"object state differs in env {e}"
     sim.close()
+
+
+def test_network_queries_push_clear():
+    """Materialized / closure / raycast queries, query-inventory transfers with stats, push, clear-inventory,
+    game-value filter, ratio / min / max rewards, game on_tick, on_after_use."""
+    from mettagrid_b200.sim import BatchedSimulation
+    from oracle.oracle import OracleEnv
+
+    cfg = cases.network_config(None, 4)
+    maps = [cases.network_map(4, seed=70 + s) for s in range(8)]
+    sim = BatchedSimulation(cfg, 8, seeds=900, maps=maps)
+    P = sim.program
+    oracles = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(8)]
+    prim, vibe = cases.random_actions(np.random.RandomState(9), 300, (8, 4), 5, len(P.action_names), 0.1)
+    for t in range(300):
+        sim.step(prim[t], vibe[t])
+        for e, o in enumerate(oracles):
+            o.step(prim[t, e], vibe[t, e])
+        if t % 4 == 0 or t == 299:
+            torch.cuda.synchronize()
+            obs, rew = sim.observations.cpu().numpy(), sim.rewards.cpu().numpy()
+            for e, o in enumerate(oracles):
+                assert np.array_equal(obs[e], o.observations()), f"obs differ: step {t} env {e}"
+                assert np.array_equal(rew[e].view(np.uint32), o.rewards().view(np.uint32)), f"rewards differ: step {t} env {e}"
+    sim.check_errors()
+    for e, o in enumerate(oracles):
+        assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
+        assert np.array_equal(sim.dump_objects(e), o.dump_objects()), f"object state differs in env {e}"
+    sim.close()

@@ -57,6 +57,16 @@ def test_world_fresh_seeds(reference_pkg, seed):
     _compare(cases.world_config(ns, 3), cases.world_config(None, 3), grid, seed, 350, p_vibe=0.2, p_invalid=0.0)
 
 
+@pytest.mark.parametrize("seed", [31, 32])
+def test_network_fresh_seeds(reference_pkg, seed):
+    """Materialized / closure / raycast queries, query-inventory transfers, push, clear-inventory, value filters."""
+    from tests import refns
+
+    ns = refns.reference_namespace()
+    grid = cases.network_map(4, seed=seed)
+    _compare(cases.network_config(ns, 4), cases.network_config(None, 4), grid, seed, 350, p_vibe=0.1, p_invalid=0.0)
+
+
 @pytest.mark.parametrize("agents", [1, 2, 8, 16])
 def test_benchmark_fresh_seeds(reference_pkg, agents):
     from mettagrid_b200 import config as C
