@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #define MG_MAGIC 0x4D47B200
-#define MG_VERSION 6
+#define MG_VERSION 7
 
 /* ---- header word indices ------------------------------------------------------------ */
 enum {
@@ -96,6 +96,7 @@ enum {
   MGH_MAX_TERR_SOURCES,
   MGH_PROXY_TEMPLATE,   /* inert template (kind 3) used by territory proxy-cell objects */
   MGH_SPAWN_AOES,       /* max AOE configs on any template a spawn mutation can create */
+  MGH_TOK_CAP,          /* most observation tokens any object can emit (per-object token cache size) */
   /* section offsets */
   MGS_OFFSETS,      /* NUM_OFFSETS x (dr, dc) */
   MGS_ACTIONS,      /* NUM_ACTIONS x MG_ACTION_WORDS */
@@ -267,9 +268,11 @@ enum {
   MGO_INVORD_LO,/* inventory iteration order: 4-bit resource ids, most recent first */
   MGO_INVORD_HI,/* ... top nibble (bits 60-63) = number of present resources */
   MGO_ID,       /* GridObject::id (insertion order; query result order) */
-  MGO_RESERVED,
-  MGO_TAGS      /* TW words, then ceil(R/2) words of u16 amounts */
+  MGO_NTOK,     /* cached token count, MG_TOK_DIRTY when the cache must be rebuilt */
+  MGO_TAGS      /* TW words, then ceil(R/2) words of u16 amounts, then ceil(TOK_CAP/2) words of cached
+                   (feature | value << 8) observation tokens */
 };
+#define MG_TOK_DIRTY 0xFFFFFFFFu
 #define MGOF_ALIVE 1
 #define MGOF_AGENT 2
 #define MGOF_OBS_INV 4 /* obs_encoder set: inventory tokens are emitted (false for spawned objects) */

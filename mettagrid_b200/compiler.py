@@ -960,7 +960,12 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     n_cells = map_height * map_width
     if spawn_headroom is None:
         spawn_headroom = n_cells if "spawn" in b.features else 0
-    obj_stride = (K["MGO_TAGS"] + TW + (R + 1) // 2 + 3) // 4 * 4
+    # token cache: tags an object can carry + vibe + every resource at full width + group/agent id
+    max_static_tags = max([bin(int(x) & 0xFFFFFFFF).count("1") for t in templates
+                           for x in [sum((b.pool[t[K["MGT_TAGS"]] + k] & 0xFFFFFFFF) << (32 * k) for k in range(TW))]] + [0])
+    max_static_tags = max([sum(bin(b.pool[t[K["MGT_TAGS"]] + k] & 0xFFFFFFFF).count("1") for k in range(TW)) for t in templates] + [0])
+    tok_cap = max_static_tags + len(b.dyn_tags) + 1 + R * b.inv_digits + 2
+    obj_stride = (K["MGO_TAGS"] + TW + (R + 1) // 2 + (tok_cap + 1) // 2 + 3) // 4 * 4
     agent_stride = K["MGAG_REWARD_PREV"] + max_rewards
     dyn = sorted(b.dyn_tags)
     dyn_slot = [-1] * len(b.tag_names)
@@ -991,7 +996,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         ("MGH_HP_RESOURCE", b.rid.get("hp", -1)),
         ("MGH_NUM_MOVE_HANDLERS", len(move_chain)), ("MGH_NUM_OBS_VALUES", len(obs_values)),
         ("MGH_NUM_EVENTS_SCHED", len(schedule)), ("MGH_NUM_TERRITORIES", len(territories)), ("MGH_NUM_MQ", len(mqs)),
-        ("MGH_GAME_ON_TICK", game_on_tick), ("MGH_NUM_DYN_TAGS", len(dyn)), ("MGH_PROXY_TEMPLATE", proxy_template),
+        ("MGH_GAME_ON_TICK", game_on_tick), ("MGH_NUM_DYN_TAGS", len(dyn)), ("MGH_PROXY_TEMPLATE", proxy_template), ("MGH_TOK_CAP", tok_cap),
     ]:  # fmt: skip
         hdr[H[key]] = int(v)
     if g.obs.aoe_mask:

@@ -96,7 +96,10 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   MgDev& d = h->d;
   memset(&d, 0, sizeof d);
   d.num_envs = num_envs;
-  d.H = P[MGH_H], d.W = P[MGH_W], d.HW = d.H * d.W, d.HWp = (d.HW + 7) & ~7;
+  d.H = P[MGH_H], d.W = P[MGH_W], d.HW = d.H * d.W;
+  d.PAD = (P[MGH_OBS_H] > P[MGH_OBS_W] ? P[MGH_OBS_H] : P[MGH_OBS_W]) / 2;
+  d.WP = d.W + 2 * d.PAD;
+  d.HWp = ((d.H + 2 * d.PAD) * d.WP + 7) & ~7;
   d.A = P[MGH_NUM_AGENTS], d.T = P[MGH_NUM_TOKENS], d.R = P[MGH_NUM_RESOURCES], d.TW = P[MGH_TAG_WORDS];
   d.OS = P[MGH_OBJ_STRIDE], d.AS = P[MGH_AGENT_STRIDE], d.SA = P[MGH_NUM_AGENT_STATS], d.SAW = (d.SA + 31) / 32;
   d.SG = P[MGH_NUM_GAME_STATS], d.SGW = (d.SG + 31) / 32, d.CW = P[MGH_COVER_WORDS], d.maxobj = P[MGH_MAX_OBJECTS];

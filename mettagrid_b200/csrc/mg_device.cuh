@@ -41,7 +41,7 @@ struct Wv {
   uint32_t* dyn_stamp;
   uint32_t step;
   int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW, maxobj;
-  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR;
+  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR, PAD, WP, TOKOFF;
   uint8_t* obs;  // this env's observation rows [A][T][3]
   // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top
   int* rs;
@@ -87,7 +87,10 @@ __device__ __forceinline__ int o_flags(const uint32_t* o) { return (int)(o[MGO_M
 __device__ __forceinline__ bool o_is_agent(const uint32_t* o) { return (o_flags(o) & MGOF_AGENT) != 0; }
 __device__ __forceinline__ bool o_alive(const uint32_t* o) { return (o_flags(o) & MGOF_ALIVE) != 0; }
 __device__ __forceinline__ int o_agent(const uint32_t* o) { return (int)o[MGO_AGENT]; }
-__device__ __forceinline__ void o_set_vibe(uint32_t* o, int v) { o[MGO_META] = (o[MGO_META] & 0xff00ffffu) | ((uint32_t)(v & 0xff) << 16); }
+__device__ __forceinline__ void o_set_vibe(uint32_t* o, int v) {
+  o[MGO_META] = (o[MGO_META] & 0xff00ffffu) | ((uint32_t)(v & 0xff) << 16);
+  o[MGO_NTOK] = MG_TOK_DIRTY;
+}
 __device__ __forceinline__ uint16_t* o_inv(const Wv& w, uint32_t* o) { return (uint16_t*)(o + MGO_TAGS + w.TW); }
 __device__ __forceinline__ bool o_has_tag(const uint32_t* o, int t) { return t >= 0 && t < 256 && ((o[MGO_TAGS + (t >> 5)] >> (t & 31)) & 1u); }
 
@@ -117,18 +120,34 @@ __device__ __forceinline__ uint64_t ord_erase(uint64_t v, int item) {
 }
 
 // ---- stats (systems/stats_tracker.hpp:57-98); lane-exclusive per (agent) or serial ----------
-__device__ __forceinline__ void astat_touch(const Wv& w, int a, int id) { w.atouched[a * w.SAW + (id >> 5)] |= 1u << (id & 31); }
+__device__ __forceinline__ void astat_touch(const Wv& w, int a, int id) {
+  uint32_t* p = w.atouched + a * w.SAW + (id >> 5);
+  const uint32_t bit = 1u << (id & 31);
+  if (!(*p & bit)) *p |= bit;
+}
 __device__ __forceinline__ void astat_add(const Wv& w, int a, int id, float v) {
-  w.astats[a * w.SA + id] = __fadd_rn(w.astats[a * w.SA + id], v);
+  float* p = w.astats + a * w.SA + id;
+  *p = __fadd_rn(*p, v);
   astat_touch(w, a, id);
 }
 __device__ __forceinline__ void astat_set(const Wv& w, int a, int id, float v) {
   w.astats[a * w.SA + id] = v;
   astat_touch(w, a, id);
 }
-__device__ __forceinline__ void gstat_touch(const Wv& w, int id) { w.gtouched[id >> 5] |= 1u << (id & 31); }
+__device__ __forceinline__ float astat_get(const Wv& w, int a, int id) { return w.astats[a * w.SA + id]; }
+__device__ __forceinline__ void gstat_touch(const Wv& w, int id) {
+  uint32_t* p = w.gtouched + (id >> 5);
+  const uint32_t bit = 1u << (id & 31);
+  if (!(*p & bit)) *p |= bit;
+}
 __device__ __forceinline__ void gstat_add(const Wv& w, int id, float v) {
-  w.gstats[id] = __fadd_rn(w.gstats[id], v);
+  float* p = w.gstats + id;
+  *p = __fadd_rn(*p, v);
+  gstat_touch(w, id);
+}
+__device__ __forceinline__ float gstat_get(const Wv& w, int id) { return w.gstats[id]; }
+__device__ __forceinline__ void gstat_set(const Wv& w, int id, float v) {
+  w.gstats[id] = v;
   gstat_touch(w, id);
 }
 
@@ -326,6 +345,7 @@ __device__ __noinline__ int inv_update(const Wv& w, uint32_t* o, int item, int a
   }
   inv[item] = (uint16_t)clamped;
   int d = clamped - initial;
+  if (d != 0) o[MGO_NTOK] = MG_TOK_DIRTY;  // cached observation tokens are stale
   if (notify && d != 0) on_inventory_change(w, o, item, d);
   if (d < 0 && is_modifier(w, o, item)) enforce_all_limits<D>(w, o);
   return d;
@@ -348,12 +368,15 @@ __device__ __noinline__ int transfer(const Wv& w, uint32_t* src, uint32_t* dst, 
 
 // ---- grid (core/grid.hpp:31-130) -----------------------------------------------------------------
 __device__ __forceinline__ bool valid_loc(const Wv& w, int r, int c) { return r >= 0 && c >= 0 && r < w.H && c < w.W; }
+__device__ __forceinline__ int cidx(const Wv& w, int r, int c) { return (r + w.PAD) * w.WP + c + w.PAD; }
+__device__ __forceinline__ int cell_at(const Wv& w, int r, int c) { return w.cells[cidx(w, r, c)]; }
 __device__ __forceinline__ void set_cell(const Wv& w, int r, int c, int s) {
-  w.cells[r * w.W + c] = (uint16_t)s;
-  w.cells_g[r * w.W + c] = (uint16_t)s;  // write-through: the staged copy is never flushed
+  int i = cidx(w, r, c);
+  w.cells[i] = (uint16_t)s;
+  w.cells_g[i] = (uint16_t)s;  // write-through: the staged copy is never flushed
 }
 __device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
-  if (!valid_loc(w, r, c) || w.cells[r * w.W + c] != 0) return false;
+  if (!valid_loc(w, r, c) || cell_at(w, r, c) != 0) return false;
   uint32_t* o = objp(w, s);
   set_cell(w, r, c, s);
   set_cell(w, o_r(o), o_c(o), 0);
@@ -373,6 +396,7 @@ __device__ __forceinline__ void init_object(const Wv& w, int slot, int t, int r,
   o[MGO_META] = (uint32_t)t | ((uint32_t)(__ldg(tp + MGT_VIBE) & 0xff) << 16) | ((uint32_t)flags << 24);
   o[MGO_AGENT] = (uint32_t)aidx;
   o[MGO_ID] = (uint32_t)slot;
+  o[MGO_NTOK] = MG_TOK_DIRTY;
   const int32_t* tg = pool(w, __ldg(tp + MGT_TAGS));
   for (int k = 0; k < w.TW; k++) o[MGO_TAGS + k] = (uint32_t)__ldg(tg + k);
   for (int k = 0; k < w.NDYN; k++) w.dyn_stamp[(size_t)slot * w.NDYN + k] = seq;  // tag-index registration order
@@ -427,19 +451,19 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
       if (scope == MGSC_GAME) {
         int id = __ldg(sec(w, MGS_RES_GSTATS) + a);
         gstat_touch(w, id);
-        return w.gstats[id];
+        return gstat_get(w, id);
       }
       return 0.0f;
     case MGV_STAT:
       if (scope == MGSC_GAME) {
         gstat_touch(w, a);
-        return w.gstats[a];
+        return gstat_get(w, a);
       }
       if (entity) {
         const uint32_t* o = objp(w, entity);
         if (o_is_agent(o) && o_agent(o) >= 0) {
           astat_touch(w, o_agent(o), a);
-          return w.astats[o_agent(o) * w.SA + a];
+          return astat_get(w, o_agent(o), a);
         }
       }
       return 0.0f;
@@ -732,7 +756,7 @@ __device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
           for (int dist = 1; dist <= range; dist++) {
             int r = o_r(so) + dr * dist, c = o_c(so) + dc * dist;
             if (!valid_loc(w, r, c)) break;
-            int o = w.cells[r * w.W + c];
+            int o = cell_at(w, r, c);
             if (!o) continue;
             bool blk = false;
             if (bn > 0) {
@@ -793,6 +817,7 @@ __device__ __forceinline__ void add_tag(const Wv& w, int s, int tag) {
   uint32_t* o = objp(w, s);
   if (tag < 0 || tag >= 256 || o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] |= 1u << (tag & 31);
+  o[MGO_NTOK] = MG_TOK_DIRTY;
   int ds = __ldg(sec(w, MGS_DYN_TAGS) + tag);
   if (ds >= 0 && s < w.maxobj) w.dyn_stamp[(size_t)s * w.NDYN + ds] = (uint32_t)(w.E[MGEV_TAG_SEQ]++);
   // on_tag_add handlers cannot be configured from Python (no add_on_tag_add_handler call in the lowering)
@@ -802,6 +827,7 @@ __device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ct
   uint32_t* o = objp(w, s);
   if (tag < 0 || tag >= 256 || !o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] &= ~(1u << (tag & 31));
+  o[MGO_NTOK] = MG_TOK_DIRTY;
   if (!ctx.skip_trigger) run_tag_handlers<D>(w, s, tag, ctx);
 }
 
@@ -991,7 +1017,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
       return;
     }
     case MGM_SPAWN_OBJECT: {
-      if (a < 0 || !valid_loc(w, ctx.tr, ctx.tc) || w.cells[ctx.tr * w.W + ctx.tc] != 0) {
+      if (a < 0 || !valid_loc(w, ctx.tr, ctx.tc) || cell_at(w, ctx.tr, ctx.tc) != 0) {
         ctx.failed = true;
         return;
       }
@@ -1012,8 +1038,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         int ent = c ? ctx.actor : ctx.target;
         float v = eval_value<D - 1>(w, d, ctx, ent);
         if (b == 0) {
-          w.gstats[a] = v;
-          gstat_touch(w, a);
+          gstat_set(w, a, v);
         } else if (ent) {
           const uint32_t* o = objp(w, ent);
           if (o_is_agent(o) && o_agent(o) >= 0) astat_set(w, o_agent(o), a, v);
@@ -1110,7 +1135,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
           for (int dist = 1; dist <= range; dist++) {
             int r = orr + __ldg(dirs + 2 * di) * dist, cc = oc + __ldg(dirs + 2 * di + 1) * dist;
             if (!valid_loc(w, r, cc)) break;
-            int ex = w.cells[r * w.W + cc];
+            int ex = cell_at(w, r, cc);
             if (ex) {
               bool blk = false;
               Ctx bc = ctx;

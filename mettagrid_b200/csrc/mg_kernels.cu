@@ -35,7 +35,9 @@ struct Smem {
   Smem* self;         // shared-memory copy of this struct
 };
 #define MG_AGENT_WORD_ARRAYS 9
-#define MG_MIN_CTAS_PER_SM 8  // 64 registers per thread -> 32 resident warps per SM
+#ifndef MG_MIN_CTAS_PER_SM
+#define MG_MIN_CTAS_PER_SM 7  // 72 registers per thread -> 28 resident warps per SM (measured best, profiles/README.md)
+#endif
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -89,7 +91,8 @@ __device__ __forceinline__ void load_cta_tables(const MgDev& d, Smem& s) {
   for (int i = threadIdx.x; i < d.NOFF; i += blockDim.x) {
     int dr = __ldg(offs + 2 * i), dc = __ldg(offs + 2 * i + 1);
     uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));  // systems/packed_coordinate.hpp:50-56
-    s.offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8);
+    // bits 0-7: dr + 8 | (dc + 8) << 4 ; bits 8-15: packed location ; bits 16-31: cell delta in the padded grid
+    s.offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8) | ((uint32_t)((dr * d.WP + dc) & 0xffff) << 16);
   }
   __syncthreads();
 }
@@ -112,7 +115,8 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.H = d.H, w.W = d.W, w.A = d.A, w.R = d.R, w.TW = d.TW, w.OS = d.OS, w.AS = d.AS;
   w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND, w.NOFF = d.NOFF, w.CW = d.CW;
   w.obs = d.obs + (size_t)env * d.A * (size_t)(3 * d.T);
-  w.maxobj = d.maxobj, w.NTERR = d.NTERR;
+  w.maxobj = d.maxobj, w.NTERR = d.NTERR, w.PAD = d.PAD, w.WP = d.WP;
+  w.TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
   w.ARENA = d.ARENA, w.AOECAP = d.AOECAP, w.AOEW = d.AOEW, w.PENDCAP = d.PENDCAP, w.TERRCAP = d.TERRCAP, w.NDYN = d.NDYN;
   w.arena = d.arena + (size_t)env * d.ARENA;
   w.aoe_src = d.aoe_src + (size_t)env * d.AOECAP * d.AOEW;
@@ -178,45 +182,28 @@ __device__ __forceinline__ int num_digits(uint32_t v, uint32_t B, int ND) {
   return n;
 }
 
-// tokens an object contributes (core/grid_object.cpp:178-203, objects/agent.cpp:142-154)
-__device__ __forceinline__ int count_tokens(const Wv& w, uint32_t* o) {
+// An object's observation tokens (core/grid_object.cpp:178-203, objects/agent.cpp:142-154) only change
+// when its tags, vibe or inventory change, so they are cached in the object record as (feature | value << 8)
+// pairs and rebuilt lazily by whichever lane observes the object first after a change.
+__device__ __noinline__ int rebuild_token_cache(const Wv& w, uint32_t* o) {
+  uint16_t* tk = (uint16_t*)(o + w.TOKOFF);
+  const int cap = w.hdr[MGH_TOK_CAP];
   int n = 0;
-  for (int k = 0; k < w.TW; k++) n += __popc(o[MGO_TAGS + k]);
-  n += o_vibe(o) != 0;
-  int fl = o_flags(o);
-  if (fl & MGOF_OBS_INV) {
-    uint64_t ord = o_order(o);
-    int cnt = ord_count(ord);
-    const uint16_t* inv = o_inv(w, o);
-    if (w.B == 256) {
-      for (int i = 0; i < cnt; i++) n += 1 + (inv[ord_item(ord, i)] >= 256);
-    } else {
-      for (int i = 0; i < cnt; i++) n += num_digits(inv[ord_item(ord, i)], (uint32_t)w.B, w.ND);
-    }
-  }
-  if (fl & MGOF_AGENT) n += 2;
-  return n;
-}
-__device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc, int feat, int val) {
-  if (pos < T) {
-    out[pos * 3 + 0] = (uint8_t)loc;
-    out[pos * 3 + 1] = (uint8_t)feat;
-    out[pos * 3 + 2] = (uint8_t)val;
-  }
-}
-__device__ __forceinline__ void write_tokens(const Wv& w, uint32_t* o, uint8_t* out, int pos, int loc) {
-  const int T = w.T;
+  auto put = [&](int feat, int val) {
+    if (n < cap) tk[n] = (uint16_t)((feat & 0xff) | ((val & 0xff) << 8));
+    n++;
+  };
   const int ftag = w.hdr[MGH_FEAT_TAG];
   for (int k = 0; k < w.TW; k++) {
     uint32_t m = o[MGO_TAGS + k];
     while (m) {
       int b = __ffs(m) - 1;
-      put_token(out, T, pos++, loc, ftag, k * 32 + b);
+      put(ftag, k * 32 + b);
       m &= m - 1;
     }
   }
   int vibe = o_vibe(o);
-  if (vibe) put_token(out, T, pos++, loc, w.hdr[MGH_FEAT_VIBE], vibe);
+  if (vibe) put(w.hdr[MGH_FEAT_VIBE], vibe);
   int fl = o_flags(o);
   if (fl & MGOF_OBS_INV) {
     uint64_t ord = o_order(o);
@@ -228,7 +215,7 @@ __device__ __forceinline__ void write_tokens(const Wv& w, uint32_t* o, uint8_t* 
       uint32_t amt = inv[it];
       int p = 0;
       do {
-        put_token(out, T, pos++, loc, __ldg(feats + it * w.ND + p), (int)(amt % (uint32_t)w.B));
+        put(__ldg(feats + it * w.ND + p), (int)(amt % (uint32_t)w.B));
         amt /= (uint32_t)w.B;
         p++;
       } while (amt > 0 && p < w.ND);
@@ -236,8 +223,21 @@ __device__ __forceinline__ void write_tokens(const Wv& w, uint32_t* o, uint8_t* 
   }
   if (fl & MGOF_AGENT) {
     int ai = o_agent(o);
-    put_token(out, T, pos++, loc, w.hdr[MGH_FEAT_GROUP], __ldg(tmpl(w, o_tmpl(o)) + MGT_GROUP));
-    put_token(out, T, pos++, loc, w.hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
+    put(w.hdr[MGH_FEAT_GROUP], __ldg(tmpl(w, o_tmpl(o)) + MGT_GROUP));
+    put(w.hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
+  }
+  if (n > cap) {
+    set_error(w, MGERR_POOL_EXHAUSTED, 19);
+    n = cap;
+  }
+  o[MGO_NTOK] = (uint32_t)n;
+  return n;
+}
+__device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc, int feat, int val) {
+  if (pos < T) {
+    out[pos * 3 + 0] = (uint8_t)loc;
+    out[pos * 3 + 1] = (uint8_t)feat;
+    out[pos * 3 + 2] = (uint8_t)val;
   }
 }
 
@@ -322,37 +322,54 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
     base = __shfl_sync(MG_FULL, base, 0);
   }
 
-  // ---- window cells in Manhattan order, 32 per pass (:756-811)
+  // ---- window cells in Manhattan order, 32 per pass (:756-811).  The grid carries an empty frame as
+  // wide as the window radius, so a cell outside the map reads as empty and needs no bounds test.
   uint32_t stale_sum = 0;
   const int fmask = w.NTERR > 0 ? w.hdr[MGH_FEAT_AOE_MASK] : 0;
   const uint32_t* me = objp(w, (int)s.a_slot[a]);
-  for (int k0 = 0; k0 < w.NOFF; k0 += 32) {
-    int k = k0 + lane;
-    int n = 0, loc = 0, mask = 0;
-    uint32_t* o = nullptr;
-    if (k < w.NOFF) {
-      uint32_t pk = s.offs[k];
-      int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
-      loc = (int)(pk >> 8);
-      if (r >= 0 && c >= 0 && r < w.H && c < w.W) {
-        if (fmask) mask = territory_mask(w, r, c, me);  // :337-362, emitted before the cell's object tokens
-        int slot = w.cells[r * w.W + c];
-        if (slot) {
-          o = objp(w, slot);
-          uint32_t vis = o[MGO_VISITED];
-          if (vis < w.step) {  // cell staleness (:787-796): agents are visited in index order
-            stale_sum += w.step - vis;
-            o[MGO_VISITED] = w.step;
-          }
-          n = count_tokens(w, o);
-        }
+  const uint16_t* centre = w.cells + cidx(w, r0, c0);
+  // byte stores into the stage may alias anything: keep the loop's operands in registers
+  const int NOFF = w.NOFF, TOKOFF = w.TOKOFF, OS = w.OS;
+  const uint32_t step = w.step;
+  uint32_t* const objs = w.objs;
+  const uint32_t* const offs = s.offs;
+  for (int k0 = 0; k0 < NOFF; k0 += 32) {
+    const int k = k0 + lane;
+    int n = 0, loc = 0, mask = 0, slot = 0;
+    if (k < NOFF) {
+      const uint32_t pk = offs[k];
+      loc = (int)((pk >> 8) & 0xffu);
+      slot = centre[(int)(short)(pk >> 16)];
+      if (fmask) {  // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens
+        const int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
+        if (valid_loc(w, r, c)) mask = territory_mask(w, r, c, me);
       }
     }
-    if (__ballot_sync(MG_FULL, (n | mask) != 0) == 0) continue;  // nothing visible in these 32 cells
+    if (__ballot_sync(MG_FULL, (slot | mask) != 0) == 0) continue;  // nothing visible in these 32 cells
+    uint32_t* o = nullptr;
+    if (slot) {
+      o = objs + (size_t)slot * OS;
+      const uint32_t vis = o[MGO_VISITED];
+      if (vis < step) {  // cell staleness (:787-796): agents are visited in index order
+        stale_sum += step - vis;
+        o[MGO_VISITED] = step;
+      }
+      n = (int)o[MGO_NTOK];
+      if ((uint32_t)n == MG_TOK_DIRTY) n = rebuild_token_cache(w, o);
+    }
     int tot;
     int p = warp_excl_scan(n + (mask != 0), lane, tot);
     if (mask) put_token(out, T, base + p, loc, fmask, mask);
-    if (n && base + p + (mask != 0) < T) write_tokens(w, o, out, base + p + (mask != 0), loc);
+    if (n) {  // copy the object's cached (feature, value) pairs behind this cell's location byte
+      const uint16_t* tk = (const uint16_t*)(o + TOKOFF);
+      int pos = base + p + (mask != 0);
+      for (int j = 0; j < n && pos < T; j++, pos++) {
+        const uint32_t e = tk[j];
+        out[pos * 3 + 0] = (uint8_t)loc;
+        out[pos * 3 + 1] = (uint8_t)e;
+        out[pos * 3 + 2] = (uint8_t)(e >> 8);
+      }
+    }
     base += tot;
   }
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
@@ -456,7 +473,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
       } else {
         init_object(w, slot, t, r, c, aidx, true, (uint32_t)slot);
         uint32_t* o = objp(w, slot);
-        w.cells_g[i] = (uint16_t)slot;
+        w.cells_g[cidx(w, r, c)] = (uint16_t)slot;
         if (kind == 1) {
           const int32_t* iv = pool(w, __ldg(tp + MGT_INIT_INV));
           int ni = __ldg(tp + MGT_INIT_INV_N);
@@ -611,7 +628,7 @@ __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg)
     for (int i = 1; i <= mh.y; i++) {
       int tr = o_r(o) + dr * i, tc = o_c(o) + dc * i;
       if (!valid_loc(w, tr, tc)) break;
-      int t = w.cells[tr * w.W + tc];
+      int t = cell_at(w, tr, tc);
       if (!t && !mh.z) continue;
       if (mh.w == MGMB_RELOCATE) {  // [TargetLocEmpty -> Relocate]
         if (t == 0 && move_object(w, slot, tr, tc)) return true;
@@ -721,7 +738,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
         const uint32_t loc = stream ? s.a_locv[a] : s.a_locp[a];
         if (loc == prev) {
           swm += 1;
-          if ((float)swm > w.astats[a * w.SA + w.hdr[MGH_ST_MAX_SWM]]) astat_set(w, a, w.hdr[MGH_ST_MAX_SWM], (float)swm);
+          if ((float)swm > astat_get(w, a, w.hdr[MGH_ST_MAX_SWM])) astat_set(w, a, w.hdr[MGH_ST_MAX_SWM], (float)swm);
         } else {
           swm = 0;
         }

@@ -5,7 +5,9 @@
 #include "../../include/mg_program.h"
 
 #define MG_FULL 0xffffffffu
+#ifndef MG_WARPS_PER_CTA
 #define MG_WARPS_PER_CTA 4
+#endif
 #define MG_RNG_WINDOW 32
 
 // Everything a kernel needs, passed by value.
@@ -13,11 +15,12 @@ struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
+  int PAD, WP;  // the grid is stored with a PAD-wide empty frame (row pitch WP) so observation windows need no bounds tests
   // persistent state
   const int16_t* init_cells;  // [N][HW] template per cell
   const float* init_gstats;   // [N][SG]
   const uint32_t* seeds;      // [N]
-  uint16_t* cells;            // [N][HWp] object slot per cell (0 = empty)
+  uint16_t* cells;            // [N][HWp] object slot per cell of the padded (H+2PAD) x WP grid (0 = empty)
   uint32_t* objs;             // [N][maxobj][OS]
   uint32_t* agents;           // [N][A][AS]
   float* astats;              // [N][A][SA]

@@ -10,7 +10,9 @@ import ctypes
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libmettagrid_b200.so"
+import os
+
+LIB_PATH = Path(os.environ.get("METTAGRID_B200_LIB", _PKG / "libmettagrid_b200.so"))
 _lib = None
 
 MG_OK, MG_E_INVALID, MG_E_CUDA, MG_E_UNSUPPORTED, MG_E_ENV = 0, -1, -2, -3, -4
