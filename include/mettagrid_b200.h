@@ -74,6 +74,11 @@ int mg_get_game_stats(mg_handle* h, int env, float* values /*[S_G]*/, uint8_t* t
  * id, type_id, r, c, vibe, agent (-1), tag word 0, #present resources, inv[R], order[R] (-1 padded) */
 int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows);
 
+/* replaces MettaGrid::set_inventory(agent_id, inventory) -- mettagrid_py.cpp:203-209, objects/agent.cpp:86-104.
+ * items/amounts: host int32 [n], in the iteration order of the unordered_map pybind11 builds from the Python
+ * dict (mettagrid_b200.compiler.pybind_dict_order). */
+int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, const int32_t* amounts, int n);
+
 /* sizes */
 int mg_num_envs(const mg_handle* h);
 int mg_num_agents(const mg_handle* h);

@@ -15,6 +15,8 @@ cudaError_t mg_configure_kernels(const MgDev& d);
 cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
+cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
+                                    cudaStream_t st);
 
 struct mg_handle {
   MgDev d;
@@ -395,6 +397,30 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
     n++;
   }
   return n;
+}
+
+int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, const int32_t* amounts, int n) {
+  if (!h || env < 0 || env >= h->d.num_envs || agent < 0 || agent >= h->d.A || n < 0 || n > h->d.R || (n && (!items || !amounts)))
+    return MG_E_INVALID;
+  for (int i = 0; i < n; i++)
+    if (items[i] < 0 || items[i] >= h->d.R || amounts[i] < 0 || amounts[i] > 65535) {
+      h->err = "mg_set_inventory: resource id or amount out of range";
+      return MG_E_INVALID;
+    }
+  CK(cudaSetDevice(h->device));
+  int32_t* buf = nullptr;
+  CK(cudaMalloc((void**)&buf, (size_t)(2 * n + 2) * 4));
+  cudaError_t e = cudaSuccess;
+  if (n) {
+    e = cudaMemcpy(buf, items, (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(buf + n, amounts, (size_t)n * 4, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = mg_launch_set_inventory(h->d, env, agent, buf, buf + n, n, h->own_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
+  cudaFree(buf);
+  CK(e);
+  return MG_OK;
 }
 
 int mg_num_envs(const mg_handle* h) { return h ? h->d.num_envs : 0; }

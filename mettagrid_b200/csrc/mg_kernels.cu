@@ -848,7 +848,41 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   if (lane == 0) w.E[MGEV_STEP] = (int32_t)w.step;
 }
 
+// Agent::set_inventory (objects/agent.cpp:86-104) for one agent of one env: a single warp, lane 0 works
+__global__ void k_set_inventory(MgDev d, int env, int agent, const int32_t* __restrict__ items,
+                                const int32_t* __restrict__ amounts, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  {
+    Smem cta;
+    carve(d, smem_raw, 0, cta);
+    load_cta_tables(d, cta);
+  }
+  Smem s0;
+  carve(d, smem_raw, 0, s0);
+  publish_warp(d, s0, env, lane);
+  Wv& w = *s0.wv;
+  if (lane != 0) return;
+  uint32_t* o = objp(w, (int)w.agents[agent * w.AS + MGAG_OBJ]);
+  const uint64_t existing = o_order(o);
+  for (int i = 0; i < ord_count(existing); i++) {
+    const int it = ord_item(existing, i);
+    inv_update<2>(w, o, it, -(int)o_inv(w, o)[it]);
+    astat_set(w, agent, __ldg(sec(w, MGS_RES_STATS) + it * 4 + 2), 0.0f);
+  }
+  for (int i = 0; i < n; i++) inv_update<2>(w, o, items[i], amounts[i] - (int)o_inv(w, o)[items[i]]);
+}
+
 }  // namespace
+
+cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
+                                    cudaStream_t st) {
+  size_t bytes = smem_per_cta(d.NOFF) + smem_per_warp(d.HWp, d.T, d.A);
+  cudaError_t e = cudaFuncSetAttribute(k_set_inventory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  k_set_inventory<<<1, 32, bytes, st>>>(d, env, agent, items, amounts, n);
+  return cudaGetLastError();
+}
 
 // ---- host-side launchers (used by mg_capi.cu) --------------------------------------------------
 size_t mg_smem_bytes(const MgDev& d) { return smem_per_cta(d.NOFF) + (size_t)MG_WARPS_PER_CTA * smem_per_warp(d.HWp, d.T, d.A); }

@@ -231,6 +231,16 @@ class BatchedSimulation:
             self._check(n)
         return out[:n]
 
+    def set_inventory(self, env: int, agent: int, inventory: dict):
+        """MettaGrid.set_inventory(agent_id, {resource: amount}) for one env (mettagrid_py.cpp:203-209)."""
+        from .compiler import pybind_dict_order
+
+        ids = {self.program.resource_names.index(k): int(v) for k, v in inventory.items()}
+        order = pybind_dict_order(list(ids.keys()))
+        items = np.asarray(order, dtype=np.int32)
+        amounts = np.asarray([ids[k] for k in order], dtype=np.int32)
+        self._check(self._L.mg_set_inventory(self._h, env, agent, items.ctypes.data, amounts.ctypes.data, len(order)))
+
     @property
     def state_bytes(self) -> int:
         return int(self._L.mg_state_bytes(self._h))

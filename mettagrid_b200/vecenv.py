@@ -1,0 +1,112 @@
+"""PufferLib-style vectorised env over a BatchedSimulation.
+
+Mirrors ``MettaGridPufferEnv.reset / step`` (python/src/mettagrid/envs/mettagrid_puffer_env.py:285-408)
+for a batch: flat ``[N*A, ...]`` views of the same CUDA buffers, the combined-index action decoding of
+``:313-394`` done on the device, and auto-reset of finished environments (``:299-302``: an env whose
+agents are all terminal or all truncated is rebuilt before its next step) through ``mg_reset`` with a
+device mask -- observations never leave HBM.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+
+from .sim import BatchedSimulation
+
+
+def decode_actions(actions: torch.Tensor, num_primary: int, vibe_action_ids: torch.Tensor):
+    """Reference decoding (mettagrid_puffer_env.py:313-394) on device.
+
+    1-D ``[n]``: values in ``[0, P)`` are primary actions with no vibe change; values in
+    ``[P, P + P*V)`` encode ``offset = v - P``, ``primary = offset // V``, ``vibe = offset % V``.
+    2-D ``[n, 2]``: column 0 primary, column 1 an index into the vibe action list.
+    Returns (core_actions, vibe_actions) as int32; vibe_actions holds env action ids (0 = none)."""
+    P, V = int(num_primary), int(vibe_action_ids.numel())
+    a = actions.to(torch.int64)
+    if a.dim() >= 2 and a.shape[-1] in (1, 2) and actions.dim() == 2:
+        core = a[:, 0]
+        if a.shape[1] == 1:
+            vibe = torch.zeros_like(core)
+        else:
+            if V <= 0:
+                raise ValueError("Received 2D actions with vibe column, but environment has no configured vibe action space")
+            raw = a[:, 1]
+            if bool((raw < 0).any()) or bool((raw >= V).any()):
+                raise ValueError(f"Vibe action indices out of range [0,{V}), min={int(raw.min())} max={int(raw.max())}")
+            vibe = vibe_action_ids.to(a.device)[raw]
+    elif a.dim() == 1:
+        if bool((a < 0).any()):
+            raise ValueError(f"Actions must be non-negative, got min={int(a.min())}")
+        enc = a >= P
+        core, vibe = a.clone(), torch.zeros_like(a)
+        if bool(enc.any()):
+            if V <= 0:
+                raise ValueError("Received encoded vibe actions, but environment has no configured vibe action space")
+            if bool((a >= P + P * V).any()):
+                raise ValueError(f"Action indices out of range [0, {P + P * V}), min={int(a.min())} max={int(a.max())}")
+            off = a - P
+            core = torch.where(enc, off // V, a)
+            vibe = torch.where(enc, vibe_action_ids.to(a.device)[(off % V).clamp(min=0)], vibe)
+    else:
+        raise ValueError(f"Expected step actions shape [num_agents] or [num_agents,2], got {tuple(actions.shape)}")
+    if bool((core < 0).any()) or bool((core >= P).any()):
+        raise ValueError(f"Core actions out of range [0,{P}), min={int(core.min())} max={int(core.max())}")
+    return core.to(torch.int32), vibe.to(torch.int32)
+
+
+class MettaGridVecEnv:
+    """N envs x A agents presented as N*A agents, buffers on the GPU."""
+
+    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, **kw):
+        self.sim = BatchedSimulation(cfg, num_envs, seeds=seed, **kw)
+        s = self.sim
+        names = s.program.action_names
+        self.action_names = [n for n in names if not n.startswith("change_vibe_")]
+        self.vibe_action_names = [n for n in names if n.startswith("change_vibe_")]
+        self.num_primary = len(self.action_names)
+        self._vibe_ids = torch.tensor([i for i, n in enumerate(names) if n.startswith("change_vibe_")],
+                                      dtype=torch.int64, device=s.device)  # fmt: skip
+        self.num_envs, self.agents_per_env = s.num_envs, s.num_agents
+        self.num_agents = s.num_envs * s.num_agents
+        self.episodes_finished = 0
+
+    # flat zero-copy views, the layout PufferLib hands to policies
+    @property
+    def observations(self) -> torch.Tensor:
+        return self.sim.observations.view(self.num_agents, self.sim.num_tokens, 3)
+
+    @property
+    def rewards(self) -> torch.Tensor:
+        return self.sim.rewards.view(-1)
+
+    @property
+    def terminals(self) -> torch.Tensor:
+        return self.sim.terminals.view(-1)
+
+    @property
+    def truncations(self) -> torch.Tensor:
+        return self.sim.truncations.view(-1)
+
+    def reset(self, seed: int | None = None):
+        seeds = None if seed is None else [seed + e for e in range(self.num_envs)]
+        self.sim.reset(seeds=seeds)
+        return self.observations, {}
+
+    def step(self, actions: torch.Tensor):
+        s = self.sim
+        # auto-reset envs that finished on the previous step (mettagrid_puffer_env.py:299-302)
+        done = s.terminals.all(dim=1) | s.truncations.all(dim=1)
+        n_done = int(done.sum())
+        if n_done:
+            s.reset(env_mask=done)
+            self.episodes_finished += n_done
+        core, vibe = decode_actions(torch.as_tensor(actions, device=s.device), self.num_primary, self._vibe_ids)
+        s.actions.copy_(core.view(s.actions.shape))
+        s.vibe_actions.copy_(vibe.view(s.vibe_actions.shape))
+        s.step()
+        return self.observations, self.rewards, self.terminals, self.truncations, {}
+
+    def close(self):
+        self.sim.close()

@@ -1590,16 +1590,16 @@ int mgo_dump_objects(void* h, int32_t* out, int max_rows) {
   }
   return n;
 }
-void mgo_set_inventory(void* h, int agent, const int32_t* amounts) {  // objects/agent.cpp:86-104
+// items/amounts in the iteration order of the pybind-built unordered_map (compiler.pybind_dict_order)
+void mgo_set_inventory(void* h, int agent, const int32_t* items, const int32_t* amounts, int n) {  // objects/agent.cpp:86-104
   Env* e = (Env*)h;
   Obj& o = e->objs[e->agents[agent].obj];
-  std::vector<uint8_t> items = o.order;
-  for (uint8_t it : items) {
+  std::vector<uint8_t> existing = o.order;
+  for (uint8_t it : existing) {
     e->inv_update(o, it, -(int)o.inv[it]);
     e->astat_set(agent, e->sec(MGS_RES_STATS)[it * 4 + 2], 0.0f);
   }
-  for (int r = 0; r < e->R; r++)
-    if (amounts[r] >= 0) e->inv_update(o, r, amounts[r] - (int)o.inv[r]);
+  for (int i = 0; i < n; i++) e->inv_update(o, items[i], amounts[i] - (int)o.inv[items[i]]);
 }
 // raw MT19937 + shuffle access for the H1 known-answer tests
 void mgo_test_shuffle(uint32_t seed, int n, int32_t* out, uint32_t* next_raw) {

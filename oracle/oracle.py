@@ -54,7 +54,7 @@ def lib():
         L.mgo_agent_stats.argtypes = [vp, vp, vp]
         L.mgo_game_stats.argtypes = [vp, vp, vp]
         L.mgo_dump_objects.argtypes = [vp, vp, ctypes.c_int]
-        L.mgo_set_inventory.argtypes = [vp, ctypes.c_int, vp]
+        L.mgo_set_inventory.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.mgo_test_shuffle.argtypes = [ctypes.c_uint32, ctypes.c_int, vp, vp]
         _lib = L
     return _lib
@@ -154,8 +154,12 @@ class OracleEnv:
         n = self._L.mgo_dump_objects(self._h, out.ctypes.data, cap)
         return out[:n]
 
-    def set_inventory(self, agent: int, amounts):
-        arr = np.full(len(self.program.resource_names), -1, dtype=np.int32)
-        for k, v in amounts.items():
-            arr[self.program.resource_names.index(k)] = v
-        self._L.mgo_set_inventory(self._h, agent, arr.ctypes.data)
+    def set_inventory(self, agent: int, inventory: dict):
+        """MettaGrid.set_inventory(agent_id, {resource: amount}) (bindings/mettagrid_py.cpp:203-209)."""
+        from mettagrid_b200.compiler import pybind_dict_order
+
+        ids = {self.program.resource_names.index(k): int(v) for k, v in inventory.items()}
+        order = pybind_dict_order(list(ids.keys()))
+        items = np.asarray(order, dtype=np.int32)
+        amounts = np.asarray([ids[k] for k in order], dtype=np.int32)
+        self._L.mgo_set_inventory(self._h, agent, items.ctypes.data, amounts.ctypes.data, len(order))
