@@ -39,10 +39,47 @@ UNIT = "agent-steps/s"
 ALGO_BYTES_PER_AGENT_STEP = 550.0  # C1/C2 (T=100, 20x20, R=10, A=16)
 
 
-def make_cfg(agents: int):
+WORKLOADS = {
+    # name: (description, default envs per GPU, agents)
+    "c2": ("C2: reference benchmark game 20x20, {A} agents/env, 13x13 obs, 100 tokens", 4096, 16),
+    "c3": ("C3: combat-heavy game 37x37 (25x25 + border 6), {A} agents in 2 teams, handler chains, 11x11 obs, 500 tokens", 16384, 24),
+    "c4": ("C4: world game 66x66, {A} agents, fixed+mobile AOE, territory + aoe_mask, events, queries, 11x11 obs, 200 tokens", 8192, 24),
+}
+
+
+def make_cfg(agents: int, workload: str = "c2"):
     from tests import cases
 
+    if workload == "c3":
+        return cases.combat_config(None, agents // 2, num_tokens=500)
+    if workload == "c4":
+        return cases.world_config(None, agents // 2, num_tokens=200)
     return cases.benchmark_config(agents)
+
+
+def make_map(cfg, agents: int, workload: str, seed: int):
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+
+    if workload == "c3":
+        return random_map(RandomMapConfig(width=37, height=37, border_width=6, seed=seed,
+                                          agents={"red": agents // 2, "blue": agents // 2},
+                                          objects={"wall": 10, "chest": 6, "altar": 4}))  # fmt: skip
+    if workload == "c4":
+        return random_map(RandomMapConfig(width=66, height=66, border_width=1, seed=seed,
+                                          agents={"red": agents // 2, "blue": agents // 2},
+                                          objects={"wall": 120, "healer": 6, "spikes": 6, "beacon_red": 5, "beacon_blue": 5,
+                                                   "mine": 12, "vault": 6}))  # fmt: skip
+    return random_map(cfg.game.map_builder, seed=seed)
+
+
+def algo_bytes(P, workload: str) -> float:
+    """B_io + B_state per agent-step."""
+    if workload == "c2":
+        return ALGO_BYTES_PER_AGENT_STEP
+    T, A, R = P.num_tokens, P.num_agents, len(P.resource_names)
+    b_io = 3 * T + 4 + 4 + 4 + 1 + 1 + 8
+    b_state = (2 * P.height * P.width + 16) / A + 2 * (4 + 4 + 4 + 1 + 2 * R + 4 * R) + 4 * 8
+    return float(b_io + b_state)
 
 
 def gen_actions(num_actions: int, num_primary: int, steps: int, envs: int, agents: int, seed: int):
@@ -58,22 +95,31 @@ def gen_actions(num_actions: int, num_primary: int, steps: int, envs: int, agent
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference C++ env on host cores
 # ------------------------------------------------------------------------------------------------
-def _ref_worker(rank: int, agents: int, envs: int, env0: int, steps: int, warmup: int, barrier, out_q):
+def _ref_worker(rank: int, agents: int, envs: int, env0: int, steps: int, warmup: int, barrier, out_q, workload="c2"):
     try:
         os.sched_setaffinity(0, {rank % os.cpu_count()})
     except Exception:
         pass
     sys.path.insert(0, str(ROOT))
-    from mettagrid_b200.mapgen import random_map
-    from oracle.ref_driver import RefEnv
+    from mettagrid_b200.compiler import compile_config
+    from oracle.ref_driver import RefEnv, RefUnsupported
 
-    cfg = make_cfg(agents)
-    sims = []
+    cfg = make_cfg(agents, workload)
+    sims, kind = [], "reference"
     for e in range(envs):
-        grid = random_map(cfg.game.map_builder, seed=42 + env0 + e)
-        sims.append(RefEnv(cfg, grid, 42 + env0 + e))
-    names_n = 5 + 152
-    prim, vibe = gen_actions(names_n, 5, 64, envs, agents, 1000 + rank)
+        grid = make_map(cfg, agents, workload, 42 + env0 + e)
+        try:
+            sims.append(RefEnv(cfg, grid, 42 + env0 + e))
+        except RefUnsupported:  # the GPU-box driver cannot build this game for the reference: time the oracle port
+            from oracle.oracle import OracleEnv
+
+            kind = "port"
+            prog = compile_config(cfg, *grid.shape)
+            cells, gs = prog.encode_map(grid, with_stats=True)
+            sims.append(OracleEnv(prog, cells, 42 + env0 + e, gs))
+    prog = compile_config(cfg, *make_map(cfg, agents, workload, 0).shape)
+    nprim = sum(1 for n in prog.action_names if not n.startswith("change_vibe_"))
+    prim, vibe = gen_actions(len(prog.action_names), nprim, 64, envs, agents, 1000 + rank)
     for t in range(warmup):
         for e, s in enumerate(sims):
             s.step(prim[t % 64, e], vibe[t % 64, e])
@@ -84,26 +130,28 @@ def _ref_worker(rank: int, agents: int, envs: int, env0: int, steps: int, warmup
             s.step(prim[t % 64, e], vibe[t % 64, e])
     dt = time.perf_counter() - t0
     barrier.wait()
-    out_q.put((rank, dt))
+    out_q.put((rank, dt, kind))
 
 
-def run_reference(agents: int, steps: int, warmup: int, envs_per_worker: int):
+def run_reference(agents: int, steps: int, warmup: int, envs_per_worker: int, workload: str = "c2"):
     import multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     P = os.cpu_count() or 1
     barrier = ctx.Barrier(P)
     q = ctx.Queue()
-    procs = [ctx.Process(target=_ref_worker, args=(r, agents, envs_per_worker, r * envs_per_worker, steps, warmup, barrier, q))
+    procs = [ctx.Process(target=_ref_worker, args=(r, agents, envs_per_worker, r * envs_per_worker, steps, warmup, barrier, q, workload))
              for r in range(P)]  # fmt: skip
     for p in procs:
         p.start()
-    times = [q.get()[1] for _ in procs]
+    res = [q.get() for _ in procs]
+    times = [r[1] for r in res]
+    kind = "port" if any(r[2] == "port" for r in res) else "reference"
     for p in procs:
         p.join()
     dt = max(times)
     total = P * envs_per_worker * agents * steps
-    return {"value": total / dt, "ms_per_step": dt / steps * 1e3, "cores": P, "envs": P * envs_per_worker, "seconds": dt}
+    return {"value": total / dt, "ms_per_step": dt / steps * 1e3, "cores": P, "envs": P * envs_per_worker, "seconds": dt, "kind": kind}
 
 
 def reference_available() -> bool:
@@ -158,11 +206,18 @@ def run_ours(args):
 
     from mettagrid_b200.shard import env_seeds, reduce_agent_stats, shard_range
 
-    envs, A = args.envs, args.agents
-    cfg = make_cfg(A)
+    wl = args.workload
+    envs = args.envs or WORKLOADS[wl][1]
+    A = args.agents or WORKLOADS[wl][2]
+    cfg = make_cfg(A, wl)
     env0, env1 = shard_range(world * envs, rank, world)  # weak scaling: `envs` environments per GPU
-    sim = BatchedSimulation(cfg, envs, seeds=env_seeds(42, env0, env1),
-                            map_seeds=[42 + e for e in range(env0, env1)], device=local_rank)  # fmt: skip
+    if wl == "c2":
+        maps = None
+        map_seeds = [42 + e for e in range(env0, env1)]
+    else:  # map instances are expensive to build on the host: cycle a pool of distinct maps
+        pool = [make_map(cfg, A, wl, 42 + i) for i in range(64)]
+        maps, map_seeds = [pool[e % 64] for e in range(env0, env1)], None
+    sim = BatchedSimulation(cfg, envs, seeds=env_seeds(42, env0, env1), maps=maps, map_seeds=map_seeds, device=local_rank)
     P = sim.program
     num_actions = len(P.action_names)
     num_primary = sum(1 for n in P.action_names if not n.startswith("change_vibe_"))
@@ -244,7 +299,8 @@ def run_ours(args):
         else:
             peak, peak_src = 6650.0, "fallback"
         per_launch_ms = total_ms / steps
-        achieved = ALGO_BYTES_PER_AGENT_STEP * envs * A / (per_launch_ms * 1e-3) / 1e9
+        ab = algo_bytes(P, wl)
+        achieved = ab * envs * A / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
@@ -253,8 +309,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
-            "config": {"workload": f"C2: reference benchmark game 20x20, {A} agents/env, {envs} envs/GPU, 13x13 obs, 100 tokens",
-                       "envs_per_gpu": envs, "agents_per_env": A, "actions": "primary uniform over 5, vibe p=0.1",
+            "config": {"workload": WORKLOADS[wl][0].format(A=A) + f", {envs} envs/GPU",
+                       "envs_per_gpu": envs, "agents_per_env": A, "actions": f"primary uniform over {num_primary}, vibe p=0.1",
                        "l2": "flushed between timed steps (256 MB fill)", "obs_write_GBps": value * 3 * P.num_tokens / 1e9,
                        "parallelism": f"env-sharded x{world}, no per-step collective",
                        "mean_move_success_per_agent": float(mean_stats[P.agent_stat_names.index("action.move.success")])},
@@ -264,13 +320,14 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_step", "peak_source": peak_src,
-                         "algorithmic_bytes_per_agent_step": ALGO_BYTES_PER_AGENT_STEP},
+                         "algorithmic_bytes_per_agent_step": ab},
         }  # fmt: skip
         if world == 1 and not args.no_cpu_baseline and reference_available():
             sim.close()
-            cb = run_reference(A, steps=args.cpu_steps, warmup=50, envs_per_worker=args.cpu_envs_per_worker)
-            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "reference",
-                                    "sample": f"{cb['envs']} envs x {args.cpu_steps} steps of the same game, one process per core "
+            cpu_steps = args.cpu_steps if wl == "c2" else max(200, args.cpu_steps // 20)
+            cb = run_reference(A, steps=cpu_steps, warmup=50, envs_per_worker=args.cpu_envs_per_worker, workload=wl)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
+                                    "sample": f"{cb['envs']} envs x {cpu_steps} steps of the same game, one process per core "
                                               f"({cb['seconds']:.1f} s)"}  # fmt: skip
         print(json.dumps(line))
     if world > 1:
@@ -284,8 +341,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
-    ap.add_argument("--agents", type=int, default=16)
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--agents", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=40000)
     ap.add_argument("--cpu-envs-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -299,17 +357,19 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (make -f oracle/Makefile.ref)"}))
             return
         # one "step" = one tick of the bounded sample (cores x envs_per_worker envs)
-        cb = run_reference(args.agents, steps=max(args.steps, 1) * 30, warmup=max(args.warmup, 3) * 10,
-                           envs_per_worker=args.cpu_envs_per_worker)  # fmt: skip
+        A = args.agents or WORKLOADS[args.workload][2]
+        tps = 30 if args.workload == "c2" else 3
+        cb = run_reference(A, steps=max(args.steps, 1) * tps, warmup=max(args.warmup, 3) * tps // 3 + 1,
+                           envs_per_worker=args.cpu_envs_per_worker, workload=args.workload)  # fmt: skip
         line = {
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
-            "config": {"workload": f"C2 sample: reference benchmark game 20x20, {args.agents} agents/env, {cb['envs']} envs on "
+            "config": {"workload": WORKLOADS[args.workload][0].format(A=A) + f" -- sample of {cb['envs']} envs on "
                                    f"{cb['cores']} host cores (reference C++ step, one process per core)",
-                       "ticks_per_step": 30},
-            "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": "reference",
-                             "sample": f"{cb['envs']} envs x {max(args.steps, 1) * 30} ticks"},
+                       "ticks_per_step": tps},
+            "cpu_baseline": {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
+                             "sample": f"{cb['envs']} envs x {max(args.steps, 1) * tps} ticks"},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }  # fmt: skip
