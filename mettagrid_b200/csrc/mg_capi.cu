@@ -155,7 +155,10 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     d.NDYN = P[MGH_NUM_DYN_TAGS];
     const int nq = (P[MGS_TEMPLATES] - P[MGS_QUERIES]) / MG_QUERY_WORDS;
     d.ARENA = (nq > 0 || P[MGH_NUM_MQ] > 0) ? 4 * d.maxobj + 64 : 0;
+    d.NTAGS = d.ARENA > 0 ? P[MGH_NUM_TAGS] : 0;
   }
+  TRY(dev_alloc(h, &d.tag_lists, N * d.NTAGS * MG_TAG_LIST_CAP));
+  TRY(dev_alloc(h, &d.tag_state, N * d.NTAGS));
   TRY(dev_alloc(h, &d.arena, N * d.ARENA));
   TRY(dev_alloc(h, &d.aoe_src, N * d.AOECAP * d.AOEW));
   TRY(dev_alloc(h, &d.aoe_pending, N * d.PENDCAP * 2));

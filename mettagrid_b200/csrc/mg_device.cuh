@@ -39,9 +39,11 @@ struct Wv {
   uint32_t* terr_src;
   int16_t* inside_tag;
   uint32_t* dyn_stamp;
+  uint16_t* tag_lists;
+  int32_t* tag_state;
   uint32_t step;
   int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW, maxobj;
-  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR, PAD, WP, TOKOFF;
+  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR, PAD, WP, TOKOFF, NTAGS;
   uint8_t* obs;  // this env's observation rows [A][T][3]
   // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top
   int* rs;
@@ -384,6 +386,46 @@ __device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
   return true;
 }
 
+// ---- tag index (core/tag_index.cpp:9-63): per tag, member slots in insertion order.  Kept only for
+// programs with queries (NTAGS > 0); a tag with more than MG_TAG_LIST_CAP members is marked -1 and
+// queried by scanning the object table instead.
+__device__ __forceinline__ void tl_append(const Wv& w, int tag, int s) {
+  if (tag >= w.NTAGS) return;
+  int n = w.tag_state[tag];
+  if (n < 0) return;
+  if (n >= MG_TAG_LIST_CAP) {
+    w.tag_state[tag] = -1;
+    return;
+  }
+  w.tag_lists[tag * MG_TAG_LIST_CAP + n] = (uint16_t)s;
+  w.tag_state[tag] = n + 1;
+}
+__device__ __forceinline__ void tl_erase(const Wv& w, int tag, int s) {
+  if (tag >= w.NTAGS) return;
+  int n = w.tag_state[tag];
+  if (n <= 0) return;
+  uint16_t* l = w.tag_lists + tag * MG_TAG_LIST_CAP;
+  int k = 0;
+  for (int i = 0; i < n; i++)
+    if (l[i] != (uint16_t)s) l[k++] = l[i];
+  w.tag_state[tag] = k;
+}
+__device__ __forceinline__ void tl_register_object(const Wv& w, int s, bool add) {
+  if (w.NTAGS == 0) return;
+  const uint32_t* o = objp(w, s);
+  for (int k = 0; k < w.TW; k++) {
+    uint32_t m = o[MGO_TAGS + k];
+    while (m) {
+      int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (add)
+        tl_append(w, k * 32 + b, s);
+      else
+        tl_erase(w, k * 32 + b, s);
+    }
+  }
+}
+
 // ---- object creation (core/grid_object_factory.cpp:62-104); used by k_reset (one lane per object)
 // and by the spawn mutations (serial) --------------------------------------------------------------
 __device__ __forceinline__ void init_object(const Wv& w, int slot, int t, int r, int c, int aidx, bool obs_inv, uint32_t seq) {
@@ -476,6 +518,12 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
     switch (op) {
       case MGV_QUERY_INVENTORY:
       case MGV_QUERY_COUNT: {
+        if (op == MGV_QUERY_COUNT) {  // plain tag count: TagIndex::count_objects_with_tag
+          const int32_t* q = sec(w, MGS_QUERIES) + b * MG_QUERY_WORDS;
+          const int tag = __ldg(q + 3);
+          if (__ldg(q) == MGQ_TAG && __ldg(q + 5) == 0 && __ldg(q + 1) < 0 && tag < w.NTAGS && w.tag_state[tag] >= 0)
+            return (float)w.tag_state[tag];
+        }
         Ctx c = ctx;
         c.actor = entity;  // HandlerContext::resolve_game_value: value_ctx.actor = entity
         int mark = arena_top(w);
@@ -638,6 +686,13 @@ __device__ __noinline__ QList collect_tag(const Wv& w, int tag) {
   int top = arena_top(w);
   uint16_t* out = w.arena + top;
   int n = 0, cap = w.ARENA - top;
+  if (tag < w.NTAGS && w.tag_state[tag] >= 0) {  // the ordered member list is available
+    n = min(w.tag_state[tag], cap);
+    const uint16_t* l = w.tag_lists + tag * MG_TAG_LIST_CAP;
+    for (int i = 0; i < n; i++) out[i] = l[i];
+    arena_set(w, top + n);
+    return QList{out, n};
+  }
   const int last = w.E[MGEV_NEXT_OBJ];
   const int word = MGO_TAGS + (tag >> 5);
   const uint32_t bit = 1u << (tag & 31);
@@ -818,6 +873,7 @@ __device__ __forceinline__ void add_tag(const Wv& w, int s, int tag) {
   if (tag < 0 || tag >= 256 || o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] |= 1u << (tag & 31);
   o[MGO_NTOK] = MG_TOK_DIRTY;
+  if (s < w.maxobj) tl_append(w, tag, s);  // territory proxy cells are not in the tag index
   int ds = __ldg(sec(w, MGS_DYN_TAGS) + tag);
   if (ds >= 0 && s < w.maxobj) w.dyn_stamp[(size_t)s * w.NDYN + ds] = (uint32_t)(w.E[MGEV_TAG_SEQ]++);
   // on_tag_add handlers cannot be configured from Python (no add_on_tag_add_handler call in the lowering)
@@ -828,6 +884,7 @@ __device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ct
   if (tag < 0 || tag >= 256 || !o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] &= ~(1u << (tag & 31));
   o[MGO_NTOK] = MG_TOK_DIRTY;
+  if (s < w.maxobj) tl_erase(w, tag, s);
   if (!ctx.skip_trigger) run_tag_handlers<D>(w, s, tag, ctx);
 }
 
@@ -873,6 +930,7 @@ __device__ __noinline__ void remove_object(const Wv& w, int slot) {  // resource
   }
   uint32_t* o = objp(w, slot);
   set_cell(w, o_r(o), o_c(o), 0);
+  tl_register_object(w, slot, false);
   o[MGO_META] &= ~((uint32_t)MGOF_ALIVE << 24);  // leaves the tag index; territory sources persist like the reference
 }
 __device__ __noinline__ int spawn_object(const Wv& w, int t, int r, int c) {  // spawn_object_mutation.cpp:27-63
@@ -883,6 +941,7 @@ __device__ __noinline__ int spawn_object(const Wv& w, int t, int r, int c) {  //
   }
   w.E[MGEV_NEXT_OBJ] = slot + 1;
   init_object(w, slot, t, r, c, -1, false, (uint32_t)(w.E[MGEV_TAG_SEQ]++));
+  tl_register_object(w, slot, true);
   set_cell(w, r, c, slot);
   const int32_t* tp = tmpl(w, t);
   int na = __ldg(tp + MGT_AOES_N);

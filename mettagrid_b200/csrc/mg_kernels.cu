@@ -124,6 +124,9 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.terr_src = d.terr_src + (size_t)env * d.TERRCAP * 4;
   w.inside_tag = d.inside_tag + (size_t)env * d.A * d.NTERR;
   w.dyn_stamp = d.dyn_stamp + (size_t)env * d.maxobj * d.NDYN;
+  w.NTAGS = d.NTAGS;
+  w.tag_lists = d.tag_lists + (size_t)env * d.NTAGS * MG_TAG_LIST_CAP;
+  w.tag_state = d.tag_state + (size_t)env * d.NTAGS;
   s.rs[4] = 0;
   w.rs = s.rs;
   w.rand = s.rand;
@@ -512,6 +515,8 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
     w.E[MGEV_NEXT_ID] = nobj + 1;
     w.E[MGEV_TAG_SEQ] = nobj + 1;
     if (nagent != d.A) set_error(w, MGERR_POOL_EXHAUSTED, -nagent - 1);
+    for (int tg = 0; tg < d.NTAGS; tg++) w.tag_state[tg] = 0;  // TagIndex::register_object in creation order (:247)
+    for (int slot = 1; slot <= nobj && d.NTAGS > 0; slot++) tl_register_object(w, slot, true);
     // AOE / territory sources register in object-creation order (:249-257); proxies for territory handlers
     if (d.AOECAP > 0 || d.TERRCAP > 0) {
       for (int slot = 1; slot <= nobj; slot++) {

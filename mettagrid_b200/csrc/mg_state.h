@@ -9,6 +9,7 @@
 #define MG_WARPS_PER_CTA 4
 #endif
 #define MG_RNG_WINDOW 32
+#define MG_TAG_LIST_CAP 64
 
 // Everything a kernel needs, passed by value.
 struct MgDev {
@@ -39,7 +40,9 @@ struct MgDev {
   uint32_t* terr_src;         // [N][TERRCAP][4]: obj slot, territory, strength, decay
   int16_t* inside_tag;        // [N][A][NTERR]: winning tag the agent stood in last tick, or -1
   uint32_t* dyn_stamp;        // [N][maxobj][NDYN]: insertion stamp of run-time-addable tags (tag-index order)
-  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN;
+  uint16_t* tag_lists;        // [N][NTAGS][MG_TAG_LIST_CAP]: the reference's TagIndex, insertion-ordered slots per tag
+  int32_t* tag_state;         // [N][NTAGS]: member count, or -1 once a tag outgrew its list (then queries scan)
+  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTAGS;
   // caller-owned buffers (aliased like the reference's numpy arrays)
   uint8_t* obs;               // [N][A][T][3]
   uint8_t* terminals;         // [N][A]
