@@ -41,11 +41,13 @@ struct Wv {
   uint32_t* dyn_stamp;
   uint16_t* tag_lists;
   int32_t* tag_state;
+  uint32_t* terr_tab;  // per-tick table of scoring territory sources (mg_world.cuh)
   uint32_t step;
   int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW, maxobj;
   int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR, PAD, WP, TOKOFF, NTAGS;
   uint8_t* obs;  // this env's observation rows [A][T][3]
-  // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top
+  // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top,
+  // [5]=territory table stale (set by anything that moves objects or edits tags)
   int* rs;
   uint32_t* rand;
 };
@@ -376,6 +378,7 @@ __device__ __forceinline__ void set_cell(const Wv& w, int r, int c, int s) {
   int i = cidx(w, r, c);
   w.cells[i] = (uint16_t)s;
   w.cells_g[i] = (uint16_t)s;  // write-through: the staged copy is never flushed
+  w.rs[5] = 1;
 }
 __device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
   if (!valid_loc(w, r, c) || cell_at(w, r, c) != 0) return false;
@@ -873,6 +876,7 @@ __device__ __forceinline__ void add_tag(const Wv& w, int s, int tag) {
   if (tag < 0 || tag >= 256 || o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] |= 1u << (tag & 31);
   o[MGO_NTOK] = MG_TOK_DIRTY;
+  w.rs[5] = 1;
   if (s < w.maxobj) tl_append(w, tag, s);  // territory proxy cells are not in the tag index
   int ds = __ldg(sec(w, MGS_DYN_TAGS) + tag);
   if (ds >= 0 && s < w.maxobj) w.dyn_stamp[(size_t)s * w.NDYN + ds] = (uint32_t)(w.E[MGEV_TAG_SEQ]++);
@@ -884,6 +888,7 @@ __device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ct
   if (tag < 0 || tag >= 256 || !o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] &= ~(1u << (tag & 31));
   o[MGO_NTOK] = MG_TOK_DIRTY;
+  w.rs[5] = 1;
   if (s < w.maxobj) tl_erase(w, tag, s);
   if (!ctx.skip_trigger) run_tag_handlers<D>(w, s, tag, ctx);
 }

@@ -122,6 +122,8 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.aoe_src = d.aoe_src + (size_t)env * d.AOECAP * d.AOEW;
   w.aoe_pending = d.aoe_pending + (size_t)env * d.PENDCAP * 2;
   w.terr_src = d.terr_src + (size_t)env * d.TERRCAP * 4;
+  w.terr_tab = d.terr_tab + (size_t)env * d.TERRCAP * 4;
+  s.rs[5] = 1;
   w.inside_tag = d.inside_tag + (size_t)env * d.A * d.NTERR;
   w.dyn_stamp = d.dyn_stamp + (size_t)env * d.maxobj * d.NDYN;
   w.NTAGS = d.NTAGS;
@@ -602,6 +604,10 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
     d.rewards[gi] = 0.0f;
   }
   __syncwarp();
+  if (w.NTERR > 0) {
+    if (lane == 0) terr_build_table(w);
+    __syncwarp();
+  }
   observe_all(w, s, lane, true);
 }
 
@@ -816,6 +822,10 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   __syncwarp();
 
   // phase 13: observations
+  if (w.NTERR > 0) {
+    if (lane == 0 && w.rs[5]) terr_build_table(w);
+    __syncwarp();
+  }
   observe_all(w, s, lane, false);
 
   // phase 14-15: rewards (systems/reward.hpp:56-77), episode rewards, truncation (:1070-1096)

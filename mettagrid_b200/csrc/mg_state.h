@@ -41,6 +41,7 @@ struct MgDev {
   int16_t* inside_tag;        // [N][A][NTERR]: winning tag the agent stood in last tick, or -1
   uint32_t* dyn_stamp;        // [N][maxobj][NDYN]: insertion stamp of run-time-addable tags (tag-index order)
   uint16_t* tag_lists;        // [N][NTAGS][MG_TAG_LIST_CAP]: the reference's TagIndex, insertion-ordered slots per tag
+  uint32_t* terr_tab;         // [N][TERRCAP][4]: per-tick table of scoring territory sources
   int32_t* tag_state;         // [N][NTAGS]: member count, or -1 once a tag outgrew its list (then queries scan)
   int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTAGS;
   // caller-owned buffers (aliased like the reference's numpy arrays)

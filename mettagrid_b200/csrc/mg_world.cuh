@@ -160,48 +160,66 @@ __device__ __forceinline__ void aoe_flush_deferred(const Wv& w) {
 
 // ---- territory (core/territory_tracker.cpp:20-50,215-346) -----------------------------------------------
 #define MG_MAX_PREFIX_TAGS 16
+// floor(sqrt(v)) for v < 2^62: a float estimate corrected with exact integer tests gives the same value as
+// the reference's bit-by-bit floor_sqrt_u64 (core/territory_tracker.cpp:20-36)
 __device__ __forceinline__ unsigned long long floor_sqrt_u64(unsigned long long v) {
-  unsigned long long root = 0, bit = 1ull << 62;
-  while (bit > v) bit >>= 2;
-  while (bit != 0) {
-    if (v >= root + bit) {
-      v -= root + bit;
-      root = (root >> 1) + bit;
-    } else {
-      root >>= 1;
-    }
-    bit >>= 2;
-  }
-  return root;
+  unsigned long long r = (unsigned long long)sqrt((double)v);
+  while (r * r > v) r--;
+  while ((r + 1) * (r + 1) <= v) r++;
+  return r;
 }
-// winning tag at (r, c) for territory ti, or -1 (read-only: callable from every lane)
-__device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti) {
-  const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
-  const int32_t* pre = pool(w, __ldg(T_));
-  const int np = min(__ldg(T_ + 1), MG_MAX_PREFIX_TAGS);
-  long long score[MG_MAX_PREFIX_TAGS];
-  for (int i = 0; i < np; i++) score[i] = 0;
+// Per-tick table of the territory sources that can own cells: (loc, range, strength | decay << 16,
+// territory | prefix index << 8).  Built by lane 0 whenever the grid changed; the ownership test below then
+// needs one 16-byte load per source and no division / object lookups.
+__device__ __noinline__ void terr_build_table(const Wv& w) {
   const int nt = w.E[MGEV_NUM_TERR];
+  int n = 0;
   for (int k = 0; k < nt; k++) {
     const uint32_t* s = w.terr_src + (size_t)k * 4;
-    if ((int)s[1] != ti) continue;
+    const int ti = (int)s[1];
+    const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
+    const int32_t* pre = pool(w, __ldg(T_));
+    const int np = min(__ldg(T_ + 1), MG_MAX_PREFIX_TAGS);
     const uint32_t* o = objp(w, (int)s[0]);
-    const int strength = (int)s[2], decay = (int)s[3];
-    const int range = decay > 0 ? strength / decay : strength;
-    long long dr = r - o_r(o), dc = c - o_c(o);
-    if (dr < -range || dr > range || dc < -range || dc > range) continue;
-    long long d2 = dr * dr + dc * dc;
-    if (d2 > (long long)range * range) continue;
     int pi = -1;
     for (int i = 0; i < np; i++)
       if (o_has_tag(o, __ldg(pre + i))) {
         pi = i;
         break;
       }
-    if (pi < 0) continue;
-    long long sc = (long long)strength * 1024 - (long long)decay * (long long)floor_sqrt_u64((unsigned long long)d2 * 1024ull * 1024ull);
-    if (sc > 0) score[pi] += sc;
+    if (pi < 0) continue;  // find_matching_tag < 0: the source scores nothing
+    const int strength = (int)s[2], decay = (int)s[3];
+    uint32_t* e = w.terr_tab + (size_t)n * 4;
+    e[0] = o[MGO_LOC];
+    e[1] = (uint32_t)(decay > 0 ? strength / decay : strength);
+    e[2] = (uint32_t)strength | ((uint32_t)decay << 16);
+    e[3] = (uint32_t)ti | ((uint32_t)pi << 8);
+    n++;
   }
+  w.E[MGEV_RESERVED] = n;  // entries in the table
+  w.rs[5] = 0;             // clean
+}
+// winning tag at (r, c) for territory ti, or -1 (read-only: callable from every lane)
+__device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti) {
+  const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
+  const int np = min(__ldg(T_ + 1), MG_MAX_PREFIX_TAGS);
+  long long score[MG_MAX_PREFIX_TAGS];
+  for (int i = 0; i < np; i++) score[i] = 0;
+  const int n = w.E[MGEV_RESERVED];
+  const uint4* tab = (const uint4*)w.terr_tab;
+  for (int k = 0; k < n; k++) {
+    const uint4 e = tab[k];
+    if ((int)(e.w & 0xffu) != ti) continue;
+    const int range = (int)e.y;
+    const int dr = r - (int)(e.x >> 16), dc = c - (int)(e.x & 0xffffu);
+    if (dr < -range || dr > range || dc < -range || dc > range) continue;
+    const long long d2 = (long long)dr * dr + (long long)dc * dc;
+    if (d2 > (long long)range * range) continue;
+    const long long strength = e.z & 0xffffu, decay = e.z >> 16;
+    const long long sc = strength * 1024 - decay * (long long)floor_sqrt_u64((unsigned long long)d2 * 1024ull * 1024ull);
+    if (sc > 0) score[(e.w >> 8) & 0xffu] += sc;
+  }
+  const int32_t* pre = pool(w, __ldg(T_));
   int win = -1;
   long long best = 0;
   bool tied = false;
@@ -246,6 +264,7 @@ __device__ __noinline__ void terr_apply(const Wv& w, int ag) {
   for (int ti = 0; ti < w.NTERR; ti++) {
     const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
     const uint32_t* to = objp(w, target);
+    if (w.rs[5]) terr_build_table(w);  // a handler moved / tagged something since the last build
     const int cur = cell_owner(w, o_r(to), o_c(to), ti);
     const int prev = w.inside_tag[ag * w.NTERR + ti];
     if (prev != cur && prev >= 0) terr_run(w, ti, __ldg(T_ + 4), __ldg(T_ + 5), prev, target);
