@@ -60,6 +60,24 @@ static int dev_alloc(mg_handle* h, T** p, size_t count) {
 }
 
 // engine limits: anything beyond them is refused loudly rather than mis-simulated
+// A "plain" program never needs the interpreter: only the two default move handlers, no on_use / on_tick /
+// on_after_use / tag handlers, no rewards, obs values, events, AOE, territory or materialized queries.
+static int program_is_plain(const int32_t* P) {
+  if (P[MGH_NUM_MOVE_HANDLERS] != 2 || P[MGH_NUM_OBS_VALUES] || P[MGH_NUM_EVENTS_SCHED] || P[MGH_NUM_TERRITORIES] ||
+      P[MGH_NUM_MQ] || P[MGH_GAME_ON_TICK] >= 0 || P[MGH_FEAT_AOE_MASK])
+    return 0;
+  const int32_t* ch = P + P[MGS_MOVE_CHAIN];
+  if (ch[3] != MGMB_RELOCATE || ch[MG_MOVEH_WORDS + 3] != MGMB_USE_TARGET) return 0;
+  const int32_t* T_ = P + P[MGS_TEMPLATES];
+  for (int t = 0; t < P[MGH_NUM_TEMPLATES]; t++) {
+    const int32_t* tp = T_ + t * MG_TEMPLATE_WORDS;
+    if (tp[MGT_ON_USE] >= 0 || tp[MGT_ON_TICK] >= 0 || tp[MGT_ON_AFTER_USE] >= 0 || tp[MGT_REWARDS_N] || tp[MGT_AOES_N] ||
+        tp[MGT_TERR_N] || tp[MGT_TAG_REMOVE_N])
+      return 0;
+  }
+  return 1;
+}
+
 static const char* unsupported_reason(const int32_t* P) {
   const int32_t* T_ = P + P[MGS_TERRITORIES];
   for (int i = 0; i < P[MGH_NUM_TERRITORIES]; i++)
@@ -106,6 +124,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   d.OS = P[MGH_OBJ_STRIDE], d.AS = P[MGH_AGENT_STRIDE], d.SA = P[MGH_NUM_AGENT_STATS], d.SAW = (d.SA + 31) / 32;
   d.SG = P[MGH_NUM_GAME_STATS], d.SGW = (d.SG + 31) / 32, d.CW = P[MGH_COVER_WORDS], d.maxobj = P[MGH_MAX_OBJECTS];
   d.NOFF = P[MGH_NUM_OFFSETS], d.B = P[MGH_TOKEN_BASE], d.ND = P[MGH_INV_DIGITS], d.NTERR = P[MGH_NUM_TERRITORIES];
+  d.plain = program_is_plain(P);
   if (d.R > 13 || d.maxobj > 65535 || d.A > 4096) {
     h->err = "mg_create: program exceeds engine limits (R<=13, objects<=65535, agents<=4096)";
     return fail(MG_E_INVALID);

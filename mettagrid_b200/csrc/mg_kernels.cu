@@ -259,7 +259,11 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
 
 // One agent's observation, composed by the whole warp (bindings/mettagrid_c.cpp:665-824).
 // Returns the number of tokens attempted; `tok` accumulates the env's token stats.
-__device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int action, uint32_t steploc, int lane) {
+#define MG_OBS_ATTR __forceinline__  // measured: inlining into observe_all beats a call per agent (profiles/README.md)
+// PLAIN = the program has no territory (no aoe_mask tokens) and no configured global game values: the common
+// case gets a version without those paths, which keeps the window loop small and out of local memory.
+template <bool PLAIN>
+__device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int action, uint32_t steploc, int lane) {
   const int T = w.T;
   uint8_t* g = w.obs + (size_t)a * (size_t)(3 * T);
   uint8_t* out = s.stage + ((uint32_t)(uintptr_t)g & 15u);
@@ -305,7 +309,7 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
   int base = total;
 
   // ---- configured global game values (:1207-1238), serial
-  int nov = w.hdr[MGH_NUM_OBS_VALUES];
+  const int nov = PLAIN ? 0 : w.hdr[MGH_NUM_OBS_VALUES];
   if (nov > 0) {
     if (lane == 0) {
       const int32_t* ov = sec(w, MGS_OBS_VALUES);
@@ -330,7 +334,7 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
   // ---- window cells in Manhattan order, 32 per pass (:756-811).  The grid carries an empty frame as
   // wide as the window radius, so a cell outside the map reads as empty and needs no bounds test.
   uint32_t stale_sum = 0;
-  const int fmask = w.NTERR > 0 ? w.hdr[MGH_FEAT_AOE_MASK] : 0;
+  const int fmask = (!PLAIN && w.NTERR > 0) ? w.hdr[MGH_FEAT_AOE_MASK] : 0;
   const uint32_t* me = objp(w, (int)s.a_slot[a]);
   const uint16_t* centre = w.cells + cidx(w, r0, c0);
   // byte stores into the stage may alias anything: keep the loop's operands in registers
@@ -388,10 +392,12 @@ __device__ __noinline__ int observe_agent(const Wv& w, const Smem& s, int a, int
 }
 
 // all agents' observations + token stats (:826-912, :640-642)
-__device__ void observe_all(const Wv& w, const Smem& s, int lane, bool initial) {
+__device__ __noinline__ void observe_all(const Wv& w, const Smem& s, int lane, bool initial) {
+  const bool plain = w.NTERR == 0 && w.hdr[MGH_NUM_OBS_VALUES] == 0;
   for (int a = 0; a < w.A; a++) {
     int action = initial ? 0 : s.a_exec[a];
-    int attempted = observe_agent(w, s, a, action, s.a_step[a], lane);
+    int attempted = plain ? observe_agent<true>(w, s, a, action, s.a_step[a], lane)
+                          : observe_agent<false>(w, s, a, action, s.a_step[a], lane);
     if (lane == 0) {
       if (attempted > w.T) {  // hard error in the reference (:364-375)
         set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
@@ -622,6 +628,9 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
 #define MGR_KIND_V_SHIFT 6
 
 // actions/move.hpp:81-115 + change_vibe.hpp:48-57 + noop.hpp:21-23 (serial)
+// PLAIN programs (no handlers anywhere: movement, vibes, observations, stats -- the reference's benchmark
+// game) never enter the interpreter: a move is "relocate into an empty cell or fail".
+template <bool PLAIN>
 __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg) {
   if (kind == MGA_NOOP) return true;
   uint32_t* o = objp(w, slot);
@@ -632,6 +641,10 @@ __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg)
   // actions/orientation.hpp:28-48
   const int dr = (arg == 0 || arg == 4 || arg == 5) ? -1 : (arg == 1 || arg == 6 || arg == 7) ? 1 : 0;
   const int dc = (arg == 2 || arg == 4 || arg == 6) ? -1 : (arg == 3 || arg == 5 || arg == 7) ? 1 : 0;
+  if constexpr (PLAIN) {
+    // [TargetLocEmpty -> Relocate] then [TargetIsUsable -> UseTarget]; without on_use handlers the second fails
+    return move_object(w, slot, o_r(o) + dr, o_c(o) + dc);
+  }
   const int32_t* chain = sec(w, MGS_MOVE_CHAIN);
   const int nh = w.hdr[MGH_NUM_MOVE_HANDLERS];
   for (int k = 0; k < nh; k++) {
@@ -660,6 +673,7 @@ __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg)
   return false;
 }
 
+template <bool PLAIN>
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_step(MgDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -711,7 +725,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
           const int4 act = __ldg((const int4*)(acts + idx * MG_ACTION_WORDS));  // kind, arg, priority, is_vibe
           if (act.w != stream || act.z != prio) continue;
           const int slot = (int)s.a_slot[a];
-          bool ok = do_action(w, slot, act.x, act.y);
+          bool ok = do_action<PLAIN>(w, slot, act.x, act.y);
           uint32_t loc = objp(w, slot)[MGO_LOC];
           if (stream == 0) {
             s.a_res[a] |= MGR_ACTED_P | (ok ? MGR_OK_P : 0u) | ((uint32_t)act.x << MGR_KIND_P_SHIFT);
@@ -771,7 +785,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   __syncwarp();
 
   // phases 6-11 (events, on_tick, AOE, territory, game on_tick): serial
-  if (lane == 0) {
+  if (!PLAIN && lane == 0) {
     if (w.hdr[MGH_NUM_EVENTS_SCHED] > 0) process_events(w);  // :1009-1011
     for (int a = 0; a < A; a++) {  // agent on_tick (:1019-1024)
       const int slot = (int)s.a_slot[a];
@@ -822,7 +836,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   __syncwarp();
 
   // phase 13: observations
-  if (w.NTERR > 0) {
+  if (!PLAIN && w.NTERR > 0) {
     if (lane == 0 && w.rs[5]) terr_build_table(w);
     __syncwarp();
   }
@@ -835,7 +849,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     uint32_t* ag = w.agents + a * w.AS;
     const int slot = (int)s.a_slot[a];
     const int32_t* tp = tmpl(w, o_tmpl(objp(w, slot)));
-    const int nr = __ldg(tp + MGT_REWARDS_N);
+    const int nr = PLAIN ? 0 : __ldg(tp + MGT_REWARDS_N);
     float reward = 0.0f;
     if (nr > 0) {
       const int32_t* rw = pool(w, __ldg(tp + MGT_REWARDS));
@@ -907,12 +921,14 @@ cudaError_t mg_configure_kernels(const MgDev& d) {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_init_buffers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
   // leave room for MG_MIN_CTAS_PER_SM CTAs' shared memory; the rest of the 256 KB stays L1
   int want_kb = (int)((bytes + 1024) * MG_MIN_CTAS_PER_SM / 1024) + 8;
   int pct = want_kb * 100 / 228 + 1;
   if (pct > 100) pct = 100;
-  return cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  if ((e = cudaFuncSetAttribute(k_step<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 static inline int mg_grid(const MgDev& d) { return (d.num_envs + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
 cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
@@ -924,6 +940,9 @@ cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStre
   return cudaGetLastError();
 }
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st) {
-  k_step<<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
+  if (d.plain)
+    k_step<true><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
+  else
+    k_step<false><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
   return cudaGetLastError();
 }

@@ -16,6 +16,7 @@ struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
+  int plain;    // 1: the program has no handlers / rewards / world systems (k_step<PLAIN> applies)
   int PAD, WP;  // the grid is stored with a PAD-wide empty frame (row pitch WP) so observation windows need no bounds tests
   // persistent state
   const int16_t* init_cells;  // [N][HW] template per cell
