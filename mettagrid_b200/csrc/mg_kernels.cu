@@ -16,6 +16,7 @@ namespace {
 struct Smem {
   int32_t* hdr;
   uint32_t* offs;
+  uint8_t* rank;      // [(dr + rr) * 16 + (dc + cr)] -> position of the offset in Manhattan order, 0xFF = outside the shape
   // per warp
   uint16_t* cells;
   uint8_t* stage;
@@ -52,13 +53,15 @@ __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {
   n += align16(sizeof(Wv)) + align16(sizeof(Smem));
   return n;
 }
-__host__ __device__ inline size_t smem_per_cta(int NOFF) { return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4); }
+__host__ __device__ inline size_t smem_per_cta(int NOFF) { return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4) + 256; }
 
 __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int warp, Smem& s) {
   s.hdr = (int32_t*)base;
   base += align16(MGH_HEADER_WORDS * 4);
   s.offs = (uint32_t*)base;
   base += align16((size_t)d.NOFF * 4);
+  s.rank = (uint8_t*)base;
+  base += 256;
   base += (size_t)warp * smem_per_warp(d.HWp, d.T, d.A);
   s.cells = (uint16_t*)base;
   base += align16((size_t)d.HWp * 2);
@@ -88,11 +91,14 @@ __device__ __forceinline__ void load_cta_tables(const MgDev& d, Smem& s) {
   __syncthreads();
   const int32_t* offs = d.P + s.hdr[MGS_OFFSETS];
   int rr = s.hdr[MGH_OBS_H] >> 1, cr = s.hdr[MGH_OBS_W] >> 1;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s.rank[i] = 0xFF;
+  __syncthreads();
   for (int i = threadIdx.x; i < d.NOFF; i += blockDim.x) {
     int dr = __ldg(offs + 2 * i), dc = __ldg(offs + 2 * i + 1);
     uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));  // systems/packed_coordinate.hpp:50-56
     // bits 0-7: dr + 8 | (dc + 8) << 4 ; bits 8-15: packed location ; bits 16-31: cell delta in the padded grid
     s.offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8) | ((uint32_t)((dr * d.WP + dc) & 0xffff) << 16);
+    s.rank[loc] = (uint8_t)i;  // loc = (dr + rr) << 4 | (dc + cr); NOFF <= 225
   }
   __syncthreads();
 }
@@ -342,6 +348,54 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
   const uint32_t step = w.step;
   uint32_t* const objs = w.objs;
   const uint32_t* const offs = s.offs;
+  // Sparse environments (at most 32 objects ever created): one lane per OBJECT instead of one per window
+  // cell.  Each visible object's position in the row is the token count of the visible objects that come
+  // earlier in Manhattan order, found by walking the few set lanes of a ballot.
+  const int nobj = w.E[MGEV_NEXT_OBJ] - 1;
+  if (nobj <= 32 && fmask == 0) {
+    const int rr = w.hdr[MGH_OBS_H] >> 1, cr = w.hdr[MGH_OBS_W] >> 1;
+    int n = 0, rank = 0xFF, loc = 0;
+    uint32_t* o = nullptr;
+    if (lane < nobj) {
+      o = objs + (size_t)(lane + 1) * OS;
+      if (o_alive(o)) {
+        const int dr = o_r(o) - r0 + rr, dc = o_c(o) - c0 + cr;
+        if (dr >= 0 && dc >= 0 && dr <= 2 * rr && dc <= 2 * cr) {
+          loc = (dr << 4) | dc;
+          rank = s.rank[loc];
+        }
+      }
+    }
+    uint32_t m = __ballot_sync(MG_FULL, rank != 0xFF);
+    if (rank != 0xFF) {
+      const uint32_t vis = o[MGO_VISITED];
+      if (vis < step) {
+        stale_sum += step - vis;
+        o[MGO_VISITED] = step;
+      }
+      n = (int)o[MGO_NTOK];
+      if ((uint32_t)n == MG_TOK_DIRTY) n = rebuild_token_cache(w, o);
+    }
+    int before = 0, tot = 0;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int rb = __shfl_sync(MG_FULL, rank, b), nb = __shfl_sync(MG_FULL, n, b);
+      before += rb < rank ? nb : 0;
+      tot += nb;
+    }
+    if (rank != 0xFF) {
+      const uint16_t* tk = (const uint16_t*)(o + TOKOFF);
+      int pos = base + before;
+      for (int j = 0; j < n && pos < T; j++, pos++) {
+        const uint32_t e = tk[j];
+        out[pos * 3 + 0] = (uint8_t)loc;
+        out[pos * 3 + 1] = (uint8_t)e;
+        out[pos * 3 + 2] = (uint8_t)(e >> 8);
+      }
+    }
+    base += tot;
+  } else
   for (int k0 = 0; k0 < NOFF; k0 += 32) {
     const int k = k0 + lane;
     int n = 0, loc = 0, mask = 0, slot = 0;
