@@ -172,3 +172,23 @@ def test_network_queries_push_clear():
         assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
         assert np.array_equal(sim.dump_objects(e), o.dump_objects()), f"object state differs in env {e}"
     sim.close()
+
+
+@pytest.mark.parametrize("walls", [24, 26, 27, 40])
+def test_object_count_around_sparse_threshold(walls):
+    """<= 32 objects take the one-lane-per-object observation path, more take the per-cell path: both sides of
+    the switch, 8-way moves so agents shuffle around the walls."""
+    import mettagrid_b200.config as C
+    from mettagrid_b200.mapgen import RandomMapConfig
+
+    cfg = C.MettaGridConfig(
+        game=C.GameConfig(
+            num_agents=6,
+            obs=C.ObsConfig(width=9, height=7, num_tokens=150, global_obs=C.GlobalObsConfig(local_position=True)),
+            max_steps=0,
+            actions=C.ActionsConfig(noop=C.NoopActionConfig(), move=C.MoveActionConfig(allowed_directions=list(cases.EIGHT_WAY))),
+            objects={"wall": C.WallConfig()},
+            map_builder=RandomMapConfig(agents=6, width=11, height=9, seed=5, objects={"wall": walls}),
+        )
+    )
+    _run_pair(cfg, num_envs=6, steps=120, p_vibe=0.2)
