@@ -183,6 +183,26 @@ __device__ __forceinline__ void flush_obs(const uint8_t* src, uint8_t* g, int n,
   if (lane < n - done) g[done + lane] = src[done + lane];
 }
 
+// Row of n bytes whose first `used` bytes are staged tokens and whose remainder is 0xFF.  The stage shares
+// the destination's 16-byte phase, so the body moves as aligned 16-byte vectors; vectors that lie entirely
+// behind the tokens are stored from a register without touching shared memory.
+__device__ __forceinline__ void flush_row(uint8_t* src, uint8_t* g, int n, int used, int lane) {
+  // pad the partial vector behind the last token (and the unaligned head) so whole vectors can be copied
+  const int pad_to = min(n, ((used + 15) & ~15) + 16);
+  if (used + lane < pad_to) src[used + lane] = 0xFF;
+  __syncwarp();
+  int head = (int)((16u - ((uint32_t)(uintptr_t)g & 15u)) & 15u);
+  if (head > n) head = n;
+  if (lane < head) g[lane] = lane < pad_to ? src[lane] : (uint8_t)0xFF;
+  const int body = (n - head) >> 4;
+  const uint4* s4 = (const uint4*)(src + head);
+  uint4* g4 = (uint4*)(g + head);
+  const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  for (int i = lane; i < body; i += 32) __stcs(g4 + i, head + 16 * i < pad_to - 15 ? s4[i] : ff);
+  const int done = head + (body << 4);
+  if (lane < n - done) g[done + lane] = done + lane < pad_to ? src[done + lane] : (uint8_t)0xFF;
+}
+
 __device__ __forceinline__ int num_digits(uint32_t v, uint32_t B, int ND) {
   int n = 1;
   v /= B;
@@ -277,14 +297,6 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
   const int r0 = (int)(loc0 >> 16), c0 = (int)(loc0 & 0xffffu);
   const int flags = w.hdr[MGH_GLOBAL_FLAGS];
   uint32_t* ag = w.agents + a * w.AS;
-
-  // the stage starts as all 0xFF (EmptyTokenByte, :940-942); tokens overwrite its head
-  {
-    uint4* st4 = (uint4*)s.stage;
-    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    for (int i = lane; i < (3 * T + 32 + 15) / 16; i += 32) st4[i] = ff;
-    __syncwarp();
-  }
 
   // ---- global tokens (:700-742), one candidate per lane, compacted in order
   int feat = 0, val = 0, have = 0;
@@ -438,9 +450,9 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
   if (lane == 0 && stale_sum) astat_add(w, a, w.hdr[MGH_ST_CELL_VISITED], (float)stale_sum);
 
-  // ---- stream out
+  // ---- stream out: token bytes come from the stage, the rest of the row is 0xFF (EmptyTokenByte, :940-942)
   __syncwarp();
-  flush_obs(out, g, 3 * T, lane);
+  flush_row(out, g, 3 * T, 3 * min(base, T), lane);
   __syncwarp();
   return base;
 }
@@ -448,19 +460,26 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
 // all agents' observations + token stats (:826-912, :640-642)
 __device__ __noinline__ void observe_all(const Wv& w, const Smem& s, int lane, bool initial) {
   const bool plain = w.NTERR == 0 && w.hdr[MGH_NUM_OBS_VALUES] == 0;
+  // token stats: one float add per agent in agent order like the reference (:659-661), carried in registers
+  const int idw = w.hdr[MGH_GST_TOKENS_WRITTEN], idf = w.hdr[MGH_GST_TOKENS_FREE];
+  float tw = w.gstats[idw], tf = w.gstats[idf];
   for (int a = 0; a < w.A; a++) {
     int action = initial ? 0 : s.a_exec[a];
     int attempted = plain ? observe_agent<true>(w, s, a, action, s.a_step[a], lane)
                           : observe_agent<false>(w, s, a, action, s.a_step[a], lane);
-    if (lane == 0) {
-      if (attempted > w.T) {  // hard error in the reference (:364-375)
-        set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
-      } else {  // one float add per agent, in agent order, like the reference (:659-661)
-        gstat_add(w, w.hdr[MGH_GST_TOKENS_WRITTEN], (float)attempted);
-        gstat_add(w, w.hdr[MGH_GST_TOKENS_DROPPED], 0.0f);
-        gstat_add(w, w.hdr[MGH_GST_TOKENS_FREE], (float)(w.T - attempted));
-      }
+    if (attempted > w.T) {  // hard error in the reference (:364-375)
+      if (lane == 0) set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
+    } else {
+      tw = __fadd_rn(tw, (float)attempted);
+      tf = __fadd_rn(tf, (float)(w.T - attempted));
     }
+  }
+  if (lane == 0) {
+    w.gstats[idw] = tw;
+    w.gstats[idf] = tf;
+    gstat_touch(w, idw);
+    gstat_touch(w, w.hdr[MGH_GST_TOKENS_DROPPED]);
+    gstat_touch(w, idf);
   }
 }
 
