@@ -433,7 +433,23 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
       if ((uint32_t)n == MG_TOK_DIRTY) n = rebuild_token_cache(w, o);
     }
     int tot;
-    int p = warp_excl_scan(n + (mask != 0), lane, tot);
+    int p;
+    {
+      const int cnt = n + (mask != 0);
+      uint32_t m = __ballot_sync(MG_FULL, cnt != 0);
+      if (__popc(m) <= 6) {  // few objects in these 32 cells: walk the set lanes instead of a 5-step scan
+        p = 0, tot = 0;
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int nb = __shfl_sync(MG_FULL, cnt, b);
+          p += b < lane ? nb : 0;
+          tot += nb;
+        }
+      } else {
+        p = warp_excl_scan(cnt, lane, tot);
+      }
+    }
     if (mask) put_token(out, T, base + p, loc, fmask, mask);
     if (n) {  // copy the object's cached (feature, value) pairs behind this cell's location byte
       const uint16_t* tk = (const uint16_t*)(o + TOKOFF);
