@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -15,6 +16,9 @@ cudaError_t mg_configure_kernels(const MgDev& d);
 cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
+MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap);
+cudaError_t mg_fast_configure(const MgFastLayout& L);
+cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, cudaStream_t st);
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st);
 
@@ -26,6 +30,8 @@ struct mg_handle {
   size_t bytes = 0;
   std::string err;
   bool buffers_set = false;
+  bool fast = false;  // k_step_fast applies (mg_fast.cu): plain program, sparse environments
+  MgFastLayout fl{};
   // device-side staging for mg_step_host
   int32_t* h_act = nullptr;
   int32_t* h_vact = nullptr;
@@ -76,6 +82,23 @@ static int program_is_plain(const int32_t* P) {
       return 0;
   }
   return 1;
+}
+
+// k_step_fast (mg_fast.cu) needs: a plain program, agents and objects that fit one warp, primary-stream actions
+// that are noop / move and vibe-stream actions that are change_vibe, well-known stat ids below 64, a window of at
+// most 15 x 15 cells.  Returns the lanes per environment (8, 16, 32) or 0.
+static int fast_group_size(const int32_t* P, const MgDev& d, int max_objects_per_env) {
+  if (!d.plain || getenv("METTAGRID_B200_NO_FAST")) return 0;
+  if (d.A > 32 || max_objects_per_env > 32 || P[MGH_OBS_H] > 15 || P[MGH_OBS_W] > 15 || P[MGH_TOK_CAP] > 126) return 0;
+  for (int k = MGH_ST_ACTION_FAILED; k <= MGH_ST_VIBE_FAILED; k++)
+    if (P[k] < 0 || P[k] >= 64) return 0;
+  const int32_t* acts = P + P[MGS_ACTIONS];
+  for (int i = 0; i < P[MGH_NUM_ACTIONS]; i++) {
+    const int kind = acts[i * MG_ACTION_WORDS], is_vibe = acts[i * MG_ACTION_WORDS + 3];
+    if (is_vibe ? kind != MGA_CHANGE_VIBE : (kind != MGA_NOOP && kind != MGA_MOVE)) return 0;
+  }
+  const int need = d.A > max_objects_per_env ? d.A : max_objects_per_env;
+  return need <= 8 ? 8 : need <= 16 ? 16 : 32;
 }
 
 static const char* unsupported_reason(const int32_t* P) {
@@ -130,6 +153,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     return fail(MG_E_INVALID);
   }
   int rc;
+  int max_objs = 0;  // most objects any env starts with
 #define TRY(x) \
   if ((rc = (x)) != MG_OK) return fail(rc)
   if (cudaSetDevice(device) != cudaSuccess) {
@@ -153,6 +177,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     size_t max_aoe = 0, max_terr = 0;
     for (size_t e = 0; e < N; e++) {
       size_t na = 0, nt = 0;
+      int no = 0;
       const int16_t* cells = init_cells + e * d.HW;
       for (int i = 0; i < d.HW; i++)
         if (cells[i] >= 0) {
@@ -160,9 +185,11 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
             h->err = "mg_create: init_cells holds a template index outside the program";
             return fail(MG_E_INVALID);
           }
+          no++;
           na += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_AOES_N];
           nt += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_TERR_N];
         }
+      max_objs = no > max_objs ? no : max_objs;
       max_aoe = na > max_aoe ? na : max_aoe;
       max_terr = nt > max_terr ? nt : max_terr;
     }
@@ -212,11 +239,34 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     return fail(MG_E_CUDA);
   }
   d.P = Pd, d.init_cells = ic, d.init_gstats = ig, d.seeds = h->seeds_dev, d.logtab = lt;
+  {
+    // window-rank table: packed offset (dr + rr) << 4 | (dc + cr) -> position in the reference's Manhattan order
+    // (core/observation_shape.cpp:19-66); 0xFF = outside the shape
+    std::vector<uint8_t> lut(256, 0xFF);
+    uint8_t* lut_dev;
+    const int32_t* offs = P + P[MGS_OFFSETS];
+    const int rr = P[MGH_OBS_H] >> 1, cr = P[MGH_OBS_W] >> 1;
+    if (P[MGH_OBS_H] <= 15 && P[MGH_OBS_W] <= 15 && d.NOFF < 255)
+      for (int i = 0; i < d.NOFF; i++) lut[((offs[2 * i] + rr) << 4) | ((offs[2 * i + 1] + cr) & 15)] = (uint8_t)i;
+    TRY(dev_alloc(h, &lut_dev, 256));
+    if (cudaMemcpy(lut_dev, lut.data(), 256, cudaMemcpyHostToDevice) != cudaSuccess) {
+      h->err = "mg_create: upload failed";
+      return fail(MG_E_CUDA);
+    }
+    d.rank_lut = lut_dev;
+  }
   cudaError_t e = mg_configure_kernels(d);
   if (e != cudaSuccess) {
     h->err = std::string("mg_create: kernel configuration failed: ") + cudaGetErrorString(e) +
              " (shared memory per CTA = " + std::to_string(mg_smem_bytes(d)) + " bytes)";
     return fail(MG_E_CUDA);
+  }
+  if (const int G = fast_group_size(P, d, max_objs)) {
+    h->fl = mg_fast_layout(d, G, P[MGH_TOK_CAP]);
+    if (h->fl.smem_bytes <= 200 * 1024 && mg_fast_configure(h->fl) == cudaSuccess)
+      h->fast = true;
+    else
+      cudaGetLastError();  // too large for shared memory: the generic kernel runs instead
   }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "mg_create: stream creation failed";
@@ -265,7 +315,7 @@ int mg_step(mg_handle* h, void* stream) {
     h->err = "mg_step: call mg_set_buffers first";
     return MG_E_INVALID;
   }
-  CK(mg_launch_step(h->d, (cudaStream_t)stream));
+  CK(h->fast ? mg_launch_step_fast(h->d, h->fl, (cudaStream_t)stream) : mg_launch_step(h->d, (cudaStream_t)stream));
   return MG_OK;
 }
 
@@ -294,7 +344,7 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
   MgDev run = d;
   run.obs = h->h_obs, run.terminals = h->h_term, run.truncations = h->h_trunc, run.rewards = h->h_rew;
   run.actions = h->h_act, run.vibe_actions = h->h_vact;
-  CK(mg_launch_step(run, st));
+  CK(h->fast ? mg_launch_step_fast(run, h->fl, st) : mg_launch_step(run, st));
   if (observations) CK(cudaMemcpyAsync(observations, h->h_obs, NA * d.T * 3, cudaMemcpyDeviceToHost, st));
   if (rewards) CK(cudaMemcpyAsync(rewards, h->h_rew, NA * 4, cudaMemcpyDeviceToHost, st));
   if (terminals) CK(cudaMemcpyAsync(terminals, h->h_term, NA, cudaMemcpyDeviceToHost, st));
@@ -450,5 +500,6 @@ int mg_num_envs(const mg_handle* h) { return h ? h->d.num_envs : 0; }
 int mg_num_agents(const mg_handle* h) { return h ? h->d.A : 0; }
 int mg_num_tokens(const mg_handle* h) { return h ? h->d.T : 0; }
 size_t mg_state_bytes(const mg_handle* h) { return h ? h->bytes : 0; }
+int mg_step_kernel(const mg_handle* h) { return !h ? MG_E_INVALID : h->fast ? h->fl.G : h->d.plain ? 1 : 0; }
 
 }  // extern "C"

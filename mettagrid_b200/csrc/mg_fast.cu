@@ -1,0 +1,684 @@
+// mg_fast.cu -- k_step_fast<G>: MettaGrid::_step (bindings/mettagrid_c.cpp:921-1102) for handler-free
+// ("plain") programs in sparse environments: at most 32 objects per env, none of them ever created or
+// removed.  This is the reference's own benchmark game (benchmarks/test_mettagrid_env_benchmark.py:21-29).
+//
+// Mapping: G = 8, 16 or 32 lanes own one environment (32 / G environments per warp).  Lane l plays two
+// roles: agent l (actions, bookkeeping, observer) and object slot l + 1 (location, vibe, token cache).
+// Nothing runs on "lane 0 only" except the application of the shuffle's swaps:
+//   * every agent decodes its own actions; noop / change_vibe never interact across agents;
+//   * moves resolve in the reference's shuffled order (:958-999) with one ballot per move: the target cell is
+//     free iff no object lane holds that location -- the occupancy grid is never read (and not maintained:
+//     nothing reads it for such a handle; mg_reset rebuilds it);
+//   * observations (:665-824): each agent lane builds sort keys (Manhattan rank, packed location, object) for
+//     the objects in its window, sorts them in registers with a Batcher network, and writes its row into a
+//     shared-memory stage of the env's whole [A][T][3] block, which the group streams out with 16-byte stores;
+//   * `cell.visited` (:787-796) goes to the lowest agent index that sees an object (a ballot per object).
+// State loads are issued in three waves (env/agents/objects/actions -> RNG/action rows/token caches ->
+// stats/coverage), stat updates are decided in registers and written back once.
+#include <cuda_runtime.h>
+
+#include "mg_state.h"
+
+namespace {
+
+#define FAST_INVALID 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+  uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+// one std::mt19937 output straight from / to the env's state in global memory
+__device__ __forceinline__ uint32_t rng_direct(uint32_t* rng, int& idx) {
+  int i = idx >= MG_RNG_WORDS ? 0 : idx;
+  int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
+  int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
+  uint32_t nw = mt_twist(rng[i], rng[i1], rng[i2]);
+  rng[i] = nw;
+  idx = i + 1;
+  return mt_temper(nw);
+}
+// Lemire multiply-shift with rejection (bits/uniform_int_dist.h:252-282)
+__device__ __forceinline__ uint32_t rng_below_direct(uint32_t* rng, int& idx, uint32_t range) {
+  uint64_t prod = (uint64_t)rng_direct(rng, idx) * range;
+  uint32_t low = (uint32_t)prod;
+  if (low < range) {
+    uint32_t thr = (0u - range) % range;
+    while (low < thr) {
+      prod = (uint64_t)rng_direct(rng, idx) * range;
+      low = (uint32_t)prod;
+    }
+  }
+  return (uint32_t)(prod >> 32);
+}
+// libstdc++ std::shuffle (bits/stl_algo.h:3719-3805), serial, for the rare tick where a draw is rejected or the
+// draws straddle the end of the 624-word state
+__device__ __noinline__ void shuffle_serial(uint32_t* rng, int32_t* E, uint8_t* v, int n) {
+  int idx = E[MGEV_RNG_IDX];
+  int i = 1;
+  if ((n & 1) == 0) {
+    int j = (int)rng_below_direct(rng, idx, 2);
+    uint8_t t = v[i];
+    v[i] = v[j], v[j] = t;
+    i++;
+  }
+  while (i < n) {
+    uint32_t sr = (uint32_t)i + 1;
+    uint32_t x = rng_below_direct(rng, idx, sr * (sr + 1));
+    int p0 = (int)(x / (sr + 1)), p1 = (int)(x % (sr + 1));
+    uint8_t t = v[i];
+    v[i] = v[p0], v[p0] = t;
+    i++;
+    t = v[i];
+    v[i] = v[p1], v[p1] = t;
+    i++;
+  }
+  E[MGEV_RNG_IDX] = idx;
+}
+
+__device__ __forceinline__ void set_error(int32_t* E, int code, int info) {
+  const int cur = E[MGEV_ERROR];
+  if (!(cur & code)) E[MGEV_ERR_INFO] = info;
+  E[MGEV_ERROR] = cur | code;
+}
+
+// An object's observation tokens (core/grid_object.cpp:178-203, objects/agent.cpp:142-154) as
+// (feature | value << 8) pairs, written to `tk`; same rules as rebuild_token_cache in mg_kernels.cu.
+struct TokDims {
+  const int32_t* P;
+  int TW, ND, B;
+};
+__device__ __noinline__ int build_tokens(const TokDims d, const int32_t* hdr, const uint32_t* o, uint32_t meta, uint16_t* tk,
+                                         int32_t* E, bool live) {
+  const int cap = hdr[MGH_TOK_CAP];
+  int n = 0;
+  auto put = [&](int feat, int val) {
+    if (n < cap) tk[n] = (uint16_t)((feat & 0xff) | ((val & 0xff) << 8));
+    n++;
+  };
+  const int ftag = hdr[MGH_FEAT_TAG];
+  for (int k = 0; k < d.TW; k++) {
+    uint32_t m = o[MGO_TAGS + k];
+    while (m) {
+      int b = __ffs(m) - 1;
+      put(ftag, k * 32 + b);
+      m &= m - 1;
+    }
+  }
+  const int vibe = (int)((meta >> 16) & 0xffu);
+  if (vibe) put(hdr[MGH_FEAT_VIBE], vibe);
+  const int fl = (int)(meta >> 24);
+  if (fl & MGOF_OBS_INV) {
+    const uint64_t ord = (uint64_t)o[MGO_INVORD_LO] | ((uint64_t)o[MGO_INVORD_HI] << 32);
+    const int cnt = (int)(ord >> 60);
+    const uint16_t* inv = (const uint16_t*)(o + MGO_TAGS + d.TW);
+    const int32_t* feats = d.P + hdr[MGS_INV_FEATS];
+    for (int i = 0; i < cnt; i++) {
+      const int it = (int)((ord >> (4 * i)) & 15u);
+      uint32_t amt = inv[it];
+      int p = 0;
+      do {
+        put(__ldg(feats + it * d.ND + p), (int)(amt % (uint32_t)d.B));
+        amt /= (uint32_t)d.B;
+        p++;
+      } while (amt > 0 && p < d.ND);
+    }
+  }
+  if (fl & MGOF_AGENT) {
+    const int ai = (int)o[MGO_AGENT];
+    put(hdr[MGH_FEAT_GROUP], __ldg(d.P + hdr[MGS_TEMPLATES] + (int)(meta & 0xffffu) * MG_TEMPLATE_WORDS + MGT_GROUP));
+    put(hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
+  }
+  if (n > cap) {
+    if (live) set_error(E, MGERR_POOL_EXHAUSTED, 19);
+    n = cap;
+  }
+  return n;
+}
+
+__device__ __forceinline__ void ce(uint32_t& a, uint32_t& b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo, b = hi;
+}
+// bitonic sorting network, fully unrolled on registers (80 exchanges for 16 keys, 240 for 32)
+template <int N>
+__device__ __forceinline__ void sort_net(uint32_t (&key)[N]) {
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const int l = i ^ j;
+        if (l > i) {
+          if ((i & k) == 0)
+            ce(key[i], key[l]);
+          else
+            ce(key[l], key[i]);
+        }
+      }
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d, const MgFastLayout L) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int GPW = 32 / G;  // environments per warp
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gl = lane & (G - 1), grp = lane / G;
+  const uint32_t gmask = G == 32 ? MG_FULL : (((1u << (G & 31)) - 1u) << (grp * G));
+  const int gshift = grp * G;
+
+  // ---- CTA tables: program header and the window-rank table (built by mg_create)
+  int32_t* hdr = (int32_t*)smem;
+  uint8_t* rank = smem + L.rank_off;
+  for (int i = tid; i < MGH_HEADER_WORDS; i += blockDim.x) hdr[i] = __ldg(d.P + i);
+  for (int i = tid; i < 64; i += blockDim.x) ((uint32_t*)rank)[i] = __ldg((const uint32_t*)d.rank_lut + i);
+
+  int env = (blockIdx.x * MG_FAST_WARPS + warp) * GPW + grp;
+  const bool live = env < d.num_envs;  // a dead group mirrors the last env but stores nothing
+  if (!live) env = d.num_envs - 1;
+  unsigned char* gb = smem + L.cta_bytes + (size_t)(warp * GPW + grp) * L.group_bytes;
+  uint32_t* toks = (uint32_t*)(gb + L.tok_off);
+  uint32_t* oloc = (uint32_t*)(gb + L.oloc_off);
+  uint32_t* ontok = oloc + G;
+  uint32_t* stale = ontok + G;
+  uint32_t* draw = stale + G;
+  uint8_t* order = (uint8_t*)(draw + G);
+
+  const int A = d.A, T = d.T;
+  const size_t g0 = (size_t)env * A;
+  const bool isA = gl < A;
+  int32_t* E = d.env + (size_t)env * MGEV_WORDS;
+  uint32_t* rng = d.rng + (size_t)env * MG_RNG_WORDS;
+
+  // ---- wave 1: env scalars, actions, agent records, object records
+  const uint32_t step = (uint32_t)E[MGEV_STEP] + 1u;  // :951
+  int idx0 = E[MGEV_RNG_IDX];
+  const int nobj = E[MGEV_NEXT_OBJ] - 1;
+  uint32_t* ag = d.agents + (g0 + (isA ? gl : 0)) * d.AS;
+  int ia = -1, iv = -1;
+  uint32_t a_slot = 1, a_spawn = 0, a_prev = 0, a_swm = 0, a_maxd = 0, a_unique = 0;
+  if (isA) {
+    ia = d.actions[g0 + gl];
+    iv = d.vibe_actions[g0 + gl];
+    a_slot = ag[MGAG_OBJ], a_spawn = ag[MGAG_SPAWN], a_prev = ag[MGAG_PREV_LOC], a_swm = ag[MGAG_SWM];
+    a_maxd = ag[MGAG_MAX_DIST], a_unique = ag[MGAG_UNIQUE];
+  }
+  const bool isO = gl < nobj;
+  uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NTERR) + (size_t)(gl + 1)) * d.OS;
+  uint32_t o_loc = FAST_INVALID, o_vis = 0, o_meta = 0, o_ntok = 0;
+  int o_agent = -1;
+  if (isO) {
+    const uint4 r = *(const uint4*)o;  // MGO_LOC, MGO_VISITED, MGO_META, MGO_AGENT
+    o_loc = r.x, o_vis = r.y, o_meta = r.z, o_agent = (int)r.w;
+    o_ntok = o[MGO_NTOK];
+  }
+  const bool o_alive = isO && ((o_meta >> 24) & MGOF_ALIVE);
+  if (!o_alive) o_loc = FAST_INVALID;
+  const uint32_t o_loc0 = o_loc, o_vis0 = o_vis, o_meta0 = o_meta;
+  __syncthreads();  // hdr, rank
+
+  // ---- wave 2: action rows, RNG words, token caches
+  const int NA = hdr[MGH_NUM_ACTIONS];
+  const int32_t* acts = d.P + hdr[MGS_ACTIONS];
+  const bool inv_p = ia < 0 || ia >= NA, inv_v = iv < 0 || iv >= NA;
+  int4 ap = make_int4(0, 0, 0, 1), av = make_int4(0, 0, 0, 0);  // kind, arg, priority, is_vibe
+  if (isA && !inv_p) ap = __ldg((const int4*)(acts + ia * MG_ACTION_WORDS));
+  if (isA && !inv_v) av = __ldg((const int4*)(acts + iv * MG_ACTION_WORDS));
+  const bool act_p = isA && !inv_p && ap.w == 0;  // executed in the primary stream (:966-999)
+  const bool act_v = isA && !inv_v && av.w == 1;  // executed in the vibe stream
+
+  const int ndraws = A < 2 ? 0 : ((A & 1) ? (A - 1) / 2 : A / 2);
+  if (idx0 >= MG_RNG_WORDS) idx0 = 0;
+  uint32_t nw = 0, rnd = 0;
+  const bool window_ok = idx0 + ndraws <= MG_RNG_WORDS;
+  if (window_ok && gl < ndraws) {
+    const int i = idx0 + gl;
+    const int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
+    const int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
+    nw = mt_twist(rng[i], rng[i1], rng[i2]);
+    rnd = mt_temper(nw);
+  }
+  const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+  const int tokw = L.tok_stride;  // words per object in the shared token table
+  {
+    const bool cached = o_alive && o_ntok != MG_TOK_DIRTY;
+    const int nwords = cached ? (int)(o_ntok + 1) >> 1 : 0;
+    for (int k = 0; k < nwords; k++) toks[gl * tokw + k] = o[TOKOFF + k];
+  }
+  if (isA) order[gl] = (uint8_t)gl;
+
+  // ---- shuffle (:958-964): every draw is decoded by its own lane, the swaps are applied by one lane
+  bool reject = !window_ok;
+  if (window_ok && gl < ndraws) {
+    const bool single = (A & 1) == 0 && gl == 0;
+    const int i = single ? 1 : ((A & 1) ? 2 * gl + 1 : 2 * gl);
+    const uint32_t sr = (uint32_t)i + 1;
+    const uint32_t range = single ? 2u : sr * (sr + 1);
+    const uint64_t prod = (uint64_t)rnd * range;
+    const uint32_t low = (uint32_t)prod, x = (uint32_t)(prod >> 32);
+    if (low < range && low < (0u - range) % range) reject = true;
+    const uint32_t p0 = single ? x : x / (sr + 1), p1 = single ? 0xffu : x % (sr + 1);
+    draw[gl] = (uint32_t)i | (p0 << 8) | (p1 << 16);
+  }
+  const uint32_t rej = __ballot_sync(MG_FULL, reject) & gmask;
+  __syncwarp();
+  if (gl == 0 && A >= 2) {
+    if (rej) {
+      if (live) shuffle_serial(rng, E, order, A);  // a mirror group leaves the state alone
+    } else {
+      for (int k = 0; k < ndraws; k++) {
+        const uint32_t dw = draw[k];
+        const int i = (int)(dw & 0xffu), p0 = (int)((dw >> 8) & 0xffu), p1 = (int)((dw >> 16) & 0xffu);
+        uint8_t t = order[i];
+        order[i] = order[p0], order[p0] = t;
+        if (p1 != 0xff) {
+          t = order[i + 1];
+          order[i + 1] = order[p1], order[p1] = t;
+        }
+      }
+    }
+  }
+  if (!rej && live && gl < ndraws) rng[idx0 + gl] = nw;
+  if (!rej && live && gl == 0 && ndraws > 0) E[MGEV_RNG_IDX] = idx0 + ndraws;
+  __syncwarp();
+
+  // ---- moves in shuffled order, highest priority first (actions/move.hpp:81-115 with the two default
+  // handlers: relocate into an empty in-map cell, else fail)
+  const int my_ol = (int)a_slot - 1;  // lane that plays this agent's object
+  const uint32_t my_loc0 = __shfl_sync(MG_FULL, o_loc, my_ol, G);
+  uint32_t my_tgt = FAST_INVALID;
+  const bool wants_move = act_p && ap.x == MGA_MOVE;
+  if (wants_move) {  // actions/orientation.hpp:28-48
+    const int arg = ap.y;
+    const int dr = (arg == 0 || arg == 4 || arg == 5) ? -1 : (arg == 1 || arg == 6 || arg == 7) ? 1 : 0;
+    const int dc = (arg == 2 || arg == 4 || arg == 6) ? -1 : (arg == 3 || arg == 5 || arg == 7) ? 1 : 0;
+    const int tr = (int)(my_loc0 >> 16) + dr, tc = (int)(my_loc0 & 0xffffu) + dc;
+    if (my_loc0 != FAST_INVALID && tr >= 0 && tr < d.H && tc >= 0 && tc < d.W) my_tgt = ((uint32_t)tr << 16) | (uint32_t)tc;
+  }
+  bool move_ok = false;
+  {
+    const int maxp = hdr[MGH_MAX_PRIORITY], pmask = hdr[MGH_PRIORITY_MASK];
+    for (int prio = maxp; prio >= 0; prio--) {
+      if (!((pmask >> prio) & 1)) continue;
+      const uint32_t movers = __ballot_sync(MG_FULL, wants_move && ap.z == prio);
+      if (movers == 0) continue;
+      for (int i = 0; i < A; i++) {
+        const int a = order[i];
+        const bool m = (movers >> (gshift + a)) & 1u;
+        const uint32_t tgt = __shfl_sync(MG_FULL, my_tgt, a, G);
+        const int ol = __shfl_sync(MG_FULL, my_ol, a, G);
+        const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
+        const bool ok = m && tgt != FAST_INVALID && occ == 0;
+        if (ok && gl == ol) o_loc = tgt;
+        if (ok && gl == a) move_ok = true;
+      }
+    }
+  }
+  const uint32_t my_loc = __shfl_sync(MG_FULL, o_loc, my_ol, G);  // observer position (:1049-1052)
+
+  // ---- per-agent outcome of both streams (actions/action_handler.hpp:78-105), in execution order
+  const bool v_first = act_p && act_v && av.z > ap.z;  // the vibe-stream action has the higher priority
+  const bool ok_p = act_p && (ap.x == MGA_MOVE ? move_ok : true);
+  const bool ok_v = act_v && (av.x == MGA_MOVE ? false : true);
+  int exec_idx = 0;
+  if (v_first) {
+    if (ok_v) exec_idx = iv;
+    if (ok_p) exec_idx = ia;
+  } else {
+    if (ok_p) exec_idx = ia;
+    if (ok_v) exec_idx = iv;
+  }
+  int new_vibe = -1;
+  {
+    const bool cp = ok_p && ap.x == MGA_CHANGE_VIBE, cv = ok_v && av.x == MGA_CHANGE_VIBE;
+    if (v_first) {
+      if (cv) new_vibe = av.y;
+      if (cp) new_vibe = ap.y;
+    } else {
+      if (cp) new_vibe = ap.y;
+      if (cv) new_vibe = av.y;
+    }
+  }
+  // object lanes pick up their agent's new vibe
+  {
+    const int nv = __shfl_sync(MG_FULL, new_vibe, o_agent >= 0 ? o_agent : 0, G);
+    if (o_alive && o_agent >= 0 && o_agent < A && nv >= 0 && (uint32_t)(nv & 0xff) != ((o_meta >> 16) & 0xffu)) {
+      o_meta = (o_meta & 0xff00ffffu) | ((uint32_t)(nv & 0xff) << 16);
+      o_ntok = MG_TOK_DIRTY;
+    }
+  }
+
+  // ---- wave 3 loads: stats, touched bits, coverage word
+  float* st = d.astats + (g0 + (isA ? gl : 0)) * d.SA;
+  uint32_t* tch = d.atouched + (g0 + (isA ? gl : 0)) * d.SAW;
+  const int npass = hdr[MGH_MAX_PRIORITY] + 1;
+  // steps-without-motion chain over the executed actions (stream order, like k_step)
+  uint32_t prev = a_prev, swm = a_swm;
+  uint32_t swm_peak = 0;  // largest value steps_without_motion took this tick
+  const int nacted = (act_p ? 1 : 0) + (act_v ? 1 : 0);
+  for (int k = 0; k < nacted; k++) {
+    if (my_loc == prev) {
+      swm += 1;
+      swm_peak = max(swm_peak, swm);
+    } else {
+      swm = 0;
+    }
+    prev = my_loc;
+  }
+  const int id_p = act_p ? hdr[(ok_p ? MGH_ST_NOOP_SUCCESS : MGH_ST_NOOP_FAILED) + 2 * ap.x] : -1;
+  const int id_v = act_v ? hdr[(ok_v ? MGH_ST_NOOP_SUCCESS : MGH_ST_NOOP_FAILED) + 2 * av.x] : -1;
+  const int nfail = (act_p && !ok_p ? 1 : 0) + (act_v && !ok_v ? 1 : 0);
+  const int ninv = (isA && inv_p ? 1 : 0) + (isA && inv_v ? 1 : 0);
+  const int id_fail = hdr[MGH_ST_ACTION_FAILED], id_inv = hdr[MGH_ST_INVALID_INDEX], id_swm = hdr[MGH_ST_MAX_SWM];
+  const int id_cv = hdr[MGH_ST_CELL_VISITED], id_un = hdr[MGH_ST_UNIQUE_VISITED], id_md = hdr[MGH_ST_MAX_DIST];
+  float s_p = 0.f, s_v = 0.f, s_fail = 0.f, s_inv = 0.f, s_swm = 0.f, s_cv = 0.f;
+  if (id_p >= 0) s_p = st[id_p];
+  if (id_v >= 0) s_v = st[id_v];
+  if (nfail) s_fail = st[id_fail];
+  if (ninv) s_inv = st[id_inv];
+  if (swm_peak) s_swm = st[id_swm];
+  if (isA) s_cv = st[id_cv];
+  uint32_t t0 = 0, t1 = 0;
+  if (isA) {
+    t0 = tch[0];
+    if (d.SAW > 1) t1 = tch[1];
+  }
+  const int r0 = (int)(my_loc >> 16), c0 = (int)(my_loc & 0xffffu);
+  const int cell = r0 * d.W + c0;
+  uint32_t* cvp = d.cover + (g0 + (isA ? gl : 0)) * d.CW + (isA ? (cell >> 5) : 0);
+  uint32_t cvw = 0;
+  if (isA) cvw = *cvp;
+  const int idw = hdr[MGH_GST_TOKENS_WRITTEN], idf = hdr[MGH_GST_TOKENS_FREE], idd = hdr[MGH_GST_TOKENS_DROPPED];
+  float* gs = d.gstats + (size_t)env * d.SG;
+  uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
+  float tw = 0.f, tf = 0.f;
+  uint32_t gtw = 0, gtd = 0, gtf = 0;
+  if (gl == 0) {
+    tw = gs[idw], tf = gs[idf];
+    gtw = gt[idw >> 5], gtd = gt[idd >> 5], gtf = gt[idf >> 5];
+  }
+
+  // ---- token caches of objects whose vibe changed (or that were never built), then the shared tables
+  if (o_alive && o_ntok == MG_TOK_DIRTY) {
+    const TokDims td = {d.P, d.TW, d.ND, d.B};
+    o_ntok = (uint32_t)build_tokens(td, hdr, o, o_meta, (uint16_t*)(toks + gl * tokw), E, live);
+    if (live) {
+      const int nwords = (int)(o_ntok + 1) >> 1;
+      for (int k = 0; k < nwords; k++) o[TOKOFF + k] = toks[gl * tokw + k];
+      o[MGO_NTOK] = o_ntok;
+    }
+  }
+  oloc[gl] = o_loc;
+  ontok[gl] = o_alive ? o_ntok : 0;
+  stale[gl] = 0;
+  // the stage shares the destination's 16-byte phase so that whole vectors can be streamed out
+  uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
+  const int nbytes = A * 3 * T;
+  uint8_t* stage = gb + ((uint32_t)(uintptr_t)gobs & 15u);
+  {
+    uint4* s4 = (uint4*)gb;
+    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // EmptyTokenByte (:940-942)
+    const int nv = (nbytes + 15 + 16) >> 4;
+    for (int v = gl; v < nv; v += G) s4[v] = ff;
+  }
+  __syncwarp();
+
+  // ---- observations: sort keys for the objects in this agent's window
+  const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
+  uint32_t key[G];
+  uint32_t vismask = 0;
+#pragma unroll
+  for (int j = 0; j < G; j++) {
+    const uint32_t ol = oloc[j];
+    const int dr = (int)(ol >> 16) - r0 + rr, dc = (int)(ol & 0xffffu) - c0 + cr;
+    const bool in = isA && ol != FAST_INVALID && (unsigned)dr <= (unsigned)(2 * rr) && (unsigned)dc <= (unsigned)(2 * cr);
+    const uint32_t loc = (uint32_t)((dr << 4) | dc) & 0xffu;
+    const uint32_t rk = rank[loc];
+    const bool vis = in && rk != 0xffu;
+    key[j] = vis ? ((rk << 16) | (loc << 8) | (uint32_t)j) : FAST_INVALID;
+    vismask |= vis ? (1u << j) : 0u;
+  }
+  // cell staleness (:787-796): the lowest agent index that sees an object claims it
+  {
+    uint32_t col = 0;
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+      const uint32_t b = (__ballot_sync(MG_FULL, (vismask >> j) & 1u) & gmask) >> gshift;
+      if (gl == j) col = b;
+    }
+    if (o_alive && col != 0) {
+      if (o_vis < step) {
+        atomicAdd(&stale[__ffs(col) - 1], step - o_vis);
+        o_vis = step;
+      }
+    }
+  }
+  sort_net<G>(key);
+
+  // global tokens (:700-742)
+  uint8_t* row = stage + gl * 3 * T;
+  int pos = 0;
+  auto put = [&](uint32_t loc, uint32_t feat, uint32_t val) {
+    if (pos < T) {
+      row[pos * 3 + 0] = (uint8_t)loc;
+      row[pos * 3 + 1] = (uint8_t)feat;
+      row[pos * 3 + 2] = (uint8_t)val;
+    }
+    pos++;
+  };
+  if (isA) {
+    const int flags = hdr[MGH_GLOBAL_FLAGS];
+    if (flags & MGG_EPISODE_PCT) {
+      const int ms = hdr[MGH_MAX_STEPS];
+      uint32_t val = 0;
+      if (ms > 0) val = step >= (uint32_t)ms ? 255u : ((256u * step / (uint32_t)ms) & 0xffu);
+      put(0xFE, hdr[MGH_FEAT_EPISODE_PCT], val);
+    }
+    if (flags & MGG_LAST_ACTION) put(0xFE, hdr[MGH_FEAT_LAST_ACTION], (uint32_t)exec_idx & 0xffu);
+    if ((flags & MGG_LAST_ACTION_MOVE) && hdr[MGH_FEAT_LAST_ACTION_MOVE] != 0)
+      put(0xFE, hdr[MGH_FEAT_LAST_ACTION_MOVE], my_loc != my_loc0);
+    if (flags & MGG_LAST_REWARD) put(0xFE, hdr[MGH_FEAT_LAST_REWARD], 0);  // rewards are zero at this point (:937-938)
+    if (flags & MGG_LOCAL_POSITION) {
+      const int de = c0 - (int)(a_spawn & 0xffffu), dn = (int)(a_spawn >> 16) - r0;
+      if (de != 0) put(0xFE, de > 0 ? hdr[MGH_FEAT_LP_EAST] : hdr[MGH_FEAT_LP_WEST], min(abs(de), 255));
+      if (dn != 0) put(0xFE, dn > 0 ? hdr[MGH_FEAT_LP_NORTH] : hdr[MGH_FEAT_LP_SOUTH], min(abs(dn), 255));
+    }
+  }
+  // window tokens in Manhattan order (:756-811)
+  bool more = true;  // keys are sorted: once no lane has a visible object left the rest is skipped
+#pragma unroll
+  for (int k = 0; k < G; k++) {
+    const uint32_t kk = key[k];
+    if (more) more = __any_sync(MG_FULL, kk != FAST_INVALID);
+    if (more && kk != FAST_INVALID) {
+      const int j = (int)(kk & 0xffu);
+      const uint32_t loc = (kk >> 8) & 0xffu;
+      const int n = (int)ontok[j];
+      const uint16_t* tk = (const uint16_t*)(toks + j * tokw);
+      for (int t = 0; t < n; t++) {
+        const uint32_t e = tk[t];
+        put(loc, e & 0xffu, e >> 8);
+      }
+    }
+  }
+  const int attempted = pos;
+  __syncwarp();
+
+  // ---- stream the env's observation block out
+  {
+    const int head = min(nbytes, (int)((16u - ((uint32_t)(uintptr_t)gobs & 15u)) & 15u));
+    if (live)
+      for (int i = gl; i < head; i += G) gobs[i] = stage[i];
+    const int body = (nbytes - head) >> 4;
+    const uint4* s4 = (const uint4*)(stage + head);
+    uint4* g4 = (uint4*)(gobs + head);
+    if (live)
+      for (int v = gl; v < body; v += G) __stcs(g4 + v, s4[v]);
+    const int done = head + (body << 4);
+    if (live)
+      for (int i = done + gl; i < nbytes; i += G) gobs[i] = stage[i];
+  }
+
+  // ---- token stats (:659-661, :640-642) and the token budget (:364-375)
+  {
+    const bool over = isA && attempted > T;
+    const uint32_t ov = (__ballot_sync(MG_FULL, over) & gmask) >> gshift;
+    int sw = (isA && !over) ? attempted : 0, sf = (isA && !over) ? T - attempted : 0;
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) {
+      sw += __shfl_xor_sync(MG_FULL, sw, off, G);
+      sf += __shfl_xor_sync(MG_FULL, sf, off, G);
+    }
+    // The reference adds one float per agent in agent order.  While the totals stay below 2^24 every such add
+    // is exact, so the sum can be added at once; beyond that the adds are replayed in order.
+    const bool slow = gl == 0 && !(tw + (float)sw < 16777216.0f && tf + (float)sf < 16777216.0f);
+    if (__any_sync(MG_FULL, slow)) {
+      for (int a = 0; a < A; a++) {
+        const int at = __shfl_sync(MG_FULL, attempted, a, G);
+        if (slow && at <= T) {
+          tw = __fadd_rn(tw, (float)at);
+          tf = __fadd_rn(tf, (float)(T - at));
+        }
+      }
+    }
+    if (gl == 0 && !slow) {
+      tw = __fadd_rn(tw, (float)sw);
+      tf = __fadd_rn(tf, (float)sf);
+    }
+    if (gl == 0 && live) {
+      gs[idw] = tw, gs[idf] = tf;
+      // touch tokens_written / tokens_dropped / tokens_free_space; the three ids may share a word
+      uint32_t* pw = gt + (idw >> 5);
+      uint32_t* pd = gt + (idd >> 5);
+      uint32_t* pf = gt + (idf >> 5);
+      const uint32_t bw = 1u << (idw & 31), bd = 1u << (idd & 31), bf = 1u << (idf & 31);
+      uint32_t nwv = gtw | bw;
+      if (pd == pw) nwv |= bd;
+      if (pf == pw) nwv |= bf;
+      if (nwv != gtw) *pw = nwv;
+      if (pd != pw) {
+        uint32_t nd = gtd | bd;
+        if (pf == pd) nd |= bf;
+        if (nd != gtd) *pd = nd;
+      }
+      if (pf != pw && pf != pd && (gtf | bf) != gtf) *pf = gtf | bf;
+    }
+    if (__any_sync(MG_FULL, ov != 0)) {  // hard error in the reference; the first agent in index order is reported
+      const int a = ov ? __ffs(ov) - 1 : 0;
+      const int at = __shfl_sync(MG_FULL, attempted, a, G);
+      if (gl == 0 && ov && live) set_error(E, MGERR_TOKEN_OVERFLOW, a | (min(at, 65535) << 16));
+    }
+  }
+
+  // ---- per-agent write-back: stats, coverage (objects/agent.cpp:49-57), flags
+  __syncwarp();
+  if (isA && live) {
+    uint32_t nt0 = t0, nt1 = t1;
+    auto touch = [&](int id) {
+      if (id < 32)
+        nt0 |= 1u << id;
+      else
+        nt1 |= 1u << (id - 32);
+    };
+    for (int k = 0; k < ninv; k++) s_inv = __fadd_rn(s_inv, (float)npass);  // once per priority pass
+    if (ninv) st[id_inv] = s_inv, touch(id_inv);
+    if (swm_peak && (float)swm_peak > s_swm) st[id_swm] = (float)swm_peak, touch(id_swm);
+    if (id_p >= 0) st[id_p] = __fadd_rn(s_p, 1.0f), touch(id_p);
+    if (id_v >= 0) st[id_v] = __fadd_rn(s_v, 1.0f), touch(id_v);
+    for (int k = 0; k < nfail; k++) s_fail = __fadd_rn(s_fail, 1.0f);
+    if (nfail) st[id_fail] = s_fail, touch(id_fail);
+    const uint32_t bit = 1u << (cell & 31);
+    if (!(cvw & bit)) {
+      *cvp = cvw | bit;
+      ag[MGAG_UNIQUE] = ++a_unique;
+    }
+    st[id_un] = (float)a_unique, touch(id_un);
+    const uint32_t dist = (uint32_t)(abs((int)(a_spawn >> 16) - r0) + abs(c0 - (int)(a_spawn & 0xffffu)));
+    const uint32_t md = max(a_maxd, dist);
+    if (md != a_maxd) ag[MGAG_MAX_DIST] = md;
+    st[id_md] = (float)md, touch(id_md);
+    const uint32_t ssum = stale[gl];
+    if (ssum) st[id_cv] = __fadd_rn(s_cv, (float)ssum), touch(id_cv);
+    if (nt0 != t0) tch[0] = nt0;
+    if (nt1 != t1) tch[1] = nt1;
+    if (prev != a_prev) ag[MGAG_PREV_LOC] = prev;
+    if (swm != a_swm) ag[MGAG_SWM] = swm;
+    bool success = ok_p;  // same update order as handle_action's caller: primary stream, then vibe stream
+    if (inv_v) success = false;
+    if (ok_v) success = true;
+    d.success[g0 + gl] = (uint8_t)success;
+    d.rewards[g0 + gl] = 0.0f;  // no reward entries in a plain program (systems/reward.hpp:56-77)
+    const int ms = hdr[MGH_MAX_STEPS];
+    if (ms > 0 && step >= (uint32_t)ms) {  // :1090-1096
+      if (hdr[MGH_EPISODE_TRUNCATES])
+        d.truncations[g0 + gl] = 1;
+      else
+        d.terminals[g0 + gl] = 1;
+    }
+  }
+  // ---- object write-back
+  if (o_alive && live) {
+    if (o_loc != o_loc0) o[MGO_LOC] = o_loc;
+    if (o_vis != o_vis0) o[MGO_VISITED] = o_vis;
+    if (o_meta != o_meta0) o[MGO_META] = o_meta;
+  }
+  if (gl == 0 && live) E[MGEV_STEP] = (int32_t)step;
+}
+
+}  // namespace
+
+// ---- host side -------------------------------------------------------------------------------------
+static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap) {
+  MgFastLayout L;
+  L.G = G;
+  L.rank_off = (int)al16(MGH_HEADER_WORDS * 4);
+  L.cta_bytes = L.rank_off + 256;
+  size_t n = al16((size_t)d.A * 3 * d.T + 16) + 16;  // stage (+ phase slack)
+  L.tok_stride = ((tok_cap + 1) / 2) | 1;               // odd word stride: conflict-free columns
+  L.tok_off = (int)n;
+  n += al16((size_t)G * L.tok_stride * 4);
+  L.oloc_off = (int)n;
+  n += al16((size_t)G * 4 * 4 + G);  // oloc, ontok, stale, draw, order
+  L.group_bytes = (int)n;
+  L.smem_bytes = L.cta_bytes + (size_t)MG_FAST_WARPS * (32 / G) * L.group_bytes;
+  return L;
+}
+
+template <int G>
+static cudaError_t launch_fast(const MgDev& d, const MgFastLayout& L, cudaStream_t st) {
+  const int envs_per_cta = MG_FAST_WARPS * (32 / G);
+  const int grid = (d.num_envs + envs_per_cta - 1) / envs_per_cta;
+  k_step_fast<G><<<grid, MG_FAST_WARPS * 32, L.smem_bytes, st>>>(d, L);
+  return cudaGetLastError();
+}
+
+cudaError_t mg_fast_configure(const MgFastLayout& L) {
+  cudaError_t e;
+  const int bytes = (int)L.smem_bytes;
+  if ((e = cudaFuncSetAttribute(k_step_fast<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_step_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_step_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  const int c = 100;  // prefer shared memory: the working set lives there, L1 only serves the program tables
+  if ((e = cudaFuncSetAttribute(k_step_fast<8>, cudaFuncAttributePreferredSharedMemoryCarveout, c)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_step_fast<16>, cudaFuncAttributePreferredSharedMemoryCarveout, c)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_step_fast<32>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+}
+
+cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, cudaStream_t st) {
+  switch (L.G) {
+    case 8: return launch_fast<8>(d, L, st);
+    case 16: return launch_fast<16>(d, L, st);
+    default: return launch_fast<32>(d, L, st);
+  }
+}

@@ -8,6 +8,9 @@
 #ifndef MG_WARPS_PER_CTA
 #define MG_WARPS_PER_CTA 4
 #endif
+#ifndef MG_FAST_WARPS
+#define MG_FAST_WARPS 2  // warps per CTA of k_step_fast (mg_fast.cu)
+#endif
 #define MG_RNG_WINDOW 32
 #define MG_TAG_LIST_CAP 64
 
@@ -16,6 +19,7 @@ struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
+  const uint8_t* rank_lut;  // [256] (dr + rr) << 4 | (dc + cr) -> position in Manhattan order, 0xFF outside the shape
   int plain;    // 1: the program has no handlers / rewards / world systems (k_step<PLAIN> applies)
   int PAD, WP;  // the grid is stored with a PAD-wide empty frame (row pitch WP) so observation windows need no bounds tests
   // persistent state
@@ -54,3 +58,11 @@ struct MgDev {
   const int32_t* vibe_actions;// [N][A]
 };
 
+
+// shared-memory layout of k_step_fast (mg_fast.cu), computed on the host
+struct MgFastLayout {
+  int G;           // lanes per environment: 8, 16 or 32
+  int rank_off, cta_bytes;
+  int tok_off, tok_stride, oloc_off, group_bytes;
+  size_t smem_bytes;
+};

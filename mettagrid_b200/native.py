@@ -39,6 +39,7 @@ SYMBOLS = {
     "mg_num_agents": (_i, [_vp]),
     "mg_num_tokens": (_i, [_vp]),
     "mg_state_bytes": (_sz, [_vp]),
+    "mg_step_kernel": (_i, [_vp]),
 }
 
 

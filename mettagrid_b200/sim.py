@@ -245,6 +245,11 @@ class BatchedSimulation:
     def state_bytes(self) -> int:
         return int(self._L.mg_state_bytes(self._h))
 
+    @property
+    def step_kernel(self) -> int:
+        """0 = generic kernel, 1 = plain kernel, 8/16/32 = sparse fast path with that many lanes per env."""
+        return int(self._L.mg_step_kernel(self._h))
+
     def close(self):
         if getattr(self, "_h", None):
             self._L.mg_destroy(self._h)
