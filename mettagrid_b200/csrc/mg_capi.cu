@@ -18,7 +18,7 @@ cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStre
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
 MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap);
 cudaError_t mg_fast_configure(const MgFastLayout& L);
-cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, cudaStream_t st);
+cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st);
 
@@ -32,6 +32,7 @@ struct mg_handle {
   bool buffers_set = false;
   bool fast = false;  // k_step_fast applies (mg_fast.cu): plain program, sparse environments
   MgFastLayout fl{};
+  MgFastHdr fh{};
   // device-side staging for mg_step_host
   int32_t* h_act = nullptr;
   int32_t* h_vact = nullptr;
@@ -89,6 +90,7 @@ static int program_is_plain(const int32_t* P) {
 // most 15 x 15 cells.  Returns the lanes per environment (8, 16, 32) or 0.
 static int fast_group_size(const int32_t* P, const MgDev& d, int max_objects_per_env) {
   if (!d.plain || getenv("METTAGRID_B200_NO_FAST")) return 0;
+  if ((d.AS & 3) || (d.OS & 3)) return 0;  // vector loads of the records
   if (d.A > 32 || max_objects_per_env > 32 || P[MGH_OBS_H] > 15 || P[MGH_OBS_W] > 15 || P[MGH_TOK_CAP] > 126) return 0;
   for (int k = MGH_ST_ACTION_FAILED; k <= MGH_ST_VIBE_FAILED; k++)
     if (P[k] < 0 || P[k] >= 64) return 0;
@@ -170,7 +172,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   if (init_gstats) TRY(dev_alloc(h, &ig, N * d.SG));
   TRY(dev_alloc(h, &h->seeds_dev, N));
   TRY(dev_alloc(h, &d.cells, N * d.HWp));
-  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NTERR) * d.OS));
+  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NTERR) * d.OS + 64));  // slack: k_step_fast reads 4 token words blind
   {
     // capacities of the world-system tables, from the program and the initial maps
     const int32_t* TP = P + P[MGS_TEMPLATES];
@@ -242,14 +244,17 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   {
     // window-rank table: packed offset (dr + rr) << 4 | (dc + cr) -> position in the reference's Manhattan order
     // (core/observation_shape.cpp:19-66); 0xFF = outside the shape
-    std::vector<uint8_t> lut(256, 0xFF);
-    uint8_t* lut_dev;
+    std::vector<uint32_t> lut(256, 0xFFFFFF00u);
+    uint32_t* lut_dev;
     const int32_t* offs = P + P[MGS_OFFSETS];
     const int rr = P[MGH_OBS_H] >> 1, cr = P[MGH_OBS_W] >> 1;
     if (P[MGH_OBS_H] <= 15 && P[MGH_OBS_W] <= 15 && d.NOFF < 255)
-      for (int i = 0; i < d.NOFF; i++) lut[((offs[2 * i] + rr) << 4) | ((offs[2 * i + 1] + cr) & 15)] = (uint8_t)i;
+      for (int i = 0; i < d.NOFF; i++) {
+        const uint32_t loc = (uint32_t)(((offs[2 * i] + rr) << 4) | ((offs[2 * i + 1] + cr) & 15));
+        lut[loc] = ((uint32_t)i << 24) | (loc << 16);
+      }
     TRY(dev_alloc(h, &lut_dev, 256));
-    if (cudaMemcpy(lut_dev, lut.data(), 256, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMemcpy(lut_dev, lut.data(), 1024, cudaMemcpyHostToDevice) != cudaSuccess) {
       h->err = "mg_create: upload failed";
       return fail(MG_E_CUDA);
     }
@@ -263,6 +268,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   }
   if (const int G = fast_group_size(P, d, max_objs)) {
     h->fl = mg_fast_layout(d, G, P[MGH_TOK_CAP]);
+    memcpy(h->fh.v, P, sizeof h->fh.v);
     if (h->fl.smem_bytes <= 200 * 1024 && mg_fast_configure(h->fl) == cudaSuccess)
       h->fast = true;
     else
@@ -315,7 +321,7 @@ int mg_step(mg_handle* h, void* stream) {
     h->err = "mg_step: call mg_set_buffers first";
     return MG_E_INVALID;
   }
-  CK(h->fast ? mg_launch_step_fast(h->d, h->fl, (cudaStream_t)stream) : mg_launch_step(h->d, (cudaStream_t)stream));
+  CK(h->fast ? mg_launch_step_fast(h->d, h->fl, h->fh, (cudaStream_t)stream) : mg_launch_step(h->d, (cudaStream_t)stream));
   return MG_OK;
 }
 
@@ -344,7 +350,7 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
   MgDev run = d;
   run.obs = h->h_obs, run.terminals = h->h_term, run.truncations = h->h_trunc, run.rewards = h->h_rew;
   run.actions = h->h_act, run.vibe_actions = h->h_vact;
-  CK(h->fast ? mg_launch_step_fast(run, h->fl, st) : mg_launch_step(run, st));
+  CK(h->fast ? mg_launch_step_fast(run, h->fl, h->fh, st) : mg_launch_step(run, st));
   if (observations) CK(cudaMemcpyAsync(observations, h->h_obs, NA * d.T * 3, cudaMemcpyDeviceToHost, st));
   if (rewards) CK(cudaMemcpyAsync(rewards, h->h_rew, NA * 4, cudaMemcpyDeviceToHost, st));
   if (terminals) CK(cudaMemcpyAsync(terminals, h->h_term, NA, cudaMemcpyDeviceToHost, st));

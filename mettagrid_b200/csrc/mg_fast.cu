@@ -88,37 +88,36 @@ __device__ __forceinline__ void set_error(int32_t* E, int code, int info) {
   E[MGEV_ERROR] = cur | code;
 }
 
-// An object's observation tokens (core/grid_object.cpp:178-203, objects/agent.cpp:142-154) as
-// (feature | value << 8) pairs, written to `tk`; same rules as rebuild_token_cache in mg_kernels.cu.
 struct TokDims {
   const int32_t* P;
   int TW, ND, B;
+  int cap, ftag, fvibe, fgroup, fagent, inv_feats, templates;  // header words, by value
 };
-__device__ __noinline__ int build_tokens(const TokDims d, const int32_t* hdr, const uint32_t* o, uint32_t meta, uint16_t* tk,
-                                         int32_t* E, bool live) {
-  const int cap = hdr[MGH_TOK_CAP];
+// An object's observation tokens (core/grid_object.cpp:178-203, objects/agent.cpp:142-154) as
+// (feature | value << 8) pairs, written to `tk`; same rules as rebuild_token_cache in mg_kernels.cu.
+__device__ __noinline__ int build_tokens(const TokDims d, const uint32_t* o, uint32_t meta, uint16_t* tk, int32_t* E, bool live) {
+  const int cap = d.cap;
   int n = 0;
   auto put = [&](int feat, int val) {
     if (n < cap) tk[n] = (uint16_t)((feat & 0xff) | ((val & 0xff) << 8));
     n++;
   };
-  const int ftag = hdr[MGH_FEAT_TAG];
   for (int k = 0; k < d.TW; k++) {
     uint32_t m = o[MGO_TAGS + k];
     while (m) {
       int b = __ffs(m) - 1;
-      put(ftag, k * 32 + b);
+      put(d.ftag, k * 32 + b);
       m &= m - 1;
     }
   }
   const int vibe = (int)((meta >> 16) & 0xffu);
-  if (vibe) put(hdr[MGH_FEAT_VIBE], vibe);
+  if (vibe) put(d.fvibe, vibe);
   const int fl = (int)(meta >> 24);
   if (fl & MGOF_OBS_INV) {
     const uint64_t ord = (uint64_t)o[MGO_INVORD_LO] | ((uint64_t)o[MGO_INVORD_HI] << 32);
     const int cnt = (int)(ord >> 60);
     const uint16_t* inv = (const uint16_t*)(o + MGO_TAGS + d.TW);
-    const int32_t* feats = d.P + hdr[MGS_INV_FEATS];
+    const int32_t* feats = d.P + d.inv_feats;
     for (int i = 0; i < cnt; i++) {
       const int it = (int)((ord >> (4 * i)) & 15u);
       uint32_t amt = inv[it];
@@ -132,8 +131,8 @@ __device__ __noinline__ int build_tokens(const TokDims d, const int32_t* hdr, co
   }
   if (fl & MGOF_AGENT) {
     const int ai = (int)o[MGO_AGENT];
-    put(hdr[MGH_FEAT_GROUP], __ldg(d.P + hdr[MGS_TEMPLATES] + (int)(meta & 0xffffu) * MG_TEMPLATE_WORDS + MGT_GROUP));
-    put(hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
+    put(d.fgroup, __ldg(d.P + d.templates + (int)(meta & 0xffffu) * MG_TEMPLATE_WORDS + MGT_GROUP));
+    put(d.fagent, ai >= 0 ? ai : 0);
   }
   if (n > cap) {
     if (live) set_error(E, MGERR_POOL_EXHAUSTED, 19);
@@ -168,27 +167,23 @@ __device__ __forceinline__ void sort_net(uint32_t (&key)[N]) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d, const MgFastLayout L) {
+__global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_fast(const MgDev d, const MgFastLayout L, const MgFastHdr HD) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int GPW = 32 / G;  // environments per warp
+  const int* const hdr = HD.v;  // the program header travels as a kernel argument: constant-bank reads, no load
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gl = lane & (G - 1), grp = lane / G;
   const uint32_t gmask = G == 32 ? MG_FULL : (((1u << (G & 31)) - 1u) << (grp * G));
   const int gshift = grp * G;
 
-  // ---- CTA tables: program header and the window-rank table (built by mg_create)
-  int32_t* hdr = (int32_t*)smem;
-  uint8_t* rank = smem + L.rank_off;
-  for (int i = tid; i < MGH_HEADER_WORDS; i += blockDim.x) hdr[i] = __ldg(d.P + i);
-  for (int i = tid; i < 64; i += blockDim.x) ((uint32_t*)rank)[i] = __ldg((const uint32_t*)d.rank_lut + i);
-
   int env = (blockIdx.x * MG_FAST_WARPS + warp) * GPW + grp;
   const bool live = env < d.num_envs;  // a dead group mirrors the last env but stores nothing
   if (!live) env = d.num_envs - 1;
+  uint32_t* lut = (uint32_t*)smem;  // window table: packed offset -> rank << 24 | offset << 16 (0xFFFFFF00 outside)
   unsigned char* gb = smem + L.cta_bytes + (size_t)(warp * GPW + grp) * L.group_bytes;
   uint32_t* toks = (uint32_t*)(gb + L.tok_off);
   uint32_t* oloc = (uint32_t*)(gb + L.oloc_off);
-  uint32_t* ontok = oloc + G;
+  uint32_t* ontok = oloc + G;  // (oloc, ontok) are used as one uint2[G] table: location, count << 8 | lane
   uint32_t* stale = ontok + G;
   uint32_t* draw = stale + G;
   uint8_t* order = (uint8_t*)(draw + G);
@@ -196,69 +191,116 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
   const int A = d.A, T = d.T;
   const size_t g0 = (size_t)env * A;
   const bool isA = gl < A;
+  const size_t ga = g0 + (isA ? gl : 0);
   int32_t* E = d.env + (size_t)env * MGEV_WORDS;
   uint32_t* rng = d.rng + (size_t)env * MG_RNG_WORDS;
+  uint32_t* ag = d.agents + ga * d.AS;
+  uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NTERR) + (size_t)min(gl + 1, d.maxobj - 1)) * d.OS;
+  float* st = d.astats + ga * d.SA;
+  uint32_t* tch = d.atouched + ga * d.SAW;
+  uint32_t* cvrow = d.cover + ga * d.CW;
+  float* gs = d.gstats + (size_t)env * d.SG;
+  uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
+  const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+  const int tokw = L.tok_stride;  // words per object in the shared token table
 
-  // ---- wave 1: env scalars, actions, agent records, object records
-  const uint32_t step = (uint32_t)E[MGEV_STEP] + 1u;  // :951
-  int idx0 = E[MGEV_RNG_IDX];
-  const int nobj = E[MGEV_NEXT_OBJ] - 1;
-  uint32_t* ag = d.agents + (g0 + (isA ? gl : 0)) * d.AS;
-  int ia = -1, iv = -1;
-  uint32_t a_slot = 1, a_spawn = 0, a_prev = 0, a_swm = 0, a_maxd = 0, a_unique = 0;
-  if (isA) {
-    ia = d.actions[g0 + gl];
-    iv = d.vibe_actions[g0 + gl];
-    a_slot = ag[MGAG_OBJ], a_spawn = ag[MGAG_SPAWN], a_prev = ag[MGAG_PREV_LOC], a_swm = ag[MGAG_SWM];
-    a_maxd = ag[MGAG_MAX_DIST], a_unique = ag[MGAG_UNIQUE];
+  // ---- wave 1: every load whose address is known up front is issued before anything is consumed
+  const int e_step = E[MGEV_STEP], e_idx = E[MGEV_RNG_IDX], e_nobj = E[MGEV_NEXT_OBJ];
+  const int ia_raw = d.actions[ga], iv_raw = d.vibe_actions[ga];
+  const uint4 ag0 = *(const uint4*)ag;        // MGAG_OBJ, MGAG_SPAWN, MGAG_PREV_LOC, MGAG_STEP_LOC
+  const uint4 ag1 = *(const uint4*)(ag + 4);  // MGAG_SWM, MGAG_MAX_DIST, MGAG_UNIQUE, MGAG_EPISODE_REWARD
+  const uint4 orec = *(const uint4*)o;        // MGO_LOC, MGO_VISITED, MGO_META, MGO_AGENT
+  const uint32_t ntok_raw = o[MGO_NTOK];
+  uint32_t tw0 = o[TOKOFF], tw1 = o[TOKOFF + 1], tw2 = o[TOKOFF + 2], tw3 = o[TOKOFF + 3];  // first 8 cached tokens
+  constexpr int LV = (64 + MG_FAST_WARPS * 32 - 1) / (MG_FAST_WARPS * 32);  // window-table vectors per thread
+  uint4 lutv[LV];
+#pragma unroll
+  for (int k = 0; k < LV; k++) {
+    const int i = tid + k * MG_FAST_WARPS * 32;
+    lutv[k] = i < 64 ? __ldg((const uint4*)d.rank_lut + i) : make_uint4(0, 0, 0, 0);
   }
+  // the rows the end of the tick updates: pull them towards L2 now
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(st));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(st + 8));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(tch));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(cvrow));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(cvrow + 8));
+  if (gl == 0) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gs + hdr[MGH_GST_TOKENS_WRITTEN]));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gt));
+  }
+
+#pragma unroll
+  for (int k = 0; k < LV; k++) {
+    const int i = tid + k * MG_FAST_WARPS * 32;
+    if (i < 64) ((uint4*)lut)[i] = lutv[k];
+  }
+  const uint32_t step = (uint32_t)e_step + 1u;  // :951
+  int idx0 = e_idx;
+  const int nobj = e_nobj - 1;
+  const int ia = isA ? ia_raw : -1, iv = isA ? iv_raw : -1;
+  const uint32_t a_slot = isA ? ag0.x : 1u, a_spawn = ag0.y, a_prev = ag0.z, a_swm = ag1.x, a_maxd = ag1.y;
+  uint32_t a_unique = ag1.z;
   const bool isO = gl < nobj;
-  uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NTERR) + (size_t)(gl + 1)) * d.OS;
-  uint32_t o_loc = FAST_INVALID, o_vis = 0, o_meta = 0, o_ntok = 0;
-  int o_agent = -1;
-  if (isO) {
-    const uint4 r = *(const uint4*)o;  // MGO_LOC, MGO_VISITED, MGO_META, MGO_AGENT
-    o_loc = r.x, o_vis = r.y, o_meta = r.z, o_agent = (int)r.w;
-    o_ntok = o[MGO_NTOK];
-  }
+  uint32_t o_loc = orec.x, o_vis = orec.y, o_meta = orec.z, o_ntok = ntok_raw;
+  const int o_agent = isO ? (int)orec.w : -1;
   const bool o_alive = isO && ((o_meta >> 24) & MGOF_ALIVE);
   if (!o_alive) o_loc = FAST_INVALID;
   const uint32_t o_loc0 = o_loc, o_vis0 = o_vis, o_meta0 = o_meta;
-  __syncthreads();  // hdr, rank
 
-  // ---- wave 2: action rows, RNG words, token caches
+  // ---- wave 2: action rows, RNG words, the rest of long token caches
   const int NA = hdr[MGH_NUM_ACTIONS];
   const int32_t* acts = d.P + hdr[MGS_ACTIONS];
   const bool inv_p = ia < 0 || ia >= NA, inv_v = iv < 0 || iv >= NA;
   int4 ap = make_int4(0, 0, 0, 1), av = make_int4(0, 0, 0, 0);  // kind, arg, priority, is_vibe
   if (isA && !inv_p) ap = __ldg((const int4*)(acts + ia * MG_ACTION_WORDS));
   if (isA && !inv_v) av = __ldg((const int4*)(acts + iv * MG_ACTION_WORDS));
-  const bool act_p = isA && !inv_p && ap.w == 0;  // executed in the primary stream (:966-999)
-  const bool act_v = isA && !inv_v && av.w == 1;  // executed in the vibe stream
-
   const int ndraws = A < 2 ? 0 : ((A & 1) ? (A - 1) / 2 : A / 2);
   if (idx0 >= MG_RNG_WORDS) idx0 = 0;
-  uint32_t nw = 0, rnd = 0;
   const bool window_ok = idx0 + ndraws <= MG_RNG_WORDS;
+  uint32_t r_cur = 0, r_nxt = 0, r_far = 0;
   if (window_ok && gl < ndraws) {
     const int i = idx0 + gl;
     const int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
     const int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
-    nw = mt_twist(rng[i], rng[i1], rng[i2]);
-    rnd = mt_temper(nw);
+    r_cur = rng[i], r_nxt = rng[i1], r_far = rng[i2];
   }
-  const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
-  const int tokw = L.tok_stride;  // words per object in the shared token table
   {
     const bool cached = o_alive && o_ntok != MG_TOK_DIRTY;
     const int nwords = cached ? (int)(o_ntok + 1) >> 1 : 0;
-    for (int k = 0; k < nwords; k++) toks[gl * tokw + k] = o[TOKOFF + k];
+    uint32_t* row = toks + gl * tokw;
+    row[0] = tw0, row[1] = tw1, row[2] = tw2, row[3] = tw3;  // tokw >= 5
+#pragma unroll 1
+    for (int k = 4; k < nwords; k++) row[k] = o[TOKOFF + k];
   }
-  if (isA) order[gl] = (uint8_t)gl;
+  // independent work while wave 2 is in flight: the observation stage starts as all EmptyTokenByte (:940-942);
+  // it shares the destination's 16-byte phase so that whole vectors can be streamed out
+  uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
+  const int nbytes = A * 3 * T;
+  uint8_t* stage = gb + ((uint32_t)(uintptr_t)gobs & 15u);
+  {
+    uint4* s4 = (uint4*)gb;
+    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    const int nv = (nbytes + 15 + 16) >> 4;
+    int v = gl;
+#pragma unroll 1
+    for (; v + 3 * G < nv; v += 4 * G) s4[v] = ff, s4[v + G] = ff, s4[v + 2 * G] = ff, s4[v + 3 * G] = ff;
+#pragma unroll 1
+    for (; v < nv; v += G) s4[v] = ff;
+  }
+  stale[gl] = 0;
+  const bool act_p = isA && !inv_p && ap.w == 0;  // executed in the primary stream (:966-999)
+  const bool act_v = isA && !inv_v && av.w == 1;  // executed in the vibe stream
 
-  // ---- shuffle (:958-964): every draw is decoded by its own lane, the swaps are applied by one lane
+  // ---- shuffle (:958-964): std::shuffle is a sequence of transpositions (pos, P[pos]), pos = 1..A-1.  Every draw
+  // is decoded by its own lane; every lane then finds the element that ends at its position by walking the
+  // transpositions backwards -- no serial swap loop.
   bool reject = !window_ok;
+  uint32_t nw = 0;
+  uint8_t* perm = order;  // P[pos]
   if (window_ok && gl < ndraws) {
+    nw = mt_twist(r_cur, r_nxt, r_far);
+    const uint32_t rnd = mt_temper(nw);
     const bool single = (A & 1) == 0 && gl == 0;
     const int i = single ? 1 : ((A & 1) ? 2 * gl + 1 : 2 * gl);
     const uint32_t sr = (uint32_t)i + 1;
@@ -266,33 +308,33 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
     const uint64_t prod = (uint64_t)rnd * range;
     const uint32_t low = (uint32_t)prod, x = (uint32_t)(prod >> 32);
     if (low < range && low < (0u - range) % range) reject = true;
-    const uint32_t p0 = single ? x : x / (sr + 1), p1 = single ? 0xffu : x % (sr + 1);
-    draw[gl] = (uint32_t)i | (p0 << 8) | (p1 << 16);
+    perm[i] = (uint8_t)(single ? x : x / (sr + 1));
+    if (!single) perm[i + 1] = (uint8_t)(x % (sr + 1));
   }
   const uint32_t rej = __ballot_sync(MG_FULL, reject) & gmask;
   __syncwarp();
-  if (gl == 0 && A >= 2) {
-    if (rej) {
-      if (live) shuffle_serial(rng, E, order, A);  // a mirror group leaves the state alone
-    } else {
-      for (int k = 0; k < ndraws; k++) {
-        const uint32_t dw = draw[k];
-        const int i = (int)(dw & 0xffu), p0 = (int)((dw >> 8) & 0xffu), p1 = (int)((dw >> 16) & 0xffu);
-        uint8_t t = order[i];
-        order[i] = order[p0], order[p0] = t;
-        if (p1 != 0xff) {
-          t = order[i + 1];
-          order[i + 1] = order[p1], order[p1] = t;
-        }
-      }
+  int my_order = gl;  // the agent that acts at step gl
+  if (rej) {        // rare: a rejected draw or the draws straddle the end of the state -- one lane replays serially
+    __syncwarp(gmask);
+    if (isA) order[gl] = (uint8_t)gl;
+    __syncwarp(gmask);
+    if (gl == 0 && A >= 2 && live) shuffle_serial(rng, E, order, A);  // a mirror group leaves the state alone
+    __syncwarp(gmask);
+    if (isA) my_order = order[gl];
+  } else {
+#pragma unroll 4
+    for (int pos = A - 1; pos >= 1; pos--) {
+      const int pp = perm[pos];
+      my_order = my_order == pos ? pp : (my_order == pp ? pos : my_order);
     }
   }
   if (!rej && live && gl < ndraws) rng[idx0 + gl] = nw;
   if (!rej && live && gl == 0 && ndraws > 0) E[MGEV_RNG_IDX] = idx0 + ndraws;
-  __syncwarp();
+  __syncthreads();  // the window table (per CTA)
 
   // ---- moves in shuffled order, highest priority first (actions/move.hpp:81-115 with the two default
-  // handlers: relocate into an empty in-map cell, else fail)
+  // handlers: relocate into an empty in-map cell, else fail).  Lane i first fetches what the agent acting at
+  // step i wants; the loop then only carries the object locations from step to step.
   const int my_ol = (int)a_slot - 1;  // lane that plays this agent's object
   const uint32_t my_loc0 = __shfl_sync(MG_FULL, o_loc, my_ol, G);
   uint32_t my_tgt = FAST_INVALID;
@@ -307,20 +349,31 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
   bool move_ok = false;
   {
     const int maxp = hdr[MGH_MAX_PRIORITY], pmask = hdr[MGH_PRIORITY_MASK];
+    const int ol_s = __shfl_sync(MG_FULL, my_ol, my_order, G);
+#pragma unroll 1
     for (int prio = maxp; prio >= 0; prio--) {
       if (!((pmask >> prio) & 1)) continue;
-      const uint32_t movers = __ballot_sync(MG_FULL, wants_move && ap.z == prio);
-      if (movers == 0) continue;
-      for (int i = 0; i < A; i++) {
-        const int a = order[i];
-        const bool m = (movers >> (gshift + a)) & 1u;
-        const uint32_t tgt = __shfl_sync(MG_FULL, my_tgt, a, G);
-        const int ol = __shfl_sync(MG_FULL, my_ol, a, G);
-        const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
-        const bool ok = m && tgt != FAST_INVALID && occ == 0;
-        if (ok && gl == ol) o_loc = tgt;
-        if (ok && gl == a) move_ok = true;
+      const bool mine = wants_move && ap.z == prio;
+      if (!__any_sync(MG_FULL, mine)) continue;
+      const uint32_t tgt_s = __shfl_sync(MG_FULL, mine ? my_tgt : FAST_INVALID, my_order, G);  // target at step gl
+      uint32_t okmask = 0;
+#pragma unroll
+      for (int i = 0; i < G; i++) {
+        if (i < A) {
+          const uint32_t tgt = __shfl_sync(MG_FULL, tgt_s, i, G);
+          const int ol = __shfl_sync(MG_FULL, ol_s, i, G);
+          const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
+          const bool ok = tgt != FAST_INVALID && occ == 0;
+          if (ok && gl == ol) o_loc = tgt;
+          okmask |= ok ? (1u << i) : 0u;
+        }
       }
+      // the step's verdict goes back to the agent that acted in it
+      __syncwarp();
+      if (isA) order[my_order] = (uint8_t)((okmask >> gl) & 1u);
+      __syncwarp();
+      if (isA && order[gl]) move_ok = true;
+      __syncwarp();
     }
   }
   const uint32_t my_loc = __shfl_sync(MG_FULL, o_loc, my_ol, G);  // observer position (:1049-1052)
@@ -328,51 +381,41 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
   // ---- per-agent outcome of both streams (actions/action_handler.hpp:78-105), in execution order
   const bool v_first = act_p && act_v && av.z > ap.z;  // the vibe-stream action has the higher priority
   const bool ok_p = act_p && (ap.x == MGA_MOVE ? move_ok : true);
-  const bool ok_v = act_v && (av.x == MGA_MOVE ? false : true);
+  const bool ok_v = act_v && av.x != MGA_MOVE;
   int exec_idx = 0;
-  if (v_first) {
-    if (ok_v) exec_idx = iv;
-    if (ok_p) exec_idx = ia;
-  } else {
-    if (ok_p) exec_idx = ia;
-    if (ok_v) exec_idx = iv;
-  }
   int new_vibe = -1;
   {
     const bool cp = ok_p && ap.x == MGA_CHANGE_VIBE, cv = ok_v && av.x == MGA_CHANGE_VIBE;
     if (v_first) {
+      if (ok_v) exec_idx = iv;
+      if (ok_p) exec_idx = ia;
       if (cv) new_vibe = av.y;
       if (cp) new_vibe = ap.y;
     } else {
+      if (ok_p) exec_idx = ia;
+      if (ok_v) exec_idx = iv;
       if (cp) new_vibe = ap.y;
       if (cv) new_vibe = av.y;
     }
   }
-  // object lanes pick up their agent's new vibe
-  {
-    const int nv = __shfl_sync(MG_FULL, new_vibe, o_agent >= 0 ? o_agent : 0, G);
-    if (o_alive && o_agent >= 0 && o_agent < A && nv >= 0 && (uint32_t)(nv & 0xff) != ((o_meta >> 16) & 0xffu)) {
-      o_meta = (o_meta & 0xff00ffffu) | ((uint32_t)(nv & 0xff) << 16);
-      o_ntok = MG_TOK_DIRTY;
-    }
-  }
 
-  // ---- wave 3 loads: stats, touched bits, coverage word
-  float* st = d.astats + (g0 + (isA ? gl : 0)) * d.SA;
-  uint32_t* tch = d.atouched + (g0 + (isA ? gl : 0)) * d.SAW;
+  // ---- wave 3 loads: stats, touched bits, coverage word (prefetched into L2 by wave 1)
   const int npass = hdr[MGH_MAX_PRIORITY] + 1;
   // steps-without-motion chain over the executed actions (stream order, like k_step)
   uint32_t prev = a_prev, swm = a_swm;
   uint32_t swm_peak = 0;  // largest value steps_without_motion took this tick
   const int nacted = (act_p ? 1 : 0) + (act_v ? 1 : 0);
-  for (int k = 0; k < nacted; k++) {
-    if (my_loc == prev) {
-      swm += 1;
-      swm_peak = max(swm_peak, swm);
-    } else {
-      swm = 0;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    if (k < nacted) {
+      if (my_loc == prev) {
+        swm += 1;
+        swm_peak = max(swm_peak, swm);
+      } else {
+        swm = 0;
+      }
+      prev = my_loc;
     }
-    prev = my_loc;
   }
   const int id_p = act_p ? hdr[(ok_p ? MGH_ST_NOOP_SUCCESS : MGH_ST_NOOP_FAILED) + 2 * ap.x] : -1;
   const int id_v = act_v ? hdr[(ok_v ? MGH_ST_NOOP_SUCCESS : MGH_ST_NOOP_FAILED) + 2 * av.x] : -1;
@@ -394,12 +437,10 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
   }
   const int r0 = (int)(my_loc >> 16), c0 = (int)(my_loc & 0xffffu);
   const int cell = r0 * d.W + c0;
-  uint32_t* cvp = d.cover + (g0 + (isA ? gl : 0)) * d.CW + (isA ? (cell >> 5) : 0);
+  uint32_t* cvp = cvrow + (isA ? (cell >> 5) : 0);
   uint32_t cvw = 0;
   if (isA) cvw = *cvp;
   const int idw = hdr[MGH_GST_TOKENS_WRITTEN], idf = hdr[MGH_GST_TOKENS_FREE], idd = hdr[MGH_GST_TOKENS_DROPPED];
-  float* gs = d.gstats + (size_t)env * d.SG;
-  uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
   float tw = 0.f, tf = 0.f;
   uint32_t gtw = 0, gtd = 0, gtf = 0;
   if (gl == 0) {
@@ -407,60 +448,93 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
     gtw = gt[idw >> 5], gtd = gt[idd >> 5], gtf = gt[idf >> 5];
   }
 
-  // ---- token caches of objects whose vibe changed (or that were never built), then the shared tables
-  if (o_alive && o_ntok == MG_TOK_DIRTY) {
-    const TokDims td = {d.P, d.TW, d.ND, d.B};
-    o_ntok = (uint32_t)build_tokens(td, hdr, o, o_meta, (uint16_t*)(toks + gl * tokw), E, live);
-    if (live) {
-      const int nwords = (int)(o_ntok + 1) >> 1;
-      for (int k = 0; k < nwords; k++) o[TOKOFF + k] = toks[gl * tokw + k];
-      o[MGO_NTOK] = o_ntok;
+  // ---- token caches: a changed vibe edits the cached list in place (tag tokens, then the vibe token, then
+  // inventory / group / agent id: core/grid_object.cpp:178-203); never-built caches are built from the record
+  {
+    const int nv = __shfl_sync(MG_FULL, new_vibe, o_agent >= 0 ? o_agent : 0, G);
+    const uint32_t oldv = (o_meta >> 16) & 0xffu, newv = (uint32_t)nv & 0xffu;
+    bool rebuild = o_alive && o_ntok == MG_TOK_DIRTY;
+    if (o_alive && o_agent >= 0 && o_agent < A && nv >= 0 && newv != oldv) {
+      o_meta = (o_meta & 0xff00ffffu) | (newv << 16);
+      uint16_t* tk = (uint16_t*)(toks + gl * tokw);
+      const int cap = hdr[MGH_TOK_CAP];
+      if (!rebuild && !(oldv == 0 && (int)o_ntok >= cap)) {
+        int n = (int)o_ntok, p = 0;
+        const uint32_t ftag = (uint32_t)hdr[MGH_FEAT_TAG] & 0xffu;
+#pragma unroll 1
+        while (p < n && (tk[p] & 0xffu) == ftag) p++;
+        const uint16_t vt = (uint16_t)(((uint32_t)hdr[MGH_FEAT_VIBE] & 0xffu) | (newv << 8));
+        if (oldv != 0 && newv != 0) {
+          tk[p] = vt;
+        } else if (oldv == 0) {
+#pragma unroll 1
+          for (int i = n; i > p; i--) tk[i] = tk[i - 1];
+          tk[p] = vt;
+          n++;
+        } else {
+#pragma unroll 1
+          for (int i = p; i + 1 < n; i++) tk[i] = tk[i + 1];
+          n--;
+        }
+        o_ntok = (uint32_t)n;
+        if (live) {
+#pragma unroll 1
+          for (int k = 0; k < (n + 1) >> 1; k++) o[TOKOFF + k] = toks[gl * tokw + k];
+          o[MGO_NTOK] = o_ntok;
+        }
+      } else {
+        rebuild = true;
+      }
+    }
+    if (rebuild) {
+      const TokDims td = {d.P, d.TW, d.ND, d.B, hdr[MGH_TOK_CAP], hdr[MGH_FEAT_TAG], hdr[MGH_FEAT_VIBE], hdr[MGH_FEAT_GROUP],
+                          hdr[MGH_FEAT_AGENT_ID], hdr[MGS_INV_FEATS], hdr[MGS_TEMPLATES]};
+      o_ntok = (uint32_t)build_tokens(td, o, o_meta, (uint16_t*)(toks + gl * tokw), E, live);
+      if (live) {
+        const int nwords = (int)(o_ntok + 1) >> 1;
+#pragma unroll 1
+        for (int k = 0; k < nwords; k++) o[TOKOFF + k] = toks[gl * tokw + k];
+        o[MGO_NTOK] = o_ntok;
+      }
     }
   }
-  oloc[gl] = o_loc;
-  ontok[gl] = o_alive ? o_ntok : 0;
-  stale[gl] = 0;
-  // the stage shares the destination's 16-byte phase so that whole vectors can be streamed out
-  uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
-  const int nbytes = A * 3 * T;
-  uint8_t* stage = gb + ((uint32_t)(uintptr_t)gobs & 15u);
-  {
-    uint4* s4 = (uint4*)gb;
-    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // EmptyTokenByte (:940-942)
-    const int nv = (nbytes + 15 + 16) >> 4;
-    for (int v = gl; v < nv; v += G) s4[v] = ff;
+  // the first eight cached tokens stay in registers for the emission below
+  if (o_ntok != ntok_raw || o_meta != o_meta0) {
+    const uint32_t* rowp = toks + gl * tokw;
+    tw0 = rowp[0], tw1 = rowp[1], tw2 = rowp[2], tw3 = rowp[3];
   }
+  const int my_n = o_alive ? (int)o_ntok : 0;
+  ((uint2*)oloc)[gl] = make_uint2(o_alive ? o_loc : 0x7FFF7FFFu,  // a dead slot lies outside every window
+                                  ((uint32_t)my_n << 8) | (uint32_t)gl);
   __syncwarp();
 
   // ---- observations: sort keys for the objects in this agent's window
-  const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
+  // key = Manhattan rank << 24 | packed offset << 16 | token count << 8 | object lane
   uint32_t key[G];
   uint32_t vismask = 0;
-#pragma unroll
-  for (int j = 0; j < G; j++) {
-    const uint32_t ol = oloc[j];
-    const int dr = (int)(ol >> 16) - r0 + rr, dc = (int)(ol & 0xffffu) - c0 + cr;
-    const bool in = isA && ol != FAST_INVALID && (unsigned)dr <= (unsigned)(2 * rr) && (unsigned)dc <= (unsigned)(2 * cr);
-    const uint32_t loc = (uint32_t)((dr << 4) | dc) & 0xffu;
-    const uint32_t rk = rank[loc];
-    const bool vis = in && rk != 0xffu;
-    key[j] = vis ? ((rk << 16) | (loc << 8) | (uint32_t)j) : FAST_INVALID;
-    vismask |= vis ? (1u << j) : 0u;
-  }
-  // cell staleness (:787-796): the lowest agent index that sees an object claims it
   {
-    uint32_t col = 0;
+    const uint32_t bias = (((uint32_t)(hdr[MGH_OBS_H] >> 1) << 16) | (uint32_t)(hdr[MGH_OBS_W] >> 1)) - my_loc;
 #pragma unroll
     for (int j = 0; j < G; j++) {
-      const uint32_t b = (__ballot_sync(MG_FULL, (vismask >> j) & 1u) & gmask) >> gshift;
-      if (gl == j) col = b;
+      // both offsets in one subtraction; a negative column borrows into the row field but then fails the test
+      const uint2 oi = ((const uint2*)oloc)[j];
+      const uint32_t df = oi.x + bias;
+      const uint32_t kk = lut[((df >> 12) & 0xf0u) | (df & 0xfu)] | oi.y;
+      const bool vis = isA && (df & 0xfff0fff0u) == 0 && kk < 0xff000000u;
+      key[j] = vis ? kk : FAST_INVALID;
+      vismask |= vis ? (1u << j) : 0u;
     }
-    if (o_alive && col != 0) {
-      if (o_vis < step) {
-        atomicAdd(&stale[__ffs(col) - 1], step - o_vis);
-        o_vis = step;
-      }
-    }
+  }
+  // which agents see this lane's object; cell staleness (:787-796) goes to the lowest agent index among them
+  uint32_t col = 0;
+#pragma unroll
+  for (int j = 0; j < G; j++) {
+    const uint32_t b = (__ballot_sync(MG_FULL, (vismask >> j) & 1u) & gmask) >> gshift;
+    if (gl == j) col = b;
+  }
+  if (o_alive && col != 0 && o_vis < step) {
+    atomicAdd(&stale[__ffs(col) - 1], step - o_vis);
+    o_vis = step;
   }
   sort_net<G>(key);
 
@@ -493,39 +567,79 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
       if (dn != 0) put(0xFE, dn > 0 ? hdr[MGH_FEAT_LP_NORTH] : hdr[MGH_FEAT_LP_SOUTH], min(abs(dn), 255));
     }
   }
-  // window tokens in Manhattan order (:756-811)
-  bool more = true;  // keys are sorted: once no lane has a visible object left the rest is skipped
+  // window tokens in Manhattan order (:756-811).  The observer walks its sorted keys once to give every visible
+  // object its first token position; the object lanes then write their own tokens into each observer's row.
+  uint32_t* tab = (uint32_t*)(gb + L.key_off);  // [observer][object] -> first token position | packed offset << 16
 #pragma unroll
   for (int k = 0; k < G; k++) {
     const uint32_t kk = key[k];
-    if (more) more = __any_sync(MG_FULL, kk != FAST_INVALID);
-    if (more && kk != FAST_INVALID) {
-      const int j = (int)(kk & 0xffu);
-      const uint32_t loc = (kk >> 8) & 0xffu;
-      const int n = (int)ontok[j];
-      const uint16_t* tk = (const uint16_t*)(toks + j * tokw);
-      for (int t = 0; t < n; t++) {
-        const uint32_t e = tk[t];
-        put(loc, e & 0xffu, e >> 8);
-      }
+    if (kk != FAST_INVALID) {
+      tab[gl * G + (int)(kk & 0xffu)] = (uint32_t)pos | (kk & 0x00ff0000u);
+      pos += (int)((kk >> 8) & 0xffu);
     }
   }
   const int attempted = pos;
+  __syncwarp();
+  while (col) {
+    const int a = __ffs(col) - 1;
+    col &= col - 1;
+    const uint32_t e = tab[a * G + gl];
+    const int start = (int)(e & 0xffffu);
+    const uint32_t loc = e >> 16;
+    const int m = min(my_n, T - start);  // tokens that fit the budget
+    uint8_t* p = stage + a * 3 * T + start * 3;
+    if (m > 0) {
+      p[0] = (uint8_t)loc, p[1] = (uint8_t)tw0, p[2] = (uint8_t)(tw0 >> 8);
+      if (m > 1) p[3] = (uint8_t)loc, p[4] = (uint8_t)(tw0 >> 16), p[5] = (uint8_t)(tw0 >> 24);
+    }
+    if (m > 2) {
+      p[6] = (uint8_t)loc, p[7] = (uint8_t)tw1, p[8] = (uint8_t)(tw1 >> 8);
+      if (m > 3) p[9] = (uint8_t)loc, p[10] = (uint8_t)(tw1 >> 16), p[11] = (uint8_t)(tw1 >> 24);
+    }
+    if (m > 4) {
+      p[12] = (uint8_t)loc, p[13] = (uint8_t)tw2, p[14] = (uint8_t)(tw2 >> 8);
+      if (m > 5) p[15] = (uint8_t)loc, p[16] = (uint8_t)(tw2 >> 16), p[17] = (uint8_t)(tw2 >> 24);
+    }
+    if (m > 6) {
+      p[18] = (uint8_t)loc, p[19] = (uint8_t)tw3, p[20] = (uint8_t)(tw3 >> 8);
+      if (m > 7) p[21] = (uint8_t)loc, p[22] = (uint8_t)(tw3 >> 16), p[23] = (uint8_t)(tw3 >> 24);
+    }
+    if (m > 8) {  // long token lists continue from the shared table
+      const uint16_t* tk = (const uint16_t*)(toks + gl * tokw);
+#pragma unroll 1
+      for (int t = 8; t < m; t++) {
+        const uint32_t x = tk[t];
+        p[3 * t] = (uint8_t)loc, p[3 * t + 1] = (uint8_t)x, p[3 * t + 2] = (uint8_t)(x >> 8);
+      }
+    }
+  }
   __syncwarp();
 
   // ---- stream the env's observation block out
   {
     const int head = min(nbytes, (int)((16u - ((uint32_t)(uintptr_t)gobs & 15u)) & 15u));
-    if (live)
+    if (live) {
+#pragma unroll 1
       for (int i = gl; i < head; i += G) gobs[i] = stage[i];
+    }
     const int body = (nbytes - head) >> 4;
     const uint4* s4 = (const uint4*)(stage + head);
     uint4* g4 = (uint4*)(gobs + head);
-    if (live)
-      for (int v = gl; v < body; v += G) __stcs(g4 + v, s4[v]);
+    if (live) {
+      int v = gl;
+#pragma unroll 1
+      for (; v + 3 * G < body; v += 4 * G) {
+        const uint4 x0 = s4[v], x1 = s4[v + G], x2 = s4[v + 2 * G], x3 = s4[v + 3 * G];
+        __stcs(g4 + v, x0), __stcs(g4 + v + G, x1), __stcs(g4 + v + 2 * G, x2), __stcs(g4 + v + 3 * G, x3);
+      }
+#pragma unroll 1
+      for (; v < body; v += G) __stcs(g4 + v, s4[v]);
+    }
     const int done = head + (body << 4);
-    if (live)
+    if (live) {
+#pragma unroll 1
       for (int i = done + gl; i < nbytes; i += G) gobs[i] = stage[i];
+    }
   }
 
   // ---- token stats (:659-661, :640-642) and the token budget (:364-375)
@@ -542,6 +656,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
     // is exact, so the sum can be added at once; beyond that the adds are replayed in order.
     const bool slow = gl == 0 && !(tw + (float)sw < 16777216.0f && tf + (float)sf < 16777216.0f);
     if (__any_sync(MG_FULL, slow)) {
+#pragma unroll 1
       for (int a = 0; a < A; a++) {
         const int at = __shfl_sync(MG_FULL, attempted, a, G);
         if (slow && at <= T) {
@@ -582,32 +697,31 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32) k_step_fast(const MgDev d,
   // ---- per-agent write-back: stats, coverage (objects/agent.cpp:49-57), flags
   __syncwarp();
   if (isA && live) {
-    uint32_t nt0 = t0, nt1 = t1;
-    auto touch = [&](int id) {
-      if (id < 32)
-        nt0 |= 1u << id;
-      else
-        nt1 |= 1u << (id - 32);
-    };
-    for (int k = 0; k < ninv; k++) s_inv = __fadd_rn(s_inv, (float)npass);  // once per priority pass
-    if (ninv) st[id_inv] = s_inv, touch(id_inv);
-    if (swm_peak && (float)swm_peak > s_swm) st[id_swm] = (float)swm_peak, touch(id_swm);
-    if (id_p >= 0) st[id_p] = __fadd_rn(s_p, 1.0f), touch(id_p);
-    if (id_v >= 0) st[id_v] = __fadd_rn(s_v, 1.0f), touch(id_v);
-    for (int k = 0; k < nfail; k++) s_fail = __fadd_rn(s_fail, 1.0f);
-    if (nfail) st[id_fail] = s_fail, touch(id_fail);
+    uint64_t touched = 0;  // well-known stat ids are below 64 (checked by mg_create)
+    const float fpass = (float)npass;
+    if (ninv >= 1) s_inv = __fadd_rn(s_inv, fpass);  // once per priority pass
+    if (ninv >= 2) s_inv = __fadd_rn(s_inv, fpass);
+    if (ninv) st[id_inv] = s_inv, touched |= 1ull << id_inv;
+    if (swm_peak && (float)swm_peak > s_swm) st[id_swm] = (float)swm_peak, touched |= 1ull << id_swm;
+    if (id_p >= 0) st[id_p] = __fadd_rn(s_p, 1.0f), touched |= 1ull << id_p;
+    if (id_v >= 0) st[id_v] = __fadd_rn(s_v, 1.0f), touched |= 1ull << id_v;
+    if (nfail >= 1) s_fail = __fadd_rn(s_fail, 1.0f);
+    if (nfail >= 2) s_fail = __fadd_rn(s_fail, 1.0f);
+    if (nfail) st[id_fail] = s_fail, touched |= 1ull << id_fail;
     const uint32_t bit = 1u << (cell & 31);
     if (!(cvw & bit)) {
       *cvp = cvw | bit;
       ag[MGAG_UNIQUE] = ++a_unique;
     }
-    st[id_un] = (float)a_unique, touch(id_un);
+    st[id_un] = (float)a_unique;
     const uint32_t dist = (uint32_t)(abs((int)(a_spawn >> 16) - r0) + abs(c0 - (int)(a_spawn & 0xffffu)));
     const uint32_t md = max(a_maxd, dist);
     if (md != a_maxd) ag[MGAG_MAX_DIST] = md;
-    st[id_md] = (float)md, touch(id_md);
+    st[id_md] = (float)md;
+    touched |= (1ull << id_un) | (1ull << id_md);
     const uint32_t ssum = stale[gl];
-    if (ssum) st[id_cv] = __fadd_rn(s_cv, (float)ssum), touch(id_cv);
+    if (ssum) st[id_cv] = __fadd_rn(s_cv, (float)ssum), touched |= 1ull << id_cv;
+    const uint32_t nt0 = t0 | (uint32_t)touched, nt1 = t1 | (uint32_t)(touched >> 32);
     if (nt0 != t0) tch[0] = nt0;
     if (nt1 != t1) tch[1] = nt1;
     if (prev != a_prev) ag[MGAG_PREV_LOC] = prev;
@@ -642,24 +756,27 @@ static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap) {
   MgFastLayout L;
   L.G = G;
-  L.rank_off = (int)al16(MGH_HEADER_WORDS * 4);
-  L.cta_bytes = L.rank_off + 256;
+  L.rank_off = 0;
+  L.cta_bytes = 1024;  // the window table
   size_t n = al16((size_t)d.A * 3 * d.T + 16) + 16;  // stage (+ phase slack)
   L.tok_stride = ((tok_cap + 1) / 2) | 1;               // odd word stride: conflict-free columns
+  if (L.tok_stride < 5) L.tok_stride = 5;               // the first four words are always staged
   L.tok_off = (int)n;
   n += al16((size_t)G * L.tok_stride * 4);
   L.oloc_off = (int)n;
   n += al16((size_t)G * 4 * 4 + G);  // oloc, ontok, stale, draw, order
+  L.key_off = (int)n;
+  n += (size_t)G * G * 4;  // sorted window keys, one column per lane
   L.group_bytes = (int)n;
   L.smem_bytes = L.cta_bytes + (size_t)MG_FAST_WARPS * (32 / G) * L.group_bytes;
   return L;
 }
 
 template <int G>
-static cudaError_t launch_fast(const MgDev& d, const MgFastLayout& L, cudaStream_t st) {
+static cudaError_t launch_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
   const int envs_per_cta = MG_FAST_WARPS * (32 / G);
   const int grid = (d.num_envs + envs_per_cta - 1) / envs_per_cta;
-  k_step_fast<G><<<grid, MG_FAST_WARPS * 32, L.smem_bytes, st>>>(d, L);
+  k_step_fast<G><<<grid, MG_FAST_WARPS * 32, L.smem_bytes, st>>>(d, L, H);
   return cudaGetLastError();
 }
 
@@ -675,10 +792,10 @@ cudaError_t mg_fast_configure(const MgFastLayout& L) {
   return cudaFuncSetAttribute(k_step_fast<32>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
 }
 
-cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, cudaStream_t st) {
+cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
   switch (L.G) {
-    case 8: return launch_fast<8>(d, L, st);
-    case 16: return launch_fast<16>(d, L, st);
-    default: return launch_fast<32>(d, L, st);
+    case 8: return launch_fast<8>(d, L, H, st);
+    case 16: return launch_fast<16>(d, L, H, st);
+    default: return launch_fast<32>(d, L, H, st);
   }
 }

@@ -11,6 +11,9 @@
 #ifndef MG_FAST_WARPS
 #define MG_FAST_WARPS 2  // warps per CTA of k_step_fast (mg_fast.cu)
 #endif
+#ifndef MG_FAST_MIN_CTAS
+#define MG_FAST_MIN_CTAS 8  // <= 128 registers: 16 resident warps per SM, one wave for 4096 envs x 16 agents
+#endif
 #define MG_RNG_WINDOW 32
 #define MG_TAG_LIST_CAP 64
 
@@ -19,7 +22,8 @@ struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
-  const uint8_t* rank_lut;  // [256] (dr + rr) << 4 | (dc + cr) -> position in Manhattan order, 0xFF outside the shape
+  const uint32_t* rank_lut;  // [256] packed window offset (dr + rr) << 4 | (dc + cr) -> rank << 24 | offset << 16, where rank is
+                             // the position in Manhattan order; 0xFFFFFF00 outside the shape
   int plain;    // 1: the program has no handlers / rewards / world systems (k_step<PLAIN> applies)
   int PAD, WP;  // the grid is stored with a PAD-wide empty frame (row pitch WP) so observation windows need no bounds tests
   // persistent state
@@ -63,6 +67,10 @@ struct MgDev {
 struct MgFastLayout {
   int G;           // lanes per environment: 8, 16 or 32
   int rank_off, cta_bytes;
-  int tok_off, tok_stride, oloc_off, group_bytes;
+  int tok_off, tok_stride, oloc_off, key_off, group_bytes;
   size_t smem_bytes;
+};
+// the program header as a kernel argument (constant bank)
+struct MgFastHdr {
+  int v[MGH_HEADER_WORDS];
 };
