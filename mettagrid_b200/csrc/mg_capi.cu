@@ -19,6 +19,8 @@ cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
 MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap);
 cudaError_t mg_fast_configure(const MgFastLayout& L);
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
+cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st);
+cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st);
 
@@ -33,6 +35,9 @@ struct mg_handle {
   bool fast = false;  // k_step_fast applies (mg_fast.cu): plain program, sparse environments
   MgFastLayout fl{};
   MgFastHdr fh{};
+  // which copy of the hot state is current on a fast handle: the generic arrays, the packed block, or both
+  enum { BOTH = 0, GENERIC = 1, PACKED = 2 };
+  int newest = GENERIC;
   // device-side staging for mg_step_host
   int32_t* h_act = nullptr;
   int32_t* h_vact = nullptr;
@@ -54,6 +59,33 @@ static std::string g_create_error;
       return MG_E_CUDA;                                                                            \
     }                                                                                              \
   } while (0)
+
+// make the generic arrays current (before anything but mg_step reads or edits them)
+static int sync_generic(mg_handle* h, cudaStream_t st) {
+  if (h->fast && h->newest == mg_handle::PACKED) {
+    CK(mg_launch_fast_unpack(h->d, h->fl, h->fh, st));
+    h->newest = mg_handle::BOTH;
+  }
+  return MG_OK;
+}
+static int launch_step(mg_handle* h, const MgDev& dev, cudaStream_t st) {
+  if (!h->fast) {
+    CK(mg_launch_step(dev, st));
+    return MG_OK;
+  }
+  if (h->newest == mg_handle::GENERIC) CK(mg_launch_fast_pack(dev, h->fl, h->fh, nullptr, st));
+  CK(mg_launch_step_fast(dev, h->fl, h->fh, st));
+  h->newest = mg_handle::PACKED;
+  return MG_OK;
+}
+
+// all queued work done and the generic arrays current: what the host-side getters read
+static int sync_host_view(mg_handle* h) {
+  CK(cudaDeviceSynchronize());
+  if (int rc = sync_generic(h, h->own_stream)) return rc;
+  CK(cudaStreamSynchronize(h->own_stream));
+  return MG_OK;
+}
 
 template <class T>
 static int dev_alloc(mg_handle* h, T** p, size_t count) {
@@ -93,7 +125,7 @@ static int fast_group_size(const int32_t* P, const MgDev& d, int max_objects_per
   if ((d.AS & 3) || (d.OS & 3)) return 0;  // vector loads of the records
   if (d.A > 32 || max_objects_per_env > 32 || P[MGH_OBS_H] > 15 || P[MGH_OBS_W] > 15 || P[MGH_TOK_CAP] > 126) return 0;
   for (int k = MGH_ST_ACTION_FAILED; k <= MGH_ST_VIBE_FAILED; k++)
-    if (P[k] < 0 || P[k] >= 64) return 0;
+    if (P[k] < 0 || P[k] >= MGFB_STATS) return 0;
   const int32_t* acts = P + P[MGS_ACTIONS];
   for (int i = 0; i < P[MGH_NUM_ACTIONS]; i++) {
     const int kind = acts[i * MG_ACTION_WORDS], is_vibe = acts[i * MG_ACTION_WORDS + 3];
@@ -269,10 +301,13 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   if (const int G = fast_group_size(P, d, max_objs)) {
     h->fl = mg_fast_layout(d, G, P[MGH_TOK_CAP]);
     memcpy(h->fh.v, P, sizeof h->fh.v);
-    if (h->fl.smem_bytes <= 200 * 1024 && mg_fast_configure(h->fl) == cudaSuccess)
+    if (h->fl.smem_bytes <= 200 * 1024 && mg_fast_configure(h->fl) == cudaSuccess) {
+      d.fast_stride = MGFB_WORDS(G);
+      TRY(dev_alloc(h, &d.fast_blk, N * d.fast_stride));
       h->fast = true;
-    else
+    } else {
       cudaGetLastError();  // too large for shared memory: the generic kernel runs instead
+    }
   }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     h->err = "mg_create: stream creation failed";
@@ -311,7 +346,9 @@ int mg_set_buffers(mg_handle* h, void* observations, void* terminals, void* trun
   d.obs = (uint8_t*)observations, d.terminals = (uint8_t*)terminals, d.truncations = (uint8_t*)truncations;
   d.rewards = (float*)rewards, d.actions = (const int32_t*)actions, d.vibe_actions = (const int32_t*)vibe_actions;
   h->buffers_set = true;
+  if (int rc = sync_generic(h, (cudaStream_t)stream)) return rc;
   CK(mg_launch_init_buffers(d, nullptr, (cudaStream_t)stream));
+  if (h->fast) h->newest = mg_handle::GENERIC;
   return MG_OK;
 }
 
@@ -321,8 +358,7 @@ int mg_step(mg_handle* h, void* stream) {
     h->err = "mg_step: call mg_set_buffers first";
     return MG_E_INVALID;
   }
-  CK(h->fast ? mg_launch_step_fast(h->d, h->fl, h->fh, (cudaStream_t)stream) : mg_launch_step(h->d, (cudaStream_t)stream));
-  return MG_OK;
+  return launch_step(h, h->d, (cudaStream_t)stream);
 }
 
 int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actions, uint8_t* observations,
@@ -350,7 +386,10 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
   MgDev run = d;
   run.obs = h->h_obs, run.terminals = h->h_term, run.truncations = h->h_trunc, run.rewards = h->h_rew;
   run.actions = h->h_act, run.vibe_actions = h->h_vact;
-  CK(h->fast ? mg_launch_step_fast(run, h->fl, h->fh, st) : mg_launch_step(run, st));
+  {
+    const int rc = launch_step(h, run, st);
+    if (rc) return rc;
+  }
   if (observations) CK(cudaMemcpyAsync(observations, h->h_obs, NA * d.T * 3, cudaMemcpyDeviceToHost, st));
   if (rewards) CK(cudaMemcpyAsync(rewards, h->h_rew, NA * 4, cudaMemcpyDeviceToHost, st));
   if (terminals) CK(cudaMemcpyAsync(terminals, h->h_term, NA, cudaMemcpyDeviceToHost, st));
@@ -366,6 +405,14 @@ int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, v
   if (new_seeds) CK(cudaMemcpyAsync(h->seeds_dev, new_seeds, (size_t)h->d.num_envs * 4, cudaMemcpyHostToDevice, st));
   CK(mg_launch_reset(h->d, env_mask, st));
   if (h->buffers_set) CK(mg_launch_init_buffers(h->d, env_mask, st));
+  if (h->fast) {
+    // a full reset makes the generic arrays the truth; a masked one re-packs just the rebuilt environments so
+    // that the others never leave the packed block
+    if (!env_mask)
+      h->newest = mg_handle::GENERIC;
+    else if (h->newest != mg_handle::GENERIC)
+      CK(mg_launch_fast_pack(h->d, h->fl, h->fh, env_mask, st));
+  }
   return MG_OK;
 }
 
@@ -410,7 +457,7 @@ int mg_get_current_steps(mg_handle* h, int32_t* out) {
   if (!h || !out) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   std::vector<int32_t> e((size_t)h->d.num_envs * MGEV_WORDS);
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_host_view(h)) return rc;
   CK(cudaMemcpy(e.data(), h->d.env, e.size() * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < h->d.num_envs; i++) out[i] = e[(size_t)i * MGEV_WORDS + MGEV_STEP];
   return MG_OK;
@@ -420,7 +467,7 @@ int mg_get_agent_stats(mg_handle* h, int env, float* values, uint8_t* touched) {
   if (!h || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   const MgDev& d = h->d;
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_host_view(h)) return rc;
   if (values) CK(cudaMemcpy(values, d.astats + (size_t)env * d.A * d.SA, (size_t)d.A * d.SA * 4, cudaMemcpyDeviceToHost));
   if (touched) {
     std::vector<uint32_t> t((size_t)d.A * d.SAW);
@@ -435,7 +482,7 @@ int mg_get_game_stats(mg_handle* h, int env, float* values, uint8_t* touched) {
   if (!h || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   const MgDev& d = h->d;
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_host_view(h)) return rc;
   if (values) CK(cudaMemcpy(values, d.gstats + (size_t)env * d.SG, (size_t)d.SG * 4, cudaMemcpyDeviceToHost));
   if (touched) {
     std::vector<uint32_t> t(d.SGW);
@@ -449,7 +496,7 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
   if (!h || !out || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   const MgDev& d = h->d;
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_host_view(h)) return rc;
   int32_t E[MGEV_WORDS];
   CK(cudaMemcpy(E, d.env + (size_t)env * MGEV_WORDS, sizeof E, cudaMemcpyDeviceToHost));
   int nobj = E[MGEV_NEXT_OBJ];
@@ -494,11 +541,12 @@ int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, con
     e = cudaMemcpy(buf, items, (size_t)n * 4, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(buf + n, amounts, (size_t)n * 4, cudaMemcpyHostToDevice);
   }
-  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && sync_host_view(h) != MG_OK) e = cudaErrorUnknown;
   if (e == cudaSuccess) e = mg_launch_set_inventory(h->d, env, agent, buf, buf + n, n, h->own_stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
   cudaFree(buf);
   CK(e);
+  if (h->fast) h->newest = mg_handle::GENERIC;
   return MG_OK;
 }
 

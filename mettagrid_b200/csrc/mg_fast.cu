@@ -59,8 +59,8 @@ __device__ __forceinline__ uint32_t rng_below_direct(uint32_t* rng, int& idx, ui
 }
 // libstdc++ std::shuffle (bits/stl_algo.h:3719-3805), serial, for the rare tick where a draw is rejected or the
 // draws straddle the end of the 624-word state
-__device__ __noinline__ void shuffle_serial(uint32_t* rng, int32_t* E, uint8_t* v, int n) {
-  int idx = E[MGEV_RNG_IDX];
+__device__ __noinline__ void shuffle_serial(uint32_t* rng, uint32_t* idx_word, uint8_t* v, int n) {
+  int idx = (int)*idx_word;
   int i = 1;
   if ((n & 1) == 0) {
     int j = (int)rng_below_direct(rng, idx, 2);
@@ -79,7 +79,7 @@ __device__ __noinline__ void shuffle_serial(uint32_t* rng, int32_t* E, uint8_t* 
     v[i] = v[p1], v[p1] = t;
     i++;
   }
-  E[MGEV_RNG_IDX] = idx;
+  *idx_word = (uint32_t)idx;
 }
 
 __device__ __forceinline__ void set_error(int32_t* E, int code, int info) {
@@ -192,26 +192,26 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const size_t g0 = (size_t)env * A;
   const bool isA = gl < A;
   const size_t ga = g0 + (isA ? gl : 0);
-  int32_t* E = d.env + (size_t)env * MGEV_WORDS;
+  int32_t* E = d.env + (size_t)env * MGEV_WORDS;  // only the error words live here
   uint32_t* rng = d.rng + (size_t)env * MG_RNG_WORDS;
-  uint32_t* ag = d.agents + ga * d.AS;
+  uint32_t* blk = d.fast_blk + (size_t)env * d.fast_stride;  // the env's packed hot state (mg_state.h)
+  uint32_t* bag = blk + MGFB_AGENT(G, gl);
+  uint32_t* bob = blk + MGFB_OBJECT(G, gl);
+  float* bst = (float*)(blk + MGFB_STAT(G, 0, gl));  // stat id at bst[id * G]
   uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NTERR) + (size_t)min(gl + 1, d.maxobj - 1)) * d.OS;
-  float* st = d.astats + ga * d.SA;
-  uint32_t* tch = d.atouched + ga * d.SAW;
   uint32_t* cvrow = d.cover + ga * d.CW;
-  float* gs = d.gstats + (size_t)env * d.SG;
-  uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
   const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
   const int tokw = L.tok_stride;  // words per object in the shared token table
 
   // ---- wave 1: every load whose address is known up front is issued before anything is consumed
-  const int e_step = E[MGEV_STEP], e_idx = E[MGEV_RNG_IDX], e_nobj = E[MGEV_NEXT_OBJ];
+  const uint4 bh0 = *(const uint4*)blk;        // step, rng index, objects, tokens_written
+  const uint4 bh1 = *(const uint4*)(blk + 4);  // tokens_free, touched game stats
   const int ia_raw = d.actions[ga], iv_raw = d.vibe_actions[ga];
-  const uint4 ag0 = *(const uint4*)ag;        // MGAG_OBJ, MGAG_SPAWN, MGAG_PREV_LOC, MGAG_STEP_LOC
-  const uint4 ag1 = *(const uint4*)(ag + 4);  // MGAG_SWM, MGAG_MAX_DIST, MGAG_UNIQUE, MGAG_EPISODE_REWARD
-  const uint4 orec = *(const uint4*)o;        // MGO_LOC, MGO_VISITED, MGO_META, MGO_AGENT
-  const uint32_t ntok_raw = o[MGO_NTOK];
-  uint32_t tw0 = o[TOKOFF], tw1 = o[TOKOFF + 1], tw2 = o[TOKOFF + 2], tw3 = o[TOKOFF + 3];  // first 8 cached tokens
+  const uint4 ag0 = *(const uint4*)bag;        // obj slot, spawn, prev_location, steps_without_motion
+  const uint4 ag1 = *(const uint4*)(bag + 4);  // max_dist, unique cells, touched bits
+  const uint4 orec = *(const uint4*)bob;       // loc, visited, meta, agent + 1 | ntok << 8 | dirty << 16
+  const uint4 otok = *(const uint4*)(bob + 4); // first eight cached tokens
+  const float s_cv0 = bst[hdr[MGH_ST_CELL_VISITED] * G];
   constexpr int LV = (64 + MG_FAST_WARPS * 32 - 1) / (MG_FAST_WARPS * 32);  // window-table vectors per thread
   uint4 lutv[LV];
 #pragma unroll
@@ -219,15 +219,13 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const int i = tid + k * MG_FAST_WARPS * 32;
     lutv[k] = i < 64 ? __ldg((const uint4*)d.rank_lut + i) : make_uint4(0, 0, 0, 0);
   }
-  // the rows the end of the tick updates: pull them towards L2 now
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(st));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(st + 8));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(tch));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(cvrow));
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(cvrow + 8));
-  if (gl == 0) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(gs + hdr[MGH_GST_TOKENS_WRITTEN]));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(gt));
+  if (gl < MGFB_STATS / 2) {  // the stat rows the end of the tick may update: pull them towards L2 now
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + MGFB_STAT(G, 2 * gl, 0)));
+    if (G > 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + MGFB_STAT(G, 2 * gl + 1, 0)));
+    if (G > 16) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + MGFB_STAT(G, 2 * gl, 16)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + MGFB_STAT(G, 2 * gl + 1, 16)));
+    }
   }
 
 #pragma unroll
@@ -235,19 +233,21 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const int i = tid + k * MG_FAST_WARPS * 32;
     if (i < 64) ((uint4*)lut)[i] = lutv[k];
   }
-  const uint32_t step = (uint32_t)e_step + 1u;  // :951
-  int idx0 = e_idx;
-  const int nobj = e_nobj - 1;
+  const uint32_t step = bh0.x + 1u;  // :951
+  int idx0 = (int)bh0.y;
+  const int nobj = (int)bh0.z;
   const int ia = isA ? ia_raw : -1, iv = isA ? iv_raw : -1;
-  const uint32_t a_slot = isA ? ag0.x : 1u, a_spawn = ag0.y, a_prev = ag0.z, a_swm = ag1.x, a_maxd = ag1.y;
-  uint32_t a_unique = ag1.z;
+  const uint32_t a_slot = isA ? ag0.x : 1u, a_spawn = ag0.y, a_prev = ag0.z, a_swm = ag0.w, a_maxd = ag1.x;
+  uint32_t a_unique = ag1.y;
   const bool isO = gl < nobj;
-  uint32_t o_loc = orec.x, o_vis = orec.y, o_meta = orec.z, o_ntok = ntok_raw;
-  const int o_agent = isO ? (int)orec.w : -1;
+  uint32_t o_loc = orec.x, o_vis = orec.y, o_meta = orec.z;
+  uint32_t o_ntok = (orec.w & MGFB_DIRTY) ? MG_TOK_DIRTY : ((orec.w >> 8) & 0xffu);
+  const uint32_t ntok_raw = o_ntok;
+  const int o_agent = isO ? (int)(orec.w & 0xffu) - 1 : -1;
+  uint32_t tw0 = otok.x, tw1 = otok.y, tw2 = otok.z, tw3 = otok.w;
   const bool o_alive = isO && ((o_meta >> 24) & MGOF_ALIVE);
   if (!o_alive) o_loc = FAST_INVALID;
   const uint32_t o_loc0 = o_loc, o_vis0 = o_vis, o_meta0 = o_meta;
-
   // ---- wave 2: action rows, RNG words, the rest of long token caches
   const int NA = hdr[MGH_NUM_ACTIONS];
   const int32_t* acts = d.P + hdr[MGS_ACTIONS];
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     uint32_t* row = toks + gl * tokw;
     row[0] = tw0, row[1] = tw1, row[2] = tw2, row[3] = tw3;  // tokw >= 5
 #pragma unroll 1
-    for (int k = 4; k < nwords; k++) row[k] = o[TOKOFF + k];
+    for (int k = 4; k < nwords; k++) row[k] = o[TOKOFF + k];  // long lists keep their tail in the object record
   }
   // independent work while wave 2 is in flight: the observation stage starts as all EmptyTokenByte (:940-942);
   // it shares the destination's 16-byte phase so that whole vectors can be streamed out
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     __syncwarp(gmask);
     if (isA) order[gl] = (uint8_t)gl;
     __syncwarp(gmask);
-    if (gl == 0 && A >= 2 && live) shuffle_serial(rng, E, order, A);  // a mirror group leaves the state alone
+    if (gl == 0 && A >= 2 && live) shuffle_serial(rng, blk + MGFB_RNG_IDX, order, A);  // a mirror group leaves the state alone
     __syncwarp(gmask);
     if (isA) my_order = order[gl];
   } else {
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     }
   }
   if (!rej && live && gl < ndraws) rng[idx0 + gl] = nw;
-  if (!rej && live && gl == 0 && ndraws > 0) E[MGEV_RNG_IDX] = idx0 + ndraws;
+  if (!rej && live && gl == 0 && ndraws > 0) blk[MGFB_RNG_IDX] = (uint32_t)(idx0 + ndraws);
   __syncthreads();  // the window table (per CTA)
 
   // ---- moves in shuffled order, highest priority first (actions/move.hpp:81-115 with the two default
@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // step i wants; the loop then only carries the object locations from step to step.
   const int my_ol = (int)a_slot - 1;  // lane that plays this agent's object
   const uint32_t my_loc0 = __shfl_sync(MG_FULL, o_loc, my_ol, G);
+  if (isA && my_loc0 != FAST_INVALID)  // the coverage word this agent most likely needs (it moves at most one cell)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(cvrow + (((my_loc0 >> 16) * d.W + (my_loc0 & 0xffffu)) >> 5)));
   uint32_t my_tgt = FAST_INVALID;
   const bool wants_move = act_p && ap.x == MGA_MOVE;
   if (wants_move) {  // actions/orientation.hpp:28-48
@@ -423,30 +425,20 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const int ninv = (isA && inv_p ? 1 : 0) + (isA && inv_v ? 1 : 0);
   const int id_fail = hdr[MGH_ST_ACTION_FAILED], id_inv = hdr[MGH_ST_INVALID_INDEX], id_swm = hdr[MGH_ST_MAX_SWM];
   const int id_cv = hdr[MGH_ST_CELL_VISITED], id_un = hdr[MGH_ST_UNIQUE_VISITED], id_md = hdr[MGH_ST_MAX_DIST];
-  float s_p = 0.f, s_v = 0.f, s_fail = 0.f, s_inv = 0.f, s_swm = 0.f, s_cv = 0.f;
-  if (id_p >= 0) s_p = st[id_p];
-  if (id_v >= 0) s_v = st[id_v];
-  if (nfail) s_fail = st[id_fail];
-  if (ninv) s_inv = st[id_inv];
-  if (swm_peak) s_swm = st[id_swm];
-  if (isA) s_cv = st[id_cv];
-  uint32_t t0 = 0, t1 = 0;
-  if (isA) {
-    t0 = tch[0];
-    if (d.SAW > 1) t1 = tch[1];
-  }
+  float s_p = 0.f, s_v = 0.f, s_fail = 0.f, s_inv = 0.f, s_swm = 0.f;
+  const float s_cv = s_cv0;
+  if (id_p >= 0) s_p = bst[id_p * G];
+  if (id_v >= 0) s_v = bst[id_v * G];
+  if (nfail) s_fail = bst[id_fail * G];
+  if (ninv) s_inv = bst[id_inv * G];
+  if (swm_peak) s_swm = bst[id_swm * G];
+  const uint32_t t0 = ag1.z;
   const int r0 = (int)(my_loc >> 16), c0 = (int)(my_loc & 0xffffu);
   const int cell = r0 * d.W + c0;
   uint32_t* cvp = cvrow + (isA ? (cell >> 5) : 0);
   uint32_t cvw = 0;
   if (isA) cvw = *cvp;
-  const int idw = hdr[MGH_GST_TOKENS_WRITTEN], idf = hdr[MGH_GST_TOKENS_FREE], idd = hdr[MGH_GST_TOKENS_DROPPED];
-  float tw = 0.f, tf = 0.f;
-  uint32_t gtw = 0, gtd = 0, gtf = 0;
-  if (gl == 0) {
-    tw = gs[idw], tf = gs[idf];
-    gtw = gt[idw >> 5], gtd = gt[idd >> 5], gtf = gt[idf >> 5];
-  }
+  float tw = __uint_as_float(bh0.w), tf = __uint_as_float(bh1.x);
 
   // ---- token caches: a changed vibe edits the cached list in place (tag tokens, then the vibe token, then
   // inventory / group / agent id: core/grid_object.cpp:178-203); never-built caches are built from the record
@@ -479,8 +471,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
         o_ntok = (uint32_t)n;
         if (live) {
 #pragma unroll 1
-          for (int k = 0; k < (n + 1) >> 1; k++) o[TOKOFF + k] = toks[gl * tokw + k];
-          o[MGO_NTOK] = o_ntok;
+          for (int k = 4; k < (n + 1) >> 1; k++) o[TOKOFF + k] = toks[gl * tokw + k];
         }
       } else {
         rebuild = true;
@@ -493,8 +484,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       if (live) {
         const int nwords = (int)(o_ntok + 1) >> 1;
 #pragma unroll 1
-        for (int k = 0; k < nwords; k++) o[TOKOFF + k] = toks[gl * tokw + k];
-        o[MGO_NTOK] = o_ntok;
+        for (int k = 4; k < nwords; k++) o[TOKOFF + k] = toks[gl * tokw + k];
       }
     }
   }
@@ -669,23 +659,9 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       tw = __fadd_rn(tw, (float)sw);
       tf = __fadd_rn(tf, (float)sf);
     }
-    if (gl == 0 && live) {
-      gs[idw] = tw, gs[idf] = tf;
-      // touch tokens_written / tokens_dropped / tokens_free_space; the three ids may share a word
-      uint32_t* pw = gt + (idw >> 5);
-      uint32_t* pd = gt + (idd >> 5);
-      uint32_t* pf = gt + (idf >> 5);
-      const uint32_t bw = 1u << (idw & 31), bd = 1u << (idd & 31), bf = 1u << (idf & 31);
-      uint32_t nwv = gtw | bw;
-      if (pd == pw) nwv |= bd;
-      if (pf == pw) nwv |= bf;
-      if (nwv != gtw) *pw = nwv;
-      if (pd != pw) {
-        uint32_t nd = gtd | bd;
-        if (pf == pd) nd |= bf;
-        if (nd != gtd) *pd = nd;
-      }
-      if (pf != pw && pf != pd && (gtf | bf) != gtf) *pf = gtf | bf;
+    if (gl == 0 && live) {  // tokens_written, tokens_free_space, and the touched flags of the three token stats
+      blk[MGFB_TOKENS_WRITTEN] = __float_as_uint(tw), blk[MGFB_TOKENS_FREE] = __float_as_uint(tf);
+      if ((bh1.y & 7u) != 7u) blk[MGFB_GTOUCHED] = bh1.y | 7u;
     }
     if (__any_sync(MG_FULL, ov != 0)) {  // hard error in the reference; the first agent in index order is reported
       const int a = ov ? __ffs(ov) - 1 : 0;
@@ -697,35 +673,32 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // ---- per-agent write-back: stats, coverage (objects/agent.cpp:49-57), flags
   __syncwarp();
   if (isA && live) {
-    uint64_t touched = 0;  // well-known stat ids are below 64 (checked by mg_create)
+    uint32_t touched = 0;  // well-known stat ids are below 16 (checked by mg_create)
     const float fpass = (float)npass;
     if (ninv >= 1) s_inv = __fadd_rn(s_inv, fpass);  // once per priority pass
     if (ninv >= 2) s_inv = __fadd_rn(s_inv, fpass);
-    if (ninv) st[id_inv] = s_inv, touched |= 1ull << id_inv;
-    if (swm_peak && (float)swm_peak > s_swm) st[id_swm] = (float)swm_peak, touched |= 1ull << id_swm;
-    if (id_p >= 0) st[id_p] = __fadd_rn(s_p, 1.0f), touched |= 1ull << id_p;
-    if (id_v >= 0) st[id_v] = __fadd_rn(s_v, 1.0f), touched |= 1ull << id_v;
+    if (ninv) bst[id_inv * G] = s_inv, touched |= 1u << id_inv;
+    if (swm_peak && (float)swm_peak > s_swm) bst[id_swm * G] = (float)swm_peak, touched |= 1u << id_swm;
+    if (id_p >= 0) bst[id_p * G] = __fadd_rn(s_p, 1.0f), touched |= 1u << id_p;
+    if (id_v >= 0) bst[id_v * G] = __fadd_rn(s_v, 1.0f), touched |= 1u << id_v;
     if (nfail >= 1) s_fail = __fadd_rn(s_fail, 1.0f);
     if (nfail >= 2) s_fail = __fadd_rn(s_fail, 1.0f);
-    if (nfail) st[id_fail] = s_fail, touched |= 1ull << id_fail;
+    if (nfail) bst[id_fail * G] = s_fail, touched |= 1u << id_fail;
     const uint32_t bit = 1u << (cell & 31);
     if (!(cvw & bit)) {
       *cvp = cvw | bit;
-      ag[MGAG_UNIQUE] = ++a_unique;
+      ++a_unique;
     }
-    st[id_un] = (float)a_unique;
+    bst[id_un * G] = (float)a_unique;
     const uint32_t dist = (uint32_t)(abs((int)(a_spawn >> 16) - r0) + abs(c0 - (int)(a_spawn & 0xffffu)));
     const uint32_t md = max(a_maxd, dist);
-    if (md != a_maxd) ag[MGAG_MAX_DIST] = md;
-    st[id_md] = (float)md;
-    touched |= (1ull << id_un) | (1ull << id_md);
+    bst[id_md * G] = (float)md;
+    touched |= (1u << id_un) | (1u << id_md);
     const uint32_t ssum = stale[gl];
-    if (ssum) st[id_cv] = __fadd_rn(s_cv, (float)ssum), touched |= 1ull << id_cv;
-    const uint32_t nt0 = t0 | (uint32_t)touched, nt1 = t1 | (uint32_t)(touched >> 32);
-    if (nt0 != t0) tch[0] = nt0;
-    if (nt1 != t1) tch[1] = nt1;
-    if (prev != a_prev) ag[MGAG_PREV_LOC] = prev;
-    if (swm != a_swm) ag[MGAG_SWM] = swm;
+    if (ssum) bst[id_cv * G] = __fadd_rn(s_cv, (float)ssum), touched |= 1u << id_cv;
+    const uint32_t nt0 = t0 | touched;
+    if (prev != a_prev || swm != a_swm) *(uint2*)(bag + 2) = make_uint2(prev, swm);
+    if (md != a_maxd || a_unique != ag1.y || nt0 != t0) *(uint4*)(bag + 4) = make_uint4(md, a_unique, nt0, 0);
     bool success = ok_p;  // same update order as handle_action's caller: primary stream, then vibe stream
     if (inv_v) success = false;
     if (ok_v) success = true;
@@ -741,11 +714,107 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   // ---- object write-back
   if (o_alive && live) {
-    if (o_loc != o_loc0) o[MGO_LOC] = o_loc;
-    if (o_vis != o_vis0) o[MGO_VISITED] = o_vis;
-    if (o_meta != o_meta0) o[MGO_META] = o_meta;
+    const uint32_t w3 = (orec.w & 0xffu) | ((o_ntok & 0xffu) << 8);
+    if (o_loc != o_loc0 || o_vis != o_vis0 || o_meta != o_meta0 || w3 != orec.w) *(uint4*)bob = make_uint4(o_loc, o_vis, o_meta, w3);
+    if (o_ntok != ntok_raw || o_meta != o_meta0) *(uint4*)(bob + 4) = make_uint4(tw0, tw1, tw2, tw3);
   }
-  if (gl == 0 && live) E[MGEV_STEP] = (int32_t)step;
+  if (gl == 0 && live) blk[MGFB_STEP] = step;
+}
+
+
+// ---- generic arrays <-> packed hot state (layout in mg_state.h); one thread per (env, lane) --------------
+__global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, const uint8_t* __restrict__ mask) {
+  const int* const hdr = HD.v;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = (int)(t / G), gl = (int)(t % G);
+  if (env >= d.num_envs || (mask && !mask[env])) return;
+  uint32_t* blk = d.fast_blk + (size_t)env * d.fast_stride;
+  const int32_t* E = d.env + (size_t)env * MGEV_WORDS;
+  const int nobj = E[MGEV_NEXT_OBJ] - 1;
+  if (gl == 0) {
+    const float* gs = d.gstats + (size_t)env * d.SG;
+    const uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
+    const int idw = hdr[MGH_GST_TOKENS_WRITTEN], idd = hdr[MGH_GST_TOKENS_DROPPED], idf = hdr[MGH_GST_TOKENS_FREE];
+    blk[MGFB_STEP] = (uint32_t)E[MGEV_STEP];
+    blk[MGFB_RNG_IDX] = (uint32_t)E[MGEV_RNG_IDX];
+    blk[MGFB_NOBJ] = (uint32_t)nobj;
+    blk[MGFB_TOKENS_WRITTEN] = __float_as_uint(gs[idw]);
+    blk[MGFB_TOKENS_FREE] = __float_as_uint(gs[idf]);
+    blk[MGFB_GTOUCHED] = ((gt[idw >> 5] >> (idw & 31)) & 1u) | (((gt[idd >> 5] >> (idd & 31)) & 1u) << 1) |
+                         (((gt[idf >> 5] >> (idf & 31)) & 1u) << 2);
+    blk[6] = blk[7] = 0;
+  }
+  uint4 a0 = make_uint4(1, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+  if (gl < d.A) {
+    const size_t ga = (size_t)env * d.A + gl;
+    const uint32_t* ag = d.agents + ga * d.AS;
+    a0 = make_uint4(ag[MGAG_OBJ], ag[MGAG_SPAWN], ag[MGAG_PREV_LOC], ag[MGAG_SWM]);
+    a1 = make_uint4(ag[MGAG_MAX_DIST], ag[MGAG_UNIQUE], d.atouched[ga * d.SAW] & 0xffffu, 0);
+    for (int id = 0; id < MGFB_STATS; id++) blk[MGFB_STAT(G, id, gl)] = id < d.SA ? __float_as_uint(d.astats[ga * d.SA + id]) : 0u;
+  } else {
+    for (int id = 0; id < MGFB_STATS; id++) blk[MGFB_STAT(G, id, gl)] = 0u;
+  }
+  *(uint4*)(blk + MGFB_AGENT(G, gl)) = a0;
+  *(uint4*)(blk + MGFB_AGENT(G, gl) + 4) = a1;
+  uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
+  if (gl < nobj && gl + 1 < d.maxobj) {
+    const uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NTERR) + (size_t)(gl + 1)) * d.OS;
+    const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+    const uint32_t ntok = o[MGO_NTOK];
+    const uint32_t w3 = (((uint32_t)((int)o[MGO_AGENT] + 1)) & 0xffu) | (ntok == MG_TOK_DIRTY ? MGFB_DIRTY : ((ntok & 0xffu) << 8));
+    o0 = make_uint4(o[MGO_LOC], o[MGO_VISITED], o[MGO_META], w3);
+    const int nw = min(4, (hdr[MGH_TOK_CAP] + 1) / 2);
+    uint32_t tk[4] = {0, 0, 0, 0};
+    for (int k = 0; k < nw; k++) tk[k] = o[TOKOFF + k];
+    o1 = make_uint4(tk[0], tk[1], tk[2], tk[3]);
+  }
+  *(uint4*)(blk + MGFB_OBJECT(G, gl)) = o0;
+  *(uint4*)(blk + MGFB_OBJECT(G, gl) + 4) = o1;
+}
+
+__global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
+  const int* const hdr = HD.v;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int env = (int)(t / G), gl = (int)(t % G);
+  if (env >= d.num_envs) return;
+  const uint32_t* blk = d.fast_blk + (size_t)env * d.fast_stride;
+  int32_t* E = d.env + (size_t)env * MGEV_WORDS;
+  const int nobj = (int)blk[MGFB_NOBJ];
+  if (gl == 0) {
+    float* gs = d.gstats + (size_t)env * d.SG;
+    uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
+    const int idw = hdr[MGH_GST_TOKENS_WRITTEN], idd = hdr[MGH_GST_TOKENS_DROPPED], idf = hdr[MGH_GST_TOKENS_FREE];
+    E[MGEV_STEP] = (int32_t)blk[MGFB_STEP];
+    E[MGEV_RNG_IDX] = (int32_t)blk[MGFB_RNG_IDX];
+    gs[idw] = __uint_as_float(blk[MGFB_TOKENS_WRITTEN]);
+    gs[idf] = __uint_as_float(blk[MGFB_TOKENS_FREE]);
+    const uint32_t g = blk[MGFB_GTOUCHED];
+    if (g & 1u) gt[idw >> 5] |= 1u << (idw & 31);
+    if (g & 2u) gt[idd >> 5] |= 1u << (idd & 31);
+    if (g & 4u) gt[idf >> 5] |= 1u << (idf & 31);
+  }
+  if (gl < d.A) {
+    const size_t ga = (size_t)env * d.A + gl;
+    uint32_t* ag = d.agents + ga * d.AS;
+    const uint4 a0 = *(const uint4*)(blk + MGFB_AGENT(G, gl)), a1 = *(const uint4*)(blk + MGFB_AGENT(G, gl) + 4);
+    ag[MGAG_PREV_LOC] = a0.z, ag[MGAG_SWM] = a0.w, ag[MGAG_MAX_DIST] = a1.x, ag[MGAG_UNIQUE] = a1.y;
+    d.atouched[ga * d.SAW] |= a1.z & 0xffffu;
+    for (int id = 0; id < MGFB_STATS && id < d.SA; id++) d.astats[ga * d.SA + id] = __uint_as_float(blk[MGFB_STAT(G, id, gl)]);
+  }
+  if (gl < nobj && gl + 1 < d.maxobj) {
+    uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NTERR) + (size_t)(gl + 1)) * d.OS;
+    const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+    const uint4 o0 = *(const uint4*)(blk + MGFB_OBJECT(G, gl)), o1 = *(const uint4*)(blk + MGFB_OBJECT(G, gl) + 4);
+    o[MGO_LOC] = o0.x, o[MGO_VISITED] = o0.y, o[MGO_META] = o0.z;
+    if (o0.w & MGFB_DIRTY) {
+      o[MGO_NTOK] = MG_TOK_DIRTY;
+    } else {
+      o[MGO_NTOK] = (o0.w >> 8) & 0xffu;
+      const int nw = min(4, (hdr[MGH_TOK_CAP] + 1) / 2);
+      const uint32_t tk[4] = {o1.x, o1.y, o1.z, o1.w};
+      for (int k = 0; k < nw; k++) o[TOKOFF + k] = tk[k];
+    }
+  }
 }
 
 }  // namespace
@@ -798,4 +867,15 @@ cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgF
     case 16: return launch_fast<16>(d, L, H, st);
     default: return launch_fast<32>(d, L, H, st);
   }
+}
+
+cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st) {
+  const size_t threads = (size_t)d.num_envs * L.G;
+  k_fast_pack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G, mask);
+  return cudaGetLastError();
+}
+cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
+  const size_t threads = (size_t)d.num_envs * L.G;
+  k_fast_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G);
+  return cudaGetLastError();
 }

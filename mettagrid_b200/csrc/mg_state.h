@@ -22,6 +22,8 @@ struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
+  uint32_t* fast_blk;    // [N][fast_stride] packed hot state of k_step_fast (layout below), or null
+  int fast_stride;       // words per env
   const uint32_t* rank_lut;  // [256] packed window offset (dr + rr) << 4 | (dc + cr) -> rank << 24 | offset << 16, where rank is
                              // the position in Manhattan order; 0xFFFFFF00 outside the shape
   int plain;    // 1: the program has no handlers / rewards / world systems (k_step<PLAIN> applies)
@@ -74,3 +76,20 @@ struct MgFastLayout {
 struct MgFastHdr {
   int v[MGH_HEADER_WORDS];
 };
+
+// ---- packed hot state of k_step_fast: one contiguous block per env, G = lanes per env -------------------
+// words [0, 8)                      : header (MGFB_*)
+// words [8 + 8a, 8 + 8a + 8)        : agent a   = {obj slot, spawn, prev_location, steps_without_motion},
+//                                                 {max_dist, unique cells, touched bits of stat ids < 16, 0}
+// words [8 + 8G + 8j, ... + 8)      : object j+1 = {loc, visited, meta, (agent + 1) | ntok << 8 | dirty << 16},
+//                                                 {first eight cached tokens}
+// words [8 + 16G + id * G + a]      : agent stat `id` (< 16) of agent a, stat-major so a tick touches whole rows
+// The block is the truth between ticks; k_fast_pack / k_fast_unpack move it from / to the generic arrays when an
+// entry point other than mg_step needs them (mg_capi.cu).
+enum { MGFB_STEP = 0, MGFB_RNG_IDX, MGFB_NOBJ, MGFB_TOKENS_WRITTEN, MGFB_TOKENS_FREE, MGFB_GTOUCHED, MGFB_HDR_WORDS = 8 };
+#define MGFB_STATS 16
+#define MGFB_AGENT(G, a) (MGFB_HDR_WORDS + 8 * (a))
+#define MGFB_OBJECT(G, j) (MGFB_HDR_WORDS + 8 * (G) + 8 * (j))
+#define MGFB_STAT(G, id, a) (MGFB_HDR_WORDS + 16 * (G) + (id) * (G) + (a))
+#define MGFB_WORDS(G) ((MGFB_HDR_WORDS + 16 * (G) + MGFB_STATS * (G) + 31) & ~31)
+#define MGFB_DIRTY (1u << 16)

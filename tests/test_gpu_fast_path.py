@@ -168,3 +168,44 @@ def test_reset_and_set_inventory_on_fast_handle():
         assert sim.get_episode_stats(e) == o.get_episode_stats()
         assert np.array_equal(sim.dump_objects(e), o.dump_objects())
     sim.close()
+
+
+def test_introspection_and_masked_reset_between_ticks():
+    """Getters, set_buffers and masked resets move state between the packed block and the generic arrays;
+    none of it may disturb the episode."""
+    from oracle.oracle import OracleEnv
+
+    cfg = cases.benchmark_config(16)
+    N = 6
+    sim = _make(cfg, N, 33, True)
+    assert sim.step_kernel == 16
+    P = sim.program
+    A = P.num_agents
+    oracles = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(N)]
+    prim, vibe = cases.random_actions(np.random.RandomState(9), 90, (N, A), 5, len(P.action_names), 0.3, 0.05)
+    for t in range(90):
+        sim.step(prim[t], vibe[t])
+        for e, o in enumerate(oracles):
+            o.step(prim[t, e], vibe[t, e])
+        if t % 7 == 3:  # read everything mid-episode
+            for e, o in enumerate(oracles):
+                assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ at step {t} env {e}"
+                assert np.array_equal(sim.dump_objects(e), o.dump_objects())
+            assert [int(x) for x in sim.current_steps] == [o.current_step for o in oracles]
+        if t == 40:  # rebuild two environments, keep the rest running
+            mask = torch.zeros(N, dtype=torch.bool, device="cuda")
+            mask[1] = mask[4] = True
+            sim.reset(mask)
+            for e in (1, 4):
+                oracles[e] = OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e])
+        if t == 60:  # a full reset right after a masked one
+            sim.reset()
+            oracles = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(N)]
+        torch.cuda.synchronize()
+        obs = sim.observations.cpu().numpy()
+        for e, o in enumerate(oracles):
+            assert np.array_equal(obs[e], o.observations()), f"obs differ at step {t} env {e}"
+    for e, o in enumerate(oracles):
+        assert sim.get_episode_stats(e) == o.get_episode_stats()
+        assert np.array_equal(sim.dump_objects(e), o.dump_objects())
+    sim.close()
