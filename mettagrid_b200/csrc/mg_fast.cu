@@ -22,6 +22,12 @@
 namespace {
 
 #define FAST_INVALID 0xFFFFFFFFu
+#ifndef MG_FAST_PREGEN
+#define MG_FAST_PREGEN 0  // generating the next tick's draws ahead of time: measured 1.7 us slower (profiles/README.md)
+#endif
+#ifndef MG_FAST_EARLY_FF
+#define MG_FAST_EARLY_FF 0  // measured slower: +33 % L2 write traffic and half-sector stores (profiles/README.md)
+#endif
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 11;
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const uint4 orec = *(const uint4*)bob;       // loc, visited, meta, agent + 1 | ntok << 8 | dirty << 16
   const uint4 otok = *(const uint4*)(bob + 4); // first eight cached tokens
   const float s_cv0 = bst[hdr[MGH_ST_CELL_VISITED] * G];
+  const uint32_t pre_nw = blk[MGFB_RAND(G, gl)];  // pre-generated state word of this lane's draw
   constexpr int LV = (64 + MG_FAST_WARPS * 32 - 1) / (MG_FAST_WARPS * 32);  // window-table vectors per thread
   uint4 lutv[LV];
 #pragma unroll
@@ -228,6 +235,22 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     }
   }
 
+  // Most of every observation row is EmptyTokenByte (:940-942).  When the env's block is 16-byte aligned it is
+  // written as such right away, while the loads are in flight; the end of the tick then only streams the vectors
+  // that hold tokens.
+  uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
+  const int nbytes = A * 3 * T;
+  const bool aligned = MG_FAST_EARLY_FF && (nbytes & 15) == 0 && ((uintptr_t)d.obs & 15u) == 0;
+  if (aligned && live) {
+    uint4* g4 = (uint4*)gobs;
+    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    const int nv = nbytes >> 4;
+    int v = gl;
+#pragma unroll 1
+    for (; v + 3 * G < nv; v += 4 * G) __stcs(g4 + v, ff), __stcs(g4 + v + G, ff), __stcs(g4 + v + 2 * G, ff), __stcs(g4 + v + 3 * G, ff);
+#pragma unroll 1
+    for (; v < nv; v += G) __stcs(g4 + v, ff);
+  }
 #pragma unroll
   for (int k = 0; k < LV; k++) {
     const int i = tid + k * MG_FAST_WARPS * 32;
@@ -258,8 +281,9 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const int ndraws = A < 2 ? 0 : ((A & 1) ? (A - 1) / 2 : A / 2);
   if (idx0 >= MG_RNG_WORDS) idx0 = 0;
   const bool window_ok = idx0 + ndraws <= MG_RNG_WORDS;
+  const bool pre_ok = MG_FAST_PREGEN && window_ok && bh1.z == (uint32_t)idx0;  // the draws were generated by the previous tick
   uint32_t r_cur = 0, r_nxt = 0, r_far = 0;
-  if (window_ok && gl < ndraws) {
+  if (window_ok && !pre_ok && gl < ndraws) {
     const int i = idx0 + gl;
     const int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
     const int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
@@ -275,8 +299,6 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   // independent work while wave 2 is in flight: the observation stage starts as all EmptyTokenByte (:940-942);
   // it shares the destination's 16-byte phase so that whole vectors can be streamed out
-  uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
-  const int nbytes = A * 3 * T;
   uint8_t* stage = gb + ((uint32_t)(uintptr_t)gobs & 15u);
   {
     uint4* s4 = (uint4*)gb;
@@ -299,7 +321,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   uint32_t nw = 0;
   uint8_t* perm = order;  // P[pos]
   if (window_ok && gl < ndraws) {
-    nw = mt_twist(r_cur, r_nxt, r_far);
+    nw = pre_ok ? pre_nw : mt_twist(r_cur, r_nxt, r_far);
     const uint32_t rnd = mt_temper(nw);
     const bool single = (A & 1) == 0 && gl == 0;
     const int i = single ? 1 : ((A & 1) ? 2 * gl + 1 : 2 * gl);
@@ -330,6 +352,18 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   if (!rej && live && gl < ndraws) rng[idx0 + gl] = nw;
   if (!rej && live && gl == 0 && ndraws > 0) blk[MGFB_RNG_IDX] = (uint32_t)(idx0 + ndraws);
+  // the state words behind the NEXT tick's draws: loaded now, twisted and stored at the end of the tick, so that
+  // the next launch finds them in its first load wave instead of chasing the state index
+  int nidx = idx0 + ndraws;
+  if (nidx >= MG_RNG_WORDS) nidx = 0;
+  const bool next_ok = MG_FAST_PREGEN && !rej && ndraws > 0 && nidx + ndraws <= MG_RNG_WORDS;
+  uint32_t n_cur = 0, n_nxt = 0, n_far = 0;
+  if (next_ok && gl < ndraws) {
+    const int i = nidx + gl;
+    const int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
+    const int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
+    n_cur = rng[i], n_nxt = rng[i1], n_far = rng[i2];
+  }
   __syncthreads();  // the window table (per CTA)
 
   // ---- moves in shuffled order, highest priority first (actions/move.hpp:81-115 with the two default
@@ -606,7 +640,18 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   __syncwarp();
 
   // ---- stream the env's observation block out
-  {
+  if (aligned) {
+    // the rest of every row is already EmptyTokenByte in HBM: each agent streams the vectors that hold its tokens
+    // (a vector shared with the neighbouring row carries identical bytes from both lanes)
+    if (isA && live) {
+      const int rs = gl * 3 * T;
+      const uint4* s4 = (const uint4*)gb;
+      uint4* g4 = (uint4*)gobs;
+      const int v1 = (rs + 3 * min(attempted, T) + 15) >> 4;
+#pragma unroll 2
+      for (int v = rs >> 4; v < v1; v++) __stcs(g4 + v, s4[v]);
+    }
+  } else {
     const int head = min(nbytes, (int)((16u - ((uint32_t)(uintptr_t)gobs & 15u)) & 15u));
     if (live) {
 #pragma unroll 1
@@ -616,14 +661,8 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const uint4* s4 = (const uint4*)(stage + head);
     uint4* g4 = (uint4*)(gobs + head);
     if (live) {
-      int v = gl;
 #pragma unroll 1
-      for (; v + 3 * G < body; v += 4 * G) {
-        const uint4 x0 = s4[v], x1 = s4[v + G], x2 = s4[v + 2 * G], x3 = s4[v + 3 * G];
-        __stcs(g4 + v, x0), __stcs(g4 + v + G, x1), __stcs(g4 + v + 2 * G, x2), __stcs(g4 + v + 3 * G, x3);
-      }
-#pragma unroll 1
-      for (; v < body; v += G) __stcs(g4 + v, s4[v]);
+      for (int v = gl; v < body; v += G) __stcs(g4 + v, s4[v]);
     }
     const int done = head + (body << 4);
     if (live) {
@@ -718,7 +757,14 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     if (o_loc != o_loc0 || o_vis != o_vis0 || o_meta != o_meta0 || w3 != orec.w) *(uint4*)bob = make_uint4(o_loc, o_vis, o_meta, w3);
     if (o_ntok != ntok_raw || o_meta != o_meta0) *(uint4*)(bob + 4) = make_uint4(tw0, tw1, tw2, tw3);
   }
-  if (gl == 0 && live) blk[MGFB_STEP] = step;
+  if (live) {
+    if (next_ok && gl < ndraws) blk[MGFB_RAND(G, gl)] = mt_twist(n_cur, n_nxt, n_far);
+    if (gl == 0) {
+      blk[MGFB_STEP] = step;
+      const uint32_t tag = next_ok ? (uint32_t)nidx : 0xFFFFFFFFu;
+      if (tag != bh1.z) blk[MGFB_RAND_IDX] = tag;
+    }
+  }
 }
 
 
@@ -742,7 +788,8 @@ __global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, cons
     blk[MGFB_TOKENS_FREE] = __float_as_uint(gs[idf]);
     blk[MGFB_GTOUCHED] = ((gt[idw >> 5] >> (idw & 31)) & 1u) | (((gt[idd >> 5] >> (idd & 31)) & 1u) << 1) |
                          (((gt[idf >> 5] >> (idf & 31)) & 1u) << 2);
-    blk[6] = blk[7] = 0;
+    blk[MGFB_RAND_IDX] = 0xFFFFFFFFu;  // no pre-generated draws
+    blk[7] = 0;
   }
   uint4 a0 = make_uint4(1, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
   if (gl < d.A) {
