@@ -151,15 +151,32 @@ __device__ __forceinline__ void ce(uint32_t& a, uint32_t& b) {
   const uint32_t lo = min(a, b), hi = max(a, b);
   a = lo, b = hi;
 }
-// bitonic sorting network, fully unrolled on registers (80 exchanges for 16 keys, 240 for 32)
-template <int N>
-__device__ __forceinline__ void sort_net(uint32_t (&key)[N]) {
+// Sorting networks on registers, fully unrolled: Batcher's odd-even merge sort for 8 and 16 keys (19 and 63
+// exchanges; tests/test_sort_network.py checks the lists below with the 0-1 principle), the bitonic network for 32
+// keys (240 exchanges).
+#define CE(a, b) ce(key[a], key[b]);
+__device__ __forceinline__ void sort_net(uint32_t (&key)[8]) {
+  /* SORT8 */
+    CE(0, 1) CE(2, 3) CE(4, 5) CE(6, 7) CE(0, 2) CE(1, 3) CE(4, 6) CE(5, 7) CE(1, 2) CE(5, 6) CE(0, 4) CE(1, 5)
+    CE(2, 6) CE(3, 7) CE(2, 4) CE(3, 5) CE(1, 2) CE(3, 4) CE(5, 6)
+}
+__device__ __forceinline__ void sort_net(uint32_t (&key)[16]) {
+  /* SORT16 */
+    CE(0, 1) CE(2, 3) CE(4, 5) CE(6, 7) CE(8, 9) CE(10, 11) CE(12, 13) CE(14, 15) CE(0, 2) CE(1, 3) CE(4, 6) CE(5, 7)
+    CE(8, 10) CE(9, 11) CE(12, 14) CE(13, 15) CE(1, 2) CE(5, 6) CE(9, 10) CE(13, 14) CE(0, 4) CE(1, 5) CE(2, 6)
+    CE(3, 7) CE(8, 12) CE(9, 13) CE(10, 14) CE(11, 15) CE(2, 4) CE(3, 5) CE(10, 12) CE(11, 13) CE(1, 2) CE(3, 4)
+    CE(5, 6) CE(9, 10) CE(11, 12) CE(13, 14) CE(0, 8) CE(1, 9) CE(2, 10) CE(3, 11) CE(4, 12) CE(5, 13) CE(6, 14)
+    CE(7, 15) CE(4, 8) CE(5, 9) CE(6, 10) CE(7, 11) CE(2, 4) CE(3, 5) CE(6, 8) CE(7, 9) CE(10, 12) CE(11, 13) CE(1, 2)
+    CE(3, 4) CE(5, 6) CE(7, 8) CE(9, 10) CE(11, 12) CE(13, 14)
+}
+#undef CE
+__device__ __forceinline__ void sort_net(uint32_t (&key)[32]) {
 #pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
+  for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
 #pragma unroll
-      for (int i = 0; i < N; i++) {
+      for (int i = 0; i < 32; i++) {
         const int l = i ^ j;
         if (l > i) {
           if ((i & k) == 0)
@@ -330,8 +347,11 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const uint64_t prod = (uint64_t)rnd * range;
     const uint32_t low = (uint32_t)prod, x = (uint32_t)(prod >> 32);
     if (low < range && low < (0u - range) % range) reject = true;
-    perm[i] = (uint8_t)(single ? x : x / (sr + 1));
-    if (!single) perm[i + 1] = (uint8_t)(x % (sr + 1));
+    // x < sr * (sr + 1) <= 1056 and sr + 1 <= 33: the float quotient of (x + 0.5) is never within 0.015 of an
+    // integer, far beyond the error of the fast division, so truncation gives the exact integer quotient
+    const uint32_t q = __float2uint_rz(__fdividef((float)x + 0.5f, (float)(sr + 1)));
+    perm[i] = (uint8_t)(single ? x : q);
+    if (!single) perm[i + 1] = (uint8_t)(x - q * (sr + 1));
   }
   const uint32_t rej = __ballot_sync(MG_FULL, reject) & gmask;
   __syncwarp();
@@ -382,37 +402,34 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const int tr = (int)(my_loc0 >> 16) + dr, tc = (int)(my_loc0 & 0xffffu) + dc;
     if (my_loc0 != FAST_INVALID && tr >= 0 && tr < d.H && tc >= 0 && tc < d.W) my_tgt = ((uint32_t)tr << 16) | (uint32_t)tc;
   }
-  bool move_ok = false;
   {
+    // the step at which each agent acts (inverse of the shuffled order), handed to the lane that plays its object
+    if (isA) order[my_order] = (uint8_t)gl;
+    __syncwarp();
+    const int a_step = isA ? (int)order[gl] : -1;
+    const int oa = o_agent >= 0 && o_agent < A ? o_agent : 0;
+    const int o_step = o_agent >= 0 && o_agent < A ? __shfl_sync(MG_FULL, a_step, oa, G) : (__shfl_sync(MG_FULL, a_step, oa, G), -1);
     const int maxp = hdr[MGH_MAX_PRIORITY], pmask = hdr[MGH_PRIORITY_MASK];
-    const int ol_s = __shfl_sync(MG_FULL, my_ol, my_order, G);
 #pragma unroll 1
     for (int prio = maxp; prio >= 0; prio--) {
       if (!((pmask >> prio) & 1)) continue;
       const bool mine = wants_move && ap.z == prio;
       if (!__any_sync(MG_FULL, mine)) continue;
-      const uint32_t tgt_s = __shfl_sync(MG_FULL, mine ? my_tgt : FAST_INVALID, my_order, G);  // target at step gl
-      uint32_t okmask = 0;
+      const uint32_t tgt_a = mine ? my_tgt : FAST_INVALID;
+      const uint32_t tgt_s = __shfl_sync(MG_FULL, tgt_a, my_order, G);  // target of the agent acting at step gl
+      const uint32_t tgt_o = __shfl_sync(MG_FULL, tgt_a, oa, G);        // target of this lane's object
 #pragma unroll
       for (int i = 0; i < G; i++) {
         if (i < A) {
           const uint32_t tgt = __shfl_sync(MG_FULL, tgt_s, i, G);
-          const int ol = __shfl_sync(MG_FULL, ol_s, i, G);
           const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
-          const bool ok = tgt != FAST_INVALID && occ == 0;
-          if (ok && gl == ol) o_loc = tgt;
-          okmask |= ok ? (1u << i) : 0u;
+          if (o_step == i && tgt_o != FAST_INVALID && occ == 0) o_loc = tgt_o;  // TargetLocEmpty -> Relocate
         }
       }
-      // the step's verdict goes back to the agent that acted in it
-      __syncwarp();
-      if (isA) order[my_order] = (uint8_t)((okmask >> gl) & 1u);
-      __syncwarp();
-      if (isA && order[gl]) move_ok = true;
-      __syncwarp();
     }
   }
   const uint32_t my_loc = __shfl_sync(MG_FULL, o_loc, my_ol, G);  // observer position (:1049-1052)
+  const bool move_ok = wants_move && my_loc != my_loc0;  // a successful move always changes the location
 
   // ---- per-agent outcome of both streams (actions/action_handler.hpp:78-105), in execution order
   const bool v_first = act_p && act_v && av.z > ap.z;  // the vibe-stream action has the higher priority
@@ -535,7 +552,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // ---- observations: sort keys for the objects in this agent's window
   // key = Manhattan rank << 24 | packed offset << 16 | token count << 8 | object lane
   uint32_t key[G];
-  uint32_t vismask = 0;
+  uint32_t col = 0;  // which agents see this lane's object
   {
     const uint32_t bias = (((uint32_t)(hdr[MGH_OBS_H] >> 1) << 16) | (uint32_t)(hdr[MGH_OBS_W] >> 1)) - my_loc;
 #pragma unroll
@@ -546,21 +563,17 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       const uint32_t kk = lut[((df >> 12) & 0xf0u) | (df & 0xfu)] | oi.y;
       const bool vis = isA && (df & 0xfff0fff0u) == 0 && kk < 0xff000000u;
       key[j] = vis ? kk : FAST_INVALID;
-      vismask |= vis ? (1u << j) : 0u;
+      const uint32_t b = __ballot_sync(MG_FULL, vis);
+      if (gl == j) col = b;
     }
+    col = (col & gmask) >> gshift;
   }
-  // which agents see this lane's object; cell staleness (:787-796) goes to the lowest agent index among them
-  uint32_t col = 0;
-#pragma unroll
-  for (int j = 0; j < G; j++) {
-    const uint32_t b = (__ballot_sync(MG_FULL, (vismask >> j) & 1u) & gmask) >> gshift;
-    if (gl == j) col = b;
-  }
+  // cell staleness (:787-796) goes to the lowest agent index among the observers
   if (o_alive && col != 0 && o_vis < step) {
     atomicAdd(&stale[__ffs(col) - 1], step - o_vis);
     o_vis = step;
   }
-  sort_net<G>(key);
+  sort_net(key);
 
   // global tokens (:700-742)
   uint8_t* row = stage + gl * 3 * T;
