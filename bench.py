@@ -301,10 +301,13 @@ def run_ours(args):
         per_launch_ms = total_ms / steps
         ab = algo_bytes(P, wl)
         achieved = ab * envs * A / (per_launch_ms * 1e-3) / 1e9
+        # which kernel mg_step launches for this handle (include/mettagrid_b200.h: mg_step_kernel)
+        sk = sim.step_kernel
+        kernel = f"k_step_fast<{sk}>" if sk >= 8 else ("k_step<true>" if sk == 1 else "k_step<false>")
         traffic = None
         tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get("k_step_dram_bytes_per_launch")
+        if tpath.exists() and wl == "c2" and envs == WORKLOADS[wl][1]:  # measured for the default workload only
+            traffic = json.loads(tpath.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -319,7 +322,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": NA * (3 * P.num_tokens + 4 + 1 + 1), "check": e2e_sum},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_step", "peak_source": peak_src,
+                         "traffic": traffic, "kernel": kernel, "peak_source": peak_src,
                          "algorithmic_bytes_per_agent_step": ab},
         }  # fmt: skip
         if world == 1 and not args.no_cpu_baseline and reference_available():

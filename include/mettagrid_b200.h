@@ -79,6 +79,14 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows);
  * dict (mettagrid_b200.compiler.pybind_dict_order). */
 int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, const int32_t* amounts, int n);
 
+/* Dense grid observations (next row 8f-3): replaces GridObsWrapper._convert --
+ * python/src/mettagrid/envs/grid_obs_wrapper.py:33-96.  mg_grid_obs_configure fixes the number of feature planes C
+ * (max feature id + 1) and the per-feature normalisation (host float[256], entries < 1 are raised to 1 like the
+ * wrapper does).  mg_obs_to_grid converts `rows` token rows uint8 [rows][T][3] (DEVICE; NULL = the handle's
+ * observation buffer, rows = N * A) into float32 [rows][C][obs_height][obs_width] (DEVICE), asynchronously. */
+int mg_grid_obs_configure(mg_handle* h, int num_features, const float* scale);
+int mg_obs_to_grid(mg_handle* h, const void* observations, int rows, void* grid, void* stream);
+
 /* sizes */
 int mg_num_envs(const mg_handle* h);
 int mg_num_agents(const mg_handle* h);

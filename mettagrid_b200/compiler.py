@@ -160,6 +160,7 @@ class Program:
     vibe_names: list[str]
     action_names: list[str]
     feature_ids: dict[str, int]
+    feature_norms: dict[str, float]  # ObservationFeatureSpec.normalization per feature (config/id_map.py:161-235)
     agent_stat_names: list[str]
     game_stat_names: list[str]
     template_names: list[str]  # template index -> canonical cell name
@@ -303,36 +304,40 @@ class _Builder:
         # config/id_map.py:161-235
         g = self.g
         feats: dict[str, int] = {}
+        norms: dict[str, float] = {}
 
-        def add(name):
+        def add(name, norm):
             feats[name] = len(feats)
+            norms[name] = float(norm)
 
-        for n in ("agent:group", "episode_completion_pct", "last_action", "last_reward", "goal", "vibe", "tag",
-                  "lp:east", "lp:west", "lp:north", "lp:south", "agent_id"):  # fmt: skip
-            add(n)
+        for n, norm in (("agent:group", 10.0), ("episode_completion_pct", 255.0), ("last_action", 10.0),
+                        ("last_reward", 100.0), ("goal", 100.0), ("vibe", 255.0), ("tag", 10.0), ("lp:east", 255.0),
+                        ("lp:west", 255.0), ("lp:north", 255.0), ("lp:south", 255.0), ("agent_id", 255.0)):  # fmt: skip
+            add(n, norm)
         base = g.obs.token_value_base
         # id_map.py:25-38 uses ceil(log_base(65536)); equal to the C++ count for every base >= 2
         self.inv_digits = _digits_needed(65535, base)
         for r in self.resource_names:
-            add(f"inv:{r}")
+            add(f"inv:{r}", base)
             for p in range(1, self.inv_digits):
-                add(f"inv:{r}:p{p}")
+                add(f"inv:{r}:p{p}", base)
         if g.protocol_details_obs:
             for r in self.resource_names:
-                add(f"protocol_input:{r}")
+                add(f"protocol_input:{r}", 100.0)
             for r in self.resource_names:
-                add(f"protocol_output:{r}")
+                add(f"protocol_output:{r}", 100.0)
         for prefix in g.obs.global_obs.obs:
-            add(prefix)
+            add(prefix, base)
             for p in range(1, self.inv_digits):
-                add(f"{prefix}:p{p}")
+                add(f"{prefix}:p{p}", base)
         if g.obs.aoe_mask:
-            add("aoe_mask")
+            add("aoe_mask", 3.0)
         if g.obs.global_obs.last_action_move:
-            add("last_action_move")
+            add("last_action_move", 1.0)
         if len(feats) > 255:
             raise CompileError(f"{len(feats)} observation features do not fit uint8 feature ids")
         self.feature_ids = feats
+        self.feature_norms = norms
 
     # -- game values (mettagrid_c_value_config.py:35-99) --------------------------------------
     def value(self, gv) -> int:
@@ -1063,7 +1068,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     prog = Program(
         blob=blob, height=map_height, width=map_width, num_agents=A, num_tokens=g.obs.num_tokens,
         resource_names=b.resource_names, tag_names=b.tag_names, vibe_names=b.vibes, action_names=action_names,
-        feature_ids=dict(fid), agent_stat_names=agent_stat_names, game_stat_names=game_stat_names,
+        feature_ids=dict(fid), feature_norms=dict(b.feature_norms), agent_stat_names=agent_stat_names, game_stat_names=game_stat_names,
         template_names=template_names, cell_to_template=cell_to_template, agent_renames=agent_renames,
         type_names=b.type_names, features=b.features,
         object_type_of_template=[t[K["MGT_TYPE_ID"]] for t in templates], objects_stat=objects_stat,

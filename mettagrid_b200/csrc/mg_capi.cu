@@ -21,6 +21,8 @@ cudaError_t mg_fast_configure(const MgFastLayout& L);
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
+cudaError_t mg_launch_obs_to_grid(const uint8_t* obs, float* grid, int rows, int T, int C, int H, int W, const float* scale,
+                                  cudaStream_t st);
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st);
 
@@ -46,6 +48,8 @@ struct mg_handle {
   uint8_t* h_term = nullptr;
   uint8_t* h_trunc = nullptr;
   uint32_t* seeds_dev = nullptr;
+  float* grid_scale = nullptr;  // device float[256], per-feature normalisation of the dense grid observations
+  int grid_features = 0;
   cudaStream_t own_stream = nullptr;
 };
 
@@ -553,6 +557,37 @@ int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, con
 int mg_num_envs(const mg_handle* h) { return h ? h->d.num_envs : 0; }
 int mg_num_agents(const mg_handle* h) { return h ? h->d.A : 0; }
 int mg_num_tokens(const mg_handle* h) { return h ? h->d.T : 0; }
+int mg_grid_obs_configure(mg_handle* h, int num_features, const float* scale) {
+  if (!h || !scale || num_features <= 0 || num_features > 256) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  if (!h->grid_scale) {
+    int rc = dev_alloc(h, &h->grid_scale, 256);
+    if (rc) return rc;
+  }
+  float s[256];
+  for (int i = 0; i < 256; i++) s[i] = scale[i] > 1.0f ? scale[i] : 1.0f;  // grid_obs_wrapper.py:43-45
+  CK(cudaMemcpy(h->grid_scale, s, sizeof s, cudaMemcpyHostToDevice));
+  h->grid_features = num_features;
+  return MG_OK;
+}
+
+int mg_obs_to_grid(mg_handle* h, const void* observations, int rows, void* grid, void* stream) {
+  if (!h || !grid || rows <= 0) return MG_E_INVALID;
+  if (!h->grid_scale) {
+    h->err = "mg_obs_to_grid: call mg_grid_obs_configure first";
+    return MG_E_INVALID;
+  }
+  const uint8_t* obs = observations ? (const uint8_t*)observations : h->d.obs;
+  if (!obs) {
+    h->err = "mg_obs_to_grid: no observation buffer (pass one or call mg_set_buffers)";
+    return MG_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(mg_launch_obs_to_grid(obs, (float*)grid, rows, h->d.T, h->grid_features, h->program[MGH_OBS_H], h->program[MGH_OBS_W],
+                           h->grid_scale, (cudaStream_t)stream));
+  return MG_OK;
+}
+
 size_t mg_state_bytes(const mg_handle* h) { return h ? h->bytes : 0; }
 int mg_step_kernel(const mg_handle* h) { return !h ? MG_E_INVALID : h->fast ? h->fl.G : h->d.plain ? 1 : 0; }
 

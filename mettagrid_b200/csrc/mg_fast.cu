@@ -419,12 +419,10 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       const uint32_t tgt_s = __shfl_sync(MG_FULL, tgt_a, my_order, G);  // target of the agent acting at step gl
       const uint32_t tgt_o = __shfl_sync(MG_FULL, tgt_a, oa, G);        // target of this lane's object
 #pragma unroll
-      for (int i = 0; i < G; i++) {
-        if (i < A) {
-          const uint32_t tgt = __shfl_sync(MG_FULL, tgt_s, i, G);
-          const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
-          if (o_step == i && tgt_o != FAST_INVALID && occ == 0) o_loc = tgt_o;  // TargetLocEmpty -> Relocate
-        }
+      for (int i = 0; i < G; i++) {  // steps beyond the agent count carry no target and change nothing
+        const uint32_t tgt = __shfl_sync(MG_FULL, tgt_s, i, G);
+        const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
+        if (o_step == i && tgt_o != FAST_INVALID && occ == 0) o_loc = tgt_o;  // TargetLocEmpty -> Relocate
       }
     }
   }

@@ -1,0 +1,71 @@
+// mg_gridobs.cu -- k_obs_to_grid: sparse observation tokens -> dense float32 (C, H, W) grids on the device
+// (SURVEY 8f-3).  Replaces GridObsWrapper._convert (python/src/mettagrid/envs/grid_obs_wrapper.py:58-96):
+// token [coord, feature, value]; coord 0xFF = padding (skipped), 0xFE = global token (placed at the window
+// centre), otherwise y = high nibble, x = low nibble; grid[feature][y][x] += value / scale[feature].
+//
+// One warp per agent row.  The row is zeroed with 16-byte streaming stores, then the tokens are scattered 32 at a
+// time.  numpy's add.at accumulates duplicates of one (feature, y, x) in token order; __match_any groups such
+// duplicates inside a chunk and the lowest lane of a group adds them in lane order, chunks follow one another, so
+// every sum is formed in the reference's order and the result is bit-exact.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FULL 0xffffffffu
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_obs_to_grid(const uint8_t* __restrict__ obs, float* __restrict__ grid, int rows, int T,
+                                                     int C, int H, int W, const float* __restrict__ scale) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const size_t cells = (size_t)C * H * W;
+  float* g = grid + (size_t)row * cells;
+  {  // zero the row: scalar head up to 16-byte alignment, vector body, scalar tail
+    const size_t head = min(cells, (size_t)(((16u - ((uint32_t)(uintptr_t)g & 15u)) & 15u) >> 2));
+    if ((size_t)lane < head) g[lane] = 0.0f;
+    float4* g4 = (float4*)(g + head);
+    const size_t n4 = (cells - head) >> 2;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = lane; i < n4; i += 32) __stcs(g4 + i, z);
+    const size_t done = head + (n4 << 2);
+    if (done + lane < cells) g[done + lane] = 0.0f;
+  }
+  __syncwarp();
+  const uint8_t* tok = obs + (size_t)row * T * 3;
+  const int cy = H / 2, cx = W / 2;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    int coord = 0xFF, fid = 0, val = 0;
+    if (t < T) coord = tok[3 * t], fid = tok[3 * t + 1], val = tok[3 * t + 2];
+    int y = (coord >> 4) & 15, x = coord & 15;
+    if (coord == 0xFE) y = cy, x = cx;
+    const bool valid = coord != 0xFF && y < H && x < W && fid < C;
+    if (!__any_sync(FULL, valid)) continue;
+    const uint32_t key = valid ? (uint32_t)((fid * H + y) * W + x) : (0x80000000u | (uint32_t)lane);
+    const float v = valid ? __fdiv_rn((float)val, scale[fid]) : 0.0f;
+    const uint32_t m = __match_any_sync(FULL, key);
+    const bool leader = valid && (__ffs(m) - 1) == lane;
+    const int cnt = __popc(m);
+    const int maxc = __reduce_max_sync(FULL, valid ? cnt : 1);
+    float acc = 0.0f;
+    if (leader) acc = __fadd_rn(__ldcg(g + key), v);
+    for (int r = 1; r < maxc; r++) {  // duplicates join in lane (= token) order
+      const bool take = leader && r < cnt;
+      const int src = take ? (int)__fns(m, 0, r + 1) : lane;
+      const float vb = __shfl_sync(FULL, v, src);
+      if (take) acc = __fadd_rn(acc, vb);
+    }
+    if (leader) g[key] = acc;
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+cudaError_t mg_launch_obs_to_grid(const uint8_t* obs, float* grid, int rows, int T, int C, int H, int W, const float* scale,
+                                  cudaStream_t st) {
+  const int warps = 8;
+  k_obs_to_grid<<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(obs, grid, rows, T, C, H, W, scale);
+  return cudaGetLastError();
+}

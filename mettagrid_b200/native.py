@@ -35,6 +35,8 @@ SYMBOLS = {
     "mg_get_game_stats": (_i, [_vp, _i, _vp, _vp]),
     "mg_dump_objects": (_i, [_vp, _i, _vp, _i]),
     "mg_set_inventory": (_i, [_vp, _i, _i, _vp, _vp, _i]),
+    "mg_grid_obs_configure": (_i, [_vp, _i, _vp]),
+    "mg_obs_to_grid": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mg_num_envs": (_i, [_vp]),
     "mg_num_agents": (_i, [_vp]),
     "mg_num_tokens": (_i, [_vp]),

@@ -241,6 +241,33 @@ class BatchedSimulation:
         amounts = np.asarray([ids[k] for k in order], dtype=np.int32)
         self._check(self._L.mg_set_inventory(self._h, env, agent, items.ctypes.data, amounts.ctypes.data, len(order)))
 
+    # ---- dense grid observations (GridObsWrapper, envs/grid_obs_wrapper.py:33-96) ------------------
+    def grid_obs_shape(self) -> tuple[int, int, int]:
+        """(C, H, W) of one agent's dense observation: C = max feature id + 1."""
+        P = self.program
+        return max(P.feature_ids.values(), default=0) + 1, P.hdr("MGH_OBS_H"), P.hdr("MGH_OBS_W")
+
+    def grid_observations(self, out: torch.Tensor | None = None, observations: torch.Tensor | None = None) -> torch.Tensor:
+        """Token observations -> float32 [N*A, C, H, W] on the device (asynchronous on the current stream)."""
+        P = self.program
+        C, H, W = self.grid_obs_shape()
+        if not getattr(self, "_grid_configured", False):
+            scale = np.ones(256, dtype=np.float32)
+            for name, fid in P.feature_ids.items():
+                scale[fid] = max(float(P.feature_norms[name]), 1.0)
+            self._check(self._L.mg_grid_obs_configure(self._h, C, scale.ctypes.data))
+            self._grid_configured = True
+        src = self.observations if observations is None else observations
+        if src.dtype != torch.uint8 or not src.is_cuda or not src.is_contiguous() or src.shape[-2:] != (self.num_tokens, 3):
+            raise ValueError("observations must be a contiguous CUDA uint8 tensor [..., num_tokens, 3]")
+        rows = src.numel() // (self.num_tokens * 3)
+        if out is None:
+            out = torch.empty((rows, C, H, W), dtype=torch.float32, device=self.device)
+        elif out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous() or out.numel() != rows * C * H * W:
+            raise ValueError(f"out must be a contiguous CUDA float32 tensor with {rows * C * H * W} elements")
+        self._check(self._L.mg_obs_to_grid(self._h, src.data_ptr(), rows, out.data_ptr(), self._stream()))
+        return out
+
     @property
     def state_bytes(self) -> int:
         return int(self._L.mg_state_bytes(self._h))
