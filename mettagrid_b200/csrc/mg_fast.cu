@@ -22,9 +22,6 @@
 namespace {
 
 #define FAST_INVALID 0xFFFFFFFFu
-#ifndef MG_FAST_PREGEN
-#define MG_FAST_PREGEN 0  // generating the next tick's draws ahead of time: measured 1.7 us slower (profiles/README.md)
-#endif
 #ifndef MG_FAST_EARLY_FF
 #define MG_FAST_EARLY_FF 0  // measured slower: +33 % L2 write traffic and half-sector stores (profiles/README.md)
 #endif
@@ -235,7 +232,6 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const uint4 orec = *(const uint4*)bob;       // loc, visited, meta, agent + 1 | ntok << 8 | dirty << 16
   const uint4 otok = *(const uint4*)(bob + 4); // first eight cached tokens
   const float s_cv0 = bst[hdr[MGH_ST_CELL_VISITED] * G];
-  const uint32_t pre_nw = blk[MGFB_RAND(G, gl)];  // pre-generated state word of this lane's draw
   constexpr int LV = (64 + MG_FAST_WARPS * 32 - 1) / (MG_FAST_WARPS * 32);  // window-table vectors per thread
   uint4 lutv[LV];
 #pragma unroll
@@ -298,9 +294,8 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const int ndraws = A < 2 ? 0 : ((A & 1) ? (A - 1) / 2 : A / 2);
   if (idx0 >= MG_RNG_WORDS) idx0 = 0;
   const bool window_ok = idx0 + ndraws <= MG_RNG_WORDS;
-  const bool pre_ok = MG_FAST_PREGEN && window_ok && bh1.z == (uint32_t)idx0;  // the draws were generated by the previous tick
   uint32_t r_cur = 0, r_nxt = 0, r_far = 0;
-  if (window_ok && !pre_ok && gl < ndraws) {
+  if (window_ok && gl < ndraws) {
     const int i = idx0 + gl;
     const int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
     const int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
@@ -338,7 +333,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   uint32_t nw = 0;
   uint8_t* perm = order;  // P[pos]
   if (window_ok && gl < ndraws) {
-    nw = pre_ok ? pre_nw : mt_twist(r_cur, r_nxt, r_far);
+    nw = mt_twist(r_cur, r_nxt, r_far);
     const uint32_t rnd = mt_temper(nw);
     const bool single = (A & 1) == 0 && gl == 0;
     const int i = single ? 1 : ((A & 1) ? 2 * gl + 1 : 2 * gl);
@@ -372,18 +367,6 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   if (!rej && live && gl < ndraws) rng[idx0 + gl] = nw;
   if (!rej && live && gl == 0 && ndraws > 0) blk[MGFB_RNG_IDX] = (uint32_t)(idx0 + ndraws);
-  // the state words behind the NEXT tick's draws: loaded now, twisted and stored at the end of the tick, so that
-  // the next launch finds them in its first load wave instead of chasing the state index
-  int nidx = idx0 + ndraws;
-  if (nidx >= MG_RNG_WORDS) nidx = 0;
-  const bool next_ok = MG_FAST_PREGEN && !rej && ndraws > 0 && nidx + ndraws <= MG_RNG_WORDS;
-  uint32_t n_cur = 0, n_nxt = 0, n_far = 0;
-  if (next_ok && gl < ndraws) {
-    const int i = nidx + gl;
-    const int i1 = i + 1 == MG_RNG_WORDS ? 0 : i + 1;
-    const int i2 = i + 397 >= MG_RNG_WORDS ? i + 397 - MG_RNG_WORDS : i + 397;
-    n_cur = rng[i], n_nxt = rng[i1], n_far = rng[i2];
-  }
   __syncthreads();  // the window table (per CTA)
 
   // ---- moves in shuffled order, highest priority first (actions/move.hpp:81-115 with the two default
@@ -768,14 +751,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     if (o_loc != o_loc0 || o_vis != o_vis0 || o_meta != o_meta0 || w3 != orec.w) *(uint4*)bob = make_uint4(o_loc, o_vis, o_meta, w3);
     if (o_ntok != ntok_raw || o_meta != o_meta0) *(uint4*)(bob + 4) = make_uint4(tw0, tw1, tw2, tw3);
   }
-  if (live) {
-    if (next_ok && gl < ndraws) blk[MGFB_RAND(G, gl)] = mt_twist(n_cur, n_nxt, n_far);
-    if (gl == 0) {
-      blk[MGFB_STEP] = step;
-      const uint32_t tag = next_ok ? (uint32_t)nidx : 0xFFFFFFFFu;
-      if (tag != bh1.z) blk[MGFB_RAND_IDX] = tag;
-    }
-  }
+  if (gl == 0 && live) blk[MGFB_STEP] = step;
 }
 
 
@@ -799,8 +775,7 @@ __global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, cons
     blk[MGFB_TOKENS_FREE] = __float_as_uint(gs[idf]);
     blk[MGFB_GTOUCHED] = ((gt[idw >> 5] >> (idw & 31)) & 1u) | (((gt[idd >> 5] >> (idd & 31)) & 1u) << 1) |
                          (((gt[idf >> 5] >> (idf & 31)) & 1u) << 2);
-    blk[MGFB_RAND_IDX] = 0xFFFFFFFFu;  // no pre-generated draws
-    blk[7] = 0;
+    blk[6] = blk[7] = 0;
   }
   uint4 a0 = make_uint4(1, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
   if (gl < d.A) {

@@ -84,16 +84,12 @@ struct MgFastHdr {
 // words [8 + 8G + 8j, ... + 8)      : object j+1 = {loc, visited, meta, (agent + 1) | ntok << 8 | dirty << 16},
 //                                                 {first eight cached tokens}
 // words [8 + 16G + id * G + a]      : agent stat `id` (< 16) of agent a, stat-major so a tick touches whole rows
-// words [8 + 32G + k]               : the new MT19937 state word behind the k-th draw of the NEXT tick's shuffle,
-//                                     generated ahead of time; valid when header word MGFB_RAND_IDX equals the
-//                                     env's (normalised) state index, 0xFFFFFFFF otherwise
 // The block is the truth between ticks; k_fast_pack / k_fast_unpack move it from / to the generic arrays when an
 // entry point other than mg_step needs them (mg_capi.cu).
-enum { MGFB_STEP = 0, MGFB_RNG_IDX, MGFB_NOBJ, MGFB_TOKENS_WRITTEN, MGFB_TOKENS_FREE, MGFB_GTOUCHED, MGFB_RAND_IDX, MGFB_HDR_WORDS = 8 };
+enum { MGFB_STEP = 0, MGFB_RNG_IDX, MGFB_NOBJ, MGFB_TOKENS_WRITTEN, MGFB_TOKENS_FREE, MGFB_GTOUCHED, MGFB_HDR_WORDS = 8 };
 #define MGFB_STATS 16
 #define MGFB_AGENT(G, a) (MGFB_HDR_WORDS + 8 * (a))
 #define MGFB_OBJECT(G, j) (MGFB_HDR_WORDS + 8 * (G) + 8 * (j))
 #define MGFB_STAT(G, id, a) (MGFB_HDR_WORDS + 16 * (G) + (id) * (G) + (a))
-#define MGFB_RAND(G, k) (MGFB_HDR_WORDS + 16 * (G) + MGFB_STATS * (G) + (k))
-#define MGFB_WORDS(G) ((MGFB_HDR_WORDS + 16 * (G) + MGFB_STATS * (G) + (G) + 31) & ~31)
+#define MGFB_WORDS(G) ((MGFB_HDR_WORDS + 16 * (G) + MGFB_STATS * (G) + 31) & ~31)
 #define MGFB_DIRTY (1u << 16)
