@@ -70,9 +70,13 @@ int mg_get_action_success(mg_handle* h, uint8_t* out /*[N][A]*/);
 int mg_get_current_steps(mg_handle* h, int32_t* out /*[N]*/);
 int mg_get_agent_stats(mg_handle* h, int env, float* values /*[A][S_A]*/, uint8_t* touched /*[A][S_A]*/);
 int mg_get_game_stats(mg_handle* h, int env, float* values /*[S_G]*/, uint8_t* touched /*[S_G]*/);
-/* one row of (8 + 2R) int32 per live object in id order:
- * id, type_id, r, c, vibe, agent (-1), tag word 0, #present resources, inv[R], order[R] (-1 padded) */
+/* one row of (8 + 2R + TW) int32 per live object in id order:
+ * id, type_id, r, c, vibe, agent (-1), tag word 0, #present resources, inv[R], order[R] (-1 padded), tags[TW] */
 int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows);
+/* per agent of one env, 4 int32: object id, group id, steps_without_motion, current_stat_reward (float bits;
+ * RewardHelper::current_reward, systems/reward.hpp:36-42) -- with mg_dump_objects everything grid_objects()
+ * (mettagrid_py.cpp:28-139) reports that the deterministic episode signature reads */
+int mg_get_agent_state(mg_handle* h, int env, int32_t* out /*[A][4]*/);
 
 /* replaces MettaGrid::set_inventory(agent_id, inventory) -- mettagrid_py.cpp:203-209, objects/agent.cpp:86-104.
  * items/amounts: host int32 [n], in the iteration order of the unordered_map pybind11 builds from the Python

@@ -817,10 +817,50 @@ class GameConfig:
 
 
 @dataclass
+class AsciiMapConfig:
+    """Mirror of AsciiMapBuilder.Config (map_builder/ascii.py:12-52): one character per cell."""
+
+    map_data: list
+    char_to_map_name: dict
+
+    def build(self):
+        import numpy as np
+
+        rows = [list(line) for line in self.map_data]
+        if any(len(r) != len(rows[0]) for r in rows):
+            raise ValueError("all lines of an ASCII map must have the same length")
+        unknown = {ch for r in rows for ch in r} - set(self.char_to_map_name)
+        if unknown:
+            raise ValueError(f"Unknown character: {sorted(unknown)!r}. Available: {list(self.char_to_map_name)}")
+        return np.array([[self.char_to_map_name[ch] for ch in r] for r in rows], dtype="<U50")
+
+
+@dataclass
 class MettaGridConfig:
     label: str = "mettagrid"
     game: GameConfig = field(default_factory=GameConfig)
     desync_episodes: bool = True
+
+    def with_ascii_map(self, map_data, char_to_map_name) -> "MettaGridConfig":
+        """config/mettagrid_config.py:341-346"""
+        self.game.map_builder = AsciiMapConfig(map_data=map_data, char_to_map_name=char_to_map_name)
+        return self
+
+    @staticmethod
+    def EmptyRoom(num_agents: int, width: int = 10, height: int = 10, border_width: int = 1,
+                  with_walls: bool = False) -> "MettaGridConfig":  # fmt: skip
+        """config/mettagrid_config.py:348-368"""
+        from .mapgen import RandomMapConfig
+
+        objects = {"wall": WallConfig()} if border_width > 0 or with_walls else {}
+        return MettaGridConfig(
+            game=GameConfig(
+                map_builder=RandomMapConfig(agents=num_agents, width=width, height=height, border_width=border_width),
+                actions=ActionsConfig(move=MoveActionConfig(), change_vibe=ChangeVibeActionConfig()),
+                num_agents=num_agents,
+                objects=objects,
+            )
+        )
 
 
 def closureQuery(source, candidates, edge_filters=None, filters=None) -> ClosureQuery:

@@ -507,7 +507,7 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
   std::vector<uint32_t> objs((size_t)nobj * d.OS);
   CK(cudaMemcpy(objs.data(), d.objs + (size_t)env * (d.maxobj + d.NTERR) * d.OS, objs.size() * 4, cudaMemcpyDeviceToHost));
   const int32_t* P = h->program.data();
-  int n = 0, stride = 8 + 2 * d.R;
+  int n = 0, stride = 8 + 2 * d.R + d.TW;
   for (int s = 1; s < nobj && n < max_rows; s++) {
     const uint32_t* o = &objs[(size_t)s * d.OS];
     int flags = o[MGO_META] >> 24;
@@ -524,9 +524,38 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
     const uint16_t* inv = (const uint16_t*)(o + MGO_TAGS + d.TW);
     for (int i = 0; i < d.R; i++) row[8 + i] = inv[i];
     for (int i = 0; i < d.R; i++) row[8 + d.R + i] = i < cnt ? (int)((ord >> (4 * i)) & 15) : -1;
+    for (int k = 0; k < d.TW; k++) row[8 + 2 * d.R + k] = (int32_t)o[MGO_TAGS + k];
     n++;
   }
   return n;
+}
+
+int mg_get_agent_state(mg_handle* h, int env, int32_t* out) {
+  if (!h || !out || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const MgDev& d = h->d;
+  if (int rc = sync_host_view(h)) return rc;
+  std::vector<uint32_t> ag((size_t)d.A * d.AS);
+  CK(cudaMemcpy(ag.data(), d.agents + (size_t)env * d.A * d.AS, ag.size() * 4, cudaMemcpyDeviceToHost));
+  const int32_t* P = h->program.data();
+  for (int a = 0; a < d.A; a++) {
+    const uint32_t* r = &ag[(size_t)a * d.AS];
+    uint32_t obj[MGO_NTOK + 1];
+    CK(cudaMemcpy(obj, d.objs + ((size_t)env * (d.maxobj + d.NTERR) + r[MGAG_OBJ]) * d.OS, sizeof obj, cudaMemcpyDeviceToHost));
+    const int t = obj[MGO_META] & 0xffff;
+    float total = 0.0f;  // RewardHelper::current_reward (systems/reward.hpp:36-42): prev values added in entry order
+    for (int i = MGAG_REWARD_PREV; i < d.AS; i++) {
+      float v;
+      memcpy(&v, &r[i], 4);
+      total += v;
+    }
+    int32_t* o = out + 4 * a;
+    o[0] = (int32_t)obj[MGO_ID];
+    o[1] = P[P[MGS_TEMPLATES] + t * MG_TEMPLATE_WORDS + MGT_GROUP];
+    o[2] = (int32_t)r[MGAG_SWM];
+    memcpy(&o[3], &total, 4);
+  }
+  return MG_OK;
 }
 
 int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, const int32_t* amounts, int n) {

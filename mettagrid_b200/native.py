@@ -34,6 +34,7 @@ SYMBOLS = {
     "mg_get_agent_stats": (_i, [_vp, _i, _vp, _vp]),
     "mg_get_game_stats": (_i, [_vp, _i, _vp, _vp]),
     "mg_dump_objects": (_i, [_vp, _i, _vp, _i]),
+    "mg_get_agent_state": (_i, [_vp, _i, _vp]),
     "mg_set_inventory": (_i, [_vp, _i, _i, _vp, _vp, _i]),
     "mg_grid_obs_configure": (_i, [_vp, _i, _vp]),
     "mg_obs_to_grid": (_i, [_vp, _vp, _i, _vp, _vp]),

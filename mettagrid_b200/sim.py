@@ -36,6 +36,8 @@ def _build_maps(game: Any, num_envs: int, map_seeds: Sequence[int] | None) -> li
         map_seeds = [None if base is None else base + e for e in range(num_envs)]
     if isinstance(mb, RandomMapConfig):
         return [random_map(mb, seed=s) for s in map_seeds]
+    if hasattr(mb, "map_data") and hasattr(mb, "build"):  # config.AsciiMapConfig: the same map for every env
+        return [mb.build()] * num_envs
     # a reference MapBuilderConfig: use its own builder (only available next to the reference package)
     maps = []
     for s in map_seeds:
@@ -222,10 +224,24 @@ class BatchedSimulation:
             "agent": [{n: float(av[a, i]) for i, n in enumerate(P.agent_stat_names) if at[a, i]} for a in range(self.num_agents)],
         }
 
+    def agent_state(self, env: int) -> np.ndarray:
+        """[A, 4] int32: object id, group id, steps_without_motion, current_stat_reward (float32 bits)."""
+        out = np.zeros((self.num_agents, 4), dtype=np.int32)
+        self._check(self._L.mg_get_agent_state(self._h, env, out.ctypes.data))
+        return out
+
+    def grid_objects(self, env: int, min_row: int = -1, max_row: int = -1, min_col: int = -1, max_col: int = -1,
+                     ignore_types: Sequence[str] = ()) -> dict:  # fmt: skip
+        """MettaGrid.grid_objects() for one env (bindings/mettagrid_py.cpp:28-139), see replay.grid_objects."""
+        from .replay import grid_objects
+
+        return grid_objects(self.program, self.dump_objects(env), self.agent_state(env), min_row, max_row, min_col, max_col,
+                            ignore_types)  # fmt: skip
+
     def dump_objects(self, env: int) -> np.ndarray:
         R = len(self.program.resource_names)
         cap = self.program.hdr("MGH_MAX_OBJECTS")
-        out = np.zeros((cap, 8 + 2 * R), dtype=np.int32)
+        out = np.zeros((cap, 8 + 2 * R + self.program.hdr("MGH_TAG_WORDS")), dtype=np.int32)
         n = self._L.mg_dump_objects(self._h, env, out.ctypes.data, cap)
         if n < 0:
             self._check(n)

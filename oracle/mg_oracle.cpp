@@ -1577,7 +1577,7 @@ void mgo_game_stats(void* h, float* vals, uint8_t* touched) {
 //   id, type_id, r, c, vibe, agent index (-1), tag word 0, number of present resources, inv[R], order[R] (-1 padded)
 int mgo_dump_objects(void* h, int32_t* out, int max_rows) {
   Env* e = (Env*)h;
-  int R = e->R, n = 0, stride = 8 + 2 * R;
+  int R = e->R, n = 0, stride = 8 + 2 * R + e->TW;
   for (int s = 1; s < e->proxy0 && n < max_rows; s++) {
     const Obj& o = e->objs[s];
     if (!o.alive) continue;
@@ -1586,9 +1586,23 @@ int mgo_dump_objects(void* h, int32_t* out, int max_rows) {
     row[6] = (int32_t)o.tags[0], row[7] = (int32_t)o.order.size();
     for (int i = 0; i < R; i++) row[8 + i] = o.inv[i];
     for (int i = 0; i < R; i++) row[8 + R + i] = i < (int)o.order.size() ? o.order[i] : -1;
+    for (int k = 0; k < e->TW; k++) row[8 + 2 * R + k] = (int32_t)o.tags[k];
     n++;
   }
   return n;
+}
+// per agent: object id, group, steps_without_motion, RewardHelper::current_reward (systems/reward.hpp:36-42)
+void mgo_agent_state(void* h, int32_t* out) {
+  Env* e = (Env*)h;
+  for (int a = 0; a < e->A; a++) {
+    const Agent& ag = e->agents[a];
+    float total = 0.0f;
+    for (float v : ag.reward_prev) total += v;
+    out[4 * a + 0] = (int32_t)e->objs[ag.obj].id;
+    out[4 * a + 1] = ag.group;
+    out[4 * a + 2] = (int32_t)ag.swm;
+    memcpy(&out[4 * a + 3], &total, 4);
+  }
 }
 // items/amounts in the iteration order of the pybind-built unordered_map (compiler.pybind_dict_order)
 void mgo_set_inventory(void* h, int agent, const int32_t* items, const int32_t* amounts, int n) {  // objects/agent.cpp:86-104

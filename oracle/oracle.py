@@ -54,6 +54,7 @@ def lib():
         L.mgo_agent_stats.argtypes = [vp, vp, vp]
         L.mgo_game_stats.argtypes = [vp, vp, vp]
         L.mgo_dump_objects.argtypes = [vp, vp, ctypes.c_int]
+        L.mgo_agent_state.argtypes = [vp, vp]
         L.mgo_set_inventory.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int]
         L.mgo_test_shuffle.argtypes = [ctypes.c_uint32, ctypes.c_int, vp, vp]
         _lib = L
@@ -150,9 +151,20 @@ class OracleEnv:
     def dump_objects(self):
         R = len(self.program.resource_names)
         cap = self.program.hdr("MGH_MAX_OBJECTS")
-        out = np.zeros((cap, 8 + 2 * R), dtype=np.int32)
+        out = np.zeros((cap, 8 + 2 * R + self.program.hdr("MGH_TAG_WORDS")), dtype=np.int32)
         n = self._L.mgo_dump_objects(self._h, out.ctypes.data, cap)
         return out[:n]
+
+    def agent_state(self):
+        out = np.zeros((self.A, 4), dtype=np.int32)
+        self._L.mgo_agent_state(self._h, out.ctypes.data)
+        return out
+
+    def grid_objects(self, *a, **k):
+        """Same dict as MettaGrid.grid_objects() (bindings/mettagrid_py.cpp:28-139)."""
+        from mettagrid_b200.replay import grid_objects
+
+        return grid_objects(self.program, self.dump_objects(), self.agent_state(), *a, **k)
 
     def set_inventory(self, agent: int, inventory: dict):
         """MettaGrid.set_inventory(agent_id, {resource: amount}) (bindings/mettagrid_py.cpp:203-209)."""

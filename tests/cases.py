@@ -367,3 +367,42 @@ def network_map(num_agents: int = 4, width: int = 16, height: int = 12, seed: in
 
     return random_map(RandomMapConfig(width=width, height=height, border_width=1, seed=seed, agents=num_agents,
                                       objects={"wall": 6, "hub": 2, "relay": 7, "crate": 4}))  # fmt: skip
+
+
+# --------------------------------------------------------------------------------------------------
+# The game of the reference's deterministic episode signature (scripts/deterministic_episode_signature.py:53-92):
+# one agent in a walled 7 x 6 room with a hub and three wires, a materialized closure query, a per-tick log reward.
+# --------------------------------------------------------------------------------------------------
+def signature_config(ns=None):
+    if ns is None:
+        ns = C
+    cfg = ns.MettaGridConfig.EmptyRoom(num_agents=1, with_walls=True).with_ascii_map(
+        [
+            ["#", "#", "#", "#", "#", "#", "#"],
+            ["#", ".", ".", ".", ".", ".", "#"],
+            ["#", ".", "W", "H", "W", ".", "#"],
+            ["#", ".", ".", "W", ".", ".", "#"],
+            ["#", ".", ".", "@", ".", ".", "#"],
+            ["#", "#", "#", "#", "#", "#", "#"],
+        ],
+        char_to_map_name={"#": "wall", "@": "agent.agent", ".": "empty", "H": "hub", "W": "wire"},
+    )
+    cfg.game.actions.noop.enabled = True
+    cfg.game.resource_names = ["gold", "silver"]
+    cfg.game.agent.inventory.initial = {"gold": 10, "silver": 5}
+    cfg.game.agent.rewards = {
+        "stability": ns.reward(
+            ns.weighted_sum([(1.0, ns.InventoryValue(item="gold")), (0.5, ns.InventoryValue(item="silver"))], log=True),
+            per_tick=True,
+        )
+    }
+    cfg.game.objects["hub"] = ns.GridObjectConfig(name="hub", map_name="hub", tags=[ns.typeTag("hub")])
+    cfg.game.objects["wire"] = ns.GridObjectConfig(name="wire", map_name="wire", tags=[ns.typeTag("wire")])
+    cfg.game.materialize_queries = [
+        ns.MaterializedQuery(
+            tag="connected_one",
+            query=ns.ClosureQuery(source=ns.typeTag("hub"), candidates=ns.query(ns.typeTag("wire")),
+                                  edge_filters=[ns.maxDistance(1)], max_items=1),  # fmt: skip
+        )
+    ]
+    return cfg
