@@ -209,3 +209,12 @@ def test_introspection_and_masked_reset_between_ticks():
         assert sim.get_episode_stats(e) == o.get_episode_stats()
         assert np.array_equal(sim.dump_objects(e), o.dump_objects())
     sim.close()
+
+
+def test_long_token_lists_with_vibe_edits():
+    # every agent carries 9 resources: 1 tag + (vibe) + 9 inventory + group + id = 12-13 cached tokens, more than the
+    # eight kept in registers / the packed block, so the tail lives in the object record and vibe edits shift it
+    cfg = cases.benchmark_config(7, num_tokens=200)
+    cfg.game.agent.inventory.initial = {"ore_red": 3, "ore_blue": 300, "ore_green": 1, "battery_red": 9, "battery_blue": 2,
+                                        "heart": 70000 % 65536, "armor": 5, "laser": 1, "blueprint": 8}  # fmt: skip
+    _triple(cfg, num_envs=10, steps=80, expect_lanes=8, p_vibe=0.6, check_every=2)
