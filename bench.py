@@ -82,9 +82,19 @@ def algo_bytes(P, workload: str) -> float:
     return float(b_io + b_state)
 
 
+ACTION_MODE = os.environ.get("METTAGRID_BENCH_ACTIONS", "effective")  # --actions (inherited by the CPU workers)
+
+
 def gen_actions(num_actions: int, num_primary: int, steps: int, envs: int, agents: int, seed: int):
-    """'effective' sampling: primary uniform over non-vibe actions, vibe change with p = 0.1"""
+    """SURVEY 8(d), both from np.random.RandomState(...).randint like the reference's benchmark
+    (benchmarks/test_mettagrid_env_benchmark.py:44-49):
+    'effective' (default): primary uniform over the non-vibe actions, vibe change with p = 0.1;
+    'verbatim': uniform over ALL action ids into the primary buffer, vibe buffer left 0 -- about 97 % of the ids
+    are change_vibe ids, which the primary stream ignores."""
     rng = np.random.RandomState(seed)
+    if ACTION_MODE == "verbatim":
+        prim = rng.randint(0, num_actions, size=(steps, envs, agents)).astype(np.int32)
+        return prim, np.zeros_like(prim)
     prim = rng.randint(0, num_primary, size=(steps, envs, agents)).astype(np.int32)
     vibe = np.zeros_like(prim)
     m = rng.rand(steps, envs, agents) < 0.1
@@ -313,7 +323,8 @@ def run_ours(args):
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
             "config": {"workload": WORKLOADS[wl][0].format(A=A) + f", {envs} envs/GPU",
-                       "envs_per_gpu": envs, "agents_per_env": A, "actions": f"primary uniform over {num_primary}, vibe p=0.1",
+                       "envs_per_gpu": envs, "agents_per_env": A, "actions": (f"verbatim: primary uniform over all {num_actions} ids, vibe buffer 0" if ACTION_MODE == "verbatim"
+                                   else f"primary uniform over {num_primary}, vibe p=0.1"),
                        "l2": "flushed between timed steps (256 MB fill)", "obs_write_GBps": value * 3 * P.num_tokens / 1e9,
                        "parallelism": f"env-sharded x{world}, no per-step collective",
                        "mean_move_success_per_agent": float(mean_stats[P.agent_stat_names.index("action.move.success")])},
@@ -345,12 +356,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--actions", default="effective", choices=["effective", "verbatim"],
+                    help="action sampling (SURVEY 8d): the default drives every agent; 'verbatim' is the reference benchmark's")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--agents", type=int, default=0)
     ap.add_argument("--cpu-steps", type=int, default=40000)
     ap.add_argument("--cpu-envs-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global ACTION_MODE
+    ACTION_MODE = args.actions
+    os.environ["METTAGRID_BENCH_ACTIONS"] = args.actions
 
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
