@@ -5,12 +5,17 @@ for a batch: flat ``[N*A, ...]`` views of the same CUDA buffers, the combined-in
 ``:313-394`` done on the device, and auto-reset of finished environments (``:299-302``: an env whose
 agents are all terminal or all truncated is rebuilt before its next step) through ``mg_reset`` with a
 device mask -- observations never leave HBM.
+
+``desync_episodes`` restates ``EarlyResetHandler`` (python/src/mettagrid/envs/early_reset_handler.py:6-27): the FIRST
+episode of every environment is truncated at a step drawn from ``numpy.random.default_rng(env seed)`` in
+``[1, max_steps]`` so that the environments of a batch do not all end on the same tick.
 """
 
 from __future__ import annotations
 
 from typing import Any
 
+import numpy as np
 import torch
 
 from .sim import BatchedSimulation
@@ -59,9 +64,14 @@ def decode_actions(actions: torch.Tensor, num_primary: int, vibe_action_ids: tor
 class MettaGridVecEnv:
     """N envs x A agents presented as N*A agents, buffers on the GPU."""
 
-    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, **kw):
+    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, desync_episodes: bool = False, **kw):
         self.sim = BatchedSimulation(cfg, num_envs, seeds=seed, **kw)
         s = self.sim
+        game = getattr(cfg, "game", cfg)
+        self._steps = torch.zeros(num_envs, dtype=torch.int64, device=s.device)  # current_step of every env
+        self._early = None
+        if desync_episodes and int(game.max_steps) > 0:
+            self._early = self._draw_early_reset_steps(int(game.max_steps))
         names = s.program.action_names
         self.action_names = [n for n in names if not n.startswith("change_vibe_")]
         self.vibe_action_names = [n for n in names if n.startswith("change_vibe_")]
@@ -89,9 +99,15 @@ class MettaGridVecEnv:
     def truncations(self) -> torch.Tensor:
         return self.sim.truncations.view(-1)
 
+    def _draw_early_reset_steps(self, max_steps: int) -> torch.Tensor:
+        # early_reset_handler.py:15-20: one draw per env from a generator seeded with the env's seed
+        steps = [int(np.random.default_rng(int(sd)).integers(1, max_steps + 1)) for sd in self.sim.seeds]
+        return torch.tensor(steps, dtype=torch.int64, device=self.sim.device)
+
     def reset(self, seed: int | None = None):
         seeds = None if seed is None else [seed + e for e in range(self.num_envs)]
         self.sim.reset(seeds=seeds)
+        self._steps.zero_()
         return self.observations, {}
 
     def step(self, actions: torch.Tensor):
@@ -101,11 +117,17 @@ class MettaGridVecEnv:
         n_done = int(done.sum())
         if n_done:
             s.reset(env_mask=done)
+            self._steps.masked_fill_(done, 0)
             self.episodes_finished += n_done
         core, vibe = decode_actions(torch.as_tensor(actions, device=s.device), self.num_primary, self._vibe_ids)
         s.actions.copy_(core.view(s.actions.shape))
         s.vibe_actions.copy_(vibe.view(s.vibe_actions.shape))
         s.step()
+        self._steps += 1
+        if self._early is not None:  # early_reset_handler.py:22-25: end_episode() = all agents truncated
+            hit = self._steps >= self._early
+            s.truncations.masked_fill_(hit.unsqueeze(1), True)
+            self._early.masked_fill_(hit, torch.iinfo(torch.int64).max)  # first episode only
         return self.observations, self.rewards, self.terminals, self.truncations, {}
 
     def close(self):

@@ -121,3 +121,28 @@ def test_vecenv_autoreset_and_flat_views():
             assert np.array_equal(term.cpu().numpy().reshape(5, 3)[e], o.terminals())
     assert env.episodes_finished == 10  # 5 envs x 2 completed 12-step episodes within 30 steps
     env.close()
+
+
+def test_vecenv_desync_episodes_like_early_reset_handler():
+    """EarlyResetHandler (envs/early_reset_handler.py): the first episode of env e ends, truncated, at the step
+    numpy.random.default_rng(seed_e).integers(1, max_steps + 1) draws; later episodes run to max_steps."""
+    from mettagrid_b200.vecenv import MettaGridVecEnv
+
+    max_steps = 20
+    env = MettaGridVecEnv(cases.benchmark_config(4, max_steps=max_steps), 6, seed=30, desync_episodes=True)
+    early = [int(np.random.default_rng(30 + e).integers(1, max_steps + 1)) for e in range(6)]
+    assert len(set(early)) > 1
+    zeros = torch.zeros(24, dtype=torch.int64, device="cuda")
+    ends = [[] for _ in range(6)]
+    for t in range(1, 61):
+        _, _, term, trunc, _ = env.step(zeros)
+        done = (term.view(6, 4).all(dim=1) | trunc.view(6, 4).all(dim=1)).cpu().numpy()
+        for e in range(6):
+            if done[e]:
+                ends[e].append(t)
+    for e in range(6):
+        want = [early[e]]
+        while want[-1] + max_steps <= 60:
+            want.append(want[-1] + max_steps)
+        assert ends[e] == want, f"env {e}: episodes ended at {ends[e]}, expected {want}"
+    env.close()
