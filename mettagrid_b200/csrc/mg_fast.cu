@@ -4,17 +4,22 @@
 //
 // Mapping: G = 8, 16 or 32 lanes own one environment (32 / G environments per warp).  Lane l plays two
 // roles: agent l (actions, bookkeeping, observer) and object slot l + 1 (location, vibe, token cache).
-// Nothing runs on "lane 0 only" except the application of the shuffle's swaps:
-//   * every agent decodes its own actions; noop / change_vibe never interact across agents;
-//   * moves resolve in the reference's shuffled order (:958-999) with one ballot per move: the target cell is
-//     free iff no object lane holds that location -- the occupancy grid is never read (and not maintained:
-//     nothing reads it for such a handle; mg_reset rebuilds it);
-//   * observations (:665-824): each agent lane builds sort keys (Manhattan rank, packed location, object) for
-//     the objects in its window, sorts them in registers with a Batcher network, and writes its row into a
-//     shared-memory stage of the env's whole [A][T][3] block, which the group streams out with 16-byte stores;
-//   * `cell.visited` (:787-796) goes to the lowest agent index that sees an object (a ballot per object).
-// State loads are issued in three waves (env/agents/objects/actions -> RNG/action rows/token caches ->
-// stats/coverage), stat updates are decided in registers and written back once.
+// No phase runs on one lane only:
+//   * state comes from the env's packed block (mg_state.h, MGFB_*) in ONE load wave; the program header is a
+//     kernel argument (constant bank);
+//   * the shuffle (:958-964) is decoded one draw per lane, and every lane finds the agent that acts at its step by
+//     walking std::shuffle's transpositions backwards;
+//   * every agent decodes its own actions; noop / change_vibe never interact across agents; moves resolve in the
+//     shuffled order (:958-999) with one ballot per step: the target cell is free iff no object lane holds that
+//     location -- the occupancy grid is never read (and not maintained: nothing reads it for such a handle;
+//     mg_reset rebuilds it);
+//   * observations (:665-824): each agent lane builds one sort key per object (Manhattan rank, packed offset, token
+//     count, object), sorts them in registers with a Batcher network and hands every visible object its first
+//     token position; the OBJECT lanes then write their cached tokens into each observer's row of a shared-memory
+//     stage of the env's whole [A][T][3] block, which the group streams out with 16-byte stores;
+//   * `cell.visited` (:787-796) goes to the lowest agent index that sees an object (one ballot per object);
+//   * stat updates are decided in registers and written back once, in the reference's float-add order.
+// k_fast_pack / k_fast_unpack move the packed block from / to the generic arrays (mg_capi.cu decides when).
 #include <cuda_runtime.h>
 
 #include "mg_state.h"
@@ -22,9 +27,6 @@
 namespace {
 
 #define FAST_INVALID 0xFFFFFFFFu
-#ifndef MG_FAST_EARLY_FF
-#define MG_FAST_EARLY_FF 0  // measured slower: +33 % L2 write traffic and half-sector stores (profiles/README.md)
-#endif
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 11;
@@ -248,22 +250,8 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     }
   }
 
-  // Most of every observation row is EmptyTokenByte (:940-942).  When the env's block is 16-byte aligned it is
-  // written as such right away, while the loads are in flight; the end of the tick then only streams the vectors
-  // that hold tokens.
   uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
   const int nbytes = A * 3 * T;
-  const bool aligned = MG_FAST_EARLY_FF && (nbytes & 15) == 0 && ((uintptr_t)d.obs & 15u) == 0;
-  if (aligned && live) {
-    uint4* g4 = (uint4*)gobs;
-    const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-    const int nv = nbytes >> 4;
-    int v = gl;
-#pragma unroll 1
-    for (; v + 3 * G < nv; v += 4 * G) __stcs(g4 + v, ff), __stcs(g4 + v + G, ff), __stcs(g4 + v + 2 * G, ff), __stcs(g4 + v + 3 * G, ff);
-#pragma unroll 1
-    for (; v < nv; v += G) __stcs(g4 + v, ff);
-  }
 #pragma unroll
   for (int k = 0; k < LV; k++) {
     const int i = tid + k * MG_FAST_WARPS * 32;
@@ -634,18 +622,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   __syncwarp();
 
   // ---- stream the env's observation block out
-  if (aligned) {
-    // the rest of every row is already EmptyTokenByte in HBM: each agent streams the vectors that hold its tokens
-    // (a vector shared with the neighbouring row carries identical bytes from both lanes)
-    if (isA && live) {
-      const int rs = gl * 3 * T;
-      const uint4* s4 = (const uint4*)gb;
-      uint4* g4 = (uint4*)gobs;
-      const int v1 = (rs + 3 * min(attempted, T) + 15) >> 4;
-#pragma unroll 2
-      for (int v = rs >> 4; v < v1; v++) __stcs(g4 + v, s4[v]);
-    }
-  } else {
+  {
     const int head = min(nbytes, (int)((16u - ((uint32_t)(uintptr_t)gobs & 15u)) & 15u));
     if (live) {
 #pragma unroll 1
@@ -655,8 +632,14 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const uint4* s4 = (const uint4*)(stage + head);
     uint4* g4 = (uint4*)(gobs + head);
     if (live) {
+      int v = gl;
 #pragma unroll 1
-      for (int v = gl; v < body; v += G) __stcs(g4 + v, s4[v]);
+      for (; v + 3 * G < body; v += 4 * G) {  // four vectors in flight per lane
+        const uint4 x0 = s4[v], x1 = s4[v + G], x2 = s4[v + 2 * G], x3 = s4[v + 3 * G];
+        __stcs(g4 + v, x0), __stcs(g4 + v + G, x1), __stcs(g4 + v + 2 * G, x2), __stcs(g4 + v + 3 * G, x3);
+      }
+#pragma unroll 1
+      for (; v < body; v += G) __stcs(g4 + v, s4[v]);
     }
     const int done = head + (body << 4);
     if (live) {
