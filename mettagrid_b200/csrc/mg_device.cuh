@@ -61,16 +61,21 @@ struct Deferred {
 };
 
 // handler/handler_context.hpp:34-55
+// Packed into 24 bytes: contexts live in local memory (they are passed by reference through the non-inlined
+// interpreter) and one is built per handler invocation.  Object slots are < 65536 (mg_create), coordinates fit
+// int16 (a line scan may step one cell outside the map).
 struct Ctx {
-  int actor, target, source;
-  int distance, tr, tc, move_dir;
+  uint16_t actor, target, source;
+  int16_t distance, tr, tc;
+  int8_t move_dir;
   bool skip_trigger, failed;
   Deferred* deferred;
 };
 __device__ __forceinline__ Ctx make_ctx() {
   Ctx c;
   c.actor = c.target = c.source = 0;
-  c.distance = c.tr = c.tc = c.move_dir = 0;
+  c.distance = c.tr = c.tc = 0;
+  c.move_dir = 0;
   c.skip_trigger = c.failed = false;
   c.deferred = nullptr;
   return c;
