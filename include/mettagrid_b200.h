@@ -60,6 +60,12 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
  * for all.  new_seeds: host uint32 [num_envs] or NULL to keep the seeds. */
 int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, void* stream);
 
+/* Replace the stored initial state of one environment (SURVEY 8b "optional new initial state", 8f-1 map-instance
+ * pool): the next mg_reset that selects `env` builds it from this map.  init_cells: host int16 [H][W] template
+ * indices; init_gstats: host float [S_G] or NULL to keep the stored ones.  The map must hold the program's agent
+ * count (else the reset raises the env's error word) and no more objects than the handle was sized for. */
+int mg_set_map(mg_handle* h, int env, const int16_t* init_cells, const float* init_gstats);
+
 /* first environment with a pending error: token-budget overflow (mettagrid_c.cpp:364-375) etc.
  * Returns MG_OK when none, MG_E_ENV otherwise.  code = MGERR_* bits, info = agent | attempted<<16. */
 int mg_poll_errors(mg_handle* h, int* env, int* code, int* info);

@@ -420,6 +420,34 @@ int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, v
   return MG_OK;
 }
 
+int mg_set_map(mg_handle* h, int env, const int16_t* init_cells, const float* init_gstats) {
+  if (!h || !init_cells || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
+  const MgDev& d = h->d;
+  const int32_t* P = h->program.data();
+  int nobj = 0;
+  for (int i = 0; i < d.HW; i++) {
+    if (init_cells[i] >= P[MGH_NUM_TEMPLATES]) {
+      h->err = "mg_set_map: init_cells holds a template index outside the program";
+      return MG_E_INVALID;
+    }
+    nobj += init_cells[i] >= 0;
+  }
+  if (nobj >= d.maxobj || (h->fast && nobj > h->fl.G)) {
+    h->err = "mg_set_map: the map holds more objects than this handle was created for";
+    return MG_E_INVALID;
+  }
+  if (init_gstats && !d.init_gstats) {
+    h->err = "mg_set_map: the handle was created without initial game stats";
+    return MG_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy((void*)(d.init_cells + (size_t)env * d.HW), init_cells, (size_t)d.HW * 2, cudaMemcpyHostToDevice));
+  if (init_gstats)
+    CK(cudaMemcpy((void*)(d.init_gstats + (size_t)env * d.SG), init_gstats, (size_t)d.SG * 4, cudaMemcpyHostToDevice));
+  return MG_OK;
+}
+
 int mg_poll_errors(mg_handle* h, int* env, int* code, int* info) {
   if (!h) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));

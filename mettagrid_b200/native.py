@@ -27,6 +27,7 @@ SYMBOLS = {
     "mg_step": (_i, [_vp, _vp]),
     "mg_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mg_reset": (_i, [_vp, _vp, _vp, _vp]),
+    "mg_set_map": (_i, [_vp, _i, _vp, _vp]),
     "mg_poll_errors": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "mg_get_episode_rewards": (_i, [_vp, _vp]),
     "mg_get_action_success": (_i, [_vp, _vp]),

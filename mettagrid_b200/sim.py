@@ -173,6 +173,16 @@ class BatchedSimulation:
         self._check(self._L.mg_reset(self._h, mask_ptr, seed_ptr, self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
+    def set_map(self, env: int, grid) -> None:
+        """Give one environment a new map (a host-side map pool); used by its next reset."""
+        cells, gstats = self.program.encode_map(np.asarray(grid), with_stats=True)
+        cells = np.ascontiguousarray(cells, dtype=np.int16)
+        gstats = np.ascontiguousarray(gstats, dtype=np.float32)
+        if cells.shape != (self.program.height, self.program.width):
+            raise ValueError(f"map must be {self.program.height} x {self.program.width}")
+        self._check(self._L.mg_set_map(self._h, env, cells.ctypes.data, gstats.ctypes.data))
+        self._init_cells[env], self._init_gstats[env] = cells, gstats
+
     def check_errors(self):
         """Raise like the reference when an env hit a hard error (token budget, mettagrid_c.cpp:364-375)."""
         env, code, info = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

@@ -146,3 +146,53 @@ def test_vecenv_desync_episodes_like_early_reset_handler():
             want.append(want[-1] + max_steps)
         assert ends[e] == want, f"env {e}: episodes ended at {ends[e]}, expected {want}"
     env.close()
+
+
+def test_set_map_gives_an_env_a_new_map_at_its_next_reset():
+    """Host-side map pool: mg_set_map replaces one env's stored initial state."""
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+    from mettagrid_b200.sim import BatchedSimulation, MettaGridError
+    from oracle.oracle import OracleEnv
+
+    for cfg, mk in (
+        (cases.benchmark_config(4), lambda s: random_map(RandomMapConfig(agents=4, width=20, height=20, seed=s))),  # fast path
+        (cases.walled_config(4, max_steps=0), lambda s: random_map(RandomMapConfig(agents=4, width=16, height=12, seed=s,
+                                                                    border_width=1, objects={"wall": 20}))),  # fmt: skip
+    ):
+        sim = BatchedSimulation(cfg, 4, seeds=50)
+        P = sim.program
+        A = P.num_agents
+        rs = np.random.RandomState(8)
+        acts = rs.randint(0, 5, size=(40, 4, A)).astype(np.int32)
+        zeros = np.zeros((4, A), np.int32)
+        for t in range(10):
+            sim.step(acts[t], zeros)
+        new_map = mk(777)
+        sim.set_map(2, new_map)
+        mask = torch.zeros(4, dtype=torch.bool, device="cuda")
+        mask[2] = True
+        sim.reset(mask)
+        cells, gs = P.encode_map(new_map, with_stats=True)
+        fresh = OracleEnv(P, cells, int(sim.seeds[2]), gs)
+        torch.cuda.synchronize()
+        assert np.array_equal(sim.observations[2].cpu().numpy(), fresh.observations())
+        for t in range(10, 40):
+            sim.step(acts[t], zeros)
+            fresh.step(acts[t, 2], zeros[2])
+        torch.cuda.synchronize()
+        assert np.array_equal(sim.observations[2].cpu().numpy(), fresh.observations())
+        assert sim.get_episode_stats(2) == fresh.get_episode_stats()
+        assert np.array_equal(sim.dump_objects(2), fresh.dump_objects())
+        sim.check_errors()
+        sim.close()
+    # a map with more objects than a fast handle was sized for is refused by the C ABI
+    from mettagrid_b200 import native
+
+    sim = BatchedSimulation(cases.benchmark_config(4), 2, seeds=1)
+    assert sim.step_kernel == 8
+    cells = sim._init_cells[0].copy()
+    free = np.argwhere(cells < 0)[:9]
+    cells[free[:, 0], free[:, 1]] = cells.max()  # 13 objects for 8 lanes
+    assert sim._L.mg_set_map(sim._h, 0, cells.ctypes.data, None) == native.MG_E_INVALID
+    assert b"more objects" in sim._L.mg_last_error(sim._h)
+    sim.close()
