@@ -218,3 +218,12 @@ def test_long_token_lists_with_vibe_edits():
     cfg.game.agent.inventory.initial = {"ore_red": 3, "ore_blue": 300, "ore_green": 1, "battery_red": 9, "battery_blue": 2,
                                         "heart": 70000 % 65536, "armor": 5, "laser": 1, "blueprint": 8}  # fmt: skip
     _triple(cfg, num_envs=10, steps=80, expect_lanes=8, p_vibe=0.6, check_every=2)
+
+
+def test_truncating_episodes_and_small_token_base():
+    # max_steps with episode_truncates (truncations, not terminals) and base-10 inventory digits in the token builder
+    cfg = cases.benchmark_config(5, num_tokens=220, max_steps=30)
+    cfg.game.episode_truncates = True
+    cfg.game.obs.token_value_base = 10
+    cfg.game.agent.inventory.initial = {"ore_red": 7, "heart": 345, "laser": 12}
+    _triple(cfg, num_envs=7, steps=45, expect_lanes=8, p_vibe=0.4)
