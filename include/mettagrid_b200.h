@@ -89,6 +89,21 @@ int mg_get_agent_state(mg_handle* h, int env, int32_t* out /*[A][4]*/);
  * dict (mettagrid_b200.compiler.pybind_dict_order). */
 int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, const int32_t* amounts, int n);
 
+/* Vectorised-env step (next row 8f-2): what MettaGridPufferEnv.step does around the C++ step
+ * (python/src/mettagrid/envs/mettagrid_puffer_env.py:296-408), entirely on the device and asynchronous.
+ * mg_vecenv_configure: the number of primary actions P, the env action ids of the V vibe actions (host int32 [V]),
+ * and optionally one early-reset step per env (host int64 [N], EarlyResetHandler: envs/early_reset_handler.py).
+ * mg_vecenv_step: `actions` is a DEVICE tensor of N * A combined indices (ncols = 1: values < P are primary actions,
+ * values in [P, P + P*V) encode primary = off / V, vibe = off % V) or N * A (primary, vibe index) pairs (ncols = 2),
+ * int32 or int64.  With auto_reset, environments whose agents were all terminal or all truncated after the
+ * previous step are rebuilt first (:299-302).  Out-of-range actions raise error bits (1 negative, 2 out of range,
+ * 4 vibe index out of range, 8 no vibe action space, 16 primary out of range) that mg_vecenv_poll returns with
+ * the number of finished episodes. */
+int mg_vecenv_configure(mg_handle* h, int num_primary, const int32_t* vibe_action_ids, int num_vibe_actions,
+                        const int64_t* early_reset_steps);
+int mg_vecenv_step(mg_handle* h, const void* actions, int is_int64, int ncols, int auto_reset, void* stream);
+int mg_vecenv_poll(mg_handle* h, int* episodes_finished, int* error_bits);
+
 /* Dense grid observations (next row 8f-3): replaces GridObsWrapper._convert --
  * python/src/mettagrid/envs/grid_obs_wrapper.py:33-96.  mg_grid_obs_configure fixes the number of feature planes C
  * (max feature id + 1) and the per-feature normalisation (host float[256], entries < 1 are raised to 1 like the

@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmettagrid_b200.so"
-SOURCES = ["mg_kernels.cu", "mg_fast.cu", "mg_gridobs.cu", "mg_capi.cu"]
+SOURCES = ["mg_kernels.cu", "mg_fast.cu", "mg_gridobs.cu", "mg_vecenv.cu", "mg_capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",  # the reference's float math is unfused mul/add

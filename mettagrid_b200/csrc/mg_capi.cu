@@ -1,5 +1,6 @@
 // mg_capi.cu -- the C ABI (include/mettagrid_b200.h): host-side handle, memory, launches.
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,6 +24,10 @@ cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgF
 cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_obs_to_grid(const uint8_t* obs, float* grid, int rows, int T, int C, int H, int W, const float* scale,
                                   cudaStream_t st);
+cudaError_t mg_launch_vecenv_prepare(const void* act, int is_int64, int ncols, int num_envs, int A, int P, int V,
+                                     const int32_t* vibe_ids, int32_t* actions, int32_t* vibe_actions, const uint8_t* term,
+                                     const uint8_t* trunc, uint8_t* done, int64_t* steps, int* counters, cudaStream_t st);
+cudaError_t mg_launch_vecenv_post(int num_envs, int A, int64_t* steps, int64_t* early, uint8_t* trunc, cudaStream_t st);
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st);
 
@@ -48,6 +53,13 @@ struct mg_handle {
   uint8_t* h_term = nullptr;
   uint8_t* h_trunc = nullptr;
   uint32_t* seeds_dev = nullptr;
+  // vectorised-env glue (mg_vecenv.cu)
+  int ve_primary = 0, ve_vibes = 0;
+  int32_t* ve_vibe_ids = nullptr;
+  uint8_t* ve_done = nullptr;
+  int64_t* ve_steps = nullptr;
+  int64_t* ve_early = nullptr;
+  int* ve_counters = nullptr;  // [0] episodes finished, [1] decoder error bits
   float* grid_scale = nullptr;  // device float[256], per-feature normalisation of the dense grid observations
   int grid_features = 0;
   cudaStream_t own_stream = nullptr;
@@ -614,6 +626,66 @@ int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, con
 int mg_num_envs(const mg_handle* h) { return h ? h->d.num_envs : 0; }
 int mg_num_agents(const mg_handle* h) { return h ? h->d.A : 0; }
 int mg_num_tokens(const mg_handle* h) { return h ? h->d.T : 0; }
+int mg_vecenv_configure(mg_handle* h, int num_primary, const int32_t* vibe_action_ids, int num_vibe_actions,
+                        const int64_t* early_reset_steps) {
+  if (!h || num_primary <= 0 || num_vibe_actions < 0 || (num_vibe_actions && !vibe_action_ids)) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t N = (size_t)h->d.num_envs;
+  int rc;
+  if (!h->ve_done) {
+    if ((rc = dev_alloc(h, &h->ve_done, N)) || (rc = dev_alloc(h, &h->ve_steps, N)) || (rc = dev_alloc(h, &h->ve_counters, 2)) ||
+        (rc = dev_alloc(h, &h->ve_vibe_ids, (size_t)(num_vibe_actions > 0 ? num_vibe_actions : 1))))
+      return rc;
+  } else if (num_vibe_actions > h->ve_vibes) {
+    h->err = "mg_vecenv_configure: the vibe action list cannot grow after the first call";
+    return MG_E_INVALID;
+  }
+  h->ve_primary = num_primary, h->ve_vibes = num_vibe_actions;
+  if (num_vibe_actions) CK(cudaMemcpy(h->ve_vibe_ids, vibe_action_ids, (size_t)num_vibe_actions * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(h->ve_steps, 0, N * 8));
+  CK(cudaMemset(h->ve_counters, 0, 8));
+  if (early_reset_steps) {
+    if (!h->ve_early && (rc = dev_alloc(h, &h->ve_early, N))) return rc;
+    CK(cudaMemcpy(h->ve_early, early_reset_steps, N * 8, cudaMemcpyHostToDevice));
+  } else if (h->ve_early) {
+    std::vector<int64_t> never(N, INT64_MAX);
+    CK(cudaMemcpy(h->ve_early, never.data(), N * 8, cudaMemcpyHostToDevice));
+  }
+  return MG_OK;
+}
+
+int mg_vecenv_step(mg_handle* h, const void* actions, int is_int64, int ncols, int auto_reset, void* stream) {
+  if (!h || !actions || (ncols != 1 && ncols != 2)) return MG_E_INVALID;
+  if (!h->ve_done || !h->buffers_set) {
+    h->err = "mg_vecenv_step: call mg_set_buffers and mg_vecenv_configure first";
+    return MG_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  MgDev& d = h->d;
+  CK(mg_launch_vecenv_prepare(actions, is_int64, ncols, d.num_envs, d.A, h->ve_primary, h->ve_vibes, h->ve_vibe_ids,
+                              (int32_t*)d.actions, (int32_t*)d.vibe_actions, d.terminals, d.truncations, h->ve_done,
+                              h->ve_steps, h->ve_counters, st));
+  if (auto_reset) {  // rebuild what finished on the previous step; CTAs without a selected env leave at once
+    if (int rc = mg_reset(h, h->ve_done, nullptr, stream)) return rc;
+  }
+  if (int rc = launch_step(h, d, st)) return rc;
+  CK(mg_launch_vecenv_post(d.num_envs, d.A, h->ve_steps, h->ve_early, d.truncations, st));
+  return MG_OK;
+}
+
+int mg_vecenv_poll(mg_handle* h, int* episodes_finished, int* error_bits) {
+  if (!h || !h->ve_counters) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  int c[2];
+  CK(cudaMemcpy(c, h->ve_counters, sizeof c, cudaMemcpyDeviceToHost));
+  if (episodes_finished) *episodes_finished = c[0];
+  if (error_bits) *error_bits = c[1];
+  if (c[1]) CK(cudaMemset(h->ve_counters + 1, 0, 4));  // reported once
+  return MG_OK;
+}
+
 int mg_grid_obs_configure(mg_handle* h, int num_features, const float* scale) {
   if (!h || !scale || num_features <= 0 || num_features > 256) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));

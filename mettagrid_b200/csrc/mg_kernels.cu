@@ -507,6 +507,10 @@ __device__ __noinline__ void observe_all(const Wv& w, const Smem& s, int lane, b
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (mask) {  // a masked launch usually selects few environments: a CTA without any leaves before loading tables
+    const int e = blockIdx.x * MG_WARPS_PER_CTA + warp;
+    if (!__syncthreads_or(e < d.num_envs && mask[e])) return;
+  }
   {
     Smem cta;
     carve(d, smem_raw, warp, cta);
@@ -665,6 +669,10 @@ __device__ __forceinline__ void load_agents(const Wv& w, const Smem& s, int lane
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d, const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (mask) {  // a masked launch usually selects few environments: a CTA without any leaves before loading tables
+    const int e = blockIdx.x * MG_WARPS_PER_CTA + warp;
+    if (!__syncthreads_or(e < d.num_envs && mask[e])) return;
+  }
   {
     Smem cta;
     carve(d, smem_raw, warp, cta);

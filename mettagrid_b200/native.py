@@ -37,6 +37,9 @@ SYMBOLS = {
     "mg_dump_objects": (_i, [_vp, _i, _vp, _i]),
     "mg_get_agent_state": (_i, [_vp, _i, _vp]),
     "mg_set_inventory": (_i, [_vp, _i, _i, _vp, _vp, _i]),
+    "mg_vecenv_configure": (_i, [_vp, _i, _vp, _i, _vp]),
+    "mg_vecenv_step": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mg_vecenv_poll": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "mg_grid_obs_configure": (_i, [_vp, _i, _vp]),
     "mg_obs_to_grid": (_i, [_vp, _vp, _i, _vp, _vp]),
     "mg_num_envs": (_i, [_vp]),

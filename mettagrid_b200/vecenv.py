@@ -62,25 +62,40 @@ def decode_actions(actions: torch.Tensor, num_primary: int, vibe_action_ids: tor
 
 
 class MettaGridVecEnv:
-    """N envs x A agents presented as N*A agents, buffers on the GPU."""
+    """N envs x A agents presented as N*A agents, buffers on the GPU.
 
-    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, desync_episodes: bool = False, **kw):
+    ``step`` is one asynchronous C-ABI call (``mg_vecenv_step``, csrc/mg_vecenv.cu): finished environments are
+    found and rebuilt, actions decoded, the tick run and the early-reset truncation applied on the device.
+    With ``validate=True`` (default, the reference's behaviour) out-of-range actions raise ``ValueError`` at
+    once, which costs one host synchronisation per step; ``validate=False`` defers the check to ``poll()``."""
+
+    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, desync_episodes: bool = False, validate: bool = True, **kw):
         self.sim = BatchedSimulation(cfg, num_envs, seeds=seed, **kw)
         s = self.sim
         game = getattr(cfg, "game", cfg)
-        self._steps = torch.zeros(num_envs, dtype=torch.int64, device=s.device)  # current_step of every env
-        self._early = None
-        if desync_episodes and int(game.max_steps) > 0:
-            self._early = self._draw_early_reset_steps(int(game.max_steps))
         names = s.program.action_names
         self.action_names = [n for n in names if not n.startswith("change_vibe_")]
         self.vibe_action_names = [n for n in names if n.startswith("change_vibe_")]
         self.num_primary = len(self.action_names)
-        self._vibe_ids = torch.tensor([i for i, n in enumerate(names) if n.startswith("change_vibe_")],
-                                      dtype=torch.int64, device=s.device)  # fmt: skip
+        vibe_ids = [i for i, n in enumerate(names) if n.startswith("change_vibe_")]
+        self._vibe_ids = torch.tensor(vibe_ids, dtype=torch.int64, device=s.device)
         self.num_envs, self.agents_per_env = s.num_envs, s.num_agents
         self.num_agents = s.num_envs * s.num_agents
-        self.episodes_finished = 0
+        self.validate = validate
+        self._episodes = 0
+        self._max_steps = int(game.max_steps)
+        self._desync = bool(desync_episodes) and self._max_steps > 0
+        self._vibe_ids_host = np.asarray(vibe_ids, dtype=np.int32)
+        self._configure()
+
+    def _configure(self):
+        early = None
+        if self._desync:  # early_reset_handler.py:15-20: one draw per env from a generator seeded with the env's seed
+            early = np.asarray([int(np.random.default_rng(int(sd)).integers(1, self._max_steps + 1)) for sd in self.sim.seeds],
+                               dtype=np.int64)  # fmt: skip
+        v = self._vibe_ids_host
+        self.sim._check(self.sim._L.mg_vecenv_configure(self.sim._h, self.num_primary, v.ctypes.data if v.size else None, int(v.size),
+                                                        None if early is None else early.ctypes.data))  # fmt: skip
 
     # flat zero-copy views, the layout PufferLib hands to policies
     @property
@@ -99,35 +114,41 @@ class MettaGridVecEnv:
     def truncations(self) -> torch.Tensor:
         return self.sim.truncations.view(-1)
 
-    def _draw_early_reset_steps(self, max_steps: int) -> torch.Tensor:
-        # early_reset_handler.py:15-20: one draw per env from a generator seeded with the env's seed
-        steps = [int(np.random.default_rng(int(sd)).integers(1, max_steps + 1)) for sd in self.sim.seeds]
-        return torch.tensor(steps, dtype=torch.int64, device=self.sim.device)
+    def poll(self) -> int:
+        """Synchronise, raise for any invalid action seen since the last poll, return the error bits (0)."""
+        import ctypes
+
+        n, err = ctypes.c_int(0), ctypes.c_int(0)
+        self.sim._check(self.sim._L.mg_vecenv_poll(self.sim._h, ctypes.byref(n), ctypes.byref(err)))
+        self._episodes = int(n.value)
+        return int(err.value)
+
+    @property
+    def episodes_finished(self) -> int:
+        self.poll()
+        return self._episodes
 
     def reset(self, seed: int | None = None):
         seeds = None if seed is None else [seed + e for e in range(self.num_envs)]
         self.sim.reset(seeds=seeds)
-        self._steps.zero_()
+        self._configure()  # step counters and, with desync, a fresh first-episode cut
         return self.observations, {}
 
     def step(self, actions: torch.Tensor):
         s = self.sim
-        # auto-reset envs that finished on the previous step (mettagrid_puffer_env.py:299-302)
-        done = s.terminals.all(dim=1) | s.truncations.all(dim=1)
-        n_done = int(done.sum())
-        if n_done:
-            s.reset(env_mask=done)
-            self._steps.masked_fill_(done, 0)
-            self.episodes_finished += n_done
-        core, vibe = decode_actions(torch.as_tensor(actions, device=s.device), self.num_primary, self._vibe_ids)
-        s.actions.copy_(core.view(s.actions.shape))
-        s.vibe_actions.copy_(vibe.view(s.vibe_actions.shape))
-        s.step()
-        self._steps += 1
-        if self._early is not None:  # early_reset_handler.py:22-25: end_episode() = all agents truncated
-            hit = self._steps >= self._early
-            s.truncations.masked_fill_(hit.unsqueeze(1), True)
-            self._early.masked_fill_(hit, torch.iinfo(torch.int64).max)  # first episode only
+        a = torch.as_tensor(actions, device=s.device)
+        if a.dtype not in (torch.int32, torch.int64):
+            a = a.to(torch.int64)
+        if a.dim() == 2 and a.shape[1] == 1:
+            a = a[:, 0]
+        if not ((a.dim() == 1 and a.shape[0] == self.num_agents) or (a.dim() == 2 and a.shape == (self.num_agents, 2))):
+            raise ValueError(f"Expected step actions shape [num_agents] or [num_agents,2], got {tuple(a.shape)}")
+        a = a.contiguous()
+        # an env can only finish through max_steps (plain termination / truncation) or the early-reset cut
+        s._check(s._L.mg_vecenv_step(s._h, a.data_ptr(), int(a.dtype == torch.int64), a.dim(), int(self._max_steps > 0), s._stream()))
+        if self.validate and self.poll():
+            decode_actions(a, self.num_primary, self._vibe_ids)  # raises the reference's ValueError for this tensor
+            raise ValueError("invalid actions")
         return self.observations, self.rewards, self.terminals, self.truncations, {}
 
     def close(self):

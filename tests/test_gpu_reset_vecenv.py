@@ -196,3 +196,32 @@ def test_set_map_gives_an_env_a_new_map_at_its_next_reset():
     assert sim._L.mg_set_map(sim._h, 0, cells.ctypes.data, None) == native.MG_E_INVALID
     assert b"more objects" in sim._L.mg_last_error(sim._h)
     sim.close()
+
+
+def test_vecenv_action_validation_on_device():
+    from mettagrid_b200.vecenv import MettaGridVecEnv
+
+    env = MettaGridVecEnv(cases.benchmark_config(2), 3, seed=2)
+    P, V = env.num_primary, len(env.vibe_action_names)
+    ok = torch.zeros(6, dtype=torch.int64, device="cuda")
+    env.step(ok)
+    bad = ok.clone()
+    bad[4] = P + P * V  # one past the combined range
+    with pytest.raises(ValueError, match="out of range"):
+        env.step(bad)
+    neg = ok.clone()
+    neg[1] = -1
+    with pytest.raises(ValueError, match="non-negative"):
+        env.step(neg)
+    with pytest.raises(ValueError, match="shape"):
+        env.step(torch.zeros((6, 3), dtype=torch.int64, device="cuda"))
+    pair = torch.zeros((6, 2), dtype=torch.int32, device="cuda")
+    pair[:, 1] = V  # vibe column out of range
+    with pytest.raises(ValueError, match="Vibe action indices"):
+        env.step(pair)
+    env.close()
+    lazy = MettaGridVecEnv(cases.benchmark_config(2), 3, seed=2, validate=False)
+    lazy.step(bad)  # no synchronisation, no exception: the offending agents do nothing
+    assert lazy.poll() & 2
+    assert lazy.poll() == 0  # reported once
+    lazy.close()
