@@ -269,6 +269,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   TRY(dev_alloc(h, &d.gtouched, N * d.SGW));
   TRY(dev_alloc(h, &d.cover, N * d.A * d.CW));
   TRY(dev_alloc(h, &d.rng, N * MG_RNG_WORDS));
+  TRY(dev_alloc(h, &d.rng_seeded, N * (MG_RNG_WORDS + 2)));
   TRY(dev_alloc(h, &d.env, N * MGEV_WORDS));
   TRY(dev_alloc(h, &d.success, N * d.A));
   TRY(dev_alloc(h, &lt, 65536));

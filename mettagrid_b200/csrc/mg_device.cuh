@@ -439,7 +439,7 @@ __device__ __forceinline__ void tl_register_object(const Wv& w, int s, bool add)
 __device__ __forceinline__ void init_object(const Wv& w, int slot, int t, int r, int c, int aidx, bool obs_inv, uint32_t seq) {
   uint32_t* o = objp(w, slot);
   const int32_t* tp = tmpl(w, t);
-  for (int k = 0; k < w.OS; k++) o[k] = 0;
+  for (int k = 0; k < w.OS / 4; k++) ((uint4*)o)[k] = make_uint4(0, 0, 0, 0);  // records are 16-byte multiples (compiler.py)
   int kind = __ldg(tp + MGT_KIND);
   int flags = MGOF_ALIVE | (obs_inv ? MGOF_OBS_INV : 0) | (kind == 1 ? MGOF_AGENT : 0) | (kind == 0 ? MGOF_WALL : 0);
   o[MGO_LOC] = ((uint32_t)r << 16) | (uint32_t)c;

@@ -540,13 +540,26 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
   if (lane == 0) {
     for (int i = 0; i < MGEV_WORDS; i++) w.E[i] = 0;
     w.E[MGEV_RNG_IDX] = MG_RNG_WORDS;
-    // std::mt19937(seed) (bits/random.tcc seed())
-    uint32_t x = d.seeds[env];
-    w.rng[0] = x;
-    for (int i = 1; i < MG_RNG_WORDS; i++) {
-      x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
-      w.rng[i] = x;
+  }
+  {
+    // std::mt19937(seed) (bits/random.tcc seed()): a 624-step serial recurrence.  The seeded state is kept per env
+    // (word 624 = the seed it was made from, word 625 = valid), so that a reset with the same seed -- every
+    // auto-reset of a vectorised env -- is a coalesced copy.
+    uint32_t* cache = d.rng_seeded + (size_t)env * (MG_RNG_WORDS + 2);
+    const uint32_t seed = d.seeds[env];
+    const bool hit = cache[MG_RNG_WORDS + 1] == 1u && cache[MG_RNG_WORDS] == seed;
+    __syncwarp();
+    if (!hit && lane == 0) {
+      uint32_t x = seed;
+      cache[0] = x;
+      for (int i = 1; i < MG_RNG_WORDS; i++) {
+        x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+        cache[i] = x;
+      }
+      cache[MG_RNG_WORDS] = seed, cache[MG_RNG_WORDS + 1] = 1u;
     }
+    __syncwarp();
+    for (int i = lane; i < MG_RNG_WORDS; i += 32) w.rng[i] = cache[i];
   }
   __syncwarp();
   if (lane == 0) {  // stat keys the constructor creates (:134-136)

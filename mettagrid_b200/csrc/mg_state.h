@@ -41,6 +41,7 @@ struct MgDev {
   uint32_t* gtouched;         // [N][SGW]
   uint32_t* cover;            // [N][A][CW]
   uint32_t* rng;              // [N][624]
+  uint32_t* rng_seeded;       // [N][626] freshly seeded state of each env + the seed it came from + valid flag (k_reset)
   int32_t* env;               // [N][MGEV_WORDS]
   uint8_t* success;           // [N][A]
   const float* logtab;        // logf(k + 1), k in [0, 65536), from the host libm
