@@ -21,6 +21,8 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap);
 cudaError_t mg_fast_configure(const MgFastLayout& L);
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st);
+cudaError_t mg_launch_fast_restore(const MgDev& d, const MgFastLayout& L, const uint32_t* snapshot, const uint8_t* mask,
+                                   cudaStream_t st);
 cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_obs_to_grid(const uint8_t* obs, float* grid, int rows, int T, int C, int H, int W, const float* scale,
                                   cudaStream_t st);
@@ -45,6 +47,12 @@ struct mg_handle {
   // which copy of the hot state is current on a fast handle: the generic arrays, the packed block, or both
   enum { BOTH = 0, GENERIC = 1, PACKED = 2 };
   int newest = GENERIC;
+  // Snapshot of the packed block right after a full reset (+ _init_buffers): lets the vectorised-env step rebuild
+  // finished environments with a copy.  `pristine` = nothing but a full reset / set_buffers happened since the
+  // generic arrays were built, i.e. the next pack holds exactly that state; any edit of what a reset starts from
+  // (seeds, maps, inventories) drops the snapshot until the next full reset.
+  uint32_t* snapshot = nullptr;
+  bool pristine = true, snap_valid = false;
   // device-side staging for mg_step_host
   int32_t* h_act = nullptr;
   int32_t* h_vact = nullptr;
@@ -89,7 +97,14 @@ static int launch_step(mg_handle* h, const MgDev& dev, cudaStream_t st) {
     CK(mg_launch_step(dev, st));
     return MG_OK;
   }
-  if (h->newest == mg_handle::GENERIC) CK(mg_launch_fast_pack(dev, h->fl, h->fh, nullptr, st));
+  if (h->newest == mg_handle::GENERIC) {
+    CK(mg_launch_fast_pack(dev, h->fl, h->fh, nullptr, st));
+    if (h->pristine && h->buffers_set && h->snapshot) {
+      CK(cudaMemcpyAsync(h->snapshot, dev.fast_blk, (size_t)dev.num_envs * dev.fast_stride * 4, cudaMemcpyDeviceToDevice, st));
+      h->snap_valid = true;
+    }
+  }
+  h->pristine = false;
   CK(mg_launch_step_fast(dev, h->fl, h->fh, st));
   h->newest = mg_handle::PACKED;
   return MG_OK;
@@ -321,6 +336,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     if (h->fl.smem_bytes <= 200 * 1024 && mg_fast_configure(h->fl) == cudaSuccess) {
       d.fast_stride = MGFB_WORDS(G);
       TRY(dev_alloc(h, &d.fast_blk, N * d.fast_stride));
+      TRY(dev_alloc(h, &h->snapshot, N * d.fast_stride));
       h->fast = true;
     } else {
       cudaGetLastError();  // too large for shared memory: the generic kernel runs instead
@@ -419,7 +435,11 @@ int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, v
   if (!h) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (new_seeds) CK(cudaMemcpyAsync(h->seeds_dev, new_seeds, (size_t)h->d.num_envs * 4, cudaMemcpyHostToDevice, st));
+  if (new_seeds) {
+    CK(cudaMemcpyAsync(h->seeds_dev, new_seeds, (size_t)h->d.num_envs * 4, cudaMemcpyHostToDevice, st));
+    h->snap_valid = false;
+  }
+  if (!env_mask) h->pristine = true;  // every env is about to hold its post-reset state again
   CK(mg_launch_reset(h->d, env_mask, st));
   if (h->buffers_set) CK(mg_launch_init_buffers(h->d, env_mask, st));
   if (h->fast) {
@@ -458,6 +478,7 @@ int mg_set_map(mg_handle* h, int env, const int16_t* init_cells, const float* in
   CK(cudaMemcpy((void*)(d.init_cells + (size_t)env * d.HW), init_cells, (size_t)d.HW * 2, cudaMemcpyHostToDevice));
   if (init_gstats)
     CK(cudaMemcpy((void*)(d.init_gstats + (size_t)env * d.SG), init_gstats, (size_t)d.SG * 4, cudaMemcpyHostToDevice));
+  h->snap_valid = false, h->pristine = false;
   return MG_OK;
 }
 
@@ -621,6 +642,7 @@ int mg_set_inventory(mg_handle* h, int env, int agent, const int32_t* items, con
   cudaFree(buf);
   CK(e);
   if (h->fast) h->newest = mg_handle::GENERIC;
+  h->snap_valid = false, h->pristine = false;
   return MG_OK;
 }
 
@@ -667,8 +689,12 @@ int mg_vecenv_step(mg_handle* h, const void* actions, int is_int64, int ncols, i
   CK(mg_launch_vecenv_prepare(actions, is_int64, ncols, d.num_envs, d.A, h->ve_primary, h->ve_vibes, h->ve_vibe_ids,
                               (int32_t*)d.actions, (int32_t*)d.vibe_actions, d.terminals, d.truncations, h->ve_done,
                               h->ve_steps, h->ve_counters, st));
-  if (auto_reset) {  // rebuild what finished on the previous step; CTAs without a selected env leave at once
-    if (int rc = mg_reset(h, h->ve_done, nullptr, stream)) return rc;
+  if (auto_reset) {  // rebuild what finished on the previous step
+    if (h->fast && h->snap_valid && h->newest == mg_handle::PACKED) {
+      CK(mg_launch_fast_restore(d, h->fl, h->snapshot, h->ve_done, st));  // a copy of the post-reset snapshot
+    } else if (int rc = mg_reset(h, h->ve_done, nullptr, stream)) {  // CTAs without a selected env leave at once
+      return rc;
+    }
   }
   if (int rc = launch_step(h, d, st)) return rc;
   CK(mg_launch_vecenv_post(d.num_envs, d.A, h->ve_steps, h->ve_early, d.truncations, st));

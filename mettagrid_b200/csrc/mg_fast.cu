@@ -833,6 +833,39 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
   }
 }
 
+
+// Rebuild selected environments of a fast handle from the snapshot of the packed block taken right after a full
+// reset: the same state k_reset + k_init_buffers + k_fast_pack would produce, for the price of a copy.  Used by the
+// vectorised-env step, where a tick follows at once (the initial observations are not written).
+__global__ void k_fast_restore(const MgDev d, const int G, const uint32_t* __restrict__ snapshot, const uint8_t* __restrict__ mask) {
+  const int env = blockIdx.x;
+  if (!mask[env]) return;
+  const int t = threadIdx.x, nt = blockDim.x;
+  uint32_t* blk = d.fast_blk + (size_t)env * d.fast_stride;
+  const uint32_t* snap = snapshot + (size_t)env * d.fast_stride;
+  for (int i = t; i < d.fast_stride; i += nt) blk[i] = snap[i];
+  // the freshly seeded generator (k_reset keeps it per env); the block's header already says "index 624"
+  const uint32_t* seeded = d.rng_seeded + (size_t)env * (MG_RNG_WORDS + 2);
+  uint32_t* rng = d.rng + (size_t)env * MG_RNG_WORDS;
+  for (int i = t; i < MG_RNG_WORDS; i += nt) rng[i] = seeded[i];
+  // coverage (objects/agent.cpp:41-47): only the spawn cell is visited
+  uint32_t* cover = d.cover + (size_t)env * d.A * d.CW;
+  for (int i = t; i < d.A * d.CW; i += nt) {
+    const int a = i / d.CW, wd = i - a * d.CW;
+    const uint32_t spawn = snap[MGFB_AGENT(G, a) + 1];
+    const int cell = (int)(spawn >> 16) * d.W + (int)(spawn & 0xffffu);
+    cover[i] = (cell >> 5) == wd ? 1u << (cell & 31) : 0u;
+  }
+  for (int a = t; a < d.A; a += nt) {  // _init_buffers (:294-319)
+    const size_t gi = (size_t)env * d.A + a;
+    d.terminals[gi] = 0, d.truncations[gi] = 0, d.rewards[gi] = 0.0f, d.success[gi] = 0;
+  }
+  if (t == 0) {
+    int32_t* E = d.env + (size_t)env * MGEV_WORDS;
+    E[MGEV_ERROR] = 0, E[MGEV_ERR_INFO] = 0;
+  }
+}
+
 }  // namespace
 
 // ---- host side -------------------------------------------------------------------------------------
@@ -893,5 +926,11 @@ cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgF
 cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
   const size_t threads = (size_t)d.num_envs * L.G;
   k_fast_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G);
+  return cudaGetLastError();
+}
+
+cudaError_t mg_launch_fast_restore(const MgDev& d, const MgFastLayout& L, const uint32_t* snapshot, const uint8_t* mask,
+                                   cudaStream_t st) {
+  k_fast_restore<<<d.num_envs, 128, 0, st>>>(d, L.G, snapshot, mask);
   return cudaGetLastError();
 }

@@ -225,3 +225,40 @@ def test_vecenv_action_validation_on_device():
     assert lazy.poll() & 2
     assert lazy.poll() == 0  # reported once
     lazy.close()
+
+
+def test_vecenv_fast_path_autoreset_matches_oracle():
+    """Auto-reset on a fast handle restores finished envs from the post-reset snapshot of the packed block; the
+    trajectories must be those of freshly constructed environments, also after the snapshot was invalidated."""
+    from mettagrid_b200.vecenv import MettaGridVecEnv
+
+    cfg = cases.benchmark_config(4, max_steps=9)
+    env = MettaGridVecEnv(cfg, 7, seed=3)
+    assert env.sim.step_kernel == 8
+    orc = _oracles(env.sim)
+    rng = np.random.RandomState(12)
+    P, V = env.num_primary, len(env.vibe_action_names)
+    for t in range(40):
+        a = rng.randint(0, P + P * V, size=28)
+        a[rng.rand(28) < 0.7] %= P
+        for e in range(7):
+            if orc[e].terminals().all() or orc[e].truncations().all():
+                orc[e] = _oracles(env.sim)[e]
+        core = np.where(a >= P, (a - P) // V, a).reshape(7, 4)
+        vib = np.where(a >= P, P + (a - P) % V, 0).reshape(7, 4)
+        if t == 20:  # an inventory edit drops the snapshot: the generic reset path takes over
+            env.sim.set_inventory(5, 2, {"heart": 4})
+            orc[5].set_inventory(2, {"heart": 4})
+        obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
+        for e, o in enumerate(orc):
+            o.step(core[e], vib[e])
+        torch.cuda.synchronize()
+        ob = obs.cpu().numpy().reshape(7, 4, -1, 3)
+        for e, o in enumerate(orc):
+            assert np.array_equal(ob[e], o.observations()), f"step {t} env {e}"
+            assert np.array_equal(term.cpu().numpy().reshape(7, 4)[e], o.terminals())
+    for e, o in enumerate(orc):
+        assert env.sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
+        assert np.array_equal(env.sim.dump_objects(e), o.dump_objects())
+    assert env.episodes_finished == 7 * 4
+    env.close()
