@@ -5,7 +5,8 @@ import torch
 from tests import cases
 from mettagrid_b200.vecenv import MettaGridVecEnv
 N, MS = int(sys.argv[1]), int(sys.argv[2])
-env = MettaGridVecEnv(cases.benchmark_config(16, max_steps=MS), N, seed=1, desync_episodes=MS > 0)
+VALIDATE = not (len(sys.argv) > 3 and sys.argv[3] == 'novalidate')
+env = MettaGridVecEnv(cases.benchmark_config(16, max_steps=MS), N, seed=1, desync_episodes=MS > 0, validate=VALIDATE)
 acts = torch.randint(0, 5, (32, N * 16), device='cuda')
 for i in range(20):
     env.step(acts[i % 32])
@@ -16,4 +17,4 @@ for i in range(K):
     env.step(acts[i % 32])
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / K
-print(f"vec-env N={N} max_steps={MS}: {dt*1e6:.1f} us/step wall, {N*16/dt:.3e} agent-steps/s, episodes finished {env.episodes_finished}")
+print(f"vec-env N={N} max_steps={MS} validate={VALIDATE}: {dt*1e6:.1f} us/step wall, {N*16/dt:.3e} agent-steps/s, episodes finished {env.episodes_finished}")
