@@ -274,7 +274,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   TRY(dev_alloc(h, &d.aoe_src, N * d.AOECAP * d.AOEW));
   TRY(dev_alloc(h, &d.aoe_pending, N * d.PENDCAP * 2));
   TRY(dev_alloc(h, &d.terr_src, N * d.TERRCAP * 4));
-  TRY(dev_alloc(h, &d.terr_tab, N * d.TERRCAP * 4));
+  TRY(dev_alloc(h, &d.terr_tab, N * (d.TERRCAP ? (d.TERRCAP + 32) * 4 : 0)));  // + MG_TERR_CAND scratch entries per env
   TRY(dev_alloc(h, &d.inside_tag, N * d.A * d.NTERR));
   TRY(dev_alloc(h, &d.dyn_stamp, N * d.maxobj * d.NDYN));
   TRY(dev_alloc(h, &d.agents, N * d.A * d.AS));

@@ -128,7 +128,7 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.aoe_src = d.aoe_src + (size_t)env * d.AOECAP * d.AOEW;
   w.aoe_pending = d.aoe_pending + (size_t)env * d.PENDCAP * 2;
   w.terr_src = d.terr_src + (size_t)env * d.TERRCAP * 4;
-  w.terr_tab = d.terr_tab + (size_t)env * d.TERRCAP * 4;
+  w.terr_tab = d.terr_tab + (size_t)env * (d.TERRCAP ? (d.TERRCAP + 32) * 4 : 0);  // table + MG_TERR_CAND scratch entries
   s.rs[5] = 1;
   w.inside_tag = d.inside_tag + (size_t)env * d.A * d.NTERR;
   w.dyn_stamp = d.dyn_stamp + (size_t)env * d.maxobj * d.NDYN;
@@ -407,7 +407,17 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
       }
     }
     base += tot;
-  } else
+  } else {
+  // territory sources in reach of this window (the per-cell tests below only look at these)
+  const uint4* ttab = (const uint4*)w.terr_tab;
+  int tn = 0;
+  if (fmask) {
+    tn = terr_window_sources(w, r0, c0, w.hdr[MGH_OBS_H] >> 1, w.hdr[MGH_OBS_W] >> 1, lane);
+    if (tn >= 0)
+      ttab += w.TERRCAP;
+    else
+      tn = w.E[MGEV_RESERVED];
+  }
   for (int k0 = 0; k0 < NOFF; k0 += 32) {
     const int k = k0 + lane;
     int n = 0, loc = 0, mask = 0, slot = 0;
@@ -417,7 +427,7 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
       slot = centre[(int)(short)(pk >> 16)];
       if (fmask) {  // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens
         const int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
-        if (valid_loc(w, r, c)) mask = territory_mask(w, r, c, me);
+        if (valid_loc(w, r, c)) mask = territory_mask(w, r, c, me, ttab, tn);
       }
     }
     if (__ballot_sync(MG_FULL, (slot | mask) != 0) == 0) continue;  // nothing visible in these 32 cells
@@ -462,6 +472,7 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
       }
     }
     base += tot;
+  }
   }
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
   if (lane == 0 && stale_sum) astat_add(w, a, w.hdr[MGH_ST_CELL_VISITED], (float)stale_sum);
@@ -906,18 +917,34 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
         handler_apply<MG_DEPTH>(w, h, c);
       }
     }
-    if (w.E[MGEV_NUM_AOE] > 0 || w.NTERR > 0 || w.E[MGEV_NUM_AOE_PENDING] > 0) {  // :1032-1042
+  }
+  __syncwarp();
+  if (!PLAIN) {
+    // fixed AOE + territory per agent in index order (:1032-1042).  The serial work stays on lane 0; before each
+    // agent's turn all lanes test which sources can matter to it at its current cell.
+    const bool any_aoe = w.E[MGEV_NUM_AOE] > 0 || w.NTERR > 0 || w.E[MGEV_NUM_AOE_PENDING] > 0;
+    if (any_aoe) {
       for (int a = 0; a < A; a++) {
-        if (w.E[MGEV_NUM_AOE] > 0) aoe_apply_fixed(w, a);
-        if (w.NTERR > 0) terr_apply(w, a);
+        uint32_t m[4];
+        const bool have_aoe = w.E[MGEV_NUM_AOE] > 0;
+        const bool masked = have_aoe && aoe_relevant_mask(w, a, lane, m);
+        if (lane == 0) {
+          if (have_aoe) aoe_apply_fixed(w, a, masked ? m : nullptr);
+          if (w.NTERR > 0) terr_apply(w, a);
+        }
+        __syncwarp();
       }
-      aoe_apply_mobile(w);
-      aoe_flush_deferred(w);
     }
-    const int gh = w.hdr[MGH_GAME_ON_TICK];
-    if (gh >= 0) {
-      Ctx c = make_ctx();
-      handler_apply<MG_DEPTH>(w, gh, c);
+    if (lane == 0) {
+      if (any_aoe) {
+        aoe_apply_mobile(w);
+        aoe_flush_deferred(w);
+      }
+      const int gh = w.hdr[MGH_GAME_ON_TICK];
+      if (gh >= 0) {
+        Ctx c = make_ctx();
+        handler_apply<MG_DEPTH>(w, gh, c);
+      }
     }
   }
   __syncwarp();

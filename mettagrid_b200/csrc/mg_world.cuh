@@ -55,7 +55,34 @@ __device__ __forceinline__ bool aoe_covers(const uint32_t* s, const int32_t* a, 
   if (aoe_is_territory(a) && range >= 2 && d2 == range * range && (dr == 0 || dc == 0)) return false;
   return true;
 }
-__device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag) {
+// All lanes: which fixed sources can matter to agent `ag` right now -- alive, fixed, and either covering the agent's
+// cell or still holding its "inside" bit (an exit is due).  One ballot per 32 sources replaces the serial scan over
+// every source in aoe_apply_fixed, which then only visits the set bits.  Returns false when there are more than 128
+// sources (the serial scan is used).
+__device__ __forceinline__ bool aoe_relevant_mask(const Wv& w, int ag, int lane, uint32_t (&m)[4]) {
+  const int na = w.E[MGEV_NUM_AOE];
+  m[0] = m[1] = m[2] = m[3] = 0;
+  if (na > 128) return false;
+  const uint32_t* to = objp(w, (int)w.agents[ag * w.AS + MGAG_OBJ]);
+  const int r = o_r(to), c = o_c(to);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (j * 32 >= na) break;
+    const int k = j * 32 + lane;
+    bool rel = false;
+    if (k < na) {
+      const uint32_t* s = aoe_rec(w, k);
+      if (s[3]) {
+        const int32_t* a = aoe_cfg(w, (int)s[1]);
+        rel = __ldg(a + 1) && (aoe_inside(s, ag) || aoe_covers(s, a, r, c));
+      }
+    }
+    m[j] = __ballot_sync(MG_FULL, rel);
+  }
+  return true;
+}
+// `m` (may be null): the sources aoe_relevant_mask selected for this agent at this moment
+__device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag, const uint32_t* m) {
   const int target = (int)w.agents[ag * w.AS + MGAG_OBJ];
   Deferred df;
   df.n = 0;
@@ -65,8 +92,10 @@ __device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag) {
   base.deferred = &df;
   const uint32_t* to = objp(w, target);
   const int na = w.E[MGEV_NUM_AOE];
+  const uint32_t loc0 = to[MGO_LOC];  // the mask was computed for this cell; a handler that moves the target voids it
   // exits: sources the target was inside whose cells no longer cover it (registration order)
   for (int k = 0; k < na; k++) {
+    if (m && !((m[k >> 5] >> (k & 31)) & 1u)) continue;
     uint32_t* s = aoe_rec(w, k);
     if (!s[3]) continue;
     const int32_t* a = aoe_cfg(w, (int)s[1]);
@@ -77,6 +106,8 @@ __device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag) {
     }
   }
   for (int k = 0; k < na; k++) {
+    if (m && to[MGO_LOC] != loc0) m = nullptr;  // moved by an earlier source's handler: scan everything from here on
+    if (m && !((m[k >> 5] >> (k & 31)) & 1u)) continue;
     uint32_t* s = aoe_rec(w, k);
     if (!s[3]) continue;
     const int32_t* a = aoe_cfg(w, (int)s[1]);
@@ -199,30 +230,56 @@ __device__ __noinline__ void terr_build_table(const Wv& w) {
   w.E[MGEV_RESERVED] = n;  // entries in the table
   w.rs[5] = 0;             // clean
 }
-// winning tag at (r, c) for territory ti, or -1 (read-only: callable from every lane)
-__device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti) {
+// winning tag at (r, c) for territory ti, or -1 (read-only: callable from every lane).  `tab` / `n`: the per-tick
+// source table, or a subset of it that holds every source in reach of (r, c) (terr_window_sources)
+#define MG_TERR_CAND 32
+__device__ __forceinline__ long long terr_score(const uint4 e, int r, int c) {
+  const int range = (int)e.y;
+  const int dr = r - (int)(e.x >> 16), dc = c - (int)(e.x & 0xffffu);
+  if (dr < -range || dr > range || dc < -range || dc > range) return 0;
+  const long long d2 = (long long)dr * dr + (long long)dc * dc;
+  if (d2 > (long long)range * range) return 0;
+  const long long strength = e.z & 0xffffu, decay = e.z >> 16;
+  const long long sc = strength * 1024 - decay * (long long)floor_sqrt_u64((unsigned long long)d2 * 1024ull * 1024ull);
+  return sc > 0 ? sc : 0;
+}
+__device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti, const uint4* tab, int n) {
   const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
   const int np = min(__ldg(T_ + 1), MG_MAX_PREFIX_TAGS);
-  long long score[MG_MAX_PREFIX_TAGS];
-  for (int i = 0; i < np; i++) score[i] = 0;
-  const int n = w.E[MGEV_RESERVED];
-  const uint4* tab = (const uint4*)w.terr_tab;
-  for (int k = 0; k < n; k++) {
-    const uint4 e = tab[k];
-    if ((int)(e.w & 0xffu) != ti) continue;
-    const int range = (int)e.y;
-    const int dr = r - (int)(e.x >> 16), dc = c - (int)(e.x & 0xffffu);
-    if (dr < -range || dr > range || dc < -range || dc > range) continue;
-    const long long d2 = (long long)dr * dr + (long long)dc * dc;
-    if (d2 > (long long)range * range) continue;
-    const long long strength = e.z & 0xffffu, decay = e.z >> 16;
-    const long long sc = strength * 1024 - decay * (long long)floor_sqrt_u64((unsigned long long)d2 * 1024ull * 1024ull);
-    if (sc > 0) score[(e.w >> 8) & 0xffu] += sc;
-  }
   const int32_t* pre = pool(w, __ldg(T_));
   int win = -1;
   long long best = 0;
   bool tied = false;
+  if (np <= 4) {  // the usual few teams: scores stay in registers
+    long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int k = 0; k < n; k++) {
+      const uint4 e = tab[k];
+      if ((int)(e.w & 0xffu) != ti) continue;
+      const long long sc = terr_score(e, r, c);
+      const int pi = (int)((e.w >> 8) & 0xffu);
+      s0 += pi == 0 ? sc : 0, s1 += pi == 1 ? sc : 0, s2 += pi == 2 ? sc : 0, s3 += pi == 3 ? sc : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const long long si = i == 0 ? s0 : i == 1 ? s1 : i == 2 ? s2 : s3;
+      if (i >= np || si <= 0) continue;
+      if (si > best) {
+        win = __ldg(pre + i);
+        best = si;
+        tied = false;
+      } else if (si == best && win >= 0) {
+        tied = true;
+      }
+    }
+    return tied ? -1 : win;
+  }
+  long long score[MG_MAX_PREFIX_TAGS];
+  for (int i = 0; i < np; i++) score[i] = 0;
+  for (int k = 0; k < n; k++) {
+    const uint4 e = tab[k];
+    if ((int)(e.w & 0xffu) != ti) continue;
+    score[(e.w >> 8) & 0xffu] += terr_score(e, r, c);
+  }
   for (int i = 0; i < np; i++) {
     if (score[i] <= 0) continue;
     if (score[i] > best) {
@@ -235,9 +292,35 @@ __device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti) {
   }
   return tied ? -1 : win;
 }
-__device__ __forceinline__ int territory_mask(const Wv& w, int r, int c, const uint32_t* observer) {  // :254-273
+// All lanes: copy the table entries whose square of influence touches the window around (r0, c0) into the env's
+// scratch behind the table, so that the per-cell ownership tests of one observation loop over a handful of
+// sources instead of all of them.  Scores are integer sums: the subset gives the same winner.  Returns the
+// entry count, or -1 when more than MG_TERR_CAND sources are in reach (the full table is used).
+__device__ __forceinline__ int terr_window_sources(const Wv& w, int r0, int c0, int rr, int cr, int lane) {
+  const int n = w.E[MGEV_RESERVED];
+  const uint4* tab = (const uint4*)w.terr_tab;
+  uint4* cand = (uint4*)w.terr_tab + w.TERRCAP;
+  int cnt = 0;
+  for (int k0 = 0; k0 < n; k0 += 32) {
+    const int k = k0 + lane;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    bool in = false;
+    if (k < n) {
+      e = tab[k];
+      const int range = (int)e.y, dr = r0 - (int)(e.x >> 16), dc = c0 - (int)(e.x & 0xffffu);
+      in = dr >= -(range + rr) && dr <= range + rr && dc >= -(range + cr) && dc <= range + cr;
+    }
+    const uint32_t b = __ballot_sync(MG_FULL, in);
+    const int pos = cnt + __popc(b & ((1u << lane) - 1u));
+    if (in && pos < MG_TERR_CAND) cand[pos] = e;
+    cnt += __popc(b);
+  }
+  __syncwarp();
+  return cnt <= MG_TERR_CAND ? cnt : -1;
+}
+__device__ __forceinline__ int territory_mask(const Wv& w, int r, int c, const uint32_t* observer, const uint4* tab, int n) {  // :254-273
   for (int ti = 0; ti < w.NTERR; ti++) {
-    int win = cell_owner(w, r, c, ti);
+    int win = cell_owner(w, r, c, ti, tab, n);
     if (win < 0) continue;
     return o_has_tag(observer, win) ? 1 : 2;
   }
@@ -265,7 +348,7 @@ __device__ __noinline__ void terr_apply(const Wv& w, int ag) {
     const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
     const uint32_t* to = objp(w, target);
     if (w.rs[5]) terr_build_table(w);  // a handler moved / tagged something since the last build
-    const int cur = cell_owner(w, o_r(to), o_c(to), ti);
+    const int cur = cell_owner(w, o_r(to), o_c(to), ti, (const uint4*)w.terr_tab, w.E[MGEV_RESERVED]);
     const int prev = w.inside_tag[ag * w.NTERR + ti];
     if (prev != cur && prev >= 0) terr_run(w, ti, __ldg(T_ + 4), __ldg(T_ + 5), prev, target);
     if (prev != cur && cur >= 0) terr_run(w, ti, __ldg(T_ + 2), __ldg(T_ + 3), cur, target);
