@@ -1,4 +1,4 @@
-"""Scratch timing helper: python tests/quick_bench.py ENVS AGENTS [flush]  (flush = evict L2 between timed steps)."""
+"""Scratch timing helper: python tools/quick_bench.py ENVS AGENTS [flush]  (flush = evict L2 between timed steps)."""
 import sys, time
 sys.path.insert(0, '.')
 import numpy as np, torch

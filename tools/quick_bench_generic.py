@@ -1,4 +1,4 @@
-"""Scratch timing helper for the generic kernel: python tests/quick_bench_generic.py c3|c4 ENVS"""
+"""Scratch timing helper for the generic kernel: python tools/quick_bench_generic.py c3|c4 ENVS"""
 import sys
 sys.path.insert(0, '.')
 import numpy as np, torch

@@ -1,4 +1,4 @@
-"""Scratch timing helper for k_obs_to_grid: python tests/quick_grid_bench.py ENVS AGENTS"""
+"""Scratch timing helper for k_obs_to_grid: python tools/quick_grid_bench.py ENVS AGENTS"""
 import sys
 sys.path.insert(0, '.')
 import torch

@@ -1,4 +1,4 @@
-"""Scratch timing helper: vec-env steps per second with auto-reset traffic.  python tests/quick_vecenv_bench.py ENVS MAX_STEPS"""
+"""Scratch timing helper: vec-env steps per second with auto-reset traffic.  python tools/quick_vecenv_bench.py ENVS MAX_STEPS"""
 import sys, time
 sys.path.insert(0, '.')
 import torch
