@@ -324,6 +324,13 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     }
     d.rank_lut = lut_dev;
   }
+  {
+    // The env's grid is read in place (L1 / L2).  Staging it in shared memory every tick -- 3 to 12 KB per warp --
+    // measured slower on every workload (profiles/README.md): C3 1259 -> 873 us, C4 6240 -> 3008 us, plain C2
+    // 97.6 -> 95.7 us.  METTAGRID_B200_STAGE_GRID=1 brings the staging back for A/B runs.
+    const char* f = getenv("METTAGRID_B200_STAGE_GRID");
+    d.stage_grid = f && f[0] == '1';
+  }
   cudaError_t e = mg_configure_kernels(d);
   if (e != cudaSuccess) {
     h->err = std::string("mg_create: kernel configuration failed: ") + cudaGetErrorString(e) +

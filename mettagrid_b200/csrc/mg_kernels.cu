@@ -43,7 +43,7 @@ struct Smem {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // bytes of dynamic shared memory per warp / per CTA (must match carve())
-__host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {
+__host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {  // HWp = 0: the grid is not staged
   size_t n = 0;
   n += align16((size_t)HWp * 2);
   n += align16((size_t)3 * T + 32);
@@ -62,9 +62,9 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   base += align16((size_t)d.NOFF * 4);
   s.rank = (uint8_t*)base;
   base += 256;
-  base += (size_t)warp * smem_per_warp(d.HWp, d.T, d.A);
+  base += (size_t)warp * smem_per_warp(d.stage_grid ? d.HWp : 0, d.T, d.A);
   s.cells = (uint16_t*)base;
-  base += align16((size_t)d.HWp * 2);
+  base += align16((size_t)(d.stage_grid ? d.HWp : 0) * 2);
   s.stage = base;
   base += align16((size_t)3 * d.T + 32);
   s.rs = (int*)base;
@@ -106,8 +106,8 @@ __device__ __forceinline__ void load_cta_tables(const MgDev& d, Smem& s) {
 __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env, Wv& w) {
   w.P = d.P;
   w.hdr = s.hdr;
-  w.cells = s.cells;
   w.cells_g = d.cells + (size_t)env * d.HWp;
+  w.cells = d.stage_grid ? s.cells : w.cells_g;  // read in place by default (mg_capi.cu: stage_grid)
   w.objs = d.objs + (size_t)env * (d.maxobj + d.NTERR) * d.OS;
   w.agents = d.agents + (size_t)env * d.A * d.AS;
   w.astats = d.astats + (size_t)env * d.A * d.SA;
@@ -151,6 +151,10 @@ __device__ __forceinline__ void publish_warp(const MgDev& d, const Smem& s, int 
 }
 
 __device__ __forceinline__ void stage_cells(const MgDev& d, const Wv& w, int lane) {
+  if (!d.stage_grid) {
+    __syncwarp();
+    return;
+  }
   const uint4* src = (const uint4*)w.cells_g;
   uint4* dst = (uint4*)w.cells;
   for (int i = lane; i < d.HWp / 8; i += 32) dst[i] = src[i];
@@ -1043,7 +1047,7 @@ __global__ void k_set_inventory(MgDev d, int env, int agent, const int32_t* __re
 
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st) {
-  size_t bytes = smem_per_cta(d.NOFF) + smem_per_warp(d.HWp, d.T, d.A);
+  size_t bytes = smem_per_cta(d.NOFF) + smem_per_warp(d.stage_grid ? d.HWp : 0, d.T, d.A);
   cudaError_t e = cudaFuncSetAttribute(k_set_inventory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
   k_set_inventory<<<1, 32, bytes, st>>>(d, env, agent, items, amounts, n);
@@ -1051,7 +1055,7 @@ cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const in
 }
 
 // ---- host-side launchers (used by mg_capi.cu) --------------------------------------------------
-size_t mg_smem_bytes(const MgDev& d) { return smem_per_cta(d.NOFF) + (size_t)MG_WARPS_PER_CTA * smem_per_warp(d.HWp, d.T, d.A); }
+size_t mg_smem_bytes(const MgDev& d) { return smem_per_cta(d.NOFF) + (size_t)MG_WARPS_PER_CTA * smem_per_warp(d.stage_grid ? d.HWp : 0, d.T, d.A); }
 
 cudaError_t mg_configure_kernels(const MgDev& d) {
   size_t bytes = mg_smem_bytes(d);

@@ -27,6 +27,7 @@ struct MgDev {
   const uint32_t* rank_lut;  // [256] packed window offset (dr + rr) << 4 | (dc + cr) -> rank << 24 | offset << 16, where rank is
                              // the position in Manhattan order; 0xFFFFFF00 outside the shape
   int plain;    // 1: the program has no handlers / rewards / world systems (k_step<PLAIN> applies)
+  int stage_grid;  // 0 (default): cells are read in place; 1: each warp stages its env's grid in shared memory (A/B switch)
   int PAD, WP;  // the grid is stored with a PAD-wide empty frame (row pitch WP) so observation windows need no bounds tests
   // persistent state
   const int16_t* init_cells;  // [N][HW] template per cell
