@@ -37,7 +37,8 @@ struct Smem {
 };
 #define MG_AGENT_WORD_ARRAYS 9
 #ifndef MG_MIN_CTAS_PER_SM
-#define MG_MIN_CTAS_PER_SM 7  // 72 registers per thread -> 28 resident warps per SM (measured best, profiles/README.md)
+#define MG_MIN_CTAS_PER_SM 8  // 64 registers per thread -> 32 resident warps per SM (measured best once the grid stopped
+                              // occupying shared memory: profiles/README.md; 7 was best before)
 #endif
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
