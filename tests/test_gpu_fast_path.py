@@ -227,3 +227,31 @@ def test_truncating_episodes_and_small_token_base():
     cfg.game.obs.token_value_base = 10
     cfg.game.agent.inventory.initial = {"ore_red": 7, "heart": 345, "laser": 12}
     _triple(cfg, num_envs=7, steps=45, expect_lanes=8, p_vibe=0.4)
+
+
+def test_token_stats_beyond_the_exact_float_range():
+    """tokens_written / tokens_free_space are float32 sums of per-agent integers.  Below 2^24 every add is exact and the
+    kernel adds a tick's total at once; beyond it the reference's per-agent add order decides the rounding and the
+    kernel replays it.  36 000 ticks of 16 agents push both stats past 2^24."""
+    from oracle.oracle import OracleEnv
+
+    cfg = cases.benchmark_config(16)
+    sim = _make(cfg, 3, 77, True)
+    assert sim.step_kernel == 16
+    P = sim.program
+    oracles = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(3)]
+    rs = np.random.RandomState(1)
+    pool = rs.randint(0, 5, size=(64, 3, 16)).astype(np.int32)
+    zeros = np.zeros((3, 16), np.int32)
+    steps = 36000
+    for t in range(steps):
+        sim.step(pool[t & 63], zeros)
+        for e, o in enumerate(oracles):
+            o.step(pool[t & 63, e], zeros[e])
+    torch.cuda.synchronize()
+    for e, o in enumerate(oracles):
+        got, want = sim.get_episode_stats(e), o.get_episode_stats()
+        assert want["game"]["tokens_free_space"] > 2**24, "the run must leave the exact range to test the replay"
+        assert got == want, f"stats differ in env {e}"
+        assert np.array_equal(sim.observations[e].cpu().numpy(), o.observations())
+    sim.close()
