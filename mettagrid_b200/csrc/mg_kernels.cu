@@ -162,31 +162,6 @@ __device__ __forceinline__ void stage_cells(const MgDev& d, const Wv& w, int lan
   __syncwarp();
 }
 
-// ---- shared-memory helpers for the observation stage --------------------------------------------
-__device__ __forceinline__ void fill_ff(uint8_t* p, int n, int lane) {
-  if (n <= 0) return;
-  int head = (int)((16u - ((uint32_t)(uintptr_t)p & 15u)) & 15u);
-  if (head > n) head = n;
-  if (lane < head) p[lane] = 0xFF;
-  int body = (n - head) >> 4;
-  uint4* p4 = (uint4*)(p + head);
-  const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-  for (int i = lane; i < body; i += 32) p4[i] = ff;
-  int done = head + (body << 4);
-  if (lane < n - done) p[done + lane] = 0xFF;
-}
-// stage and destination share the same 16-byte phase, so the body moves as aligned 16-byte vectors
-__device__ __forceinline__ void flush_obs(const uint8_t* src, uint8_t* g, int n, int lane) {
-  int head = (int)((16u - ((uint32_t)(uintptr_t)g & 15u)) & 15u);
-  if (head > n) head = n;
-  if (lane < head) g[lane] = src[lane];
-  int body = (n - head) >> 4;
-  const uint4* s4 = (const uint4*)(src + head);
-  uint4* g4 = (uint4*)(g + head);
-  for (int i = lane; i < body; i += 32) __stcs(g4 + i, s4[i]);
-  int done = head + (body << 4);
-  if (lane < n - done) g[done + lane] = src[done + lane];
-}
 
 // Row of n bytes whose first `used` bytes are staged tokens and whose remainder is 0xFF.  The stage shares
 // the destination's 16-byte phase, so the body moves as aligned 16-byte vectors; vectors that lie entirely
@@ -208,15 +183,6 @@ __device__ __forceinline__ void flush_row(uint8_t* src, uint8_t* g, int n, int u
   if (lane < n - done) g[done + lane] = done + lane < pad_to ? src[done + lane] : (uint8_t)0xFF;
 }
 
-__device__ __forceinline__ int num_digits(uint32_t v, uint32_t B, int ND) {
-  int n = 1;
-  v /= B;
-  while (v > 0 && n < ND) {
-    v /= B;
-    n++;
-  }
-  return n;
-}
 
 // An object's observation tokens (core/grid_object.cpp:178-203, objects/agent.cpp:142-154) only change
 // when its tags, vibe or inventory change, so they are cached in the object record as (feature | value << 8)
@@ -538,7 +504,6 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
   Smem s0;
   carve(d, smem_raw, warp, s0);
   publish_warp(d, s0, env, lane);
-  const Smem& s = *s0.self;
   Wv& w = *s0.wv;
 
   for (int i = lane; i < d.HWp; i += 32) w.cells_g[i] = 0;
