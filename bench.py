@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the batched MettaGrid step (BASELINE.json metric: agent-steps/s including observations).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E] [--agents A]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4|toy] [--envs E]
 
-Workload (config.workload): BASELINE.json configs[1] ("C2") -- the reference benchmark game
-(benchmarks/test_mettagrid_env_benchmark.py:21-29: 20x20 RandomMapBuilder map, 16 agents, 13x13
-observation window, 100 tokens, noop + 4-way move + 152 vibes, max_steps=0) batched to 4096 envs per
-GPU, env e using map seed 42+e and env seed 42+e, "effective" random actions.
+Headline workload (config.workload): BASELINE.json configs[1] ("C2") -- the reference benchmark game
+(benchmarks/test_mettagrid_env_benchmark.py:21-29: 20x20 RandomMapBuilder map, 16 agents, 13x13 observation
+window, 100 tokens, noop + 4-way move + 152 vibes, max_steps=0) batched to 4096 envs per GPU, env e using map seed
+42+e and env seed 42+e, "effective" random actions.
 
-A step = one tick of every env.  `value` is measured with all inputs resident in HBM (CUDA events
-around mg_step only, L2 flushed between timed steps); `e2e` is the same tick through the C ABI's
-host-buffer entry point (mg_step_host: pinned host actions in, observations/rewards/flags out).
+A step = `ticks_per_step` (default 50) consecutive ticks of every env, so that the timed region of K steps lasts long
+enough for the clock sampler to see the GPU under load.  `value` is measured with all inputs resident in HBM: one pair
+of CUDA events around every mg_step launch, L2 flushed (256 MB fill) before every tick, the flushes outside the event
+pairs; ms_per_step is the sum of a step's tick times.  `e2e` is the same ticks through the C ABI's host-buffer entry
+point (mg_step_host: pinned host actions in, observations / rewards / flags out, wall clock).
 
-`--impl reference` times the UNMODIFIED reference C++ step (oracle/_ref, built from /root/reference
-by oracle/Makefile.ref) on the host cores: one worker process per core, each stepping its own share
-of a bounded sample of the same workload.  The only places this file touches oracle/ are that arm
-and the `cpu_baseline` leg.
+After the headline the default run also times BASELINE configs 3-5 and attaches them as config.extra:
+  c3  combat-heavy game, 16384 envs x 24 agents per GPU          c4  world game, 8192 envs x 24 agents per GPU
+  c5  the C2 game at 262144 envs TOTAL, split over the N ranks (strong scaling; the headline is weak scaling)
+  toy the reference's perf_benchmark.py "toy" preset (40x40 walled map, 20 agents), 4096 envs per GPU
+each with its own roofline and, at N=1, its own cpu_baseline.  --no-extras skips them.
+
+`--impl reference` times the UNMODIFIED reference C++ step (oracle/_ref, built from /root/reference by
+oracle/Makefile.ref) on the host cores: one worker process per core, each stepping its own share of a bounded sample
+of the same workload.  The only places this file touches oracle/ are that arm and the `cpu_baseline` legs.
 """
 
 from __future__ import annotations
@@ -34,72 +41,14 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+from mettagrid_b200.workloads import WORKLOADS, algo_bytes, gen_actions, make_cfg, make_map  # noqa: E402
+
 METRIC = "agent_steps_per_sec_incl_obs"
 UNIT = "agent-steps/s"
-ALGO_BYTES_PER_AGENT_STEP = 550.0  # C1/C2 (T=100, 20x20, R=10, A=16)
-
-
-WORKLOADS = {
-    # name: (description, default envs per GPU, agents)
-    "c2": ("C2: reference benchmark game 20x20, {A} agents/env, 13x13 obs, 100 tokens", 4096, 16),
-    "c3": ("C3: combat-heavy game 37x37 (25x25 + border 6), {A} agents in 2 teams, handler chains, 11x11 obs, 500 tokens", 16384, 24),
-    "c4": ("C4: world game 66x66, {A} agents, fixed+mobile AOE, territory + aoe_mask, events, queries, 11x11 obs, 200 tokens", 8192, 24),
-}
-
-
-def make_cfg(agents: int, workload: str = "c2"):
-    from tests import cases
-
-    if workload == "c3":
-        return cases.combat_config(None, agents // 2, num_tokens=500)
-    if workload == "c4":
-        return cases.world_config(None, agents // 2, num_tokens=200)
-    return cases.benchmark_config(agents)
-
-
-def make_map(cfg, agents: int, workload: str, seed: int):
-    from mettagrid_b200.mapgen import RandomMapConfig, random_map
-
-    if workload == "c3":
-        return random_map(RandomMapConfig(width=37, height=37, border_width=6, seed=seed,
-                                          agents={"red": agents // 2, "blue": agents // 2},
-                                          objects={"wall": 10, "chest": 6, "altar": 4}))  # fmt: skip
-    if workload == "c4":
-        return random_map(RandomMapConfig(width=66, height=66, border_width=1, seed=seed,
-                                          agents={"red": agents // 2, "blue": agents // 2},
-                                          objects={"wall": 120, "healer": 6, "spikes": 6, "beacon_red": 5, "beacon_blue": 5,
-                                                   "mine": 12, "vault": 6}))  # fmt: skip
-    return random_map(cfg.game.map_builder, seed=seed)
-
-
-def algo_bytes(P, workload: str) -> float:
-    """B_io + B_state per agent-step."""
-    if workload == "c2":
-        return ALGO_BYTES_PER_AGENT_STEP
-    T, A, R = P.num_tokens, P.num_agents, len(P.resource_names)
-    b_io = 3 * T + 4 + 4 + 4 + 1 + 1 + 8
-    b_state = (2 * P.height * P.width + 16) / A + 2 * (4 + 4 + 4 + 1 + 2 * R + 4 * R) + 4 * 8
-    return float(b_io + b_state)
-
+DTYPE = "u8/i32 (f32 stats)"
+C5_TOTAL_ENVS = 262144
 
 ACTION_MODE = os.environ.get("METTAGRID_BENCH_ACTIONS", "effective")  # --actions (inherited by the CPU workers)
-
-
-def gen_actions(num_actions: int, num_primary: int, steps: int, envs: int, agents: int, seed: int):
-    """SURVEY 8(d), both from np.random.RandomState(...).randint like the reference's benchmark
-    (benchmarks/test_mettagrid_env_benchmark.py:44-49):
-    'effective' (default): primary uniform over the non-vibe actions, vibe change with p = 0.1;
-    'verbatim': uniform over ALL action ids into the primary buffer, vibe buffer left 0 -- about 97 % of the ids
-    are change_vibe ids, which the primary stream ignores."""
-    rng = np.random.RandomState(seed)
-    if ACTION_MODE == "verbatim":
-        prim = rng.randint(0, num_actions, size=(steps, envs, agents)).astype(np.int32)
-        return prim, np.zeros_like(prim)
-    prim = rng.randint(0, num_primary, size=(steps, envs, agents)).astype(np.int32)
-    vibe = np.zeros_like(prim)
-    m = rng.rand(steps, envs, agents) < 0.1
-    vibe[m] = rng.randint(num_primary, num_actions, size=int(m.sum()))
-    return prim, vibe
 
 
 # ------------------------------------------------------------------------------------------------
@@ -117,7 +66,7 @@ def _ref_worker(rank: int, agents: int, envs: int, env0: int, steps: int, warmup
     cfg = make_cfg(agents, workload)
     sims, kind = [], "reference"
     for e in range(envs):
-        grid = make_map(cfg, agents, workload, 42 + env0 + e)
+        grid = make_map(cfg, agents, workload, env0 + e)
         try:
             sims.append(RefEnv(cfg, grid, 42 + env0 + e))
         except RefUnsupported:  # the GPU-box driver cannot build this game for the reference: time the oracle port
@@ -129,7 +78,7 @@ def _ref_worker(rank: int, agents: int, envs: int, env0: int, steps: int, warmup
             sims.append(OracleEnv(prog, cells, 42 + env0 + e, gs))
     prog = compile_config(cfg, *make_map(cfg, agents, workload, 0).shape)
     nprim = sum(1 for n in prog.action_names if not n.startswith("change_vibe_"))
-    prim, vibe = gen_actions(len(prog.action_names), nprim, 64, envs, agents, 1000 + rank)
+    prim, vibe = gen_actions(len(prog.action_names), nprim, 64, envs, agents, 1000 + rank, ACTION_MODE)
     for t in range(warmup):
         for e, s in enumerate(sims):
             s.step(prim[t % 64, e], vibe[t % 64, e])
@@ -170,6 +119,13 @@ def reference_available() -> bool:
     return reference.so_path() is not None
 
 
+def cpu_baseline(workload: str, agents: int, cpu_steps: int, envs_per_worker: int):
+    steps = cpu_steps if workload in ("c2", "toy") else max(200, cpu_steps // 20)
+    cb = run_reference(agents, steps=steps, warmup=50, envs_per_worker=envs_per_worker, workload=workload)
+    return {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
+            "sample": f"{cb['envs']} envs x {steps} ticks of the same game, one process per core ({cb['seconds']:.1f} s)"}  # fmt: skip
+
+
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     def __init__(self, index: int):
@@ -192,13 +148,134 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons)}  # fmt: skip
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}  # fmt: skip
+
+
+def kernel_name(sk: int) -> str:
+    return f"k_step_fast<{sk}>" if sk >= 8 else ("k_step<true>" if sk == 1 else "k_step<false>")
+
+
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class Workload:
+    """One handle on this rank's GPU plus a pool of device-resident action batches."""
+
+    POOL = 16
+
+    def __init__(self, wl: str, envs: int, agents: int, env0: int, device: int, seed: int, mode: str = None):
+        import torch
+
+        from mettagrid_b200.shard import env_seeds
+        from mettagrid_b200.sim import BatchedSimulation
+
+        self.wl, self.envs, self.A = wl, envs, agents
+        cfg = make_cfg(agents, wl)
+        if wl in ("c2", "toy"):
+            maps, map_seeds = None, [42 + e for e in range(env0, env0 + envs)]
+        else:
+            maps, map_seeds = [make_map(cfg, agents, wl, e) for e in range(env0, env0 + envs)], None
+        self.sim = BatchedSimulation(cfg, envs, seeds=env_seeds(42, env0, env0 + envs), maps=maps, map_seeds=map_seeds, device=device)
+        P = self.P = self.sim.program
+        self.num_actions = len(P.action_names)
+        self.num_primary = sum(1 for n in P.action_names if not n.startswith("change_vibe_"))
+        self.set_actions(seed, mode or ACTION_MODE)
+        self.tick = 0
+        self.torch = torch
+
+    def set_actions(self, seed: int, mode: str):
+        import torch
+
+        self.prim_h, self.vibe_h = gen_actions(self.num_actions, self.num_primary, self.POOL, self.envs, self.A, seed, mode)
+        self.prim = torch.from_numpy(self.prim_h).cuda()
+        self.vibe = torch.from_numpy(self.vibe_h).cuda()
+
+    def load_actions(self):
+        i = self.tick % self.POOL
+        self.sim.actions.copy_(self.prim[i])
+        self.sim.vibe_actions.copy_(self.vibe[i])
+        self.tick += 1
+
+    def run_ticks(self, n: int, flush, timed: bool):
+        """n ticks; with `timed`, a CUDA-event pair around each mg_step launch (the L2 flush and the action copy of
+        a tick stay outside its pair).  Returns the event pairs."""
+        torch = self.torch
+        evs = []
+        for _ in range(n):
+            self.load_actions()  # inputs resident in HBM before the timed region of this tick
+            if flush is not None:
+                flush.fill_(self.tick & 0xFF)  # evict L2 between timed launches
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                self.sim.step()
+                b.record()
+                evs.append((a, b))
+            else:
+                self.sim.step()
+        return evs
+
+    def roofline(self, ms_per_tick: float, traffic=None):
+        peak, src = peak_hbm()
+        ab = algo_bytes(self.P, self.wl)
+        achieved = ab * self.envs * self.A / (ms_per_tick * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": kernel_name(self.sim.step_kernel), "peak_source": src,
+                "algorithmic_bytes_per_agent_step": ab, "agent_steps_per_launch": self.envs * self.A}  # fmt: skip
+
+    def close(self):
+        self.sim.close()
+        self.torch.cuda.empty_cache()
+
+
+def measured_traffic(kernel: str, wl: str):
+    tpath = ROOT / "profiles" / "traffic.json"
+    if not tpath.exists():
+        return None
+    return json.loads(tpath.read_text()).get(f"{wl}:{kernel}", {}).get("dram_bytes_per_launch")
+
+
+def time_extra(wl: str, envs: int, agents: int, env0: int, world: int, rank: int, local_rank: int, ticks: int, flush, args,
+               scaling: str):  # fmt: skip
+    """One of the BASELINE configs 3-5: a few warm-up ticks, `ticks` timed ticks, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    w = Workload(wl, envs, agents, env0, local_rank, 7 + rank)
+    w.run_ticks(3, None, False)
+    torch.cuda.synchronize()
+    w.sim.check_errors()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = w.run_ticks(ticks, flush, True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    w.sim.check_errors()
+    per_tick = ms / ticks
+    out = {
+        "workload": WORKLOADS[wl][0].format(A=agents) + f", {envs} envs/GPU", "value": world * envs * agents * ticks / (ms * 1e-3),
+        "unit": UNIT, "ticks": ticks, "ms_per_tick": per_tick, "envs_per_gpu": envs, "total_envs": world * envs, "scaling": scaling,
+        "roofline": w.roofline(per_tick, measured_traffic(kernel_name(w.sim.step_kernel), wl)), "gpu_launches": ticks,
+    }  # fmt: skip
+    w.close()
+    return out
 
 
 def run_ours(args):
@@ -209,68 +286,42 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    from mettagrid_b200.shard import bind_to_gpu_numa, reduce_agent_stats, shard_range
+
+    numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation: host staging lands next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    from mettagrid_b200.sim import BatchedSimulation
-
-    from mettagrid_b200.shard import env_seeds, reduce_agent_stats, shard_range
 
     wl = args.workload
     envs = args.envs or WORKLOADS[wl][1]
     A = args.agents or WORKLOADS[wl][2]
-    cfg = make_cfg(A, wl)
-    env0, env1 = shard_range(world * envs, rank, world)  # weak scaling: `envs` environments per GPU
-    if wl == "c2":
-        maps = None
-        map_seeds = [42 + e for e in range(env0, env1)]
-    else:  # map instances are expensive to build on the host: cycle a pool of distinct maps
-        pool = [make_map(cfg, A, wl, 42 + i) for i in range(64)]
-        maps, map_seeds = [pool[e % 64] for e in range(env0, env1)], None
-    sim = BatchedSimulation(cfg, envs, seeds=env_seeds(42, env0, env1), maps=maps, map_seeds=map_seeds, device=local_rank)
-    P = sim.program
-    num_actions = len(P.action_names)
-    num_primary = sum(1 for n in P.action_names if not n.startswith("change_vibe_"))
-    POOL = 16
-    prim_h, vibe_h = gen_actions(num_actions, num_primary, POOL, envs, A, 7 + rank)
-    prim = torch.from_numpy(prim_h).cuda()
-    vibe = torch.from_numpy(vibe_h).cuda()
+    env0, _ = shard_range(world * envs, rank, world)  # weak scaling: `envs` environments per GPU
+    w = Workload(wl, envs, A, env0, local_rank, 7 + rank)
+    sim, P = w.sim, w.P
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    steps, warmup = args.steps, max(args.warmup, 3)
+    steps, warmup, tps = args.steps, max(args.warmup, 3), args.ticks_per_step
 
-    def one_step(i):
-        sim.actions.copy_(prim[i % POOL])
-        sim.vibe_actions.copy_(vibe[i % POOL])
-
-    for i in range(warmup):
-        one_step(i)
-        sim.step()
+    w.run_ticks(warmup * tps, None, False)
     torch.cuda.synchronize()
     sim.check_errors()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    for i in range(steps):
-        one_step(warmup + i)  # inputs resident in HBM before the timed region of this step
-        flush.fill_(i & 0xFF)  # evict L2 between timed iterations
-        ev[i][0].record()
-        sim.step()
-        ev[i][1].record()
+    evs = w.run_ticks(steps * tps, flush, True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    launches = steps  # one k_step launch per tick
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = steps * tps  # one step-kernel launch per tick
     clocks = sampler.stop()
 
     # ---- e2e: host buffers through the C ABI (pinned), copies inside the timed region
     NA = envs * A
-    h_prim = torch.from_numpy(prim_h[0].copy()).pin_memory()
-    h_vibe = torch.from_numpy(vibe_h[0].copy()).pin_memory()
+    h_prim = torch.from_numpy(w.prim_h[0].copy()).pin_memory()
+    h_vibe = torch.from_numpy(w.vibe_h[0].copy()).pin_memory()
     h_obs = torch.empty((envs, A, P.num_tokens, 3), dtype=torch.uint8).pin_memory()
     h_rew = torch.empty((envs, A), dtype=torch.float32).pin_memory()
     h_term = torch.empty((envs, A), dtype=torch.uint8).pin_memory()
@@ -281,10 +332,11 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    e2e_ticks = steps * min(tps, args.e2e_ticks_per_step)
     t0 = time.perf_counter()
-    for i in range(steps):
-        h_prim.copy_(torch.from_numpy(prim_h[i % POOL]))  # next step's host inputs (host memcpy, part of e2e)
-        h_vibe.copy_(torch.from_numpy(vibe_h[i % POOL]))
+    for i in range(e2e_ticks):
+        h_prim.copy_(torch.from_numpy(w.prim_h[i % w.POOL]))  # next tick's host inputs (host memcpy, part of e2e)
+        h_vibe.copy_(torch.from_numpy(w.vibe_h[i % w.POOL]))
         sim.step_host(hs(h_prim), hs(h_vibe), hs(h_obs), hs(h_rew), hs(h_term), hs(h_trunc))
     e2e_s = time.perf_counter() - t0
     e2e_sum = float(h_rew.sum()) + float(h_obs[0, 0, 0, 0])  # consume the result on the host
@@ -298,51 +350,64 @@ def run_ours(args):
     av = np.concatenate([sim.stats_arrays(e)[0] for e in range(min(envs, 8))])
     mean_stats = reduce_agent_stats(torch.from_numpy(av).cuda(), torch.tensor(av.shape[0], device="cuda"))
     total_ms, e2e_ms = float(t[0]), float(t[1])
-    agent_steps = world * envs * A * steps
-    value = agent_steps / (total_ms * 1e-3)
-    e2e_value = agent_steps / (e2e_ms * 1e-3)
+    value = world * envs * A * steps * tps / (total_ms * 1e-3)
+    e2e_value = world * envs * A * e2e_ticks / (e2e_ms * 1e-3)
+    per_tick_ms = total_ms / (steps * tps)
+    roof = w.roofline(per_tick_ms, measured_traffic(kernel_name(sim.step_kernel), wl))
+
+    # ---- the reference benchmark's verbatim action sampling on the same handle (report both)
+    other = "verbatim" if ACTION_MODE == "effective" else "effective"
+    w.set_actions(107 + rank, other)
+    w.run_ticks(3, None, False)
+    torch.cuda.synchronize()
+    evs = w.run_ticks(40, flush, True)
+    torch.cuda.synchronize()
+    tv = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+    other_line = {"value": world * envs * A * 40 / (float(tv[0]) * 1e-3), "ms_per_tick": float(tv[0]) / 40, "ticks": 40}
+    sim.check_errors()
+    w.close()
+
+    extra = {}
+    if not args.no_extras and wl == "c2" and not args.envs:
+        for name in ("c3", "c4", "toy"):
+            n, a = WORKLOADS[name][1], WORKLOADS[name][2]
+            extra[name] = time_extra(name, n, a, rank * n, world, rank, local_rank, args.extra_ticks, flush, args, "weak")
+        n5 = C5_TOTAL_ENVS // world
+        extra["c5"] = time_extra("c2", n5, 16, rank * n5, world, rank, local_rank, args.extra_ticks, flush, args, "strong")
+        extra["c5"]["workload"] = f"C5: the C2 game at {C5_TOTAL_ENVS} envs in total, {n5} per GPU"
 
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured"
-        else:
-            peak, peak_src = 6650.0, "fallback"
-        per_launch_ms = total_ms / steps
-        ab = algo_bytes(P, wl)
-        achieved = ab * envs * A / (per_launch_ms * 1e-3) / 1e9
-        # which kernel mg_step launches for this handle (include/mettagrid_b200.h: mg_step_kernel)
-        sk = sim.step_kernel
-        kernel = f"k_step_fast<{sk}>" if sk >= 8 else ("k_step<true>" if sk == 1 else "k_step<false>")
-        traffic = None
-        tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists() and wl == "c2" and envs == WORKLOADS[wl][1]:  # measured for the default workload only
-            traffic = json.loads(tpath.read_text()).get(kernel, {}).get("dram_bytes_per_launch")
+        num_actions, num_primary = w.num_actions, w.num_primary
+        desc = {"effective": f"primary uniform over {num_primary}, vibe p=0.1",
+                "verbatim": f"verbatim: primary uniform over all {num_actions} ids, vibe buffer 0"}  # fmt: skip
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
+            "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": WORKLOADS[wl][0].format(A=A) + f", {envs} envs/GPU",
-                       "envs_per_gpu": envs, "agents_per_env": A, "actions": (f"verbatim: primary uniform over all {num_actions} ids, vibe buffer 0" if ACTION_MODE == "verbatim"
-                                   else f"primary uniform over {num_primary}, vibe p=0.1"),
-                       "l2": "flushed between timed steps (256 MB fill)", "obs_write_GBps": value * 3 * P.num_tokens / 1e9,
-                       "parallelism": f"env-sharded x{world}, no per-step collective",
-                       "mean_move_success_per_agent": float(mean_stats[P.agent_stat_names.index("action.move.success")])},
+                       "envs_per_gpu": envs, "agents_per_env": A, "ticks_per_step": tps, "ms_per_tick": per_tick_ms,
+                       "actions": desc[ACTION_MODE], "other_action_sampling": {"actions": desc[other], **other_line},
+                       "l2": "flushed before every timed tick (256 MB fill, outside the event pairs)",
+                       "obs_write_GBps": value * 3 * P.num_tokens / 1e9,
+                       "parallelism": f"env-sharded x{world}, no per-step collective", "numa_binding": numa,
+                       "mean_move_success_per_agent": float(mean_stats[P.agent_stat_names.index("action.move.success")]),
+                       "extra": extra},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * NA * 4,
-                    "d2h_bytes_per_step": NA * (3 * P.num_tokens + 4 + 1 + 1), "check": e2e_sum},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * NA * 4 * (e2e_ticks // steps),
+                    "d2h_bytes_per_step": NA * (3 * P.num_tokens + 4 + 1 + 1) * (e2e_ticks // steps),
+                    "ticks_per_step": e2e_ticks // steps, "check": e2e_sum},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kernel, "peak_source": peak_src,
-                         "algorithmic_bytes_per_agent_step": ab},
+            "roofline": roof,
         }  # fmt: skip
         if world == 1 and not args.no_cpu_baseline and reference_available():
-            sim.close()
-            cpu_steps = args.cpu_steps if wl == "c2" else max(200, args.cpu_steps // 20)
-            cb = run_reference(A, steps=cpu_steps, warmup=50, envs_per_worker=args.cpu_envs_per_worker, workload=wl)
-            line["cpu_baseline"] = {"value": cb["value"], "unit": UNIT, "cores": cb["cores"], "kind": cb["kind"],
-                                    "sample": f"{cb['envs']} envs x {cpu_steps} steps of the same game, one process per core "
-                                              f"({cb['seconds']:.1f} s)"}  # fmt: skip
+            line["cpu_baseline"] = cpu_baseline(wl, A, args.cpu_steps, args.cpu_envs_per_worker)
+            for name, x in extra.items():
+                if name == "c5":
+                    x["cpu_baseline"] = dict(line["cpu_baseline"], sample=line["cpu_baseline"]["sample"] + " (the C2 game)")
+                else:
+                    x["cpu_baseline"] = cpu_baseline(name, WORKLOADS[name][2], args.cpu_steps, args.cpu_envs_per_worker)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -352,8 +417,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--ticks-per-step", type=int, default=50, help="ticks of every env per timed step")
+    ap.add_argument("--e2e-ticks-per-step", type=int, default=10, help="ticks per step of the host-buffer (e2e) leg")
+    ap.add_argument("--extra-ticks", type=int, default=30, help="timed ticks of each config.extra workload")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--actions", default="effective", choices=["effective", "verbatim"],
@@ -363,6 +431,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=40000)
     ap.add_argument("--cpu-envs-per-worker", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     global ACTION_MODE
     ACTION_MODE = args.actions
@@ -375,15 +444,15 @@ def main():
         if not reference_available():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (make -f oracle/Makefile.ref)"}))
             return
-        # one "step" = one tick of the bounded sample (cores x envs_per_worker envs)
+        # one "step" = ticks_per_step ticks of the bounded sample (cores x envs_per_worker envs)
         A = args.agents or WORKLOADS[args.workload][2]
-        tps = 30 if args.workload == "c2" else 3
+        tps = args.ticks_per_step if args.workload in ("c2", "toy") else max(2, args.ticks_per_step // 10)
         cb = run_reference(A, steps=max(args.steps, 1) * tps, warmup=max(args.warmup, 3) * tps // 3 + 1,
                            envs_per_worker=args.cpu_envs_per_worker, workload=args.workload)  # fmt: skip
         line = {
             "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/i32 (f32 stats)", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"] * tps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload][0].format(A=A) + f" -- sample of {cb['envs']} envs on "
                                    f"{cb['cores']} host cores (reference C++ step, one process per core)",
                        "ticks_per_step": tps},

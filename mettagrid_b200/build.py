@@ -32,32 +32,41 @@ def needs_build() -> bool:
     return LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps)
 
 
-def build_native(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+def build_native(force: bool = False, verbose: bool = False, out: Path | None = None, extra_flags: list[str] | None = None) -> Path:
+    """Build the library.  `out` / `extra_flags` produce an A/B variant (e.g. -DMG_PHASE_TIMING) next to the product
+    without touching it: python -m mettagrid_b200.build --variant NAME -DFLAG ... -> variants/lib_NAME.so"""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
-    build_dir = PKG / "build"
-    build_dir.mkdir(exist_ok=True)
+    build_dir = PKG / "build" if out is None else PKG / "build" / Path(out).stem
+    build_dir.mkdir(parents=True, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = build_dir / (Path(src).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *(extra_flags or []), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     for cmd, p in procs:
-        out, _ = p.communicate(timeout=1200)
-        if verbose and out:
-            print(out)
+        log, _ = p.communicate(timeout=1200)
+        if verbose and log:
+            print(log)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{out}")
-    subprocess.check_call([nvcc, "-shared", "-o", str(LIB), *objs])
-    return LIB
+            raise RuntimeError(f"nvcc failed: {' '.join(cmd)}\n{log}")
+    target = LIB if out is None else Path(out)
+    target.parent.mkdir(parents=True, exist_ok=True)
+    subprocess.check_call([nvcc, "-shared", "-o", str(target), *objs])
+    return target
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        name, flags = sys.argv[i + 1], [a for a in sys.argv[i + 2 :] if a != "-v"]
+        print(build_native(verbose="-v" in sys.argv, out=PKG.parent / "variants" / f"lib_{name}.so", extra_flags=flags))
+    else:
+        print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -61,6 +61,9 @@ struct mg_handle {
   uint8_t* h_term = nullptr;
   uint8_t* h_trunc = nullptr;
   uint32_t* seeds_dev = nullptr;
+  bool host_inited = false;     // staging set initialised (only needed when the caller never called mg_set_buffers)
+  cudaStream_t last_stream = nullptr;  // the caller stream the most recent asynchronous entry point was given
+  bool foreign_pending = true;  // work may be queued on a caller stream that own_stream is not ordered after
   // vectorised-env glue (mg_vecenv.cu)
   int ve_primary = 0, ve_vibes = 0;
   int32_t* ve_vibe_ids = nullptr;
@@ -110,9 +113,16 @@ static int launch_step(mg_handle* h, const MgDev& dev, cudaStream_t st) {
   return MG_OK;
 }
 
+// Wait for the work this handle queued: the caller stream of the latest asynchronous entry point and the handle's
+// own stream.  Stream-scoped on purpose -- a getter must not stall unrelated streams of a training process.
+static int sync_streams(mg_handle* h) {
+  CK(cudaStreamSynchronize(h->last_stream));
+  if (h->own_stream) CK(cudaStreamSynchronize(h->own_stream));
+  return MG_OK;
+}
 // all queued work done and the generic arrays current: what the host-side getters read
 static int sync_host_view(mg_handle* h) {
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_streams(h)) return rc;
   if (int rc = sync_generic(h, h->own_stream)) return rc;
   CK(cudaStreamSynchronize(h->own_stream));
   return MG_OK;
@@ -123,7 +133,8 @@ static int dev_alloc(mg_handle* h, T** p, size_t count) {
   size_t bytes = (count ? count : 1) * sizeof(T);
   bytes = (bytes + 255) & ~(size_t)255;
   CK(cudaMalloc((void**)p, bytes));
-  CK(cudaMemset(*p, 0, bytes));
+  CK(cudaMemset(*p, 0, bytes));  // legacy stream: callers synchronise the device before launching on own_stream
+  h->foreign_pending = true;
   h->allocs.push_back(*p);
   h->bytes += bytes;
   return MG_OK;
@@ -353,7 +364,8 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     h->err = "mg_create: stream creation failed";
     return fail(MG_E_CUDA);
   }
-  e = mg_launch_reset(d, nullptr, h->own_stream);
+  e = cudaDeviceSynchronize();  // the zero fills above ran on the legacy stream, own_stream does not wait for it
+  if (e == cudaSuccess) e = mg_launch_reset(d, nullptr, h->own_stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
   if (e != cudaSuccess) {
     h->err = std::string("mg_create: reset kernel failed: ") + cudaGetErrorString(e);
@@ -386,6 +398,7 @@ int mg_set_buffers(mg_handle* h, void* observations, void* terminals, void* trun
   d.obs = (uint8_t*)observations, d.terminals = (uint8_t*)terminals, d.truncations = (uint8_t*)truncations;
   d.rewards = (float*)rewards, d.actions = (const int32_t*)actions, d.vibe_actions = (const int32_t*)vibe_actions;
   h->buffers_set = true;
+  h->foreign_pending = true, h->last_stream = (cudaStream_t)stream;
   if (int rc = sync_generic(h, (cudaStream_t)stream)) return rc;
   CK(mg_launch_init_buffers(d, nullptr, (cudaStream_t)stream));
   if (h->fast) h->newest = mg_handle::GENERIC;
@@ -398,7 +411,17 @@ int mg_step(mg_handle* h, void* stream) {
     h->err = "mg_step: call mg_set_buffers first";
     return MG_E_INVALID;
   }
+  CK(cudaSetDevice(h->device));
+  h->foreign_pending = true, h->last_stream = (cudaStream_t)stream;
   return launch_step(h, h->d, (cudaStream_t)stream);
+}
+
+// the handle's own staging set as a step descriptor: used by mg_step_host only, h->d keeps the caller's buffers
+static MgDev host_dev(const mg_handle* h) {
+  MgDev run = h->d;
+  run.obs = h->h_obs, run.terminals = h->h_term, run.truncations = h->h_trunc, run.rewards = h->h_rew;
+  run.actions = h->h_act, run.vibe_actions = h->h_vact;
+  return run;
 }
 
 int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actions, uint8_t* observations,
@@ -413,19 +436,26 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
         (rc = dev_alloc(h, &h->h_obs, NA * d.T * 3)) || (rc = dev_alloc(h, &h->h_rew, NA)) ||
         (rc = dev_alloc(h, &h->h_term, NA)) || (rc = dev_alloc(h, &h->h_trunc, NA)))
       return rc;
-    rc = mg_set_buffers(h, h->h_obs, h->h_term, h->h_trunc, h->h_rew, h->h_act, h->h_vact, h->own_stream);
-    if (rc) return rc;
   }
   cudaStream_t st = h->own_stream;
+  if (h->foreign_pending) {  // own_stream is non-blocking: order it after whatever the caller queued elsewhere
+    CK(cudaDeviceSynchronize());
+    h->foreign_pending = false;
+  }
+  const MgDev run = host_dev(h);
+  if (!h->buffers_set && !h->host_inited) {
+    // a caller that only ever uses host buffers: _init_buffers (coverage, flags) against the staging set.  A handle
+    // whose buffers were set keeps its episode state untouched -- mg_set_buffers already ran _init_buffers.
+    if (int rc = sync_generic(h, st)) return rc;
+    CK(mg_launch_init_buffers(run, nullptr, st));
+    if (h->fast) h->newest = mg_handle::GENERIC;
+    h->host_inited = true;
+  }
   CK(cudaMemcpyAsync(h->h_act, actions, NA * 4, cudaMemcpyHostToDevice, st));
   if (vibe_actions)
     CK(cudaMemcpyAsync(h->h_vact, vibe_actions, NA * 4, cudaMemcpyHostToDevice, st));
   else
     CK(cudaMemsetAsync(h->h_vact, 0, NA * 4, st));
-  // the handle may have been pointed at caller buffers since; step on the staging set
-  MgDev run = d;
-  run.obs = h->h_obs, run.terminals = h->h_term, run.truncations = h->h_trunc, run.rewards = h->h_rew;
-  run.actions = h->h_act, run.vibe_actions = h->h_vact;
   {
     const int rc = launch_step(h, run, st);
     if (rc) return rc;
@@ -442,13 +472,18 @@ int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, v
   if (!h) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  h->foreign_pending = true, h->last_stream = st;
   if (new_seeds) {
     CK(cudaMemcpyAsync(h->seeds_dev, new_seeds, (size_t)h->d.num_envs * 4, cudaMemcpyHostToDevice, st));
     h->snap_valid = false;
+    if (env_mask) h->pristine = false;  // the unmasked envs keep generator states seeded from their old seeds
   }
   if (!env_mask) h->pristine = true;  // every env is about to hold its post-reset state again
   CK(mg_launch_reset(h->d, env_mask, st));
-  if (h->buffers_set) CK(mg_launch_init_buffers(h->d, env_mask, st));
+  if (h->buffers_set)
+    CK(mg_launch_init_buffers(h->d, env_mask, st));
+  else if (h->host_inited)
+    CK(mg_launch_init_buffers(host_dev(h), env_mask, st));
   if (h->fast) {
     // a full reset makes the generic arrays the truth; a masked one re-packs just the rebuilt environments so
     // that the others never leave the packed block
@@ -481,7 +516,7 @@ int mg_set_map(mg_handle* h, int env, const int16_t* init_cells, const float* in
     return MG_E_INVALID;
   }
   CK(cudaSetDevice(h->device));
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_streams(h)) return rc;
   CK(cudaMemcpy((void*)(d.init_cells + (size_t)env * d.HW), init_cells, (size_t)d.HW * 2, cudaMemcpyHostToDevice));
   if (init_gstats)
     CK(cudaMemcpy((void*)(d.init_gstats + (size_t)env * d.SG), init_gstats, (size_t)d.SG * 4, cudaMemcpyHostToDevice));
@@ -493,7 +528,7 @@ int mg_poll_errors(mg_handle* h, int* env, int* code, int* info) {
   if (!h) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
   std::vector<int32_t> e((size_t)h->d.num_envs * MGEV_WORDS);
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_streams(h)) return rc;
   CK(cudaMemcpy(e.data(), h->d.env, e.size() * 4, cudaMemcpyDeviceToHost));
   for (int i = 0; i < h->d.num_envs; i++)
     if (e[(size_t)i * MGEV_WORDS + MGEV_ERROR]) {
@@ -512,7 +547,7 @@ int mg_get_episode_rewards(mg_handle* h, float* out) {
   CK(cudaSetDevice(h->device));
   const MgDev& d = h->d;
   std::vector<uint32_t> ag((size_t)d.num_envs * d.A * d.AS);
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_streams(h)) return rc;
   CK(cudaMemcpy(ag.data(), d.agents, ag.size() * 4, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < (size_t)d.num_envs * d.A; i++) memcpy(&out[i], &ag[i * d.AS + MGAG_EPISODE_REWARD], 4);
   return MG_OK;
@@ -521,7 +556,7 @@ int mg_get_episode_rewards(mg_handle* h, float* out) {
 int mg_get_action_success(mg_handle* h, uint8_t* out) {
   if (!h || !out) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_streams(h)) return rc;
   CK(cudaMemcpy(out, h->d.success, (size_t)h->d.num_envs * h->d.A, cudaMemcpyDeviceToHost));
   return MG_OK;
 }
@@ -693,6 +728,7 @@ int mg_vecenv_step(mg_handle* h, const void* actions, int is_int64, int ncols, i
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   MgDev& d = h->d;
+  h->foreign_pending = true, h->last_stream = st;
   CK(mg_launch_vecenv_prepare(actions, is_int64, ncols, d.num_envs, d.A, h->ve_primary, h->ve_vibes, h->ve_vibe_ids,
                               (int32_t*)d.actions, (int32_t*)d.vibe_actions, d.terminals, d.truncations, h->ve_done,
                               h->ve_steps, h->ve_counters, st));
@@ -711,7 +747,7 @@ int mg_vecenv_step(mg_handle* h, const void* actions, int is_int64, int ncols, i
 int mg_vecenv_poll(mg_handle* h, int* episodes_finished, int* error_bits) {
   if (!h || !h->ve_counters) return MG_E_INVALID;
   CK(cudaSetDevice(h->device));
-  CK(cudaDeviceSynchronize());
+  if (int rc = sync_streams(h)) return rc;
   int c[2];
   CK(cudaMemcpy(c, h->ve_counters, sizeof c, cudaMemcpyDeviceToHost));
   if (episodes_finished) *episodes_finished = c[0];

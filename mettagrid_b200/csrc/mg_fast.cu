@@ -814,7 +814,7 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
     uint32_t* ag = d.agents + ga * d.AS;
     const uint4 a0 = *(const uint4*)(blk + MGFB_AGENT(G, gl)), a1 = *(const uint4*)(blk + MGFB_AGENT(G, gl) + 4);
     ag[MGAG_PREV_LOC] = a0.z, ag[MGAG_SWM] = a0.w, ag[MGAG_MAX_DIST] = a1.x, ag[MGAG_UNIQUE] = a1.y;
-    d.atouched[ga * d.SAW] |= a1.z & 0xffffu;
+    d.atouched[ga * d.SAW] = (d.atouched[ga * d.SAW] & ~0xffffu) | (a1.z & 0xffffu);  // the block owns stat ids < 16
     for (int id = 0; id < MGFB_STATS && id < d.SA; id++) d.astats[ga * d.SA + id] = __uint_as_float(blk[MGFB_STAT(G, id, gl)]);
   }
   if (gl < nobj && gl + 1 < d.maxobj) {
@@ -830,6 +830,16 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
       const uint32_t tk[4] = {o1.x, o1.y, o1.z, o1.w};
       for (int k = 0; k < nw; k++) o[TOKOFF + k] = tk[k];
     }
+  }
+  // k_step_fast never reads or writes the occupancy grid; rebuild it for the generic consumers (k_init_buffers after a
+  // mid-episode mg_set_buffers, the generic step kernels): objects are never created or removed on this path.
+  // A group's G threads share one warp (G divides 32).
+  uint16_t* cells = d.cells + (size_t)env * d.HWp;
+  for (int i = gl; i < d.HWp; i += G) cells[i] = 0;
+  __syncwarp();
+  if (gl < nobj && gl + 1 < d.maxobj) {
+    const uint32_t loc = blk[MGFB_OBJECT(G, gl)];
+    cells[((int)(loc >> 16) + d.PAD) * d.WP + (int)(loc & 0xffffu) + d.PAD] = (uint16_t)(gl + 1);
   }
 }
 

@@ -11,6 +11,33 @@
 #include "mg_device.cuh"
 #include "mg_world.cuh"
 
+#ifdef MG_PHASE_TIMING
+// A/B build only (python -m mettagrid_b200.build --variant prof -DMG_PHASE_TIMING): lane 0 of every warp adds the cycles
+// it spent in each phase of k_step; tools/phase_timing.py reads the totals through mg_debug_phase_cycles.
+__device__ unsigned long long g_phase_cycles[16];
+#define MG_PHASE(k)                                        \
+  do {                                                     \
+    __syncwarp();                                          \
+    if (lane == 0) {                                       \
+      const long long now_ = clock64();                    \
+      atomicAdd(&g_phase_cycles[k], (unsigned long long)(now_ - ph_t0)); \
+      ph_t0 = now_;                                        \
+    }                                                      \
+  } while (0)
+#define MG_PHASE_BEGIN() long long ph_t0 = clock64()
+extern "C" int mg_debug_phase_cycles(unsigned long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof g_phase_cycles) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+  }
+  return 0;
+}
+#else
+#define MG_PHASE(k) do { } while (0)
+#define MG_PHASE_BEGIN() do { } while (0)
+#endif
+
 namespace {
 
 struct Smem {
@@ -768,6 +795,7 @@ template <bool PLAIN>
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_step(MgDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MG_PHASE_BEGIN();
   {
     Smem cta;
     carve(d, smem_raw, warp, cta);
@@ -797,6 +825,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   }
   rng_window_fill(w, lane);
   __syncwarp();
+  MG_PHASE(0);
 
   // phase 4-5: shuffled, sequential action resolution (:958-999)
   if (lane == 0) {
@@ -830,6 +859,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     }
   }
   __syncwarp();
+  MG_PHASE(1);
 
   // per-agent bookkeeping of handle_action (actions/action_handler.hpp:78-105), one lane per agent.
   // It only touches the acting agent's own counters, so it is order-independent across agents.
@@ -874,6 +904,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     }
   }
   __syncwarp();
+  MG_PHASE(2);
 
   // phases 6-11 (events, on_tick, AOE, territory, game on_tick): serial
   if (!PLAIN && lane == 0) {
@@ -889,6 +920,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     }
   }
   __syncwarp();
+  MG_PHASE(3);
   if (!PLAIN) {
     // fixed AOE + territory per agent in index order (:1032-1042).  The serial work stays on lane 0; before each
     // agent's turn all lanes test which sources can matter to it at its current cell.
@@ -918,6 +950,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     }
   }
   __syncwarp();
+  MG_PHASE(4);
 
   // phase 12: coverage (objects/agent.cpp:49-57), one lane per agent
   for (int a = lane; a < A; a += 32) {
@@ -947,7 +980,9 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
     if (lane == 0 && w.rs[5]) terr_build_table(w);
     __syncwarp();
   }
+  MG_PHASE(5);
   observe_all(w, s, lane, false);
+  MG_PHASE(6);
 
   // phase 14-15: rewards (systems/reward.hpp:56-77), episode rewards, truncation (:1070-1096)
   const int ms = w.hdr[MGH_MAX_STEPS];
@@ -982,6 +1017,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   }
   rng_window_commit(w, lane);
   if (lane == 0) w.E[MGEV_STEP] = (int32_t)w.step;
+  MG_PHASE(7);
 }
 
 // Agent::set_inventory (objects/agent.cpp:86-104) for one agent of one env: a single warp, lane 0 works

@@ -255,3 +255,82 @@ def test_token_stats_beyond_the_exact_float_range():
         assert got == want, f"stats differ in env {e}"
         assert np.array_equal(sim.observations[e].cpu().numpy(), o.observations())
     sim.close()
+
+
+def test_set_buffers_mid_episode_on_a_fast_handle_sees_the_moved_agents():
+    """mg_set_buffers re-runs _init_buffers (mettagrid_c.cpp:1165-1184): the observations it writes must show the agents
+    where they are now -- the fast kernel does not maintain the occupancy grid, k_fast_unpack rebuilds it."""
+    from mettagrid_b200.sim import BatchedSimulation
+    from oracle.oracle import OracleEnv
+
+    sim = BatchedSimulation(cases.benchmark_config(8), 6, seeds=21)
+    assert sim.step_kernel >= 8
+    P = sim.program
+    orc = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(6)]
+    prim, vibe = cases.random_actions(np.random.RandomState(3), 60, (6, 8), 5, len(P.action_names), 0.2)
+    for t in range(60):
+        if t in (25, 26, 50):
+            N, A, T = 6, 8, P.num_tokens
+            bufs = (torch.empty((N, A, T, 3), dtype=torch.uint8, device="cuda"), torch.zeros((N, A), dtype=torch.bool, device="cuda"),
+                    torch.zeros((N, A), dtype=torch.bool, device="cuda"), torch.zeros((N, A), dtype=torch.float32, device="cuda"),
+                    torch.zeros((N, A), dtype=torch.int32, device="cuda"), torch.zeros((N, A), dtype=torch.int32, device="cuda"))  # fmt: skip
+            sim.set_buffers(*bufs)
+            torch.cuda.synchronize()
+            obs = sim.observations.cpu().numpy()
+            for e, o in enumerate(orc):
+                o.reinit_buffers()
+                assert np.array_equal(obs[e], o.observations()), f"set_buffers at tick {t}: env {e}"
+        sim.step(prim[t], vibe[t])
+        for e, o in enumerate(orc):
+            o.step(prim[t, e], vibe[t, e])
+    torch.cuda.synchronize()
+    obs = sim.observations.cpu().numpy()
+    for e, o in enumerate(orc):
+        assert np.array_equal(obs[e], o.observations())
+        assert sim.get_episode_stats(e) == o.get_episode_stats()
+    sim.close()
+
+
+@pytest.mark.parametrize("game", ["benchmark", "walled", "combat"])
+def test_step_host_leaves_the_callers_buffers_bound(game):
+    """mg_step_host steps on the handle's own staging set and must not rebind the handle: device steps, host steps and
+    resets interleave on one handle, and the caller's tensors keep receiving the device steps' results."""
+    from mettagrid_b200.sim import BatchedSimulation
+    from oracle.oracle import OracleEnv
+
+    if game == "benchmark":
+        cfg, maps, nprim = cases.benchmark_config(4), None, 5
+    elif game == "walled":
+        cfg, maps, nprim = cases.walled_config(4, max_steps=0), None, 5
+    else:
+        cfg, maps, nprim = cases.combat_config(None, 2), [cases.combat_map(2, seed=s) for s in range(3)], 9
+    sim = BatchedSimulation(cfg, 3, seeds=8, maps=maps)
+    P = sim.program
+    A, T = P.num_agents, P.num_tokens
+    mk = lambda: [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(3)]  # noqa: E731
+    orc = mk()
+    prim, vibe = cases.random_actions(np.random.RandomState(6), 50, (3, A), nprim, len(P.action_names), 0.2)
+    h_obs = np.zeros((3, A, T, 3), np.uint8)
+    h_rew, h_term, h_trunc = np.zeros((3, A), np.float32), np.zeros((3, A), np.uint8), np.zeros((3, A), np.uint8)
+    for t in range(50):
+        if t == 30:
+            sim.reset()
+            orc = mk()
+            torch.cuda.synchronize()
+            assert np.array_equal(sim.observations.cpu().numpy(), np.stack([o.observations() for o in orc])), "reset obs"
+        host = t % 3 == 1
+        if host:
+            sim.step_host(prim[t], vibe[t], h_obs, h_rew, h_term, h_trunc)
+        else:
+            sim.step(prim[t], vibe[t])
+            torch.cuda.synchronize()
+        for e, o in enumerate(orc):
+            o.step(prim[t, e], vibe[t, e])
+        got = h_obs if host else sim.observations.cpu().numpy()
+        rew = h_rew if host else sim.rewards.cpu().numpy()
+        for e, o in enumerate(orc):
+            assert np.array_equal(got[e], o.observations()), f"tick {t} ({'host' if host else 'device'}): env {e}"
+            assert np.array_equal(rew[e].view(np.uint32), o.rewards().view(np.uint32))
+    for e, o in enumerate(orc):
+        assert sim.get_episode_stats(e) == o.get_episode_stats()
+    sim.close()

@@ -98,3 +98,72 @@ def test_batch_invariance_and_determinism():
     assert np.array_equal(small.observations.cpu().numpy(), big_obs)
     assert [small.get_episode_stats(e) for e in range(8)] == big_stats
     small.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# C3 / C4 / toy at the shapes bench.py times (same configs, same recorded MapGen pools, same action sampling):
+# every env against its own oracle for the first ticks, 32 sampled envs over a long run.
+# ---------------------------------------------------------------------------------------------------------------
+def _full_shape(wl, num_envs, all_ticks, check_at, long_ticks, long_check):
+    from mettagrid_b200 import workloads as W
+    from mettagrid_b200.sim import BatchedSimulation
+    from tests.oracle_batch import OracleBatch
+
+    agents = W.WORKLOADS[wl][2]
+    cfg = W.make_cfg(agents, wl)
+    if wl in ("c3", "c4"):
+        sim = BatchedSimulation(cfg, num_envs, seeds=42, maps=[W.make_map(cfg, agents, wl, e) for e in range(num_envs)])
+    else:
+        sim = BatchedSimulation(cfg, num_envs, seeds=42)
+    P = sim.program
+    na = len(P.action_names)
+    nprim = sum(1 for n in P.action_names if not n.startswith("change_vibe_"))
+    orc = OracleBatch(sim)
+    prim, vibe = W.gen_actions(na, nprim, all_ticks, num_envs, agents, 11)
+    for t in range(all_ticks):
+        sim.step(prim[t], vibe[t])
+        orc.step(prim[t], vibe[t])
+        if t in check_at:
+            torch.cuda.synchronize()
+            bad = orc.first_mismatch(sim.observations.cpu().numpy(), sim.rewards.cpu().numpy(), sim.action_success())
+            assert bad is None, f"{wl} tick {t}: {bad}"
+    sim.check_errors()
+    sample = list(range(0, num_envs, num_envs // 32))
+    for e in sample[:8]:
+        assert sim.get_episode_stats(e) == orc.orc[e].get_episode_stats(), f"{wl}: stats differ in env {e}"
+    keep = OracleBatch.__new__(OracleBatch)
+    keep.envs, keep.pool, keep.orc = sample, orc.pool, [orc.orc[e] for e in sample]
+    orc.orc = None
+    rs = np.random.RandomState(5)
+    for t in range(all_ticks, long_ticks):
+        p = rs.randint(0, nprim, size=(num_envs, agents)).astype(np.int32)
+        v = np.zeros_like(p)
+        if na > nprim:
+            v = np.where(rs.rand(num_envs, agents) < 0.1, rs.randint(nprim, na, size=(num_envs, agents)), 0).astype(np.int32)
+        sim.step(p, v)
+        keep.step(p, v)
+        if t % long_check == 0 or t == long_ticks - 1:
+            torch.cuda.synchronize()
+            bad = keep.first_mismatch(sim.observations[sample].cpu().numpy(), sim.rewards[sample].cpu().numpy())
+            assert bad is None, f"{wl} tick {t}: {bad}"
+    sim.check_errors()
+    for i, e in enumerate(sample):
+        assert sim.get_episode_stats(e) == keep.orc[i].get_episode_stats(), f"{wl}: stats differ in env {e}"
+        assert np.array_equal(sim.dump_objects(e), keep.orc[i].dump_objects()), f"{wl}: objects differ in env {e}"
+    keep.close()
+    sim.close()
+
+
+def test_c3_combat_at_bench_shape():
+    """BASELINE config 3: 16 384 envs x 24 agents, 37 x 37 arena maps, 500 tokens."""
+    _full_shape("c3", 16384, 16, (0, 7, 15), 500, 97)
+
+
+def test_c4_world_at_bench_shape():
+    """BASELINE config 4: 8192 envs x 24 agents, 66 x 66 MapGen maps, 200 tokens, AOE + territory + events."""
+    _full_shape("c4", 8192, 12, (0, 5, 11), 400, 83)
+
+
+def test_toy_preset_at_bench_shape():
+    """The reference's perf_benchmark.py toy preset: 4096 envs x 20 agents, 40 x 40 walled maps, 8-way moves."""
+    _full_shape("toy", 4096, 32, (0, 15, 31), 600, 101)

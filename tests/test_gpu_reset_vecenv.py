@@ -262,3 +262,60 @@ def test_vecenv_fast_path_autoreset_matches_oracle():
         assert np.array_equal(env.sim.dump_objects(e), o.dump_objects())
     assert env.episodes_finished == 7 * 4
     env.close()
+
+
+def test_vecenv_fast_path_stats_read_mid_episode_then_autoreset():
+    """Stats read mid-episode (unpack) must not leak touched keys into the episode that follows a snapshot restore."""
+    from mettagrid_b200.vecenv import MettaGridVecEnv
+
+    cfg = cases.benchmark_config(4, max_steps=9)
+    env = MettaGridVecEnv(cfg, 3, seed=13)
+    assert env.sim.step_kernel == 8
+    orc = _oracles(env.sim)
+    P = env.num_primary
+    rng = np.random.RandomState(2)
+    for t in range(14):
+        a = rng.randint(0, P, size=12)
+        if t < 8:
+            a[:] = 1  # everyone pushes north: some moves fail, 'action.failed' gets touched in episode 1
+        else:
+            a[:] = 0  # episode 2 only noops: 'action.failed' must not exist
+        for e in range(3):
+            if orc[e].terminals().all() or orc[e].truncations().all():
+                orc[e] = _oracles(env.sim)[e]
+        env.step(torch.from_numpy(a).cuda())
+        for e, o in enumerate(orc):
+            o.step(a.reshape(3, 4)[e], np.zeros(4, np.int32))
+        if t == 6:
+            for e, o in enumerate(orc):
+                assert env.sim.get_episode_stats(e) == o.get_episode_stats()
+    for e, o in enumerate(orc):
+        assert env.sim.get_episode_stats(e) == o.get_episode_stats(), f"env {e}"
+    env.close()
+
+
+def test_masked_reset_with_new_seeds_then_autoreset_uses_the_new_seeds():
+    from mettagrid_b200.vecenv import MettaGridVecEnv
+
+    cfg = cases.benchmark_config(4, max_steps=6)
+    env = MettaGridVecEnv(cfg, 4, seed=40)
+    sim = env.sim
+    new_seeds = [900 + e for e in range(4)]
+    mask = torch.tensor([1, 0, 0, 0], dtype=torch.bool, device="cuda")
+    sim.reset(env_mask=mask, seeds=new_seeds)  # before any step: every later reset of env e uses new_seeds[e]
+    orc = _oracles(sim, [900, 40 + 1, 40 + 2, 40 + 3])
+    rng = np.random.RandomState(1)
+    P = env.num_primary
+    for t in range(20):
+        a = rng.randint(0, P, size=16)
+        for e in range(4):
+            if orc[e].terminals().all() or orc[e].truncations().all():
+                orc[e] = _oracles(sim, new_seeds)[e]
+        obs, *_ = env.step(torch.from_numpy(a).cuda())
+        for e, o in enumerate(orc):
+            o.step(a.reshape(4, 4)[e], np.zeros(4, np.int32))
+        torch.cuda.synchronize()
+        ob = obs.cpu().numpy().reshape(4, 4, -1, 3)
+        for e, o in enumerate(orc):
+            assert np.array_equal(ob[e], o.observations()), f"step {t} env {e}"
+    env.close()

@@ -7,7 +7,7 @@ import torch
 
 from mettagrid_b200.sim import BatchedSimulation
 from oracle.oracle import OracleEnv
-from tests import cases
+from mettagrid_b200 import workloads as cases
 
 name, seed, steps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 cfg = getattr(cases, f"{name}_config")(None)

@@ -2,7 +2,7 @@
 import sys, time
 sys.path.insert(0, '.')
 import numpy as np, torch
-from tests import cases
+from mettagrid_b200 import workloads as cases
 from mettagrid_b200.sim import BatchedSimulation
 N, A = int(sys.argv[1]), int(sys.argv[2])
 flush = len(sys.argv) > 3 and sys.argv[3] == "flush"

@@ -2,7 +2,7 @@
 import sys
 sys.path.insert(0, '.')
 import torch
-from tests import cases
+from mettagrid_b200 import workloads as cases
 from mettagrid_b200.sim import BatchedSimulation
 N, A = int(sys.argv[1]), int(sys.argv[2])
 sim = BatchedSimulation(cases.benchmark_config(A), N, seeds=42)

@@ -2,7 +2,7 @@
 import sys, time
 sys.path.insert(0, '.')
 import torch
-from tests import cases
+from mettagrid_b200 import workloads as cases
 from mettagrid_b200.vecenv import MettaGridVecEnv
 N, MS = int(sys.argv[1]), int(sys.argv[2])
 VALIDATE = not (len(sys.argv) > 3 and sys.argv[3] == 'novalidate')
