@@ -128,33 +128,64 @@ def cpu_baseline(workload: str, agents: int, cpu_steps: int, envs_per_worker: in
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region: NVML (pynvml, ~10 ms period), nvidia-smi as a fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self._stop_evt = index, [], set(), threading.Event()
-        self.max_mhz = None
+        self.max_mhz, self.source = None, "nvml"
+        try:
+            import pynvml
 
-    def run(self):
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(ids[index] if index < len(ids) else index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv, self.source = None, "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):  # fmt: skip
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")  # fmt: skip
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")  # fmt: skip
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for n, v in zip(self.NAMES, out[2:]):
+            if v.strip().lower() == "active":
+                self.reasons.add(n)
+
+    def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")  # fmt: skip
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower() == "active":
-                        self.reasons.add(n)
+                if self._nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+                if self._nv is not None:  # an NVML call this driver lacks: fall back once
+                    self._nv, self.source = None, "nvidia-smi"
+            self._stop_evt.wait(0.01 if self._nv is not None else 0.1)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=5)
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}  # fmt: skip
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}  # fmt: skip
 
 
 def kernel_name(sk: int) -> str:
@@ -417,7 +448,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--ticks-per-step", type=int, default=50, help="ticks of every env per timed step")
     ap.add_argument("--e2e-ticks-per-step", type=int, default=10, help="ticks per step of the host-buffer (e2e) leg")

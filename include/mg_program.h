@@ -18,7 +18,7 @@
 #include <stdint.h>
 
 #define MG_MAGIC 0x4D47B200
-#define MG_VERSION 7
+#define MG_VERSION 8
 
 /* ---- header word indices ------------------------------------------------------------ */
 enum {
@@ -97,6 +97,10 @@ enum {
   MGH_PROXY_TEMPLATE,   /* inert template (kind 3) used by territory proxy-cell objects */
   MGH_SPAWN_AOES,       /* max AOE configs on any template a spawn mutation can create */
   MGH_TOK_CAP,          /* most observation tokens any object can emit (per-object token cache size) */
+  /* compile-time effect analysis (mettagrid_b200/compiler.py: analyze_effects) */
+  MGH_MOVE_REACH,       /* longest line a move handler scans (max max_range over the chain) */
+  MGH_CHAIN_EMPTY_CLASS,/* MGC_* class of the custom move handlers that accept an empty target cell */
+  MGH_PAR_FLAGS,        /* MGP_* bits: which per-agent phases may run one lane per agent */
   /* section offsets */
   MGS_OFFSETS,      /* NUM_OFFSETS x (dr, dc) */
   MGS_ACTIONS,      /* NUM_ACTIONS x MG_ACTION_WORDS */
@@ -118,9 +122,22 @@ enum {
   MGS_RES_GSTATS,   /* R x 1: game stat id of "<res>.amount" (InventoryValue w/o actor) or -1 */
   MGS_INV_FEATS,    /* R x INV_DIGITS feature ids */
   MGS_DYN_TAGS,     /* NUM_TAGS x 1: dynamic-tag slot or -1 */
+  MGS_TMPL_CLASS,   /* NUM_TEMPLATES x 1: MGC_* class (bits 0-1) | MGC_DISPLACES of a move whose line holds such an object */
   MGS_POOL,         /* variable-length int lists */
   MGH_HEADER_WORDS
 };
+
+/* Effect classes of one agent's action (what it may read / write besides itself and the objects in its line):
+   LOCAL  -- only the actor, the objects in the scanned line and those cells;
+   SHARED -- also env-wide structures whose update order matters (game stats, tag index, object table, AOE tables):
+             such actions run in the shuffled order relative to each other, but independently of LOCAL ones elsewhere;
+   SERIAL -- reads or writes arbitrary objects (queries, raycasts, push chains): the whole pass runs in order. */
+enum { MGC_LOCAL = 0, MGC_SHARED = 1, MGC_SERIAL = 2 };
+#define MGC_DISPLACES 4 /* may move the TARGET agent (swap): the target's own move then starts from the actor's cell */
+/* MGH_PAR_FLAGS */
+#define MGP_ON_TICK 1 /* agent on_tick handlers only read and write their own agent */
+#define MGP_AOE 2     /* AOE / territory handlers only write their target agent and read nothing another lane writes */
+#define MGP_ACTIONS 4 /* action passes may resolve independent agents concurrently */
 
 /* MGH_GLOBAL_FLAGS bits (cpp/bindings/mettagrid_c.cpp:700-742) */
 #define MGG_EPISODE_PCT 1
@@ -277,6 +294,7 @@ enum {
 #define MGOF_AGENT 2
 #define MGOF_OBS_INV 4 /* obs_encoder set: inventory tokens are emitted (false for spawned objects) */
 #define MGOF_WALL 8
+#define MGOF_TERR_SRC 16 /* registered as a territory source: moving / re-tagging it invalidates the ownership map */
 
 /* agent record words (stride = MGH_AGENT_STRIDE) */
 enum {
@@ -304,7 +322,11 @@ enum {
   MGEV_NUM_AOE,      /* registered AOE sources */
   MGEV_NUM_AOE_PENDING,
   MGEV_NUM_TERR,
-  MGEV_RESERVED,
+  MGEV_RESERVED,     /* entries in the per-tick territory source table */
+  MGEV_TERR_STALE,   /* a territory source moved / changed tags since the ownership map was built */
+  MGEV_PAD0,
+  MGEV_PAD1,
+  MGEV_PAD2,
   MGEV_WORDS
 };
 #define MGERR_TOKEN_OVERFLOW 1

@@ -680,6 +680,204 @@ class _Builder:
         return limit_of, reachable, res_order, mod_mask
 
 
+# ==================================================================================================
+# Compile-time effect analysis: which parts of a tick may run one lane per agent instead of serially.
+# The reference resolves everything sequentially (cpp/bindings/mettagrid_c.cpp:966-1052); the kernel may only reorder
+# work whose reads and writes provably do not meet.  Everything here is conservative: an op this table does not know
+# forces the serial path.
+# ==================================================================================================
+class _Effects:
+    def __init__(self, b: "_Builder", templates: list[list[int]], have_aoe: bool, have_tag_index: bool):
+        self.b, self.templates = b, templates
+        self.have_aoe, self.have_tag_index = have_aoe, have_tag_index
+        self._vc: dict[int, int] = {}
+        tag_remove = [0]
+        self._tag_remove_class = 0
+        for t in templates:  # on_tag_remove handlers may fire from any tag removal
+            off, n = t[K["MGT_TAG_REMOVE"]], t[K["MGT_TAG_REMOVE_N"]]
+            for i in range(n):
+                tag_remove.append(self.handler(b.pool[off + 2 * i + 1], use=None)[0])
+        self._tag_remove_class = max(tag_remove)
+
+    # ---- values / filters --------------------------------------------------------------------------------
+    def value(self, node: int) -> int:
+        if node in self._vc:
+            return self._vc[node]
+        self._vc[node] = K["MGC_SERIAL"]  # cycle guard
+        op, scope, a, b_, c, d = self.b.values[node]
+        pool = self.b.pool
+        if op in (K["MGV_INVENTORY"], K["MGV_STAT"]):
+            cls = K["MGC_SHARED"] if scope == K["MGSC_GAME"] else K["MGC_LOCAL"]  # game stats: shared words + touched bits
+        elif op == K["MGV_CONST"]:
+            cls = K["MGC_LOCAL"]
+        elif op in (K["MGV_SUM"], K["MGV_MAX"], K["MGV_MIN"]):
+            cls = max([self.value(pool[a + i]) for i in range(b_)] + [0])
+        elif op == K["MGV_RATIO"]:
+            cls = max(self.value(a), self.value(b_))
+        else:  # query values read arbitrary objects
+            cls = K["MGC_SERIAL"]
+        self._vc[node] = cls
+        return cls
+
+    def filter(self, fi: int) -> int:
+        op, ent, a, b_, c, d = self.b.filters[fi]
+        if op in (K["MGF_VIBE"], K["MGF_RESOURCE"], K["MGF_SHARED_TAG_PREFIX"], K["MGF_TAG_PREFIX"], K["MGF_TARGET_LOC_EMPTY"],
+                  K["MGF_TARGET_IS_USABLE"], K["MGF_PERIODIC"]):  # fmt: skip
+            return K["MGC_LOCAL"]
+        if op == K["MGF_GAME_VALUE"]:
+            return max(self.value(a), self.value(b_))
+        if op in (K["MGF_NEG"], K["MGF_OR"]):
+            return max([self.filter(a + i) for i in range(b_)] + [0])
+        if op == K["MGF_MAX_DISTANCE"] and a < 0:
+            return K["MGC_LOCAL"]
+        return K["MGC_SERIAL"]
+
+    def filter_reads_actor_inventory(self, fi: int) -> bool:
+        op, ent, a, b_, c, d = self.b.filters[fi]
+        if op in (K["MGF_NEG"], K["MGF_OR"]):
+            return any(self.filter_reads_actor_inventory(a + i) for i in range(b_))
+        return op in (K["MGF_RESOURCE"], K["MGF_GAME_VALUE"]) and ent != K["MGE_TARGET"]
+
+    # ---- mutations / handlers ----------------------------------------------------------------------------
+    def mutation(self, mi: int, use) -> tuple[int, bool]:
+        """(class, displaces).  `use` = (class, displaces) the USE_TARGET op stands for in this context, or None when the
+        target cannot be used (empty cell)."""
+        op, e1, e2, a, b_, c, d, e = self.b.mutations[mi]
+        L, S, X = K["MGC_LOCAL"], K["MGC_SHARED"], K["MGC_SERIAL"]
+        if op in (K["MGM_RESOURCE_DELTA"], K["MGM_CLEAR_INVENTORY"], K["MGM_ATTACK"], K["MGM_CHANGE_VIBE"], K["MGM_RELOCATE"]):
+            return L, False
+        if op == K["MGM_RESOURCE_TRANSFER"]:
+            if c:  # remove_source_when_empty: leaves the tag index and drops AOE presence from every agent inside
+                return (X if (self.have_aoe or self.have_tag_index) else S), False
+            return L, False
+        if op == K["MGM_SWAP"]:
+            return L, True
+        if op == K["MGM_STATS"]:
+            return max(S if b_ == 0 else L, self.value(d)), False
+        if op == K["MGM_GAME_VALUE"]:
+            vop, vscope = self.b.values[a][0], self.b.values[a][1]
+            tgt = S if vscope == K["MGSC_GAME"] else L
+            if vop not in (K["MGV_INVENTORY"], K["MGV_STAT"]):
+                tgt = L  # the op ignores other target nodes
+            return max(tgt, self.value(b_)), False
+        if op in (K["MGM_ADD_TAG"], K["MGM_REMOVE_TAG"], K["MGM_REMOVE_TAGS_PREFIX"]):
+            return max(S, self._tag_remove_class), False  # tag index order + insertion stamps
+        if op == K["MGM_SPAWN_OBJECT"]:
+            return S, False  # object slots / ids / tag index in creation order
+        if op == K["MGM_USE_TARGET"]:
+            return (L, False) if use is None else use
+        return X, False  # queries, materialized queries, raycast spawn, push
+
+    def handler(self, h: int, use) -> tuple[int, bool]:
+        if h < 0:
+            return K["MGC_LOCAL"], False
+        kind, a, b_, c, d = self.b.handlers[h]
+        if kind == K["MGHK_SIMPLE"]:
+            cls = max([self.filter(a + i) for i in range(b_)] + [0])
+            disp = False
+            for i in range(d):
+                mc_, md = self.mutation(c + i, use)
+                cls, disp = max(cls, mc_), disp or md
+            return cls, disp
+        out = [self.handler(self.b.pool[a + i], use) for i in range(b_)]
+        return max([o[0] for o in out] + [0]), any(o[1] for o in out)
+
+    # ---- per-agent world phases -----------------------------------------------------------------------------
+    def self_local(self, h: int, target_only: bool, actor_is_agent: bool) -> bool:
+        """True when the handler tree only reads class-LOCAL state and only writes the TARGET agent's inventory / stats
+        (`target_only`: the actor is another object -- an AOE source or a territory proxy)."""
+        if h < 0:
+            return True
+        kind, a, b_, c, d = self.b.handlers[h]
+        if kind != K["MGHK_SIMPLE"]:
+            return all(self.self_local(self.b.pool[a + i], target_only, actor_is_agent) for i in range(b_))
+        return self.rows_self_local(a, b_, c, d, target_only, actor_is_agent)
+
+    def rows_self_local(self, f0, fn, m0, mn, target_only: bool, actor_is_agent: bool) -> bool:
+        for i in range(fn):
+            if self.filter(f0 + i) != K["MGC_LOCAL"]:
+                return False
+            if target_only and actor_is_agent and self.filter_reads_actor_inventory(f0 + i):
+                return False  # another lane may be editing that agent's inventory
+        for i in range(mn):
+            op, e1, e2, a, b_, c, d, e = self.b.mutations[m0 + i]
+            tgt_ok = (not target_only) or e1 == K["MGE_TARGET"]
+            if op in (K["MGM_RESOURCE_DELTA"], K["MGM_CLEAR_INVENTORY"]) and tgt_ok:
+                continue
+            if op == K["MGM_CHANGE_VIBE"] and not target_only:
+                continue
+            if op == K["MGM_STATS"] and b_ == 1 and self.value(d) == K["MGC_LOCAL"] and ((not target_only) or c == 0):
+                continue
+            if op == K["MGM_GAME_VALUE"] and tgt_ok and self.mutation(m0 + i, None)[0] == K["MGC_LOCAL"]:
+                continue
+            return False
+        return True
+
+
+def analyze_effects(b: "_Builder", templates, move_chain, territories, n_queries_or_mq: int):
+    """-> (tmpl_class rows, move_reach, chain_empty_class, par_flags)"""
+    TW = b.tw
+    have_aoe = len(b.aoes) > 0
+    fx = _Effects(b, templates, have_aoe, n_queries_or_mq > 0)
+    agent_templates = [t for t in templates if t[K["MGT_KIND"]] == 1]
+    after = [fx.handler(t[K["MGT_ON_AFTER_USE"]], use=None) for t in agent_templates]
+    after_cls, after_disp = max([x[0] for x in after] + [0]), any(x[1] for x in after)
+    # tags that can appear at run time on any object: a static tag filter cannot rule a template out for those
+    addable = set(b.dyn_tags)
+
+    def mask_words(off):
+        return [b.pool[off + k] & 0xFFFFFFFF for k in range(TW)]
+
+    def may_apply(h: int, t: list[int]) -> bool:
+        kind, a, fn, c, d = b.handlers[h]
+        if kind != K["MGHK_SIMPLE"]:
+            return True
+        static = mask_words(t[K["MGT_TAGS"]])
+        for i in range(fn):
+            op, ent, fa = b.filters[a + i][0], b.filters[a + i][1], b.filters[a + i][2]
+            if op == K["MGF_TAG_PREFIX"] and ent == K["MGE_TARGET"]:
+                m = mask_words(fa)
+                live = any(m[k] & static[k] for k in range(TW)) or any((m[tg >> 5] >> (tg & 31)) & 1 for tg in addable)
+                if not live:
+                    return False
+        return True
+
+    rows = []
+    for t in templates:
+        use = None
+        if t[K["MGT_ON_USE"]] >= 0:
+            uc, ud = fx.handler(t[K["MGT_ON_USE"]], use=None)
+            use = (max(uc, after_cls), ud or after_disp)
+        cls, disp = (use if use is not None else (K["MGC_LOCAL"], False))  # the built-in [usable -> use_target] handler
+        for hid, _rng, _acc, builtin in move_chain:
+            if builtin != K["MGMB_GENERIC"] or not may_apply(hid, t):
+                continue
+            hc, hd = fx.handler(hid, use)
+            cls, disp = max(cls, hc), disp or hd
+        rows.append([cls | (K["MGC_DISPLACES"] if disp else 0)])
+    empty_cls = 0
+    for hid, _rng, acc, builtin in move_chain:
+        if builtin == K["MGMB_GENERIC"] and acc:
+            empty_cls = max(empty_cls, fx.handler(hid, None)[0])
+    reach = max([r for _h, r, _a, _b in move_chain] + [1])
+
+    par = K["MGP_ACTIONS"]
+    if all(fx.self_local(t[K["MGT_ON_TICK"]], False, True) for t in agent_templates):
+        par |= K["MGP_ON_TICK"]
+    aoe_ok = True
+    for t in templates:
+        for k in range(t[K["MGT_AOES"]], t[K["MGT_AOES"]] + t[K["MGT_AOES_N"]]):
+            row = b.aoes[k]
+            aoe_ok = aoe_ok and fx.rows_self_local(row[3], row[4], row[5], row[6], True, t[K["MGT_KIND"]] == 1)
+    for terr in territories:
+        for off, n in ((terr[2], terr[3]), (terr[4], terr[5]), (terr[6], terr[7])):
+            for i in range(n):
+                aoe_ok = aoe_ok and fx.self_local(b.pool[off + i], True, False)
+    if aoe_ok:
+        par |= K["MGP_AOE"]
+    return rows, reach, empty_cls, par
+
+
 def compile_config(cfg: Any, map_height: int | None = None, map_width: int | None = None, spawn_headroom: int | None = None) -> Program:
     """Compile ``MettaGridConfig`` (or its ``.game``) for a given map size.
 
@@ -948,6 +1146,9 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
             if m[0] in (K["MGM_SPAWN_OBJECT"], K["MGM_RAYCAST_SPAWN"]) and m[3] == code:
                 m[3] = tmpl
 
+    tmpl_class, move_reach, chain_empty_class, par_flags = analyze_effects(
+        b, templates, move_chain, territories, len(b.queries) + len(mqs))
+
     # ---- header -------------------------------------------------------------------------------------
     gobs = g.obs.global_obs
     flags = (
@@ -1002,6 +1203,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         ("MGH_NUM_MOVE_HANDLERS", len(move_chain)), ("MGH_NUM_OBS_VALUES", len(obs_values)),
         ("MGH_NUM_EVENTS_SCHED", len(schedule)), ("MGH_NUM_TERRITORIES", len(territories)), ("MGH_NUM_MQ", len(mqs)),
         ("MGH_GAME_ON_TICK", game_on_tick), ("MGH_NUM_DYN_TAGS", len(dyn)), ("MGH_PROXY_TEMPLATE", proxy_template), ("MGH_TOK_CAP", tok_cap),
+        ("MGH_MOVE_REACH", move_reach), ("MGH_CHAIN_EMPTY_CLASS", chain_empty_class), ("MGH_PAR_FLAGS", par_flags),
     ]:  # fmt: skip
         hdr[H[key]] = int(v)
     if g.obs.aoe_mask:
@@ -1054,6 +1256,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     section("MGS_RES_GSTATS", [[x] for x in res_gstats], 1)
     section("MGS_INV_FEATS", inv_feats, b.inv_digits)
     section("MGS_DYN_TAGS", [[x] for x in dyn_slot], 1)
+    section("MGS_TMPL_CLASS", tmpl_class, 1)
     section("MGS_POOL", [b.pool])
     hdr[H["MGH_TOTAL_WORDS"]] = K["MGH_HEADER_WORDS"] + len(body)
 

@@ -17,6 +17,7 @@ cudaError_t mg_configure_kernels(const MgDev& d);
 cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
+cudaError_t mg_launch_clear_outputs(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap);
 cudaError_t mg_fast_configure(const MgFastLayout& L);
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
@@ -223,6 +224,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   d.OS = P[MGH_OBJ_STRIDE], d.AS = P[MGH_AGENT_STRIDE], d.SA = P[MGH_NUM_AGENT_STATS], d.SAW = (d.SA + 31) / 32;
   d.SG = P[MGH_NUM_GAME_STATS], d.SGW = (d.SG + 31) / 32, d.CW = P[MGH_COVER_WORDS], d.maxobj = P[MGH_MAX_OBJECTS];
   d.NOFF = P[MGH_NUM_OFFSETS], d.B = P[MGH_TOKEN_BASE], d.ND = P[MGH_INV_DIGITS], d.NTERR = P[MGH_NUM_TERRITORIES];
+  d.NPROXY = d.NTERR * d.A;
   d.plain = program_is_plain(P);
   if (d.R > 13 || d.maxobj > 65535 || d.A > 4096) {
     h->err = "mg_create: program exceeds engine limits (R<=13, objects<=65535, agents<=4096)";
@@ -246,7 +248,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   if (init_gstats) TRY(dev_alloc(h, &ig, N * d.SG));
   TRY(dev_alloc(h, &h->seeds_dev, N));
   TRY(dev_alloc(h, &d.cells, N * d.HWp));
-  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NTERR) * d.OS + 64));  // slack: k_step_fast reads 4 token words blind
+  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NPROXY) * d.OS + 64));  // slack: k_step_fast reads 4 token words blind
   {
     // capacities of the world-system tables, from the program and the initial maps
     const int32_t* TP = P + P[MGS_TEMPLATES];
@@ -285,8 +287,9 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   TRY(dev_alloc(h, &d.aoe_src, N * d.AOECAP * d.AOEW));
   TRY(dev_alloc(h, &d.aoe_pending, N * d.PENDCAP * 2));
   TRY(dev_alloc(h, &d.terr_src, N * d.TERRCAP * 4));
-  TRY(dev_alloc(h, &d.terr_tab, N * (d.TERRCAP ? (d.TERRCAP + 32) * 4 : 0)));  // + MG_TERR_CAND scratch entries per env
+  TRY(dev_alloc(h, &d.terr_tab, N * d.TERRCAP * 4));
   TRY(dev_alloc(h, &d.inside_tag, N * d.A * d.NTERR));
+  TRY(dev_alloc(h, &d.owner_map, N * d.NTERR * d.HW));
   TRY(dev_alloc(h, &d.dyn_stamp, N * d.maxobj * d.NDYN));
   TRY(dev_alloc(h, &d.agents, N * d.A * d.AS));
   TRY(dev_alloc(h, &d.astats, N * d.A * d.SA));
@@ -480,10 +483,12 @@ int mg_reset(mg_handle* h, const uint8_t* env_mask, const uint32_t* new_seeds, v
   }
   if (!env_mask) h->pristine = true;  // every env is about to hold its post-reset state again
   CK(mg_launch_reset(h->d, env_mask, st));
-  if (h->buffers_set)
+  if (h->buffers_set) {
     CK(mg_launch_init_buffers(h->d, env_mask, st));
-  else if (h->host_inited)
+    if (h->h_act) CK(mg_launch_clear_outputs(host_dev(h), env_mask, st));  // the staging set's flags start over too
+  } else if (h->host_inited) {
     CK(mg_launch_init_buffers(host_dev(h), env_mask, st));
+  }
   if (h->fast) {
     // a full reset makes the generic arrays the truth; a masked one re-packs just the rebuilt environments so
     // that the others never leave the packed block
@@ -609,7 +614,7 @@ int mg_dump_objects(mg_handle* h, int env, int32_t* out, int max_rows) {
   CK(cudaMemcpy(E, d.env + (size_t)env * MGEV_WORDS, sizeof E, cudaMemcpyDeviceToHost));
   int nobj = E[MGEV_NEXT_OBJ];
   std::vector<uint32_t> objs((size_t)nobj * d.OS);
-  CK(cudaMemcpy(objs.data(), d.objs + (size_t)env * (d.maxobj + d.NTERR) * d.OS, objs.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(objs.data(), d.objs + (size_t)env * (d.maxobj + d.NPROXY) * d.OS, objs.size() * 4, cudaMemcpyDeviceToHost));
   const int32_t* P = h->program.data();
   int n = 0, stride = 8 + 2 * d.R + d.TW;
   for (int s = 1; s < nobj && n < max_rows; s++) {
@@ -645,7 +650,7 @@ int mg_get_agent_state(mg_handle* h, int env, int32_t* out) {
   for (int a = 0; a < d.A; a++) {
     const uint32_t* r = &ag[(size_t)a * d.AS];
     uint32_t obj[MGO_NTOK + 1];
-    CK(cudaMemcpy(obj, d.objs + ((size_t)env * (d.maxobj + d.NTERR) + r[MGAG_OBJ]) * d.OS, sizeof obj, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(obj, d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + r[MGAG_OBJ]) * d.OS, sizeof obj, cudaMemcpyDeviceToHost));
     const int t = obj[MGO_META] & 0xffff;
     float total = 0.0f;  // RewardHelper::current_reward (systems/reward.hpp:36-42): prev values added in entry order
     for (int i = MGAG_REWARD_PREV; i < d.AS; i++) {

@@ -42,12 +42,12 @@ struct Wv {
   uint16_t* tag_lists;
   int32_t* tag_state;
   uint32_t* terr_tab;  // per-tick table of scoring territory sources (mg_world.cuh)
+  uint8_t* owner;      // [NTERR][H*W] winning prefix index + 1 per cell and territory (0 = nobody), mg_world.cuh
   uint32_t step;
   int H, W, A, R, TW, OS, AS, SA, SAW, T, B, ND, NOFF, CW, maxobj;
-  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR, PAD, WP, TOKOFF, NTAGS;
+  int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTERR, NPROXY, PAD, WP, TOKOFF, NTAGS;
   uint8_t* obs;  // this env's observation rows [A][T][3]
-  // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top,
-  // [5]=territory table stale (set by anything that moves objects or edits tags)
+  // rng window + arena top (shared memory): [0]=consumed, [1]=count, [2]=direct mode, [3]=idx0, [4]=arena top
   int* rs;
   uint32_t* rand;
 };
@@ -162,7 +162,7 @@ __device__ __forceinline__ void gstat_set(const Wv& w, int id, float v) {
 
 __device__ __forceinline__ void set_error(const Wv& w, int code, int info) {
   if (!(w.E[MGEV_ERROR] & code)) w.E[MGEV_ERR_INFO] = info;
-  w.E[MGEV_ERROR] |= code;
+  atomicOr(&w.E[MGEV_ERROR], code);  // several lanes of an env may report at once
 }
 
 // ---- MT19937.  Outputs are identical to std::mt19937: the generator is advanced
@@ -383,7 +383,10 @@ __device__ __forceinline__ void set_cell(const Wv& w, int r, int c, int s) {
   int i = cidx(w, r, c);
   w.cells[i] = (uint16_t)s;
   w.cells_g[i] = (uint16_t)s;  // write-through: the staged copy is never flushed
-  w.rs[5] = 1;
+}
+// the territory ownership map (mg_world.cuh) depends on where the territory sources stand and on their tags
+__device__ __forceinline__ void terr_touch(const Wv& w, const uint32_t* o) {
+  if (o_flags(o) & MGOF_TERR_SRC) w.E[MGEV_TERR_STALE] = 1;
 }
 __device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
   if (!valid_loc(w, r, c) || cell_at(w, r, c) != 0) return false;
@@ -391,6 +394,7 @@ __device__ __forceinline__ bool move_object(const Wv& w, int s, int r, int c) {
   set_cell(w, r, c, s);
   set_cell(w, o_r(o), o_c(o), 0);
   o[MGO_LOC] = ((uint32_t)r << 16) | (uint32_t)c;
+  terr_touch(w, o);
   return true;
 }
 
@@ -881,7 +885,7 @@ __device__ __forceinline__ void add_tag(const Wv& w, int s, int tag) {
   if (tag < 0 || tag >= 256 || o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] |= 1u << (tag & 31);
   o[MGO_NTOK] = MG_TOK_DIRTY;
-  w.rs[5] = 1;
+  terr_touch(w, o);
   if (s < w.maxobj) tl_append(w, tag, s);  // territory proxy cells are not in the tag index
   int ds = __ldg(sec(w, MGS_DYN_TAGS) + tag);
   if (ds >= 0 && s < w.maxobj) w.dyn_stamp[(size_t)s * w.NDYN + ds] = (uint32_t)(w.E[MGEV_TAG_SEQ]++);
@@ -893,7 +897,7 @@ __device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ct
   if (tag < 0 || tag >= 256 || !o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] &= ~(1u << (tag & 31));
   o[MGO_NTOK] = MG_TOK_DIRTY;
-  w.rs[5] = 1;
+  terr_touch(w, o);
   if (s < w.maxobj) tl_erase(w, tag, s);
   if (!ctx.skip_trigger) run_tag_handlers<D>(w, s, tag, ctx);
 }
@@ -902,11 +906,11 @@ __device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ct
 __device__ __forceinline__ uint32_t* aoe_rec(const Wv& w, int k) { return w.aoe_src + (size_t)k * w.AOEW; }
 __device__ __forceinline__ const int32_t* aoe_cfg(const Wv& w, int cfg) { return sec(w, MGS_AOES) + cfg * MG_AOE_WORDS; }
 __device__ __forceinline__ bool aoe_inside(const uint32_t* s, int ag) { return (s[4 + (ag >> 5)] >> (ag & 31)) & 1u; }
-__device__ __forceinline__ void aoe_set_inside(uint32_t* s, int ag, bool v) {
+__device__ __forceinline__ void aoe_set_inside(uint32_t* s, int ag, bool v) {  // agents of one word may run on different lanes
   if (v)
-    s[4 + (ag >> 5)] |= 1u << (ag & 31);
+    atomicOr(&s[4 + (ag >> 5)], 1u << (ag & 31));
   else
-    s[4 + (ag >> 5)] &= ~(1u << (ag & 31));
+    atomicAnd(&s[4 + (ag >> 5)], ~(1u << (ag & 31)));
 }
 __device__ __noinline__ void apply_presence(const Wv& w, const int32_t* a, int target, int mult) {
   const int32_t* pd = pool(w, __ldg(a + 7));
@@ -1069,6 +1073,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
       set_cell(w, (int)(ly >> 16), (int)(ly & 0xffff), ctx.actor);
       x[MGO_LOC] = ly;
       y[MGO_LOC] = lx;
+      terr_touch(w, x), terr_touch(w, y);
       if (o_agent(x) >= 0) astat_add(w, o_agent(x), w.hdr[MGH_ST_ACTIONS_SWAP], 1.0f);
       return;
     }

@@ -5,9 +5,10 @@
 //   k_init_buffers : _init_buffers (:294-319): clear flags, reset coverage, initial observations
 //   k_step         : MettaGrid::_step (:921-1102), all 15 phases fused in one launch
 //
-// Mapping: one warp = one environment; MG_WARPS_PER_CTA envs per CTA.  The
-// env's grid is staged in shared memory, each agent's observation is composed in shared memory and
-// streamed to HBM with 16-byte stores.
+// Mapping: one warp = one environment; MG_WARPS_PER_CTA envs per CTA; lane = agent wherever
+// the compiler's effect analysis allows (action passes, on_tick, AOE, territory, coverage, rewards), lane 0 only
+// for what must stay in the reference's order.  The env's grid is read in place (L1 / L2); each agent's observation
+// row is composed in shared memory and streamed to HBM with 16-byte stores.
 #include "mg_device.cuh"
 #include "mg_world.cuh"
 
@@ -59,6 +60,7 @@ struct Smem {
   uint32_t* a_locv;   // location right after the vibe-stream action
   int32_t* a_exec;    // executed action (last successful)
   uint16_t* a_order;  // shuffled agent order
+  uint16_t* a_pos;    // agent -> position in the shuffled order
   Wv* wv;             // this warp's env view, kept in shared memory
   Smem* self;         // shared-memory copy of this struct
 };
@@ -77,7 +79,7 @@ __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {  // HWp
   n += align16((size_t)3 * T + 32);
   n += align16(8 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
   n += align16((size_t)A * 4) * MG_AGENT_WORD_ARRAYS;
-  n += align16((size_t)A * 2);
+  n += 2 * align16((size_t)A * 2);
   n += align16(sizeof(Wv)) + align16(sizeof(Smem));
   return n;
 }
@@ -109,6 +111,7 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   s.a_locv = (uint32_t*)base, base += aw;
   s.a_exec = (int32_t*)base, base += aw;
   s.a_order = (uint16_t*)base, base += align16((size_t)d.A * 2);
+  s.a_pos = (uint16_t*)base, base += align16((size_t)d.A * 2);
   s.wv = (Wv*)base, base += align16(sizeof(Wv));
   s.self = (Smem*)base;
 }
@@ -136,7 +139,7 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.hdr = s.hdr;
   w.cells_g = d.cells + (size_t)env * d.HWp;
   w.cells = d.stage_grid ? s.cells : w.cells_g;  // read in place by default (mg_capi.cu: stage_grid)
-  w.objs = d.objs + (size_t)env * (d.maxobj + d.NTERR) * d.OS;
+  w.objs = d.objs + (size_t)env * (d.maxobj + d.NPROXY) * d.OS;
   w.agents = d.agents + (size_t)env * d.A * d.AS;
   w.astats = d.astats + (size_t)env * d.A * d.SA;
   w.atouched = d.atouched + (size_t)env * d.A * d.SAW;
@@ -149,15 +152,15 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.H = d.H, w.W = d.W, w.A = d.A, w.R = d.R, w.TW = d.TW, w.OS = d.OS, w.AS = d.AS;
   w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND, w.NOFF = d.NOFF, w.CW = d.CW;
   w.obs = d.obs + (size_t)env * d.A * (size_t)(3 * d.T);
-  w.maxobj = d.maxobj, w.NTERR = d.NTERR, w.PAD = d.PAD, w.WP = d.WP;
+  w.maxobj = d.maxobj, w.NTERR = d.NTERR, w.NPROXY = d.NPROXY, w.PAD = d.PAD, w.WP = d.WP;
   w.TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
   w.ARENA = d.ARENA, w.AOECAP = d.AOECAP, w.AOEW = d.AOEW, w.PENDCAP = d.PENDCAP, w.TERRCAP = d.TERRCAP, w.NDYN = d.NDYN;
   w.arena = d.arena + (size_t)env * d.ARENA;
   w.aoe_src = d.aoe_src + (size_t)env * d.AOECAP * d.AOEW;
   w.aoe_pending = d.aoe_pending + (size_t)env * d.PENDCAP * 2;
   w.terr_src = d.terr_src + (size_t)env * d.TERRCAP * 4;
-  w.terr_tab = d.terr_tab + (size_t)env * (d.TERRCAP ? (d.TERRCAP + 32) * 4 : 0);  // table + MG_TERR_CAND scratch entries
-  s.rs[5] = 1;
+  w.terr_tab = d.terr_tab + (size_t)env * d.TERRCAP * 4;
+  w.owner = d.owner_map + (size_t)env * d.NTERR * d.HW;
   w.inside_tag = d.inside_tag + (size_t)env * d.A * d.NTERR;
   w.dyn_stamp = d.dyn_stamp + (size_t)env * d.maxobj * d.NDYN;
   w.NTAGS = d.NTAGS;
@@ -270,20 +273,10 @@ __device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc,
   }
 }
 
-__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total) {
-  int x = v;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    int y = __shfl_up_sync(MG_FULL, x, off);
-    if (lane >= off) x += y;
-  }
-  total = __shfl_sync(MG_FULL, x, 31);
-  return x - v;
-}
-
 // One agent's observation, composed by the whole warp (bindings/mettagrid_c.cpp:665-824).
 // Returns the number of tokens attempted; `tok` accumulates the env's token stats.
 #define MG_OBS_ATTR __forceinline__  // measured: inlining into observe_all beats a call per agent (profiles/README.md)
+#define MG_OBS_GROUP 4               // window passes (32 cells each) whose loads are issued together
 // PLAIN = the program has no territory (no aoe_mask tokens) and no configured global game values: the common
 // case gets a version without those paths, which keeps the window loop small and out of local memory.
 template <bool PLAIN>
@@ -295,6 +288,7 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
   const int r0 = (int)(loc0 >> 16), c0 = (int)(loc0 & 0xffffu);
   const int flags = w.hdr[MGH_GLOBAL_FLAGS];
   uint32_t* ag = w.agents + a * w.AS;
+  const uint32_t lt = (1u << lane) - 1u;
 
   // ---- global tokens (:700-742), one candidate per lane, compacted in order
   int feat = 0, val = 0, have = 0;
@@ -319,10 +313,9 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
                        : (dd > 0 ? w.hdr[MGH_FEAT_LP_NORTH] : w.hdr[MGH_FEAT_LP_SOUTH]);
     }
   }
-  int total;
-  int pre = warp_excl_scan(have, lane, total);
-  if (have) put_token(out, T, pre, 0xFE, feat, val);
-  int base = total;
+  const uint32_t gm = __ballot_sync(MG_FULL, have);
+  if (have) put_token(out, T, __popc(gm & lt), 0xFE, feat, val);
+  int base = __popc(gm);
 
   // ---- configured global game values (:1207-1238), serial
   const int nov = PLAIN ? 0 : w.hdr[MGH_NUM_OBS_VALUES];
@@ -406,71 +399,79 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
     }
     base += tot;
   } else {
-  // territory sources in reach of this window (the per-cell tests below only look at these)
-  const uint4* ttab = (const uint4*)w.terr_tab;
-  int tn = 0;
-  if (fmask) {
-    tn = terr_window_sources(w, r0, c0, w.hdr[MGH_OBS_H] >> 1, w.hdr[MGH_OBS_W] >> 1, lane);
-    if (tn >= 0)
-      ttab += w.TERRCAP;
-    else
-      tn = w.E[MGEV_RESERVED];
-  }
-  for (int k0 = 0; k0 < NOFF; k0 += 32) {
-    const int k = k0 + lane;
-    int n = 0, loc = 0, mask = 0, slot = 0;
-    if (k < NOFF) {
-      const uint32_t pk = offs[k];
-      loc = (int)((pk >> 8) & 0xffu);
-      slot = centre[(int)(short)(pk >> 16)];
-      if (fmask) {  // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens
-        const int r = r0 + (int)(pk & 15u) - 8, c = c0 + (int)((pk >> 4) & 15u) - 8;
-        if (valid_loc(w, r, c)) mask = territory_mask(w, r, c, me, ttab, tn);
+    // Dense environments: one lane per window cell.  The loads of MG_OBS_GROUP passes -- cell ids, then the heads of
+    // the objects standing there (visited stamp, cached token count, first token pair) -- are issued back to back,
+    // so a group costs two memory round trips instead of two per pass.  Token positions come from two ballots (an
+    // object with one token -- every wall -- needs no scan); the few multi-token objects are copied by the whole
+    // warp, one token per lane.
+    const int W_ = w.W;
+    for (int k0 = 0; k0 < NOFF; k0 += 32 * MG_OBS_GROUP) {
+      uint32_t pk[MG_OBS_GROUP], slot[MG_OBS_GROUP], vis[MG_OBS_GROUP], nt[MG_OBS_GROUP], t0[MG_OBS_GROUP];
+#pragma unroll
+      for (int p = 0; p < MG_OBS_GROUP; p++) {
+        const int k = k0 + 32 * p + lane;
+        pk[p] = k < NOFF ? offs[k] : 0u;
+        slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
       }
-    }
-    if (__ballot_sync(MG_FULL, (slot | mask) != 0) == 0) continue;  // nothing visible in these 32 cells
-    uint32_t* o = nullptr;
-    if (slot) {
-      o = objs + (size_t)slot * OS;
-      const uint32_t vis = o[MGO_VISITED];
-      if (vis < step) {  // cell staleness (:787-796): agents are visited in index order
-        stale_sum += step - vis;
-        o[MGO_VISITED] = step;
-      }
-      n = (int)o[MGO_NTOK];
-      if ((uint32_t)n == MG_TOK_DIRTY) n = rebuild_token_cache(w, o);
-    }
-    int tot;
-    int p;
-    {
-      const int cnt = n + (mask != 0);
-      uint32_t m = __ballot_sync(MG_FULL, cnt != 0);
-      if (__popc(m) <= 6) {  // few objects in these 32 cells: walk the set lanes instead of a 5-step scan
-        p = 0, tot = 0;
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const int nb = __shfl_sync(MG_FULL, cnt, b);
-          p += b < lane ? nb : 0;
-          tot += nb;
+#pragma unroll
+      for (int p = 0; p < MG_OBS_GROUP; p++) {
+        vis[p] = nt[p] = t0[p] = 0;
+        if (slot[p]) {
+          const uint32_t* o = objs + (size_t)slot[p] * OS;
+          vis[p] = o[MGO_VISITED], nt[p] = o[MGO_NTOK], t0[p] = o[TOKOFF];
         }
-      } else {
-        p = warp_excl_scan(cnt, lane, tot);
+      }
+#pragma unroll
+      for (int p = 0; p < MG_OBS_GROUP; p++) {
+        if (k0 + 32 * p >= NOFF) break;
+        const int loc = (int)((pk[p] >> 8) & 0xffu);
+        int mask = 0, n = 0;
+        if (fmask && k0 + 32 * p + lane < NOFF) {  // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens
+          const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
+          if (valid_loc(w, r, c)) mask = territory_mask(w, r * W_ + c, me);
+        }
+        if (__ballot_sync(MG_FULL, (slot[p] | (uint32_t)mask) != 0) == 0) continue;  // nothing visible in these 32 cells
+        if (slot[p]) {
+          uint32_t* o = objs + (size_t)slot[p] * OS;
+          if (vis[p] < step) {  // cell staleness (:787-796): agents are visited in index order
+            stale_sum += step - vis[p];
+            o[MGO_VISITED] = step;
+          }
+          n = (int)nt[p];
+          if ((uint32_t)n == MG_TOK_DIRTY) {
+            n = rebuild_token_cache(w, o);
+            t0[p] = o[TOKOFF];
+          }
+        }
+        const int cnt = n + (mask != 0);
+        const uint32_t m_any = __ballot_sync(MG_FULL, cnt != 0);
+        uint32_t m_multi = __ballot_sync(MG_FULL, cnt > 1);
+        int pos = base + __popc(m_any & lt), tot = __popc(m_any);
+        while (m_multi) {
+          const int b = __ffs(m_multi) - 1;
+          m_multi &= m_multi - 1;
+          const int extra = __shfl_sync(MG_FULL, cnt, b) - 1;
+          pos += b < lane ? extra : 0;
+          tot += extra;
+        }
+        if (mask) put_token(out, T, pos, loc, fmask, mask);
+        pos += mask != 0;
+        if (n == 1) put_token(out, T, pos, loc, (int)(t0[p] & 0xffu), (int)((t0[p] >> 8) & 0xffu));
+        uint32_t m_obj = __ballot_sync(MG_FULL, n > 1);
+        while (m_obj) {  // copy an object's cached (feature, value) pairs behind its location byte, one lane per token
+          const int b = __ffs(m_obj) - 1;
+          m_obj &= m_obj - 1;
+          const int nb = __shfl_sync(MG_FULL, n, b), pb = __shfl_sync(MG_FULL, pos, b), lb = __shfl_sync(MG_FULL, loc, b);
+          const uint32_t sb = __shfl_sync(MG_FULL, slot[p], b);
+          const uint16_t* tk = (const uint16_t*)(objs + (size_t)sb * OS + TOKOFF);
+          for (int j = lane; j < nb; j += 32) {
+            const uint32_t e = tk[j];
+            put_token(out, T, pb + j, lb, (int)(e & 0xffu), (int)(e >> 8));
+          }
+        }
+        base += tot;
       }
     }
-    if (mask) put_token(out, T, base + p, loc, fmask, mask);
-    if (n) {  // copy the object's cached (feature, value) pairs behind this cell's location byte
-      const uint16_t* tk = (const uint16_t*)(o + TOKOFF);
-      int pos = base + p + (mask != 0);
-      for (int j = 0; j < n && pos < T; j++, pos++) {
-        const uint32_t e = tk[j];
-        out[pos * 3 + 0] = (uint8_t)loc;
-        out[pos * 3 + 1] = (uint8_t)e;
-        out[pos * 3 + 2] = (uint8_t)(e >> 8);
-      }
-    }
-    base += tot;
-  }
   }
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
   if (lane == 0 && stale_sum) astat_add(w, a, w.hdr[MGH_ST_CELL_VISITED], (float)stale_sum);
@@ -655,21 +656,25 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
           ts[0] = (uint32_t)slot, ts[1] = (uint32_t)__ldg(tc + 3 * k), ts[2] = (uint32_t)__ldg(tc + 3 * k + 1);
           ts[3] = (uint32_t)__ldg(tc + 3 * k + 2);
           w.E[MGEV_NUM_TERR] = n + 1;
+          objp(w, slot)[MGO_META] |= (uint32_t)MGOF_TERR_SRC << 24;
         }
       }
     }
-    for (int ti = 0; ti < d.NTERR; ti++) {
+    for (int ti = 0; ti < d.NPROXY; ti++) {  // one proxy per (territory, agent)
       uint32_t* po = objp(w, d.maxobj + ti);
       for (int k = 0; k < d.OS; k++) po[k] = 0;
       po[MGO_META] = (uint32_t)w.hdr[MGH_PROXY_TEMPLATE];  // not alive, not in the grid
       po[MGO_AGENT] = (uint32_t)-1;
     }
+    w.E[MGEV_TERR_STALE] = 3;
     if (w.hdr[MGH_NUM_MQ] > 0) {  // QuerySystem::compute_all (core/query_system.cpp:91-114)
       Ctx g = make_ctx();
       const int32_t* mq = sec(w, MGS_MQ);
       for (int i = 0; i < w.hdr[MGH_NUM_MQ]; i++) recompute_mq<MG_DEPTH>(w, __ldg(mq + 2 * i), g, false);
     }
   }
+  __syncwarp();
+  terr_refresh(w, lane);  // source table + ownership map (all lanes)
 }
 
 // load per-agent slot/location into shared memory (all lanes)
@@ -728,10 +733,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
     d.rewards[gi] = 0.0f;
   }
   __syncwarp();
-  if (w.NTERR > 0) {
-    if (lane == 0) terr_build_table(w);
-    __syncwarp();
-  }
+  terr_refresh(w, lane);
   observe_all(w, s, lane, true);
 }
 
@@ -791,6 +793,152 @@ __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg)
   return false;
 }
 
+// One agent's action of one stream, with the bookkeeping inputs the per-agent pass below needs (:966-999)
+template <bool PLAIN>
+__device__ __forceinline__ void run_action(const Wv& w, const Smem& s, int a, int stream, int idx, int kind, int arg) {
+  const int slot = (int)s.a_slot[a];
+  const bool ok = do_action<PLAIN>(w, slot, kind, arg);
+  const uint32_t loc = objp(w, slot)[MGO_LOC];
+  if (stream == 0) {
+    s.a_res[a] |= MGR_ACTED_P | (ok ? MGR_OK_P : 0u) | ((uint32_t)kind << MGR_KIND_P_SHIFT);
+    s.a_locp[a] = loc;
+  } else {
+    s.a_res[a] |= MGR_ACTED_V | (ok ? MGR_OK_V : 0u) | ((uint32_t)kind << MGR_KIND_V_SHIFT);
+    s.a_locv[a] = loc;
+  }
+  if (ok) s.a_exec[a] = idx;
+}
+
+// lane 0: one (priority, stream) pass in the shuffled order -- the reference's loop as it is written
+template <bool PLAIN>
+__device__ __noinline__ void action_pass_serial(const Wv& w, const Smem& s, int stream, int prio) {
+  const int NA = w.hdr[MGH_NUM_ACTIONS];
+  const int32_t* acts = sec(w, MGS_ACTIONS);
+  for (int i = 0; i < w.A; i++) {
+    const int a = s.a_order[i];
+    const int idx = stream ? s.a_vact[a] : s.a_act[a];
+    if (idx < 0 || idx >= NA) continue;  // invalid indices are accounted per agent below
+    const int4 act = __ldg((const int4*)(acts + idx * MG_ACTION_WORDS));  // kind, arg, priority, is_vibe
+    if (act.w != stream || act.z != prio) continue;
+    run_action<PLAIN>(w, s, a, stream, idx, act.x, act.y);
+  }
+}
+
+// All lanes, lane = agent (A <= 32): one (priority, stream) pass with independent agents resolved concurrently.
+//
+// The reference runs the agents one after the other in the shuffled order.  An action reads and writes only the
+// actor, the cells of the line its move scans (MGH_MOVE_REACH cells in its direction) and the objects standing there
+// -- unless the compiler's effect analysis says otherwise (MGS_TMPL_CLASS: SHARED actions also update env-wide
+// structures and keep their mutual order; SERIAL ones send the whole pass down the serial loop).  Two agents whose
+// footprints (bounding box of own cell + line) do not meet cannot observe each other, so any interleaving of them
+// gives the sequential result.  Agents are grouped into components of the "footprints meet" relation (transitive
+// closure over 32-bit rows); inside a component they run in shuffled order, one per round; different components run
+// in the same rounds on different lanes.  A swap moves its TARGET, whose own action then starts from the swapper's
+// cell: every agent standing in the line of an action that may swap gets that cell's neighbourhood added to its
+// footprint, which keeps the component's region closed under displacement.
+template <bool PLAIN>
+__device__ __noinline__ void action_pass(const Wv& w, const Smem& s, int lane, int stream, int prio, int mypos) {
+  const int A = w.A, NA = w.hdr[MGH_NUM_ACTIONS];
+  int idx = -1, kind = 0, arg = 0;
+  bool active = false;
+  if (lane < A) {
+    idx = stream ? s.a_vact[lane] : s.a_act[lane];
+    if (idx >= 0 && idx < NA) {
+      const int4 act = __ldg((const int4*)(sec(w, MGS_ACTIONS) + idx * MG_ACTION_WORDS));  // kind, arg, priority, is_vibe
+      active = act.w == stream && act.z == prio;
+      kind = act.x, arg = act.y;
+    }
+  }
+  const uint32_t m_active = __ballot_sync(MG_FULL, active);
+  if (!m_active) return;
+  if (!__ballot_sync(MG_FULL, active && kind == MGA_MOVE)) {  // noop / change_vibe only touch the acting agent
+    if (active) run_action<PLAIN>(w, s, lane, stream, idx, kind, arg);
+    __syncwarp();
+    return;
+  }
+  // ---- footprints
+  const int R = w.hdr[MGH_MOVE_REACH];
+  int r = 0, c = 0, cls = MGC_LOCAL;
+  uint32_t victims = 0;
+  if (lane < A) {
+    const uint32_t loc = objp(w, (int)s.a_slot[lane])[MGO_LOC];
+    r = (int)(loc >> 16), c = (int)(loc & 0xffffu);
+  }
+  int r0 = r, r1 = r, c0 = c, c1 = c;
+  if (active && kind == MGA_MOVE) {
+    const int dr = (arg == 0 || arg == 4 || arg == 5) ? -1 : (arg == 1 || arg == 6 || arg == 7) ? 1 : 0;
+    const int dc = (arg == 2 || arg == 4 || arg == 6) ? -1 : (arg == 3 || arg == 5 || arg == 7) ? 1 : 0;
+    if (!PLAIN) cls = w.hdr[MGH_CHAIN_EMPTY_CLASS];
+    const int32_t* tcls = sec(w, MGS_TMPL_CLASS);
+    for (int k = 1; k <= R; k++) {
+      const int rr = r + dr * k, cc = c + dc * k;
+      if (!valid_loc(w, rr, cc)) break;
+      r0 = min(r0, rr), r1 = max(r1, rr), c0 = min(c0, cc), c1 = max(c1, cc);
+      if (PLAIN) continue;
+      const int t = cell_at(w, rr, cc);
+      if (!t) continue;
+      const uint32_t* to = objp(w, t);
+      const int tc = __ldg(tcls + o_tmpl(to));
+      cls = max(cls, tc & 3);
+      if ((tc & MGC_DISPLACES) && o_is_agent(to) && o_agent(to) >= 0) victims |= 1u << o_agent(to);
+    }
+  }
+  if (lane >= A) r0 = 1, r1 = 0;  // an empty box meets nothing
+  if (__ballot_sync(MG_FULL, cls >= MGC_SERIAL)) {
+    if (lane == 0) action_pass_serial<PLAIN>(w, s, stream, prio);
+    __syncwarp();
+    return;
+  }
+  if (__ballot_sync(MG_FULL, victims != 0)) {
+    for (int i = 0; i < A; i++) {
+      const uint32_t vi = __shfl_sync(MG_FULL, victims, i);
+      const int ri = __shfl_sync(MG_FULL, r, i), ci = __shfl_sync(MG_FULL, c, i);
+      if ((vi >> lane) & 1u) {
+        r0 = min(r0, max(ri - R, 0)), r1 = max(r1, min(ri + R, w.H - 1));
+        c0 = min(c0, max(ci - R, 0)), c1 = max(c1, min(ci + R, w.W - 1));
+      }
+    }
+  }
+  // ---- components
+  uint32_t comp = lane < A ? 1u << lane : 0u;
+  for (int j = 0; j < A; j++) {
+    const int a0 = __shfl_sync(MG_FULL, r0, j), a1 = __shfl_sync(MG_FULL, r1, j);
+    const int b0 = __shfl_sync(MG_FULL, c0, j), b1 = __shfl_sync(MG_FULL, c1, j);
+    if (a0 <= r1 && r0 <= a1 && b0 <= c1 && c0 <= b1) comp |= 1u << j;
+  }
+  const uint32_t m_shared = __ballot_sync(MG_FULL, cls == MGC_SHARED);
+  if (cls == MGC_SHARED) comp |= m_shared;
+  for (int k = 0; k < A; k++) {  // Warshall: whoever reaches k also reaches what k reaches
+    const uint32_t rk = __shfl_sync(MG_FULL, comp, k);
+    if ((comp >> k) & 1u) comp |= rk;
+  }
+  // ---- rounds: an agent's turn = the number of acting members of its component that come earlier in the order
+  const uint32_t peers = comp & m_active & ~(1u << lane);
+  int turn = 0;
+  if (__ballot_sync(MG_FULL, active && peers != 0)) {
+    for (int j = 0; j < A; j++) {
+      const int pj = __shfl_sync(MG_FULL, mypos, j);
+      turn += (((peers >> j) & 1u) && pj < mypos) ? 1 : 0;
+    }
+  }
+  const int last = __reduce_max_sync(MG_FULL, active ? turn : 0);
+  for (int rd = 0; rd <= last; rd++) {
+    if (active && turn == rd) run_action<PLAIN>(w, s, lane, stream, idx, kind, arg);
+    __syncwarp();
+  }
+}
+
+// Agent::apply_on_tick (objects/agent.cpp:63-67) of one agent
+__device__ __forceinline__ void on_tick_one(const Wv& w, const Smem& s, int a) {
+  const int slot = (int)s.a_slot[a];
+  const int h = __ldg(tmpl(w, o_tmpl(objp(w, slot))) + MGT_ON_TICK);
+  if (h >= 0) {
+    Ctx c = make_ctx();
+    c.actor = c.target = slot;
+    handler_apply<MG_DEPTH>(w, h, c);
+  }
+}
+
 template <bool PLAIN>
 __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_step(MgDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -827,35 +975,31 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   __syncwarp();
   MG_PHASE(0);
 
-  // phase 4-5: shuffled, sequential action resolution (:958-999)
-  if (lane == 0) {
-    rng_shuffle(w, s.a_order, A);
-    const int NA = w.hdr[MGH_NUM_ACTIONS];
-    const int32_t* acts = sec(w, MGS_ACTIONS);
+  // phase 4-5: shuffled action resolution (:958-999): by components of independent agents when every agent has a
+  // lane, else (or when a SERIAL-class action shows up in a pass) in the reference's order on lane 0
+  {
+    const bool par = A <= 32 && (w.hdr[MGH_PAR_FLAGS] & MGP_ACTIONS);
+    if (lane == 0) rng_shuffle(w, s.a_order, A);
+    __syncwarp();
+    int mypos = 0xffff;
+    if (par) {
+      if (lane < A) s.a_pos[s.a_order[lane]] = (uint16_t)lane;
+      __syncwarp();
+      if (lane < A) mypos = s.a_pos[lane];
+    }
     const int maxp = w.hdr[MGH_MAX_PRIORITY];
     const int pmask = w.hdr[MGH_PRIORITY_MASK];
     for (int off = 0; off <= maxp; off++) {
       const int prio = maxp - off;
       if (!((pmask >> prio) & 1)) continue;  // no action has this priority: the pass only re-reports invalid indices
-      for (int stream = 0; stream < 2; stream++)
-        for (int i = 0; i < A; i++) {
-          const int a = s.a_order[i];
-          const int idx = stream ? s.a_vact[a] : s.a_act[a];
-          if (idx < 0 || idx >= NA) continue;  // invalid indices are accounted per agent below
-          const int4 act = __ldg((const int4*)(acts + idx * MG_ACTION_WORDS));  // kind, arg, priority, is_vibe
-          if (act.w != stream || act.z != prio) continue;
-          const int slot = (int)s.a_slot[a];
-          bool ok = do_action<PLAIN>(w, slot, act.x, act.y);
-          uint32_t loc = objp(w, slot)[MGO_LOC];
-          if (stream == 0) {
-            s.a_res[a] |= MGR_ACTED_P | (ok ? MGR_OK_P : 0u) | ((uint32_t)act.x << MGR_KIND_P_SHIFT);
-            s.a_locp[a] = loc;
-          } else {
-            s.a_res[a] |= MGR_ACTED_V | (ok ? MGR_OK_V : 0u) | ((uint32_t)act.x << MGR_KIND_V_SHIFT);
-            s.a_locv[a] = loc;
-          }
-          if (ok) s.a_exec[a] = idx;
+      for (int stream = 0; stream < 2; stream++) {
+        if (par) {
+          action_pass<PLAIN>(w, s, lane, stream, prio, mypos);
+        } else {
+          if (lane == 0) action_pass_serial<PLAIN>(w, s, stream, prio);
+          __syncwarp();
         }
+      }
     }
   }
   __syncwarp();
@@ -906,29 +1050,35 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   __syncwarp();
   MG_PHASE(2);
 
-  // phases 6-11 (events, on_tick, AOE, territory, game on_tick): serial
-  if (!PLAIN && lane == 0) {
-    if (w.hdr[MGH_NUM_EVENTS_SCHED] > 0) process_events(w);  // :1009-1011
-    for (int a = 0; a < A; a++) {  // agent on_tick (:1019-1024)
-      const int slot = (int)s.a_slot[a];
-      const int h = __ldg(tmpl(w, o_tmpl(objp(w, slot))) + MGT_ON_TICK);
-      if (h >= 0) {
-        Ctx c = make_ctx();
-        c.actor = c.target = slot;
-        handler_apply<MG_DEPTH>(w, h, c);
-      }
-    }
-  }
-  __syncwarp();
-  MG_PHASE(3);
+  // phases 6-11 (:1009-1052).  Events and the game on_tick handler are serial.  The per-agent systems -- agent
+  // on_tick, fixed AOE, territory handlers, mobile AOE -- run one lane per agent when the compiler proved that they
+  // only write their own agent and read nothing another lane writes (MGH_PAR_FLAGS), else on lane 0 in agent order.
   if (!PLAIN) {
-    // fixed AOE + territory per agent in index order (:1032-1042).  The serial work stays on lane 0; before each
-    // agent's turn all lanes test which sources can matter to it at its current cell.
-    const bool any_aoe = w.E[MGEV_NUM_AOE] > 0 || w.NTERR > 0 || w.E[MGEV_NUM_AOE_PENDING] > 0;
-    if (any_aoe) {
+    const int parf = w.hdr[MGH_PAR_FLAGS];
+    if (lane == 0 && w.hdr[MGH_NUM_EVENTS_SCHED] > 0) process_events(w);  // :1009-1011
+    __syncwarp();
+    if (parf & MGP_ON_TICK) {  // :1019-1024
+      for (int a = lane; a < A; a += 32) on_tick_one(w, s, a);
+    } else if (lane == 0) {
+      for (int a = 0; a < A; a++) on_tick_one(w, s, a);
+    }
+    __syncwarp();
+    MG_PHASE(3);
+    const bool have_aoe = w.E[MGEV_NUM_AOE] > 0;
+    const bool any_aoe = have_aoe || w.NTERR > 0 || w.E[MGEV_NUM_AOE_PENDING] > 0;
+    if (any_aoe && (parf & MGP_AOE)) {
+      terr_refresh(w, lane);  // events or actions may have moved a territory source
+      for (int a = lane; a < A; a += 32) {  // :1032-1042
+        if (have_aoe) aoe_apply_fixed(w, a, nullptr);
+        if (w.NTERR > 0) terr_apply(w, a);
+        if (have_aoe) aoe_apply_mobile_agent(w, a);
+      }
+      __syncwarp();
+      if (lane == 0) aoe_flush_deferred(w);
+    } else if (any_aoe) {
+      // serial form: before each agent's turn all lanes test which sources can matter to it at its current cell
       for (int a = 0; a < A; a++) {
         uint32_t m[4];
-        const bool have_aoe = w.E[MGEV_NUM_AOE] > 0;
         const bool masked = have_aoe && aoe_relevant_mask(w, a, lane, m);
         if (lane == 0) {
           if (have_aoe) aoe_apply_fixed(w, a, masked ? m : nullptr);
@@ -936,12 +1086,12 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
         }
         __syncwarp();
       }
-    }
-    if (lane == 0) {
-      if (any_aoe) {
+      if (lane == 0) {
         aoe_apply_mobile(w);
         aoe_flush_deferred(w);
       }
+    }
+    if (lane == 0) {
       const int gh = w.hdr[MGH_GAME_ON_TICK];
       if (gh >= 0) {
         Ctx c = make_ctx();
@@ -976,10 +1126,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   __syncwarp();
 
   // phase 13: observations
-  if (!PLAIN && w.NTERR > 0) {
-    if (lane == 0 && w.rs[5]) terr_build_table(w);
-    __syncwarp();
-  }
+  if (!PLAIN) terr_refresh(w, lane);  // the aoe_mask tokens read the ownership map
   MG_PHASE(5);
   observe_all(w, s, lane, false);
   MG_PHASE(6);
@@ -1053,6 +1200,19 @@ cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const in
   cudaError_t e = cudaFuncSetAttribute(k_set_inventory, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) return e;
   k_set_inventory<<<1, 32, bytes, st>>>(d, env, agent, items, amounts, n);
+  return cudaGetLastError();
+}
+
+// flags / rewards of a second buffer set (mg_step_host's staging) after a reset of the selected envs
+__global__ void k_clear_outputs(int num_envs, int A, const uint8_t* __restrict__ mask, uint8_t* terminals, uint8_t* truncations,
+                                float* rewards) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)num_envs * A || (mask && !mask[i / A])) return;
+  terminals[i] = 0, truncations[i] = 0, rewards[i] = 0.0f;
+}
+cudaError_t mg_launch_clear_outputs(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
+  const size_t n = (size_t)d.num_envs * d.A;
+  k_clear_outputs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.num_envs, d.A, mask, d.terminals, d.truncations, d.rewards);
   return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@ struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
+  int NPROXY;  // territory proxy objects behind the object pool: one per territory and agent
   uint32_t* fast_blk;    // [N][fast_stride] packed hot state of k_step_fast (layout below), or null
   int fast_stride;       // words per env
   const uint32_t* rank_lut;  // [256] packed window offset (dr + rr) << 4 | (dc + cr) -> rank << 24 | offset << 16, where rank is
@@ -55,6 +56,7 @@ struct MgDev {
   uint32_t* dyn_stamp;        // [N][maxobj][NDYN]: insertion stamp of run-time-addable tags (tag-index order)
   uint16_t* tag_lists;        // [N][NTAGS][MG_TAG_LIST_CAP]: the reference's TagIndex, insertion-ordered slots per tag
   uint32_t* terr_tab;         // [N][TERRCAP][4]: per-tick table of scoring territory sources
+  uint8_t* owner_map;         // [N][NTERR][HW]: winning prefix index + 1 per cell (mg_world.cuh: terr_refresh)
   int32_t* tag_state;         // [N][NTAGS]: member count, or -1 once a tag outgrew its list (then queries scan)
   int ARENA, AOECAP, AOEW, PENDCAP, TERRCAP, NDYN, NTAGS;
   // caller-owned buffers (aliased like the reference's numpy arrays)

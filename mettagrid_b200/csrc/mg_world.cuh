@@ -1,5 +1,6 @@
-// mg_world.cuh -- per-tick world systems: events, AOE, territory (all serial on lane 0 except the
-// read-only territory ownership test, which every lane evaluates for its own observation cell).
+// mg_world.cuh -- per-tick world systems: events, AOE, territory.  Events are serial (lane 0); the per-agent systems
+// (fixed / mobile AOE, territory handlers) run one lane per agent when the compiler proved that their handlers only
+// write the target agent (MGP_AOE, compiler.py: analyze_effects), else serially in the reference's order.
 #pragma once
 #include "mg_device.cuh"
 
@@ -138,6 +139,44 @@ __device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag, const uint32_t
     if (df.delta[rid] != 0) inv_update<2>(w, objp(w, target), rid, df.delta[rid]);
   }
 }
+// one mobile source against one agent (aoe_tracker.cpp:364-415)
+__device__ __forceinline__ void aoe_mobile_one(const Wv& w, uint32_t* s, const int32_t* a, int ag) {
+  const int so = (int)s[0], mn = __ldg(a + 6);
+  const long long range = __ldg(a);
+  const int t = (int)w.agents[ag * w.AS + MGAG_OBJ];
+  if (!__ldg(a + 2) && so == t) return;
+  const bool was = aoe_inside(s, ag);
+  const uint32_t *x = objp(w, so), *y = objp(w, t);
+  long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
+  if (dr * dr + dc * dc > range * range) {
+    if (was) {
+      aoe_set_inside(s, ag, false);
+      apply_presence(w, a, t, -1);
+    }
+    return;
+  }
+  Ctx c = make_ctx();
+  c.actor = so;
+  c.target = t;
+  const bool now = filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c);
+  if (now) {
+    if (!was) {
+      aoe_set_inside(s, ag, true);
+      apply_presence(w, a, t, +1);
+    }
+    if (mn > 0) {
+      Ctx c2 = make_ctx();
+      c2.actor = so;
+      c2.target = t;
+      if (filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c2))
+        for (int i = 0; i < mn; i++) mutate<MG_DEPTH>(w, __ldg(a + 5) + i, c2);
+    }
+  } else if (was) {
+    aoe_set_inside(s, ag, false);
+    apply_presence(w, a, t, -1);
+  }
+}
+// serial form: sources in registration order, agents in index order
 __device__ __noinline__ void aoe_apply_mobile(const Wv& w) {
   const int na = w.E[MGEV_NUM_AOE];
   for (int k = 0; k < na; k++) {
@@ -145,42 +184,18 @@ __device__ __noinline__ void aoe_apply_mobile(const Wv& w) {
     if (!s[3]) continue;
     const int32_t* a = aoe_cfg(w, (int)s[1]);
     if (__ldg(a + 1)) continue;
-    const int so = (int)s[0], mn = __ldg(a + 6);
-    const long long range = __ldg(a);
-    for (int ag = 0; ag < w.A; ag++) {
-      const int t = (int)w.agents[ag * w.AS + MGAG_OBJ];
-      if (!__ldg(a + 2) && so == t) continue;
-      const bool was = aoe_inside(s, ag);
-      const uint32_t *x = objp(w, so), *y = objp(w, t);
-      long long dr = o_r(x) - o_r(y), dc = o_c(x) - o_c(y);
-      if (dr * dr + dc * dc > range * range) {
-        if (was) {
-          aoe_set_inside(s, ag, false);
-          apply_presence(w, a, t, -1);
-        }
-        continue;
-      }
-      Ctx c = make_ctx();
-      c.actor = so;
-      c.target = t;
-      const bool now = filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c);
-      if (now) {
-        if (!was) {
-          aoe_set_inside(s, ag, true);
-          apply_presence(w, a, t, +1);
-        }
-        if (mn > 0) {
-          Ctx c2 = make_ctx();
-          c2.actor = so;
-          c2.target = t;
-          if (filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c2))
-            for (int i = 0; i < mn; i++) mutate<MG_DEPTH>(w, __ldg(a + 5) + i, c2);
-        }
-      } else if (was) {
-        aoe_set_inside(s, ag, false);
-        apply_presence(w, a, t, -1);
-      }
-    }
+    for (int ag = 0; ag < w.A; ag++) aoe_mobile_one(w, s, a, ag);
+  }
+}
+// lane-per-agent form (MGP_AOE programs: the effects only touch the target agent): every source against agent `ag`
+__device__ __noinline__ void aoe_apply_mobile_agent(const Wv& w, int ag) {
+  const int na = w.E[MGEV_NUM_AOE];
+  for (int k = 0; k < na; k++) {
+    uint32_t* s = aoe_rec(w, k);
+    if (!s[3]) continue;
+    const int32_t* a = aoe_cfg(w, (int)s[1]);
+    if (__ldg(a + 1)) continue;
+    aoe_mobile_one(w, s, a, ag);
   }
 }
 __device__ __forceinline__ void aoe_flush_deferred(const Wv& w) {
@@ -199,9 +214,11 @@ __device__ __forceinline__ unsigned long long floor_sqrt_u64(unsigned long long 
   while ((r + 1) * (r + 1) <= v) r++;
   return r;
 }
-// Per-tick table of the territory sources that can own cells: (loc, range, strength | decay << 16,
-// territory | prefix index << 8).  Built by lane 0 whenever the grid changed; the ownership test below then
-// needs one 16-byte load per source and no division / object lookups.
+// Table of the territory sources that can own cells: (loc, range, strength | decay << 16, territory | prefix index << 8),
+// and from it the OWNERSHIP MAP: per territory and cell the winning prefix index + 1.  Both only change when a
+// territory source moves or changes tags (terr_touch sets MGEV_TERR_STALE: bit 0 = table, bit 1 = map), which in
+// most games is never after the reset -- so the per-cell influence sums of compute_cell_ownership
+// (territory_tracker.cpp:215-252) are paid once per episode instead of once per observed cell per tick.
 __device__ __noinline__ void terr_build_table(const Wv& w) {
   const int nt = w.E[MGEV_NUM_TERR];
   int n = 0;
@@ -228,11 +245,8 @@ __device__ __noinline__ void terr_build_table(const Wv& w) {
     n++;
   }
   w.E[MGEV_RESERVED] = n;  // entries in the table
-  w.rs[5] = 0;             // clean
+  w.E[MGEV_TERR_STALE] &= ~1;
 }
-// winning tag at (r, c) for territory ti, or -1 (read-only: callable from every lane).  `tab` / `n`: the per-tick
-// source table, or a subset of it that holds every source in reach of (r, c) (terr_window_sources)
-#define MG_TERR_CAND 32
 __device__ __forceinline__ long long terr_score(const uint4 e, int r, int c) {
   const int range = (int)e.y;
   const int dr = r - (int)(e.x >> 16), dc = c - (int)(e.x & 0xffffu);
@@ -243,10 +257,10 @@ __device__ __forceinline__ long long terr_score(const uint4 e, int r, int c) {
   const long long sc = strength * 1024 - decay * (long long)floor_sqrt_u64((unsigned long long)d2 * 1024ull * 1024ull);
   return sc > 0 ? sc : 0;
 }
-__device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti, const uint4* tab, int n) {
+// winning prefix index at (r, c) for territory ti, or -1 (read-only: callable from every lane)
+__device__ __noinline__ int cell_owner_index(const Wv& w, int r, int c, int ti, const uint4* tab, int n) {
   const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
   const int np = min(__ldg(T_ + 1), MG_MAX_PREFIX_TAGS);
-  const int32_t* pre = pool(w, __ldg(T_));
   int win = -1;
   long long best = 0;
   bool tied = false;
@@ -264,7 +278,7 @@ __device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti, const 
       const long long si = i == 0 ? s0 : i == 1 ? s1 : i == 2 ? s2 : s3;
       if (i >= np || si <= 0) continue;
       if (si > best) {
-        win = __ldg(pre + i);
+        win = i;
         best = si;
         tied = false;
       } else if (si == best && win >= 0) {
@@ -283,7 +297,7 @@ __device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti, const 
   for (int i = 0; i < np; i++) {
     if (score[i] <= 0) continue;
     if (score[i] > best) {
-      win = __ldg(pre + i);
+      win = i;
       best = score[i];
       tied = false;
     } else if (score[i] == best && win >= 0) {
@@ -292,42 +306,50 @@ __device__ __noinline__ int cell_owner(const Wv& w, int r, int c, int ti, const 
   }
   return tied ? -1 : win;
 }
-// All lanes: copy the table entries whose square of influence touches the window around (r0, c0) into the env's
-// scratch behind the table, so that the per-cell ownership tests of one observation loop over a handful of
-// sources instead of all of them.  Scores are integer sums: the subset gives the same winner.  Returns the
-// entry count, or -1 when more than MG_TERR_CAND sources are in reach (the full table is used).
-__device__ __forceinline__ int terr_window_sources(const Wv& w, int r0, int c0, int rr, int cr, int lane) {
-  const int n = w.E[MGEV_RESERVED];
-  const uint4* tab = (const uint4*)w.terr_tab;
-  uint4* cand = (uint4*)w.terr_tab + w.TERRCAP;
-  int cnt = 0;
-  for (int k0 = 0; k0 < n; k0 += 32) {
-    const int k = k0 + lane;
-    uint4 e = make_uint4(0, 0, 0, 0);
-    bool in = false;
-    if (k < n) {
-      e = tab[k];
-      const int range = (int)e.y, dr = r0 - (int)(e.x >> 16), dc = c0 - (int)(e.x & 0xffffu);
-      in = dr >= -(range + rr) && dr <= range + rr && dc >= -(range + cr) && dc <= range + cr;
-    }
-    const uint32_t b = __ballot_sync(MG_FULL, in);
-    const int pos = cnt + __popc(b & ((1u << lane) - 1u));
-    if (in && pos < MG_TERR_CAND) cand[pos] = e;
-    cnt += __popc(b);
-  }
-  __syncwarp();
-  return cnt <= MG_TERR_CAND ? cnt : -1;
+__device__ __forceinline__ int terr_prefix_tag(const Wv& w, int ti, int idx) {
+  return idx < 0 ? -1 : __ldg(pool(w, __ldg(sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS)) + idx);
 }
-__device__ __forceinline__ int territory_mask(const Wv& w, int r, int c, const uint32_t* observer, const uint4* tab, int n) {  // :254-273
+// All lanes (convergent): bring the source table and the ownership map up to date.
+__device__ __noinline__ void terr_refresh(const Wv& w, int lane) {
+  if (w.NTERR == 0) return;
+  const int stale = w.E[MGEV_TERR_STALE];
+  __syncwarp();
+  if (!stale) return;
+  if (lane == 0 && (stale & 1)) terr_build_table(w);
+  __syncwarp();
+  const int n = w.E[MGEV_RESERVED], HW = w.H * w.W;
+  const uint4* tab = (const uint4*)w.terr_tab;
+  for (int ti = 0; ti < w.NTERR; ti++)
+    for (int cell = lane; cell < HW; cell += 32) {
+      const int r = cell / w.W, c = cell - r * w.W;
+      w.owner[(size_t)ti * HW + cell] = (uint8_t)(cell_owner_index(w, r, c, ti, tab, n) + 1);
+    }
+  __syncwarp();
+  if (lane == 0) w.E[MGEV_TERR_STALE] = 0;
+  __syncwarp();
+}
+// winning tag at (r, c) or -1.  Serial callers may run while the map is stale (a handler just moved a source): they
+// rebuild the table and evaluate the cell directly; the map itself is refreshed at the next convergent point.
+__device__ __forceinline__ int terr_owner_tag(const Wv& w, int r, int c, int ti) {
+  const int stale = w.E[MGEV_TERR_STALE];
+  if (!stale) return terr_prefix_tag(w, ti, (int)w.owner[(size_t)ti * w.H * w.W + r * w.W + c] - 1);
+  if (stale & 1) terr_build_table(w);
+  return terr_prefix_tag(w, ti, cell_owner_index(w, r, c, ti, (const uint4*)w.terr_tab, w.E[MGEV_RESERVED]));
+}
+// aoe_mask token of one in-map cell (:254-273); the map must be fresh (terr_refresh)
+__device__ __forceinline__ int territory_mask(const Wv& w, int cell, const uint32_t* observer) {
+  const int HW = w.H * w.W;
   for (int ti = 0; ti < w.NTERR; ti++) {
-    int win = cell_owner(w, r, c, ti, tab, n);
-    if (win < 0) continue;
-    return o_has_tag(observer, win) ? 1 : 2;
+    const int v = w.owner[(size_t)ti * HW + cell];
+    if (!v) continue;
+    return o_has_tag(observer, terr_prefix_tag(w, ti, v - 1)) ? 1 : 2;
   }
   return 0;
 }
-__device__ __noinline__ void terr_run(const Wv& w, int ti, int list_off, int n, int tag, int target) {
-  const int px = w.maxobj + ti;
+// territory handlers run with a proxy-cell object as actor (territory_tracker.cpp:103-107,275-346); every agent has
+// its own proxy per territory so that agents can be processed on different lanes
+__device__ __noinline__ void terr_run(const Wv& w, int ti, int list_off, int n, int tag, int target, int ag) {
+  const int px = w.maxobj + ti * w.A + ag;
   uint32_t* po = objp(w, px);
   for (int k = 0; k < w.TW; k++) po[MGO_TAGS + k] = 0;
   po[MGO_TAGS + (tag >> 5)] = 1u << (tag & 31);
@@ -347,12 +369,11 @@ __device__ __noinline__ void terr_apply(const Wv& w, int ag) {
   for (int ti = 0; ti < w.NTERR; ti++) {
     const int32_t* T_ = sec(w, MGS_TERRITORIES) + ti * MG_TERR_WORDS;
     const uint32_t* to = objp(w, target);
-    if (w.rs[5]) terr_build_table(w);  // a handler moved / tagged something since the last build
-    const int cur = cell_owner(w, o_r(to), o_c(to), ti, (const uint4*)w.terr_tab, w.E[MGEV_RESERVED]);
+    const int cur = terr_owner_tag(w, o_r(to), o_c(to), ti);
     const int prev = w.inside_tag[ag * w.NTERR + ti];
-    if (prev != cur && prev >= 0) terr_run(w, ti, __ldg(T_ + 4), __ldg(T_ + 5), prev, target);
-    if (prev != cur && cur >= 0) terr_run(w, ti, __ldg(T_ + 2), __ldg(T_ + 3), cur, target);
+    if (prev != cur && prev >= 0) terr_run(w, ti, __ldg(T_ + 4), __ldg(T_ + 5), prev, target, ag);
+    if (prev != cur && cur >= 0) terr_run(w, ti, __ldg(T_ + 2), __ldg(T_ + 3), cur, target, ag);
     w.inside_tag[ag * w.NTERR + ti] = (int16_t)cur;
-    if (cur >= 0) terr_run(w, ti, __ldg(T_ + 6), __ldg(T_ + 7), cur, target);
+    if (cur >= 0) terr_run(w, ti, __ldg(T_ + 6), __ldg(T_ + 7), cur, target, ag);
   }
 }
