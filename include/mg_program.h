@@ -101,6 +101,7 @@ enum {
   MGH_MOVE_REACH,       /* longest line a move handler scans (max max_range over the chain) */
   MGH_CHAIN_EMPTY_CLASS,/* MGC_* class of the custom move handlers that accept an empty target cell */
   MGH_PAR_FLAGS,        /* MGP_* bits: which per-agent phases may run one lane per agent */
+  MGH_SPAWN_CLASS,      /* highest MGC_* class of any template a SpawnObject mutation can create (0 = nothing spawns) */
   /* section offsets */
   MGS_OFFSETS,      /* NUM_OFFSETS x (dr, dc) */
   MGS_ACTIONS,      /* NUM_ACTIONS x MG_ACTION_WORDS */

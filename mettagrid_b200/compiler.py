@@ -1204,6 +1204,7 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
         ("MGH_NUM_EVENTS_SCHED", len(schedule)), ("MGH_NUM_TERRITORIES", len(territories)), ("MGH_NUM_MQ", len(mqs)),
         ("MGH_GAME_ON_TICK", game_on_tick), ("MGH_NUM_DYN_TAGS", len(dyn)), ("MGH_PROXY_TEMPLATE", proxy_template), ("MGH_TOK_CAP", tok_cap),
         ("MGH_MOVE_REACH", move_reach), ("MGH_CHAIN_EMPTY_CLASS", chain_empty_class), ("MGH_PAR_FLAGS", par_flags),
+        ("MGH_SPAWN_CLASS", max([tmpl_class[m[3]][0] & 3 for m in b.mutations if m[0] == K["MGM_SPAWN_OBJECT"] and m[3] >= 0] + [0])),
     ]:  # fmt: skip
         hdr[H[key]] = int(v)
     if g.obs.aoe_mask:

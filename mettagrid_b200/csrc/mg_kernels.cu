@@ -61,10 +61,12 @@ struct Smem {
   int32_t* a_exec;    // executed action (last successful)
   uint16_t* a_order;  // shuffled agent order
   uint16_t* a_pos;    // agent -> position in the shuffled order
+  uint32_t* fp;       // action footprints, MG_FP_WORDS per agent lane (action_pass)
   Wv* wv;             // this warp's env view, kept in shared memory
   Smem* self;         // shared-memory copy of this struct
 };
 #define MG_AGENT_WORD_ARRAYS 9
+#define MG_FP_WORDS 8  // own cell + up to 3 line cells, victim box rows / cols, class as a target, spare
 #ifndef MG_MIN_CTAS_PER_SM
 #define MG_MIN_CTAS_PER_SM 8  // 64 registers per thread -> 32 resident warps per SM (measured best once the grid stopped
                               // occupying shared memory: profiles/README.md; 7 was best before)
@@ -80,6 +82,7 @@ __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {  // HWp
   n += align16(8 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
   n += align16((size_t)A * 4) * MG_AGENT_WORD_ARRAYS;
   n += 2 * align16((size_t)A * 2);
+  n += align16((size_t)(A < 32 ? A : 32) * MG_FP_WORDS * 4);
   n += align16(sizeof(Wv)) + align16(sizeof(Smem));
   return n;
 }
@@ -112,6 +115,7 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   s.a_exec = (int32_t*)base, base += aw;
   s.a_order = (uint16_t*)base, base += align16((size_t)d.A * 2);
   s.a_pos = (uint16_t*)base, base += align16((size_t)d.A * 2);
+  s.fp = (uint32_t*)base, base += align16((size_t)(d.A < 32 ? d.A : 32) * MG_FP_WORDS * 4);
   s.wv = (Wv*)base, base += align16(sizeof(Wv));
   s.self = (Smem*)base;
 }
@@ -830,12 +834,16 @@ __device__ __noinline__ void action_pass_serial(const Wv& w, const Smem& s, int 
 // actor, the cells of the line its move scans (MGH_MOVE_REACH cells in its direction) and the objects standing there
 // -- unless the compiler's effect analysis says otherwise (MGS_TMPL_CLASS: SHARED actions also update env-wide
 // structures and keep their mutual order; SERIAL ones send the whole pass down the serial loop).  Two agents whose
-// footprints (bounding box of own cell + line) do not meet cannot observe each other, so any interleaving of them
-// gives the sequential result.  Agents are grouped into components of the "footprints meet" relation (transitive
-// closure over 32-bit rows); inside a component they run in shuffled order, one per round; different components run
-// in the same rounds on different lanes.  A swap moves its TARGET, whose own action then starts from the swapper's
-// cell: every agent standing in the line of an action that may swap gets that cell's neighbourhood added to its
-// footprint, which keeps the component's region closed under displacement.
+// footprints (own cell + line cells) share no cell cannot observe each other, so any interleaving of them gives the
+// sequential result.  Agents are grouped into components of the "footprints meet" relation (transitive closure over
+// 32-bit rows); inside a component they run in shuffled order, one per round; different components run in the same
+// rounds on different lanes.
+//  * A swap moves its TARGET, whose own action then starts from the swapper's cell: every agent standing in the line of
+//    an action that may swap gets the box around that cell added to its footprint, which keeps a component's region
+//    closed under displacement.
+//  * What an action may do depends on what it meets, and members of its component may walk (or be swapped, or spawn
+//    something) into its line before its turn: an agent with company takes the highest class any member could offer
+//    it as a target, and joins the SHARED chain if that makes it SHARED.
 template <bool PLAIN>
 __device__ __noinline__ void action_pass(const Wv& w, const Smem& s, int lane, int stream, int prio, int mypos) {
   const int A = w.A, NA = w.hdr[MGH_NUM_ACTIONS];
@@ -858,22 +866,28 @@ __device__ __noinline__ void action_pass(const Wv& w, const Smem& s, int lane, i
   }
   // ---- footprints
   const int R = w.hdr[MGH_MOVE_REACH];
-  int r = 0, c = 0, cls = MGC_LOCAL;
-  uint32_t victims = 0;
+  const bool mover = active && kind == MGA_MOVE;
+  const uint32_t NONE = 0xffffffffu;
+  int r = 0, c = 0, cls = MGC_LOCAL, as_target = MGC_LOCAL;
+  uint32_t victims = 0, cell[4] = {NONE, NONE, NONE, NONE};
+  const int32_t* tcls = sec(w, MGS_TMPL_CLASS);
   if (lane < A) {
-    const uint32_t loc = objp(w, (int)s.a_slot[lane])[MGO_LOC];
-    r = (int)(loc >> 16), c = (int)(loc & 0xffffu);
+    const uint32_t* me = objp(w, (int)s.a_slot[lane]);
+    r = o_r(me), c = o_c(me);
+    cell[0] = me[MGO_LOC];
+    if (!PLAIN) as_target = __ldg(tcls + o_tmpl(me)) & 3;
   }
-  int r0 = r, r1 = r, c0 = c, c1 = c;
-  if (active && kind == MGA_MOVE) {
+  int r0 = r, r1 = r, c0 = c, c1 = c;        // bounding box of everything below (cheap first test)
+  int br0 = 1, br1 = 0, bc0 = 1, bc1 = 0;    // box part of the footprint: empty unless displaced / long lines
+  if (mover) {
     const int dr = (arg == 0 || arg == 4 || arg == 5) ? -1 : (arg == 1 || arg == 6 || arg == 7) ? 1 : 0;
     const int dc = (arg == 2 || arg == 4 || arg == 6) ? -1 : (arg == 3 || arg == 5 || arg == 7) ? 1 : 0;
     if (!PLAIN) cls = w.hdr[MGH_CHAIN_EMPTY_CLASS];
-    const int32_t* tcls = sec(w, MGS_TMPL_CLASS);
     for (int k = 1; k <= R; k++) {
       const int rr = r + dr * k, cc = c + dc * k;
       if (!valid_loc(w, rr, cc)) break;
       r0 = min(r0, rr), r1 = max(r1, rr), c0 = min(c0, cc), c1 = max(c1, cc);
+      if (k <= 3) cell[k] = ((uint32_t)rr << 16) | (uint32_t)cc;
       if (PLAIN) continue;
       const int t = cell_at(w, rr, cc);
       if (!t) continue;
@@ -882,8 +896,8 @@ __device__ __noinline__ void action_pass(const Wv& w, const Smem& s, int lane, i
       cls = max(cls, tc & 3);
       if ((tc & MGC_DISPLACES) && o_is_agent(to) && o_agent(to) >= 0) victims |= 1u << o_agent(to);
     }
+    if (R > 3) br0 = r0, br1 = r1, bc0 = c0, bc1 = c1;  // lines longer than the cell list: their box stands in
   }
-  if (lane >= A) r0 = 1, r1 = 0;  // an empty box meets nothing
   if (__ballot_sync(MG_FULL, cls >= MGC_SERIAL)) {
     if (lane == 0) action_pass_serial<PLAIN>(w, s, stream, prio);
     __syncwarp();
@@ -894,23 +908,82 @@ __device__ __noinline__ void action_pass(const Wv& w, const Smem& s, int lane, i
       const uint32_t vi = __shfl_sync(MG_FULL, victims, i);
       const int ri = __shfl_sync(MG_FULL, r, i), ci = __shfl_sync(MG_FULL, c, i);
       if ((vi >> lane) & 1u) {
-        r0 = min(r0, max(ri - R, 0)), r1 = max(r1, min(ri + R, w.H - 1));
-        c0 = min(c0, max(ci - R, 0)), c1 = max(c1, min(ci + R, w.W - 1));
+        const int a0 = max(ri - R, 0), a1 = min(ri + R, w.H - 1), b0 = max(ci - R, 0), b1 = min(ci + R, w.W - 1);
+        if (br0 > br1) br0 = a0, br1 = a1, bc0 = b0, bc1 = b1;
+        else br0 = min(br0, a0), br1 = max(br1, a1), bc0 = min(bc0, b0), bc1 = max(bc1, b1);
       }
     }
+    if (br0 <= br1) r0 = min(r0, br0), r1 = max(r1, br1), c0 = min(c0, bc0), c1 = max(c1, bc1);
   }
-  // ---- components
-  uint32_t comp = lane < A ? 1u << lane : 0u;
+  if (lane >= A) r0 = 1, r1 = 0;  // an empty box meets nothing
+  if (lane < A) {
+    uint32_t* f = s.fp + lane * MG_FP_WORDS;
+    f[0] = cell[0], f[1] = cell[1], f[2] = cell[2], f[3] = cell[3];
+    f[4] = (uint32_t)br0 | ((uint32_t)br1 << 16), f[5] = (uint32_t)bc0 | ((uint32_t)bc1 << 16);
+    f[6] = (uint32_t)as_target;
+  }
+  // ---- who meets whom: bounding boxes first (registers), exact cells for the few candidates (shared memory)
+  uint32_t cand = 0;
   for (int j = 0; j < A; j++) {
     const int a0 = __shfl_sync(MG_FULL, r0, j), a1 = __shfl_sync(MG_FULL, r1, j);
     const int b0 = __shfl_sync(MG_FULL, c0, j), b1 = __shfl_sync(MG_FULL, c1, j);
-    if (a0 <= r1 && r0 <= a1 && b0 <= c1 && c0 <= b1) comp |= 1u << j;
+    if (a0 <= r1 && r0 <= a1 && b0 <= c1 && c0 <= b1) cand |= 1u << j;
   }
-  const uint32_t m_shared = __ballot_sync(MG_FULL, cls == MGC_SHARED);
-  if (cls == MGC_SHARED) comp |= m_shared;
-  for (int k = 0; k < A; k++) {  // Warshall: whoever reaches k also reaches what k reaches
-    const uint32_t rk = __shfl_sync(MG_FULL, comp, k);
-    if ((comp >> k) & 1u) comp |= rk;
+  __syncwarp();
+  uint32_t comp = lane < A ? 1u << lane : 0u;
+  auto in_box = [](uint32_t cl, int x0, int x1, int y0, int y1) {
+    const int rr = (int)(cl >> 16), cc = (int)(cl & 0xffffu);
+    return cl != 0xffffffffu && rr >= x0 && rr <= x1 && cc >= y0 && cc <= y1;
+  };
+  if (lane < A) {
+    uint32_t m = cand & ~(1u << lane);
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t* f = s.fp + j * MG_FP_WORDS;
+      const int jr0 = (int)(f[4] & 0xffffu), jr1 = (int)(f[4] >> 16), jc0 = (int)(f[5] & 0xffffu), jc1 = (int)(f[5] >> 16);
+      bool meet = br0 <= br1 && jr0 <= jr1 && jr0 <= br1 && br0 <= jr1 && jc0 <= bc1 && bc0 <= jc1;
+#pragma unroll
+      for (int x = 0; x < 4; x++) {
+        const uint32_t fj = f[x];
+        meet = meet || in_box(fj, br0, br1, bc0, bc1) || in_box(cell[x], jr0, jr1, jc0, jc1);
+#pragma unroll
+        for (int y = 0; y < 4; y++) meet = meet || (fj != NONE && fj == cell[y]);
+      }
+      if (meet) comp |= 1u << j;
+    }
+  }
+  // the relation is symmetric by construction; close it, then settle the classes
+  const int spawn_cls = PLAIN ? 0 : w.hdr[MGH_SPAWN_CLASS];
+  for (int iter = 0;; iter++) {
+    for (int k = 0; k < A; k++) {  // Warshall: whoever reaches k also reaches what k reaches
+      const uint32_t rk = __shfl_sync(MG_FULL, comp, k);
+      if ((comp >> k) & 1u) comp |= rk;
+    }
+    if (PLAIN) break;
+    int up = cls;
+    if (mover) {
+      uint32_t m = comp & ~(1u << lane);
+      if (m) up = max(up, spawn_cls);
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        up = max(up, (int)s.fp[j * MG_FP_WORDS + 6]);
+      }
+    }
+    const bool changed = up != cls;
+    cls = up;
+    if (__ballot_sync(MG_FULL, cls >= MGC_SERIAL) || iter >= 6) {
+      if (lane == 0) action_pass_serial<PLAIN>(w, s, stream, prio);
+      __syncwarp();
+      return;
+    }
+    const uint32_t m_shared = __ballot_sync(MG_FULL, mover && cls == MGC_SHARED);
+    if (mover && cls == MGC_SHARED) comp |= m_shared;
+    if (!__ballot_sync(MG_FULL, changed)) {
+      if (iter == 0 && m_shared) continue;  // the SHARED chain was just linked: close once more
+      break;
+    }
   }
   // ---- rounds: an agent's turn = the number of acting members of its component that come earlier in the order
   const uint32_t peers = comp & m_active & ~(1u << lane);

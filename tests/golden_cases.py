@@ -9,7 +9,7 @@ import json
 
 import numpy as np
 
-from tests import cases
+from tests import cases, edge_cases as ec
 
 
 def _bench(ns, agents, **kw):
@@ -60,6 +60,13 @@ CASES = {
                           lambda: cases.combat_map(4, seed=5), 5, 300, 0.3, 0.01),  # fmt: skip
     "world_3v3": (lambda ns: cases.world_config(ns, 3), lambda: cases.world_map(3, seed=2), 2, 400, 0.2, 0.0),
     "network_4": (lambda ns: cases.network_config(ns, 4), lambda: cases.network_map(4, seed=6), 6, 400, 0.1, 0.0),
+    # corner cases the reference's own tests encode (tests/edge_cases.py)
+    "c1_a8_wrong_stream": (lambda ns: _bench(ns, 8), lambda: _bench_map(8, 11), 11, 400, 0.0, 0.0),
+    "beam_chain": (lambda ns: ec.beam_chain_config(ns), lambda: ec.beam_chain_map(3), 3, 500, 0.35, 0.0),
+    "aoe_round": (lambda ns: ec.aoe_round_config(ns), lambda: ec.aoe_round_map(4), 4, 400, 0.0, 0.0),
+    "dyn_limits": (lambda ns: ec.dyn_limits_config(ns), lambda: ec.dyn_limits_map(5), 5, 500, 0.3, 0.0),
+    "event_targets": (lambda ns: ec.event_targets_config(ns), lambda: ec.event_targets_map(6), 6, 300, 0.0, 0.0),
+    "many_tagged": (lambda ns: ec.many_tagged_config(ns), lambda: ec.many_tagged_map(7), 7, 200, 0.0, 0.0),
     "world_2v2_nospawn_trunc": (lambda ns: cases.world_config(ns, 2, spawn=False, max_steps=120, num_tokens=160),
                                 lambda: cases.world_map(2, width=15, height=12, seed=9), 9, 150, 0.25, 0.01),  # fmt: skip
 }
@@ -69,6 +76,8 @@ def case_actions(name, prog):
     _, _, seed, steps, p_vibe, p_inv = CASES[name]
     A = prog.num_agents
     nprim = sum(1 for n in prog.action_names if not n.startswith("change_vibe_"))
+    if name == "c1_a8_wrong_stream":
+        return ec.wrong_stream_actions(np.random.RandomState(seed), steps, A, nprim, len(prog.action_names))
     if name == "c1_a4":  # the SURVEY 8(c) known-answer run
         return np.random.RandomState(42).randint(0, 5, size=(1000, 4)).astype(np.int32), np.zeros((1000, 4), np.int32)
     return cases.random_actions(np.random.RandomState(seed), steps, (A,), nprim, len(prog.action_names), p_vibe, p_inv)
