@@ -190,7 +190,8 @@ enum {
   MGM_RESOURCE_TRANSFER,  /* e1=source, e2=dest, a=resource, b=amount(-1 all), c=remove_source_when_empty */
   MGM_CLEAR_INVENTORY,    /* e1=entity, a=pool offset of resources, b=count (0 = everything) */
   MGM_ATTACK,             /* a=weapon, b=armor, c=health, d=damage pct */
-  MGM_STATS,              /* a=stat id, b=0 game/1 agent, c=0 target/1 actor, d=value node */
+  MGM_STATS,              /* a=stat id, b=0 game/1 agent, c=0 target/1 actor, d=value node; e=1 when the value is
+                             "this stat + integer constant" (logStat), the constant's float bits then sit in e2 */
   MGM_ADD_TAG,            /* e1, a=tag */
   MGM_REMOVE_TAG,         /* e1, a=tag */
   MGM_GAME_VALUE,         /* e1=target entity, a=value node, b=source node */
@@ -290,6 +291,8 @@ enum {
   MGO_TAGS      /* TW words, then ceil(R/2) words of u16 amounts, then ceil(TOK_CAP/2) words of cached
                    (feature | value << 8) observation tokens */
 };
+/* first word of the cached tokens: behind the tags and the inventory, rounded up to a 16-byte boundary */
+#define MG_TOKOFF(TW, R) ((MGO_TAGS + (TW) + ((R) + 1) / 2 + 3) & ~3)
 #define MG_TOK_DIRTY 0xFFFFFFFFu
 #define MGOF_ALIVE 1
 #define MGOF_AGENT 2

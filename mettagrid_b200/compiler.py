@@ -542,7 +542,20 @@ class _Builder:
             elif mt == "stats":
                 is_agent = _ev(m.target) == "agent"
                 sid = self.astat(m.stat) if is_agent else self.gstat(m.stat)
-                node(K["MGM_STATS"], 0, 0, sid, int(is_agent), int(_ev(m.entity) == "actor"), self.value(m.source))
+                vnode = self.value(m.source)
+                # logStat lowers to "stat := Sum([stat, const])" (mutation/stats_mutation.py:62-86): an increment.  With
+                # an integer constant the float adds commute exactly (below 2^24), so an engine may apply them
+                # atomically in any order; word 7 marks the pattern, word 2 carries the constant's bits.
+                inc, bits = 0, 0
+                v = self.values[vnode]
+                if v[0] == K["MGV_SUM"] and v[3] == 2 and v[4] < 0 and not v[5]:
+                    k0, k1 = self.values[self.pool[v[2]]], self.values[self.pool[v[2] + 1]]
+                    want_scope = K["MGSC_AGENT"] if is_agent else K["MGSC_GAME"]
+                    if (k0[0] == K["MGV_STAT"] and k0[1] == want_scope and k0[2] == sid and not k0[3] and k1[0] == K["MGV_CONST"]):
+                        c = struct.unpack("<f", struct.pack("<I", int(k1[2]) & 0xFFFFFFFF))[0]
+                        if float(c).is_integer() and abs(float(c)) <= 1024:
+                            inc, bits = 1, int(k1[2])
+                node(K["MGM_STATS"], 0, bits, sid, int(is_agent), int(_ev(m.entity) == "actor"), vnode, inc)
                 self.features.add("game_value")
             elif mt == "add_tag":
                 if m.tag not in self.tid:
@@ -691,6 +704,11 @@ class _Effects:
         self.b, self.templates = b, templates
         self.have_aoe, self.have_tag_index = have_aoe, have_tag_index
         self._vc: dict[int, int] = {}
+        # game stats some value node reads (other than the "stat" operand of an increment itself): an increment of such a
+        # stat must stay ordered with its readers
+        own = {b.pool[b.values[m[6]][2]] for m in b.mutations if m[0] == K["MGM_STATS"] and m[7]}
+        self.read_gstats = {v[2] for i, v in enumerate(b.values)
+                            if v[0] == K["MGV_STAT"] and v[1] == K["MGSC_GAME"] and i not in own}
         tag_remove = [0]
         self._tag_remove_class = 0
         for t in templates:  # on_tag_remove handlers may fire from any tag removal
@@ -753,6 +771,8 @@ class _Effects:
         if op == K["MGM_SWAP"]:
             return L, True
         if op == K["MGM_STATS"]:
+            if e and (b_ == 1 or a not in self.read_gstats):  # integer increment nobody reads mid-tick: atomic, order-free
+                return L, False
             return max(S if b_ == 0 else L, self.value(d)), False
         if op == K["MGM_GAME_VALUE"]:
             vop, vscope = self.b.values[a][0], self.b.values[a][1]
@@ -1171,7 +1191,8 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
                            for x in [sum((b.pool[t[K["MGT_TAGS"]] + k] & 0xFFFFFFFF) << (32 * k) for k in range(TW))]] + [0])
     max_static_tags = max([sum(bin(b.pool[t[K["MGT_TAGS"]] + k] & 0xFFFFFFFF).count("1") for k in range(TW)) for t in templates] + [0])
     tok_cap = max_static_tags + len(b.dyn_tags) + 1 + R * b.inv_digits + 2
-    obj_stride = (K["MGO_TAGS"] + TW + (R + 1) // 2 + (tok_cap + 1) // 2 + 3) // 4 * 4
+    tok_off = (K["MGO_TAGS"] + TW + (R + 1) // 2 + 3) // 4 * 4  # the token cache starts 16-byte aligned (one vector load)
+    obj_stride = (tok_off + (tok_cap + 1) // 2 + 3) // 4 * 4
     agent_stride = K["MGAG_REWARD_PREV"] + max_rewards
     dyn = sorted(b.dyn_tags)
     dyn_slot = [-1] * len(b.tag_names)

@@ -15,7 +15,9 @@
 
 #include "mg_state.h"
 
+#ifndef MG_DEPTH
 #define MG_DEPTH 8
+#endif
 
 // Per-warp view of one environment (lives in shared memory).
 struct Wv {
@@ -147,7 +149,7 @@ __device__ __forceinline__ float astat_get(const Wv& w, int a, int id) { return 
 __device__ __forceinline__ void gstat_touch(const Wv& w, int id) {
   uint32_t* p = w.gtouched + (id >> 5);
   const uint32_t bit = 1u << (id & 31);
-  if (!(*p & bit)) *p |= bit;
+  if (!(*p & bit)) atomicOr(p, bit);  // agents of one env may report from different lanes
 }
 __device__ __forceinline__ void gstat_add(const Wv& w, int id, float v) {
   float* p = w.gstats + id;
@@ -1110,6 +1112,17 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
     switch (op) {
       case MGM_STATS: {  // stats_mutation.hpp:21-41
         int ent = c ? ctx.actor : ctx.target;
+        if (__ldg(m + 7)) {  // "stat := stat + integer": exact in any order below 2^24, so game stats take it atomically
+          const float delta = __int_as_float(__ldg(m + 2));
+          if (b == 0) {
+            gstat_touch(w, a);
+            atomicAdd(w.gstats + a, delta);
+          } else if (ent) {
+            const uint32_t* o = objp(w, ent);
+            if (o_is_agent(o) && o_agent(o) >= 0) astat_add(w, o_agent(o), a, delta);
+          }
+          return;
+        }
         float v = eval_value<D - 1>(w, d, ctx, ent);
         if (b == 0) {
           gstat_set(w, a, v);

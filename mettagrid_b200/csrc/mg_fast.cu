@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   float* bst = (float*)(blk + MGFB_STAT(G, 0, gl));  // stat id at bst[id * G]
   uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)min(gl + 1, d.maxobj - 1)) * d.OS;
   uint32_t* cvrow = d.cover + ga * d.CW;
-  const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+  const int TOKOFF = MG_TOKOFF(d.TW, d.R);
   const int tokw = L.tok_stride;  // words per object in the shared token table
 
   // ---- wave 1: every load whose address is known up front is issued before anything is consumed
@@ -775,7 +775,7 @@ __global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, cons
   uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
   if (gl < nobj && gl + 1 < d.maxobj) {
     const uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)(gl + 1)) * d.OS;
-    const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+    const int TOKOFF = MG_TOKOFF(d.TW, d.R);
     const uint32_t ntok = o[MGO_NTOK];
     const uint32_t w3 = (((uint32_t)((int)o[MGO_AGENT] + 1)) & 0xffu) | (ntok == MG_TOK_DIRTY ? MGFB_DIRTY : ((ntok & 0xffu) << 8));
     o0 = make_uint4(o[MGO_LOC], o[MGO_VISITED], o[MGO_META], w3);
@@ -819,7 +819,7 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
   }
   if (gl < nobj && gl + 1 < d.maxobj) {
     uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)(gl + 1)) * d.OS;
-    const int TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+    const int TOKOFF = MG_TOKOFF(d.TW, d.R);
     const uint4 o0 = *(const uint4*)(blk + MGFB_OBJECT(G, gl)), o1 = *(const uint4*)(blk + MGFB_OBJECT(G, gl) + 4);
     o[MGO_LOC] = o0.x, o[MGO_VISITED] = o0.y, o[MGO_META] = o0.z;
     if (o0.w & MGFB_DIRTY) {

@@ -157,7 +157,7 @@ __device__ __forceinline__ void bind_env(const MgDev& d, const Smem& s, int env,
   w.SA = d.SA, w.SAW = d.SAW, w.T = d.T, w.B = d.B, w.ND = d.ND, w.NOFF = d.NOFF, w.CW = d.CW;
   w.obs = d.obs + (size_t)env * d.A * (size_t)(3 * d.T);
   w.maxobj = d.maxobj, w.NTERR = d.NTERR, w.NPROXY = d.NPROXY, w.PAD = d.PAD, w.WP = d.WP;
-  w.TOKOFF = MGO_TAGS + d.TW + (d.R + 1) / 2;
+  w.TOKOFF = MG_TOKOFF(d.TW, d.R);
   w.ARENA = d.ARENA, w.AOECAP = d.AOECAP, w.AOEW = d.AOEW, w.PENDCAP = d.PENDCAP, w.TERRCAP = d.TERRCAP, w.NDYN = d.NDYN;
   w.arena = d.arena + (size_t)env * d.ARENA;
   w.aoe_src = d.aoe_src + (size_t)env * d.AOECAP * d.AOEW;
@@ -461,16 +461,33 @@ __device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int 
         if (mask) put_token(out, T, pos, loc, fmask, mask);
         pos += mask != 0;
         if (n == 1) put_token(out, T, pos, loc, (int)(t0[p] & 0xffu), (int)((t0[p] >> 8) & 0xffu));
+        // multi-token objects (agents, chests ...): the whole warp copies each one's cached (feature, value) pairs behind
+        // its location byte, one lane per token; the loads of up to four objects are in flight together
         uint32_t m_obj = __ballot_sync(MG_FULL, n > 1);
-        while (m_obj) {  // copy an object's cached (feature, value) pairs behind its location byte, one lane per token
-          const int b = __ffs(m_obj) - 1;
-          m_obj &= m_obj - 1;
-          const int nb = __shfl_sync(MG_FULL, n, b), pb = __shfl_sync(MG_FULL, pos, b), lb = __shfl_sync(MG_FULL, loc, b);
-          const uint32_t sb = __shfl_sync(MG_FULL, slot[p], b);
-          const uint16_t* tk = (const uint16_t*)(objs + (size_t)sb * OS + TOKOFF);
-          for (int j = lane; j < nb; j += 32) {
-            const uint32_t e = tk[j];
-            put_token(out, T, pb + j, lb, (int)(e & 0xffu), (int)(e >> 8));
+        while (m_obj) {
+          uint32_t ev[4], sv[4];
+          int nv[4], pv[4], lv[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            nv[q] = 0;
+            if (m_obj) {
+              const int b = __ffs(m_obj) - 1;
+              m_obj &= m_obj - 1;
+              nv[q] = __shfl_sync(MG_FULL, n, b), pv[q] = __shfl_sync(MG_FULL, pos, b), lv[q] = __shfl_sync(MG_FULL, loc, b);
+              sv[q] = __shfl_sync(MG_FULL, slot[p], b);
+              if (lane < nv[q]) ev[q] = ((const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF))[lane];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (lane < nv[q]) put_token(out, T, pv[q] + lane, lv[q], (int)(ev[q] & 0xffu), (int)(ev[q] >> 8));
+            if (nv[q] > 32) {  // longer lists than lanes: the rest straight from the record
+              const uint16_t* tk = (const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF);
+              for (int j = lane + 32; j < nv[q]; j += 32) {
+                const uint32_t e = tk[j];
+                put_token(out, T, pv[q] + j, lv[q], (int)(e & 0xffu), (int)(e >> 8));
+              }
+            }
           }
         }
         base += tot;
@@ -493,6 +510,13 @@ __device__ __noinline__ void observe_all(const Wv& w, const Smem& s, int lane, b
   // token stats: one float add per agent in agent order like the reference (:659-661), carried in registers
   const int idw = w.hdr[MGH_GST_TOKENS_WRITTEN], idf = w.hdr[MGH_GST_TOKENS_FREE];
   float tw = w.gstats[idw], tf = w.gstats[idf];
+  // agents are the objects whose tokens change most (inventory, vibe): rebuild their caches one lane per agent instead
+  // of lazily on whichever single lane meets them first
+  for (int a = lane; a < w.A; a += 32) {
+    uint32_t* o = objp(w, (int)s.a_slot[a]);
+    if (o[MGO_NTOK] == MG_TOK_DIRTY) rebuild_token_cache(w, o);
+  }
+  __syncwarp();
   for (int a = 0; a < w.A; a++) {
     int action = initial ? 0 : s.a_exec[a];
     int attempted = plain ? observe_agent<true>(w, s, a, action, s.a_step[a], lane)
