@@ -78,6 +78,9 @@ struct mg_handle {
 };
 
 static std::string g_create_error;
+#ifndef MG_STACK_BYTES
+#define MG_STACK_BYTES 8192
+#endif
 
 #define CK(call)                                                                                   \
   do {                                                                                             \
@@ -301,6 +304,15 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   TRY(dev_alloc(h, &d.rng_seeded, N * (MG_RNG_WORDS + 2)));
   TRY(dev_alloc(h, &d.env, N * MGEV_WORDS));
   TRY(dev_alloc(h, &d.success, N * d.A));
+  TRY(dev_alloc(h, &d.obs_in, N * d.A));
+  TRY(dev_alloc(h, &d.tok_attempted, N * d.A));
+  {
+    // tokens a configured global observation value can take: the base-B digits of a 32-bit value (encoding_utils.hpp:16-35)
+    int digits = 1;
+    for (unsigned long long v = (unsigned long long)(d.B > 1 ? d.B : 2); v <= 0xffffffffull; v *= (unsigned long long)(d.B > 1 ? d.B : 2)) digits++;
+    d.OVW = P[MGH_NUM_OBS_VALUES] > 0 ? 1 + P[MGH_NUM_OBS_VALUES] * digits : 0;
+    TRY(dev_alloc(h, &d.obsval, N * d.A * d.OVW));
+  }
   TRY(dev_alloc(h, &lt, 65536));
   {
     // logf through the HOST libm, the same function the reference calls (core/game_value.cpp:91)
@@ -344,6 +356,14 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     // 97.6 -> 95.7 us.  METTAGRID_B200_STAGE_GRID=1 brings the staging back for A/B runs.
     const char* f = getenv("METTAGRID_B200_STAGE_GRID");
     d.stage_grid = f && f[0] == '1';
+  }
+  {
+    // The handler interpreter (mg_device.cuh) is recursive -- one copy of each function instead of one per nesting
+    // level keeps the hot code inside the instruction cache -- so its stack cannot be sized statically: frames are at
+    // most ~0.5 KB and the nesting is capped at MG_DEPTH = 8 levels of handlers / filters / values / queries.
+    size_t cur = 0;
+    if (cudaDeviceGetLimit(&cur, cudaLimitStackSize) == cudaSuccess && cur < MG_STACK_BYTES)
+      cudaDeviceSetLimit(cudaLimitStackSize, MG_STACK_BYTES);
   }
   cudaError_t e = mg_configure_kernels(d);
   if (e != cudaSuccess) {

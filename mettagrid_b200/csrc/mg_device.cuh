@@ -1,14 +1,17 @@
 // mg_device.cuh -- per-environment device state view and the game-program interpreter.
 //
 // One WARP owns one environment for a whole tick.  The reference's conflict
-// semantics are sequential per env (bindings/mettagrid_c.cpp:958-999), so everything that mutates
-// shared env state runs on lane 0 ("serial" functions below); per-agent and per-cell work fans out
-// over the 32 lanes.  Nothing here is shared with oracle/.
+// semantics are sequential per env (bindings/mettagrid_c.cpp:958-999); the interpreter below is free of
+// warp intrinsics, so the step kernel may run it on lane 0 only (what must keep the reference's order)
+// or on one lane per agent (what the compiler's effect analysis proved independent).  Nothing here is
+// shared with oracle/.
 //
 // The interpreter functions call each other recursively (handler -> mutation -> handler, filter ->
-// query -> filter, value -> query ...).  Recursion is bounded by a template depth D that every nested
-// call decrements, and each instantiation is a real (__noinline__) function: inlining the web grows
-// code exponentially.  A program that nests deeper sets MGERR_UNSUPPORTED instead of misbehaving.
+// query -> filter, value -> query ...).  It is REAL recursion: every function exists once and takes the
+// remaining nesting budget D as an argument (MG_DEPTH at the roots); a program that nests deeper sets
+// MGERR_UNSUPPORTED instead of misbehaving.  Round 1 instantiated every function once per nesting level
+// (template depth): 83 k instructions for k_step, 26 % of the stall samples waiting for instructions.
+// The stack is sized by mg_create (cudaLimitStackSize, MG_STACK_BYTES).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -307,10 +310,8 @@ __device__ __forceinline__ void on_inventory_change(const Wv& w, uint32_t* o, in
   astat_set(w, a, __ldg(rs + 2), (float)amount);
   if (amount == 0 && delta < 0 && item == w.hdr[MGH_HP_RESOURCE]) astat_add(w, a, w.hdr[MGH_ST_DEATH], 1.0f);
 }
-template <int D>
-__device__ __noinline__ int inv_update(const Wv& w, uint32_t* o, int item, int attempted, bool ignore_limits = false, bool notify = true);
-template <int D>
-__device__ __noinline__ void enforce_all_limits(const Wv& w, uint32_t* o) {
+__device__ __noinline__ int inv_update(const Wv& w, int D, uint32_t* o, int item, int attempted, bool ignore_limits = false, bool notify = true);
+__device__ __noinline__ void enforce_all_limits(const Wv& w, int D, uint32_t* o) {
   const int32_t* t = tmpl(w, o_tmpl(o));
   const int32_t* lo = pool(w, __ldg(t + MGT_LIMIT_ORDER));
   int nl = __ldg(t + MGT_LIMIT_ORDER_N);
@@ -325,8 +326,8 @@ __device__ __noinline__ void enforce_all_limits(const Wv& w, uint32_t* o) {
       int it = __ldg(mem + k);
       int drop = min((int)o_inv(w, o)[it], excess);
       if (drop > 0) {
-        if constexpr (D > 0)
-          inv_update<D - 1>(w, o, it, -drop);
+        if (D > 0)
+          inv_update(w, D - 1, o, it, -drop);
         else
           set_error(w, MGERR_UNSUPPORTED, 1);
         excess = limit_amount(w, o, lim) - effective_limit(w, o, lim);
@@ -335,8 +336,7 @@ __device__ __noinline__ void enforce_all_limits(const Wv& w, uint32_t* o) {
     }
   }
 }
-template <int D>
-__device__ __noinline__ int inv_update(const Wv& w, uint32_t* o, int item, int attempted, bool ignore_limits, bool notify) {
+__device__ __noinline__ int inv_update(const Wv& w, int D, uint32_t* o, int item, int attempted, bool ignore_limits, bool notify) {
   uint16_t* inv = o_inv(w, o);
   int initial = inv[item];
   int na = initial + attempted;
@@ -358,7 +358,7 @@ __device__ __noinline__ int inv_update(const Wv& w, uint32_t* o, int item, int a
   int d = clamped - initial;
   if (d != 0) o[MGO_NTOK] = MG_TOK_DIRTY;  // cached observation tokens are stale
   if (notify && d != 0) on_inventory_change(w, o, item, d);
-  if (d < 0 && is_modifier(w, o, item)) enforce_all_limits<D>(w, o);
+  if (d < 0 && is_modifier(w, o, item)) enforce_all_limits(w, D, o);
   return d;
 }
 __device__ __forceinline__ int free_space(const Wv& w, uint32_t* o, int item) {
@@ -372,8 +372,8 @@ __device__ __noinline__ int transfer(const Wv& w, uint32_t* src, uint32_t* dst, 
   if (delta <= 0) return 0;
   int give = min((int)o_inv(w, src)[item], delta);
   int amount = min(give, free_space(w, dst, item));
-  inv_update<2>(w, src, item, -amount);
-  inv_update<2>(w, dst, item, amount);
+  inv_update(w, 2, src, item, -amount);
+  inv_update(w, 2, dst, item, amount);
   return amount;
 }
 
@@ -459,7 +459,7 @@ __device__ __forceinline__ void init_object(const Wv& w, int slot, int t, int r,
   // initial inventory, stored in emission order; inserting back to front reproduces it
   const int32_t* iv = pool(w, __ldg(tp + MGT_INIT_INV));
   int ni = __ldg(tp + MGT_INIT_INV_N);
-  for (int k = ni - 1; k >= 0; k--) inv_update<0>(w, o, __ldg(iv + 2 * k), __ldg(iv + 2 * k + 1), true, false);
+  for (int k = ni - 1; k >= 0; k--) inv_update(w, 0, o, __ldg(iv + 2 * k), __ldg(iv + 2 * k + 1), true, false);
 }
 
 // ==================================================================================================
@@ -469,21 +469,15 @@ struct QList {
   uint16_t* p;
   int n;
 };
-template <int D>
-__device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, int entity);
-template <int D>
-__device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx);
-template <int D>
-__device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx);
-template <int D>
-__device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx);
-template <int D>
-__device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx);
+__device__ __noinline__ float eval_value(const Wv& w, int D, int node, const Ctx& ctx, int entity);
+__device__ __noinline__ bool filter_pass(const Wv& w, int D, int fi, const Ctx& ctx);
+__device__ __noinline__ QList query_eval(const Wv& w, int D, int qi, const Ctx& ctx);
+__device__ __noinline__ void mutate(const Wv& w, int D, int mi, Ctx& ctx);
+__device__ __noinline__ bool handler_apply(const Wv& w, int D, int h, Ctx& ctx);
 
-template <int D>
-__device__ __forceinline__ bool filters_pass(const Wv& w, int f0, int n, const Ctx& ctx) {
+__device__ __forceinline__ bool filters_pass(const Wv& w, int D, int f0, int n, const Ctx& ctx) {
   for (int i = 0; i < n; i++)
-    if (!filter_pass<D>(w, f0 + i, ctx)) return false;
+    if (!filter_pass(w, D, f0 + i, ctx)) return false;
   return true;
 }
 __device__ __forceinline__ int resolve_entity(const Ctx& c, int e) { return e == MGE_ACTOR ? c.actor : e == MGE_TARGET ? c.target : c.source; }
@@ -497,8 +491,7 @@ __device__ __forceinline__ float host_logf_plus1(const Wv& w, float term) {
   if (x >= 1.0f && x <= 65536.0f && truncf(x) == x) return __ldg(w.logtab + (int)x - 1);
   return (float)log((double)x);  // non-integer argument: correctly rounded double log (<= 1 ulp vs glibc)
 }
-template <int D>
-__device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, int entity) {
+__device__ __noinline__ float eval_value(const Wv& w, int D, int node, const Ctx& ctx, int entity) {
   const int32_t* v = sec(w, MGS_VALUES) + node * MG_VALUE_WORDS;
   int op = __ldg(v), scope = __ldg(v + 1), a = __ldg(v + 2), b = __ldg(v + 3);
   switch (op) {
@@ -528,7 +521,7 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
     default:
       break;
   }
-  if constexpr (D > 0) {
+  if (D > 0) {
     switch (op) {
       case MGV_QUERY_INVENTORY:
       case MGV_QUERY_COUNT: {
@@ -541,7 +534,7 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
         Ctx c = ctx;
         c.actor = entity;  // HandlerContext::resolve_game_value: value_ctx.actor = entity
         int mark = arena_top(w);
-        QList q = query_eval<D - 1>(w, b, c);
+        QList q = query_eval(w, D - 1, b, c);
         float total = 0.0f;
         if (op == MGV_QUERY_COUNT) {
           total = (float)q.n;
@@ -556,7 +549,7 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
         const int32_t* kids = pool(w, a);
         int woff = __ldg(v + 4), lg = __ldg(v + 5);
         for (int i = 0; i < b; i++) {
-          float term = eval_value<D - 1>(w, __ldg(kids + i), ctx, entity);
+          float term = eval_value(w, D - 1, __ldg(kids + i), ctx, entity);
           if (lg) term = host_logf_plus1(w, term);
           if (woff >= 0) term = __fmul_rn(term, __int_as_float(__ldg(pool(w, woff) + i)));
           total = __fadd_rn(total, term);
@@ -564,7 +557,7 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
         return total;
       }
       case MGV_RATIO: {
-        float num = eval_value<D - 1>(w, a, ctx, entity), den = eval_value<D - 1>(w, b, ctx, entity);
+        float num = eval_value(w, D - 1, a, ctx, entity), den = eval_value(w, D - 1, b, ctx, entity);
         return den > 0.0f ? __fdiv_rn(num, den) : num;
       }
       case MGV_MAX:
@@ -573,7 +566,7 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
         const int32_t* kids = pool(w, a);
         float best = op == MGV_MAX ? -3.402823466e+38f : 3.402823466e+38f;
         for (int i = 0; i < b; i++) {
-          float x = eval_value<D - 1>(w, __ldg(kids + i), ctx, entity);
+          float x = eval_value(w, D - 1, __ldg(kids + i), ctx, entity);
           // std::max(a, b) = (a < b) ? b : a ; std::min(a, b) = (b < a) ? b : a
           if (op == MGV_MAX)
             best = (best < x) ? x : best;
@@ -591,8 +584,7 @@ __device__ __noinline__ float eval_value(const Wv& w, int node, const Ctx& ctx, 
 }
 
 // ---- filters (handler/filters/*.hpp) -------------------------------------------------------------
-template <int D>
-__device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx) {
+__device__ __noinline__ bool filter_pass(const Wv& w, int D, int fi, const Ctx& ctx) {
   const int32_t* f = sec(w, MGS_FILTERS) + fi * MG_FILTER_WORDS;
   int op = __ldg(f), a = __ldg(f + 2), b = __ldg(f + 3);
   int e = resolve_entity(ctx, __ldg(f + 1));
@@ -638,21 +630,21 @@ __device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx) {
     default:
       break;
   }
-  if constexpr (D > 0) {
+  if (D > 0) {
     switch (op) {
       case MGF_GAME_VALUE:
-        return eval_value<D - 1>(w, a, ctx, e) >= eval_value<D - 1>(w, b, ctx, e);
+        return eval_value(w, D - 1, a, ctx, e) >= eval_value(w, D - 1, b, ctx, e);
       case MGF_NEG:
         for (int i = 0; i < b; i++)
-          if (!filter_pass<D - 1>(w, a + i, ctx)) return true;
+          if (!filter_pass(w, D - 1, a + i, ctx)) return true;
         return false;
       case MGF_OR:
         for (int i = 0; i < b; i++)
-          if (filter_pass<D - 1>(w, a + i, ctx)) return true;
+          if (filter_pass(w, D - 1, a + i, ctx)) return true;
         return false;
       case MGF_MAX_DISTANCE: {  // unary form: within radius of any query result (:49-62)
         int mark = arena_top(w);
-        QList q = query_eval<D - 1>(w, a, ctx);
+        QList q = query_eval(w, D - 1, a, ctx);
         bool ok = false;
         if (b == 0) {
           ok = q.n > 0;
@@ -669,7 +661,7 @@ __device__ __noinline__ bool filter_pass(const Wv& w, int fi, const Ctx& ctx) {
       }
       case MGF_QUERY_RESOURCE: {  // query_resource_filter.hpp:26-43
         int mark = arena_top(w);
-        QList q = query_eval<D - 1>(w, a, ctx);
+        QList q = query_eval(w, D - 1, a, ctx);
         const int32_t* rq = pool(w, b);
         int nreq = __ldg(f + 4);
         bool ok = true;
@@ -736,33 +728,31 @@ __device__ __noinline__ QList collect_tag(const Wv& w, int tag) {
   arena_set(w, top + n);
   return QList{out, n};
 }
-template <int D>
-__device__ __forceinline__ bool matches(const Wv& w, int s, int f0, int n, const Ctx& ctx) {
+__device__ __forceinline__ bool matches(const Wv& w, int D, int s, int f0, int n, const Ctx& ctx) {
   if (n == 0) return true;
   Ctx c = ctx;
   c.target = s;
-  return filters_pass<D>(w, f0, n, c);
+  return filters_pass(w, D, f0, n, c);
 }
-template <int D>
-__device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
+__device__ __noinline__ QList query_eval(const Wv& w, int D, int qi, const Ctx& ctx) {
   const int32_t* q = sec(w, MGS_QUERIES) + qi * MG_QUERY_WORDS;
   const int kind = __ldg(q), mark = arena_top(w);
   uint16_t* res = w.arena + mark;
   int n = 0;
-  if constexpr (D > 0) {
+  if (D > 0) {
     if (kind == MGQ_TAG || kind == MGQ_FILTERED) {
-      QList c = kind == MGQ_TAG ? collect_tag(w, __ldg(q + 3)) : query_eval<D - 1>(w, __ldg(q + 3), ctx);
+      QList c = kind == MGQ_TAG ? collect_tag(w, __ldg(q + 3)) : query_eval(w, D - 1, __ldg(q + 3), ctx);
       int f0 = __ldg(q + 4), fn = __ldg(q + 5);
       for (int i = 0; i < c.n; i++) {  // in-place compaction; nested scratch lives above the list
         uint16_t s = c.p[i];
-        if (matches<D - 1>(w, s, f0, fn, ctx)) res[n++] = s;
+        if (matches(w, D - 1, s, f0, fn, ctx)) res[n++] = s;
       }
     } else if (kind == MGQ_CLOSURE) {
-      QList roots = query_eval<D - 1>(w, __ldg(q + 3), ctx);
+      QList roots = query_eval(w, D - 1, __ldg(q + 3), ctx);
       if (__ldg(q + 4) < 0) {
         n = roots.n;
       } else {
-        QList cand = query_eval<D - 1>(w, __ldg(q + 4), ctx);
+        QList cand = query_eval(w, D - 1, __ldg(q + 4), ctx);
         int top = arena_top(w);
         uint16_t* out = w.arena + top;
         int cap = w.ARENA - top, m = 0;
@@ -787,18 +777,18 @@ __device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
                 Ctx e = ctx;
                 e.source = cur;
                 e.target = cd;
-                if (!filters_pass<D - 1>(w, e0, en, e)) continue;
+                if (!filters_pass(w, D - 1, e0, en, e)) continue;
               }
               out[m++] = cd;
             }
           }
           int r0 = __ldg(q + 7), rn = __ldg(q + 8);
           for (int i = 0; i < m; i++)
-            if (matches<D - 1>(w, out[i], r0, rn, ctx)) res[n++] = out[i];  // res < out: forward copy is safe
+            if (matches(w, D - 1, out[i], r0, rn, ctx)) res[n++] = out[i];  // res < out: forward copy is safe
         }
       }
     } else if (kind == MGQ_RAYCAST) {
-      QList srcs = query_eval<D - 1>(w, __ldg(q + 3), ctx);
+      QList srcs = query_eval(w, D - 1, __ldg(q + 3), ctx);
       int top = arena_top(w);
       uint16_t* out = w.arena + top;
       int cap = w.ARENA - top, m = 0;
@@ -811,7 +801,7 @@ __device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
         sc.actor = s;
         sc.target = s;
         arena_set(w, top + m);
-        int range = (int)eval_value<D - 1>(w, __ldg(q + 4), sc, s);
+        int range = (int)eval_value(w, D - 1, __ldg(q + 4), sc, s);
         if (range <= 0) continue;
         const uint32_t* so = objp(w, s);
         for (int d = 0; d < nd; d++) {
@@ -832,7 +822,7 @@ __device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
               Ctx bc = ctx;
               bc.target = o;
               arena_set(w, top + m);
-              for (int i = 0; i < bn && !blk; i++) blk = filter_pass<D - 1>(w, b0 + i, bc);
+              for (int i = 0; i < bn && !blk; i++) blk = filter_pass(w, D - 1, b0 + i, bc);
             }
             bool dup = false;
             for (int k = 0; k < m && !dup; k++) dup = out[k] == o;
@@ -853,7 +843,7 @@ __device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
     if (__ldg(q + 2)) rng_shuffle(w, res, n);
     int mi = __ldg(q + 1);
     if (mi >= 0) {
-      int mx = (int)eval_value<D - 1>(w, mi, ctx, ctx.actor);
+      int mx = (int)eval_value(w, D - 1, mi, ctx, ctx.actor);
       if (mx >= 0 && n > mx) n = mx;
     }
     arena_set(w, mark + n);
@@ -864,8 +854,7 @@ __device__ __noinline__ QList query_eval(const Wv& w, int qi, const Ctx& ctx) {
 }
 
 // ---- tags (core/grid_object.cpp:91-141) ------------------------------------------------------------
-template <int D>
-__device__ __noinline__ void run_tag_handlers(const Wv& w, int s, int tag, const Ctx& ctx) {
+__device__ __noinline__ void run_tag_handlers(const Wv& w, int D, int s, int tag, const Ctx& ctx) {
   const int32_t* t = tmpl(w, o_tmpl(objp(w, s)));
   const int32_t* pr = pool(w, __ldg(t + MGT_TAG_REMOVE));
   int n = __ldg(t + MGT_TAG_REMOVE_N);
@@ -876,8 +865,8 @@ __device__ __noinline__ void run_tag_handlers(const Wv& w, int s, int tag, const
   h.skip_trigger = false;
   for (int i = 0; i < n; i++)
     if (__ldg(pr + 2 * i) == tag) {
-      if constexpr (D > 0)
-        handler_apply<D - 1>(w, __ldg(pr + 2 * i + 1), h);
+      if (D > 0)
+        handler_apply(w, D - 1, __ldg(pr + 2 * i + 1), h);
       else
         set_error(w, MGERR_UNSUPPORTED, 12);
     }
@@ -893,15 +882,14 @@ __device__ __forceinline__ void add_tag(const Wv& w, int s, int tag) {
   if (ds >= 0 && s < w.maxobj) w.dyn_stamp[(size_t)s * w.NDYN + ds] = (uint32_t)(w.E[MGEV_TAG_SEQ]++);
   // on_tag_add handlers cannot be configured from Python (no add_on_tag_add_handler call in the lowering)
 }
-template <int D>
-__device__ __forceinline__ void remove_tag(const Wv& w, int s, int tag, const Ctx& ctx) {
+__device__ __forceinline__ void remove_tag(const Wv& w, int D, int s, int tag, const Ctx& ctx) {
   uint32_t* o = objp(w, s);
   if (tag < 0 || tag >= 256 || !o_has_tag(o, tag)) return;
   o[MGO_TAGS + (tag >> 5)] &= ~(1u << (tag & 31));
   o[MGO_NTOK] = MG_TOK_DIRTY;
   terr_touch(w, o);
   if (s < w.maxobj) tl_erase(w, tag, s);
-  if (!ctx.skip_trigger) run_tag_handlers<D>(w, s, tag, ctx);
+  if (!ctx.skip_trigger) run_tag_handlers(w, D, s, tag, ctx);
 }
 
 // ---- AOE bookkeeping shared by mutations (core/aoe_tracker.cpp:141-145,207-276) ----------------------
@@ -918,7 +906,7 @@ __device__ __noinline__ void apply_presence(const Wv& w, const int32_t* a, int t
   const int32_t* pd = pool(w, __ldg(a + 7));
   int n = __ldg(a + 8);
   uint32_t* o = objp(w, target);
-  for (int i = 0; i < n; i++) inv_update<2>(w, o, __ldg(pd + 2 * i), __ldg(pd + 2 * i + 1) * mult);
+  for (int i = 0; i < n; i++) inv_update(w, 2, o, __ldg(pd + 2 * i), __ldg(pd + 2 * i + 1) * mult);
 }
 __device__ __forceinline__ void register_aoe(const Wv& w, int slot, int cfg) {
   int k = w.E[MGEV_NUM_AOE];
@@ -975,9 +963,8 @@ __device__ __noinline__ int spawn_object(const Wv& w, int t, int r, int c) {  //
 }
 
 // ---- materialized queries (core/query_system.cpp:91-175) ---------------------------------------------
-template <int D>
-__device__ __noinline__ void recompute_mq(const Wv& w, int tag, const Ctx& ctx, bool fire_handlers) {
-  if constexpr (D > 1) {
+__device__ __noinline__ void recompute_mq(const Wv& w, int D, int tag, const Ctx& ctx, bool fire_handlers) {
+  if (D > 1) {
     const int32_t* mq = sec(w, MGS_MQ);
     int nmq = w.hdr[MGH_NUM_MQ];
     Ctx tc = ctx;
@@ -986,15 +973,15 @@ __device__ __noinline__ void recompute_mq(const Wv& w, int tag, const Ctx& ctx, 
       if (__ldg(mq + 2 * i) != tag) continue;
       int mark = arena_top(w);
       QList lost = collect_tag(w, tag);
-      for (int k = 0; k < lost.n; k++) remove_tag<D - 1>(w, lost.p[k], tag, tc);
-      QList keep = query_eval<D - 1>(w, __ldg(mq + 2 * i + 1), ctx);
+      for (int k = 0; k < lost.n; k++) remove_tag(w, D - 1, lost.p[k], tag, tc);
+      QList keep = query_eval(w, D - 1, __ldg(mq + 2 * i + 1), ctx);
       for (int k = 0; k < keep.n; k++) add_tag(w, keep.p[k], tag);
       if (fire_handlers) {
         tc.skip_trigger = false;
         for (int k = 0; k < lost.n; k++) {
           bool kept = false;
           for (int j = 0; j < keep.n && !kept; j++) kept = keep.p[j] == lost.p[k];
-          if (!kept) run_tag_handlers<D - 1>(w, lost.p[k], tag, tc);
+          if (!kept) run_tag_handlers(w, D - 1, lost.p[k], tag, tc);
         }
       }
       arena_set(w, mark);
@@ -1006,8 +993,7 @@ __device__ __noinline__ void recompute_mq(const Wv& w, int tag, const Ctx& ctx, 
 }
 
 // ---- mutations + handlers (handler/mutations/*.hpp, handler.cpp:76-103, multi_handler.cpp:8-21) ---
-template <int D>
-__device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
+__device__ __noinline__ void mutate(const Wv& w, int D, int mi, Ctx& ctx) {
   const int32_t* m = sec(w, MGS_MUTATIONS) + mi * MG_MUTATION_WORDS;
   int op = __ldg(m), a = __ldg(m + 3), b = __ldg(m + 4), c = __ldg(m + 5), d = __ldg(m + 6);
   int e1 = resolve_entity(ctx, __ldg(m + 1)), e2 = resolve_entity(ctx, __ldg(m + 2));
@@ -1023,7 +1009,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         df.delta[a] += b;
         return;
       }
-      if (e1) inv_update<2>(w, objp(w, e1), a, b);
+      if (e1) inv_update(w, 2, objp(w, e1), a, b);
       return;
     case MGM_RESOURCE_TRANSFER: {
       if (!e1 || !e2) return;
@@ -1042,13 +1028,13 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         int n = ord_count(ord);
         for (int i = 0; i < n; i++) {
           int it = ord_item(ord, i);
-          inv_update<2>(w, o, it, -(int)o_inv(w, o)[it]);
+          inv_update(w, 2, o, it, -(int)o_inv(w, o)[it]);
         }
       } else {
         const int32_t* ids = pool(w, a);
         for (int i = 0; i < b; i++) {
           int it = __ldg(ids + i);
-          inv_update<2>(w, o, it, -(int)o_inv(w, o)[it]);
+          inv_update(w, 2, o, it, -(int)o_inv(w, o)[it]);
         }
       }
       return;
@@ -1057,7 +1043,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
       if (!ctx.actor || !ctx.target) return;
       int weapon = o_inv(w, objp(w, ctx.actor))[a], armor = o_inv(w, objp(w, ctx.target))[b];
       int dmg = max(0, weapon * d / 100 - armor);
-      if (dmg > 0) inv_update<2>(w, objp(w, ctx.target), c, -dmg);
+      if (dmg > 0) inv_update(w, 2, objp(w, ctx.target), c, -dmg);
       return;
     }
     case MGM_ADD_TAG:
@@ -1108,7 +1094,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
     default:
       break;
   }
-  if constexpr (D > 0) {
+  if (D > 0) {
     switch (op) {
       case MGM_STATS: {  // stats_mutation.hpp:21-41
         int ent = c ? ctx.actor : ctx.target;
@@ -1123,7 +1109,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
           }
           return;
         }
-        float v = eval_value<D - 1>(w, d, ctx, ent);
+        float v = eval_value(w, D - 1, d, ctx, ent);
         if (b == 0) {
           gstat_set(w, a, v);
         } else if (ent) {
@@ -1133,12 +1119,12 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         return;
       }
       case MGM_GAME_VALUE: {  // game_value_mutation.hpp:18-25
-        float delta = eval_value<D - 1>(w, b, ctx, e1);
+        float delta = eval_value(w, D - 1, b, ctx, e1);
         const int32_t* v = sec(w, MGS_VALUES) + a * MG_VALUE_WORDS;
         int vop = __ldg(v), vscope = __ldg(v + 1), va = __ldg(v + 2);
         if (vop == MGV_INVENTORY) {
           if (e1)
-            inv_update<2>(w, objp(w, e1), va, (int)delta);
+            inv_update(w, 2, objp(w, e1), va, (int)delta);
           else if (vscope == MGSC_GAME)
             gstat_add(w, __ldg(sec(w, MGS_RES_GSTATS) + va), delta);
         } else if (vop == MGV_STAT) {
@@ -1152,20 +1138,20 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         return;
       }
       case MGM_REMOVE_TAG:
-        if (e1) remove_tag<D - 1>(w, e1, a, ctx);
+        if (e1) remove_tag(w, D - 1, e1, a, ctx);
         return;
       case MGM_REMOVE_TAGS_PREFIX: {
         if (!e1) return;
         const int32_t* ids = pool(w, a);
-        for (int i = 0; i < b; i++) remove_tag<D - 1>(w, e1, __ldg(ids + i), ctx);
+        for (int i = 0; i < b; i++) remove_tag(w, D - 1, e1, __ldg(ids + i), ctx);
         return;
       }
       case MGM_RECOMPUTE_MQ:
-        recompute_mq<D - 1>(w, a, ctx, true);
+        recompute_mq(w, D - 1, a, ctx, true);
         return;
       case MGM_QUERY_INVENTORY: {  // query_inventory_mutation.hpp:24-52
         int mark = arena_top(w);
-        QList q = query_eval<D - 1>(w, a, ctx);
+        QList q = query_eval(w, D - 1, a, ctx);
         const int32_t* pr = pool(w, b);
         int stat_off = __ldg(m + 7);
         if (d) {
@@ -1183,7 +1169,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
           }
         } else {
           for (int k = 0; k < q.n; k++)
-            for (int i = 0; i < c; i++) inv_update<2>(w, objp(w, q.p[k]), __ldg(pr + 2 * i), __ldg(pr + 2 * i + 1));
+            for (int i = 0; i < c; i++) inv_update(w, 2, objp(w, q.p[k]), __ldg(pr + 2 * i), __ldg(pr + 2 * i + 1));
         }
         arena_set(w, mark);
         return;
@@ -1197,14 +1183,14 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         bool ok = false;
         if (h >= 0) {
           Ctx u = ctx;
-          ok = handler_apply<D - 1>(w, h, u);
+          ok = handler_apply(w, D - 1, h, u);
         }
         if (!ok) {
           ctx.failed = true;
           return;
         }
         int after = __ldg(tmpl(w, o_tmpl(objp(w, ctx.actor))) + MGT_ON_AFTER_USE);
-        if (after >= 0) handler_apply<D - 1>(w, after, ctx);  // shares ctx (objects/agent.cpp:73-77)
+        if (after >= 0) handler_apply(w, D - 1, after, ctx);  // shares ctx (objects/agent.cpp:73-77)
         return;
       }
       case MGM_RAYCAST_SPAWN: {  // raycast_spawn_mutation.cpp:16-93
@@ -1214,7 +1200,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
         }
         const uint32_t* org = objp(w, ctx.target);
         int orr = o_r(org), oc = o_c(org);
-        int range = (int)eval_value<D - 1>(w, d, ctx, ctx.target);
+        int range = (int)eval_value(w, D - 1, d, ctx, ctx.target);
         if (range <= 0) return;
         const int32_t* dirs = pool(w, b);
         int b0 = __ldg(m + 7), bn = __ldg(m + 2);
@@ -1227,7 +1213,7 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
               bool blk = false;
               Ctx bc = ctx;
               bc.target = ex;
-              for (int i = 0; i < bn && !blk; i++) blk = filter_pass<D - 1>(w, b0 + i, bc);
+              for (int i = 0; i < bn && !blk; i++) blk = filter_pass(w, D - 1, b0 + i, bc);
               if (blk) break;
               continue;
             }
@@ -1242,25 +1228,24 @@ __device__ __noinline__ void mutate(const Wv& w, int mi, Ctx& ctx) {
   set_error(w, MGERR_UNSUPPORTED, 5 | (op << 8));
 }
 
-template <int D>
-__device__ __noinline__ bool handler_apply(const Wv& w, int h, Ctx& ctx) {
+__device__ __noinline__ bool handler_apply(const Wv& w, int D, int h, Ctx& ctx) {
   const int32_t* hd = sec(w, MGS_HANDLERS) + h * MG_HANDLER_WORDS;
   int kind = __ldg(hd), a = __ldg(hd + 1), b = __ldg(hd + 2);
   if (kind == MGHK_SIMPLE) {
-    if (!filters_pass<D>(w, a, b, ctx)) return false;
+    if (!filters_pass(w, D, a, b, ctx)) return false;
     int m0 = __ldg(hd + 3), mn = __ldg(hd + 4);
     ctx.failed = false;
     for (int i = 0; i < mn; i++) {
-      mutate<D>(w, m0 + i, ctx);
+      mutate(w, D, m0 + i, ctx);
       if (ctx.failed) return false;
     }
     return true;
   }
-  if constexpr (D > 0) {
+  if (D > 0) {
     bool any = false;
     const int32_t* kids = pool(w, a);
     for (int i = 0; i < b; i++)
-      if (handler_apply<D - 1>(w, __ldg(kids + i), ctx)) {
+      if (handler_apply(w, D - 1, __ldg(kids + i), ctx)) {
         any = true;
         if (kind == MGHK_FIRST_MATCH) return true;
       }

@@ -2,19 +2,22 @@
 //
 //   k_reset        : build per-env state from the template map (the reference's constructor,
 //                    bindings/mettagrid_c.cpp:42-191,200-269)
-//   k_init_buffers : _init_buffers (:294-319): clear flags, reset coverage, initial observations
-//   k_step         : MettaGrid::_step (:921-1102), all 15 phases fused in one launch
-//
-// Mapping: one warp = one environment; MG_WARPS_PER_CTA envs per CTA; lane = agent wherever
-// the compiler's effect analysis allows (action passes, on_tick, AOE, territory, coverage, rewards), lane 0 only
-// for what must stay in the reference's order.  The env's grid is read in place (L1 / L2); each agent's observation
-// row is composed in shared memory and streamed to HBM with 16-byte stores.
+//   k_init_buffers : _init_buffers (:294-319): clear flags, reset coverage (+ k_observe / k_finish: initial observations)
+//   one tick, MettaGrid::_step (:921-1102), is three launches on one stream:
+//   k_world        : phases 1-12 -- actions, events, on_tick, AOE, territory, coverage.  One warp = one environment;
+//                    lane = agent wherever the compiler's effect analysis allows (action passes, on_tick, AOE,
+//                    territory, coverage), lane 0 only for what must stay in the reference's order.
+//   k_observe      : phase 13, the observation pass.  One warp = one AGENT: rows are independent once the cell
+//                    staleness owner is decided analytically; each row is composed in shared memory and streamed
+//                    to HBM with 16-byte stores.  Its register budget is its own (the interpreter wants 64 registers
+//                    and many resident warps, the window loop wants its loads in flight together).
+//   k_finish       : phases 14-15 -- token stats in agent order, rewards, episode rewards, truncation.
 #include "mg_device.cuh"
 #include "mg_world.cuh"
 
 #ifdef MG_PHASE_TIMING
 // A/B build only (python -m mettagrid_b200.build --variant prof -DMG_PHASE_TIMING): lane 0 of every warp adds the cycles
-// it spent in each phase of k_step; tools/phase_timing.py reads the totals through mg_debug_phase_cycles.
+// it spent in each phase of k_world; tools/phase_timing.py reads the totals through mg_debug_phase_cycles.
 __device__ unsigned long long g_phase_cycles[16];
 #define MG_PHASE(k)                                        \
   do {                                                     \
@@ -47,7 +50,6 @@ struct Smem {
   uint8_t* rank;      // [(dr + rr) * 16 + (dc + cr)] -> position of the offset in Manhattan order, 0xFF = outside the shape
   // per warp
   uint16_t* cells;
-  uint8_t* stage;
   int* rs;
   uint32_t* rand;
   uint32_t* a_slot;   // agent -> object slot
@@ -78,7 +80,6 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {  // HWp = 0: the grid is not staged
   size_t n = 0;
   n += align16((size_t)HWp * 2);
-  n += align16((size_t)3 * T + 32);
   n += align16(8 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
   n += align16((size_t)A * 4) * MG_AGENT_WORD_ARRAYS;
   n += 2 * align16((size_t)A * 2);
@@ -98,8 +99,6 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   base += (size_t)warp * smem_per_warp(d.stage_grid ? d.HWp : 0, d.T, d.A);
   s.cells = (uint16_t*)base;
   base += align16((size_t)(d.stage_grid ? d.HWp : 0) * 2);
-  s.stage = base;
-  base += align16((size_t)3 * d.T + 32);
   s.rs = (int*)base;
   s.rand = (uint32_t*)(base + 8 * sizeof(int));
   base += align16(8 * sizeof(int) + 2 * MG_RNG_WINDOW * sizeof(uint32_t));
@@ -220,17 +219,26 @@ __device__ __forceinline__ void flush_row(uint8_t* src, uint8_t* g, int n, int u
 
 // An object's observation tokens (core/grid_object.cpp:178-203, objects/agent.cpp:142-154) only change
 // when its tags, vibe or inventory change, so they are cached in the object record as (feature | value << 8)
-// pairs and rebuilt lazily by whichever lane observes the object first after a change.
-__device__ __noinline__ int rebuild_token_cache(const Wv& w, uint32_t* o) {
-  uint16_t* tk = (uint16_t*)(o + w.TOKOFF);
-  const int cap = w.hdr[MGH_TOK_CAP];
+// pairs and rebuilt lazily: agents by k_world (one lane per agent), anything else by whichever observer meets it
+// first.  Concurrent observers may rebuild the same object: they write identical words, and the count is published
+// behind a fence.
+struct TokCtx {
+  const int32_t* P;
+  const int32_t* hdr;
+  int32_t* E;
+  int TW, B, ND, TOKOFF;
+};
+__device__ __forceinline__ TokCtx tok_ctx(const Wv& w) { return TokCtx{w.P, w.hdr, w.E, w.TW, w.B, w.ND, w.TOKOFF}; }
+__device__ __noinline__ int rebuild_token_cache(const TokCtx c, uint32_t* o) {
+  uint16_t* tk = (uint16_t*)(o + c.TOKOFF);
+  const int cap = c.hdr[MGH_TOK_CAP];
   int n = 0;
   auto put = [&](int feat, int val) {
     if (n < cap) tk[n] = (uint16_t)((feat & 0xff) | ((val & 0xff) << 8));
     n++;
   };
-  const int ftag = w.hdr[MGH_FEAT_TAG];
-  for (int k = 0; k < w.TW; k++) {
+  const int ftag = c.hdr[MGH_FEAT_TAG];
+  for (int k = 0; k < c.TW; k++) {
     uint32_t m = o[MGO_TAGS + k];
     while (m) {
       int b = __ffs(m) - 1;
@@ -239,33 +247,35 @@ __device__ __noinline__ int rebuild_token_cache(const Wv& w, uint32_t* o) {
     }
   }
   int vibe = o_vibe(o);
-  if (vibe) put(w.hdr[MGH_FEAT_VIBE], vibe);
+  if (vibe) put(c.hdr[MGH_FEAT_VIBE], vibe);
   int fl = o_flags(o);
   if (fl & MGOF_OBS_INV) {
     uint64_t ord = o_order(o);
     int cnt = ord_count(ord);
-    const uint16_t* inv = o_inv(w, o);
-    const int32_t* feats = sec(w, MGS_INV_FEATS);
+    const uint16_t* inv = (const uint16_t*)(o + MGO_TAGS + c.TW);
+    const int32_t* feats = c.P + c.hdr[MGS_INV_FEATS];
     for (int i = 0; i < cnt; i++) {
       int it = ord_item(ord, i);
       uint32_t amt = inv[it];
       int p = 0;
       do {
-        put(__ldg(feats + it * w.ND + p), (int)(amt % (uint32_t)w.B));
-        amt /= (uint32_t)w.B;
+        put(__ldg(feats + it * c.ND + p), (int)(amt % (uint32_t)c.B));
+        amt /= (uint32_t)c.B;
         p++;
-      } while (amt > 0 && p < w.ND);
+      } while (amt > 0 && p < c.ND);
     }
   }
   if (fl & MGOF_AGENT) {
     int ai = o_agent(o);
-    put(w.hdr[MGH_FEAT_GROUP], __ldg(tmpl(w, o_tmpl(o)) + MGT_GROUP));
-    put(w.hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
+    put(c.hdr[MGH_FEAT_GROUP], __ldg(c.P + c.hdr[MGS_TEMPLATES] + o_tmpl(o) * MG_TEMPLATE_WORDS + MGT_GROUP));
+    put(c.hdr[MGH_FEAT_AGENT_ID], ai >= 0 ? ai : 0);
   }
   if (n > cap) {
-    set_error(w, MGERR_POOL_EXHAUSTED, 19);
+    if (!(c.E[MGEV_ERROR] & MGERR_POOL_EXHAUSTED)) c.E[MGEV_ERR_INFO] = 19;
+    atomicOr(&c.E[MGEV_ERROR], MGERR_POOL_EXHAUSTED);
     n = cap;
   }
+  __threadfence();
   o[MGO_NTOK] = (uint32_t)n;
   return n;
 }
@@ -277,266 +287,302 @@ __device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc,
   }
 }
 
-// One agent's observation, composed by the whole warp (bindings/mettagrid_c.cpp:665-824).
-// Returns the number of tokens attempted; `tok` accumulates the env's token stats.
-#define MG_OBS_ATTR __forceinline__  // measured: inlining into observe_all beats a call per agent (profiles/README.md)
-#define MG_OBS_GROUP 4               // window passes (32 cells each) whose loads are issued together
-// PLAIN = the program has no territory (no aoe_mask tokens) and no configured global game values: the common
-// case gets a version without those paths, which keeps the window loop small and out of local memory.
-template <bool PLAIN>
-__device__ MG_OBS_ATTR int observe_agent(const Wv& w, const Smem& s, int a, int action, uint32_t steploc, int lane) {
-  const int T = w.T;
-  uint8_t* g = w.obs + (size_t)a * (size_t)(3 * T);
-  uint8_t* out = s.stage + ((uint32_t)(uintptr_t)g & 15u);
-  const uint32_t loc0 = s.a_loc[a];
-  const int r0 = (int)(loc0 >> 16), c0 = (int)(loc0 & 0xffffu);
-  const int flags = w.hdr[MGH_GLOBAL_FLAGS];
-  uint32_t* ag = w.agents + a * w.AS;
+// =================================================================================================
+// k_observe: the observation pass (bindings/mettagrid_c.cpp:665-912), ONE WARP PER AGENT.
+//
+// k_world (or k_init_buffers) leaves, per agent, {executed action, start-of-tick location, location, object slot}
+// in d.obs_in and the tokens of the configured global game values in d.obsval; from there on an agent's row depends
+// on nothing another agent's row computes -- with one exception, the reference's cell staleness (:787-796):
+// an object's `visited` stamp is advanced by the FIRST agent, in index order, that sees it this tick, and the ticks
+// since go to that agent's cell.visited stat.  "First" is decided without communication: agent a owns an object iff no
+// agent a' < a has it inside its own window, and the warp tests that against the positions of the (few) earlier agents
+// close enough to share cells with a.  Only the owner reads or writes the stamp.
+// =================================================================================================
+#define MG_OBS_WARPS 8
+#ifndef MG_OBS_MIN_CTAS
+#define MG_OBS_MIN_CTAS 3  // 80 registers: 24 resident warps per SM (A/B: profiles/README.md)
+#endif
+
+__host__ __device__ inline size_t obs_smem_bytes(int NOFF, int T) {
+  return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4) + 256 + (size_t)MG_OBS_WARPS * align16((size_t)3 * T + 32);
+}
+
+// NP = window passes of 32 cells whose loads are issued together: 4 (up to 11 x 11 windows) or 8 (up to 15 x 15)
+template <bool PLAIN, int NP>
+__global__ void __launch_bounds__(MG_OBS_WARPS * 32, MG_OBS_MIN_CTAS) k_observe(MgDev d, const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* const hdr = (int32_t*)smem_raw;
+  uint32_t* const offs = (uint32_t*)(smem_raw + align16(MGH_HEADER_WORDS * 4));
+  uint8_t* const rank = (uint8_t*)offs + align16((size_t)d.NOFF * 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* const stage0 = rank + 256 + (size_t)warp * align16((size_t)3 * d.T + 32);
+  const int A = d.A, T = d.T;
+  {
+    const long long g_first = (long long)blockIdx.x * MG_OBS_WARPS, g_last = g_first + MG_OBS_WARPS - 1;
+    if (mask) {  // a masked launch usually selects few environments
+      const int e0 = (int)(g_first / A), e1 = (int)min(g_last / A, (long long)d.num_envs - 1);
+      bool any = false;
+      for (int e = e0; e <= e1; e++) any = any || mask[e];
+      if (!any) return;
+    }
+  }
+  for (int i = threadIdx.x; i < MGH_HEADER_WORDS; i += blockDim.x) hdr[i] = __ldg(d.P + i);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) rank[i] = 0xFF;
+  __syncthreads();
+  {
+    const int32_t* po = d.P + hdr[MGS_OFFSETS];
+    const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
+    for (int i = threadIdx.x; i < d.NOFF; i += blockDim.x) {
+      const int dr = __ldg(po + 2 * i), dc = __ldg(po + 2 * i + 1);
+      const uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));  // systems/packed_coordinate.hpp:50-56
+      // bits 0-7: dr + 8 | (dc + 8) << 4 ; bits 8-15: packed location ; bits 16-31: cell delta in the padded grid
+      offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8) | ((uint32_t)((dr * d.WP + dc) & 0xffff) << 16);
+      rank[loc] = (uint8_t)i;
+    }
+  }
+  __syncthreads();
+  const long long g = (long long)blockIdx.x * MG_OBS_WARPS + warp;
+  if (g >= (long long)d.num_envs * A) return;
+  const int env = (int)(g / A), a = (int)(g - (long long)env * A);
+  if (mask && !mask[env]) return;
+
+  const uint4* const oin = d.obs_in + (size_t)env * A;
+  const uint4 me_in = oin[a];  // executed action, start-of-tick location, location, object slot
+  const int r0 = (int)(me_in.z >> 16), c0 = (int)(me_in.z & 0xffffu);
+  int32_t* const E = d.env + (size_t)env * MGEV_WORDS;
+  const uint32_t step = (uint32_t)E[MGEV_STEP];
+  uint32_t* const objs = d.objs + (size_t)env * (d.maxobj + d.NPROXY) * d.OS;
+  const uint16_t* const centre = d.cells + (size_t)env * d.HWp + (r0 + d.PAD) * d.WP + c0 + d.PAD;
+  uint8_t* const g_row = d.obs + ((size_t)env * A + a) * (size_t)(3 * T);
+  uint8_t* const out = stage0 + ((uint32_t)(uintptr_t)g_row & 15u);
+  const int OS = d.OS, NOFF = d.NOFF, TOKOFF = MG_TOKOFF(d.TW, d.R);
   const uint32_t lt = (1u << lane) - 1u;
+  const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
+  const int flags = hdr[MGH_GLOBAL_FLAGS];
 
   // ---- global tokens (:700-742), one candidate per lane, compacted in order
   int feat = 0, val = 0, have = 0;
   if (lane == 0 && (flags & MGG_EPISODE_PCT)) {
-    int ms = w.hdr[MGH_MAX_STEPS];
-    have = 1, feat = w.hdr[MGH_FEAT_EPISODE_PCT];
-    if (ms > 0) val = w.step >= (uint32_t)ms ? 255 : (int)((256u * w.step / (uint32_t)ms) & 0xffu);
+    const int ms = hdr[MGH_MAX_STEPS];
+    have = 1, feat = hdr[MGH_FEAT_EPISODE_PCT];
+    if (ms > 0) val = step >= (uint32_t)ms ? 255 : (int)((256u * step / (uint32_t)ms) & 0xffu);
   } else if (lane == 1 && (flags & MGG_LAST_ACTION)) {
-    have = 1, feat = w.hdr[MGH_FEAT_LAST_ACTION], val = action & 0xff;
-  } else if (lane == 2 && (flags & MGG_LAST_ACTION_MOVE) && w.hdr[MGH_FEAT_LAST_ACTION_MOVE] != 0) {
-    have = 1, feat = w.hdr[MGH_FEAT_LAST_ACTION_MOVE], val = loc0 != steploc;
+    have = 1, feat = hdr[MGH_FEAT_LAST_ACTION], val = (int)me_in.x & 0xff;
+  } else if (lane == 2 && (flags & MGG_LAST_ACTION_MOVE) && hdr[MGH_FEAT_LAST_ACTION_MOVE] != 0) {
+    have = 1, feat = hdr[MGH_FEAT_LAST_ACTION_MOVE], val = me_in.z != me_in.y;
   } else if (lane == 3 && (flags & MGG_LAST_REWARD)) {
     // rewards are zeroed before and written after the observation pass (:937-938,1062,1070): always 0
-    have = 1, feat = w.hdr[MGH_FEAT_LAST_REWARD], val = 0;
+    have = 1, feat = hdr[MGH_FEAT_LAST_REWARD], val = 0;
   } else if ((lane == 4 || lane == 5) && (flags & MGG_LOCAL_POSITION)) {
-    uint32_t sp = ag[MGAG_SPAWN];
-    int dd = lane == 4 ? c0 - (int)(sp & 0xffffu) : (int)(sp >> 16) - r0;
+    const uint32_t sp = d.agents[((size_t)env * A + a) * d.AS + MGAG_SPAWN];
+    const int dd = lane == 4 ? c0 - (int)(sp & 0xffffu) : (int)(sp >> 16) - r0;
     if (dd != 0) {
       have = 1;
       val = min(abs(dd), 255);
-      feat = lane == 4 ? (dd > 0 ? w.hdr[MGH_FEAT_LP_EAST] : w.hdr[MGH_FEAT_LP_WEST])
-                       : (dd > 0 ? w.hdr[MGH_FEAT_LP_NORTH] : w.hdr[MGH_FEAT_LP_SOUTH]);
+      feat = lane == 4 ? (dd > 0 ? hdr[MGH_FEAT_LP_EAST] : hdr[MGH_FEAT_LP_WEST]) : (dd > 0 ? hdr[MGH_FEAT_LP_NORTH] : hdr[MGH_FEAT_LP_SOUTH]);
     }
   }
   const uint32_t gm = __ballot_sync(MG_FULL, have);
   if (have) put_token(out, T, __popc(gm & lt), 0xFE, feat, val);
   int base = __popc(gm);
-
-  // ---- configured global game values (:1207-1238), serial
-  const int nov = PLAIN ? 0 : w.hdr[MGH_NUM_OBS_VALUES];
-  if (nov > 0) {
-    if (lane == 0) {
-      const int32_t* ov = sec(w, MGS_OBS_VALUES);
-      int me = (int)s.a_slot[a];
-      for (int i = 0; i < nov; i++) {
-        Ctx vc = make_ctx();
-        vc.actor = vc.target = me;
-        uint32_t enc = (uint32_t)eval_value<MG_DEPTH>(w, __ldg(ov + 2 * i + 1), vc, me);
-        int f = __ldg(ov + 2 * i);
-        put_token(out, T, base++, 0xFE, f, (int)(enc % (uint32_t)w.B));
-        enc /= (uint32_t)w.B;
-        while (enc > 0) {
-          f++;
-          put_token(out, T, base++, 0xFE, f, (int)(enc % (uint32_t)w.B));
-          enc /= (uint32_t)w.B;
-        }
-      }
-    }
-    base = __shfl_sync(MG_FULL, base, 0);
+  // ---- configured global game values (:1207-1238): evaluated by k_world, one (feature | value << 8) pair per token
+  if (!PLAIN && d.OVW > 0) {
+    const uint16_t* ov = d.obsval + ((size_t)env * A + a) * d.OVW;
+    const int n = ov[0];
+    for (int j = lane; j < n; j += 32) put_token(out, T, base + j, 0xFE, ov[1 + j] & 0xff, ov[1 + j] >> 8);
+    base += n;
   }
 
-  // ---- window cells in Manhattan order, 32 per pass (:756-811).  The grid carries an empty frame as
-  // wide as the window radius, so a cell outside the map reads as empty and needs no bounds test.
+  // ---- earlier agents that can share window cells with this one (cell staleness ownership, see above)
+  uint32_t near_loc = 0xffffffffu;  // lane j < min(a, 32): agent j's location when it is that close
+  if (lane < a) {
+    near_loc = oin[lane].z;
+    const int dr = (int)(near_loc >> 16) - r0, dc = (int)(near_loc & 0xffffu) - c0;
+    if (dr < -2 * rr || dr > 2 * rr || dc < -2 * cr || dc > 2 * cr) near_loc = 0xffffffffu;
+  }
+  const uint32_t near = __ballot_sync(MG_FULL, near_loc != 0xffffffffu);
+  // does an agent with a smaller index see the cell (r, c)?  (uniform loops: every lane asks about its own cell)
+  auto seen_earlier = [&](int r, int c) {
+    bool seen = false;
+    uint32_t m = near;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t lj = __shfl_sync(MG_FULL, near_loc, j);
+      const int dr = r - (int)(lj >> 16) + rr, dc = c - (int)(lj & 0xffffu) + cr;
+      if (dr >= 0 && dc >= 0 && dr <= 2 * rr && dc <= 2 * cr && rank[(dr << 4) | dc] != 0xFF) seen = true;
+    }
+    for (int j0 = 32; j0 < a; j0 += 32) {  // more than 32 agents per env: the rest, 32 at a time
+      uint32_t lj = 0xffffffffu;
+      if (j0 + lane < a) lj = oin[j0 + lane].z;
+      for (int j = 0; j < 32 && j0 + j < a; j++) {
+        const uint32_t l2 = __shfl_sync(MG_FULL, lj, j);
+        const int dr = r - (int)(l2 >> 16) + rr, dc = c - (int)(l2 & 0xffffu) + cr;
+        if (dr >= 0 && dc >= 0 && dr <= 2 * rr && dc <= 2 * cr && rank[(dr << 4) | dc] != 0xFF) seen = true;
+      }
+    }
+    return seen;
+  };
+
+  // ---- window cells in Manhattan order, 32 per pass (:756-811).  The grid carries an empty frame as wide as the
+  // window radius, so a cell outside the map reads as empty and needs no bounds test.  All cell ids are loaded
+  // first, then the heads of the objects standing there (visited stamp, cached token count, first token pair):
+  // two memory round trips per agent.  Token positions come from two ballots (an object with one token -- every
+  // wall -- needs no scan); multi-token objects are copied by the whole warp, one token per lane, four at a time.
   uint32_t stale_sum = 0;
-  const int fmask = (!PLAIN && w.NTERR > 0) ? w.hdr[MGH_FEAT_AOE_MASK] : 0;
-  const uint32_t* me = objp(w, (int)s.a_slot[a]);
-  const uint16_t* centre = w.cells + cidx(w, r0, c0);
-  // byte stores into the stage may alias anything: keep the loop's operands in registers
-  const int NOFF = w.NOFF, TOKOFF = w.TOKOFF, OS = w.OS;
-  const uint32_t step = w.step;
-  uint32_t* const objs = w.objs;
-  const uint32_t* const offs = s.offs;
-  // Sparse environments (at most 32 objects ever created): one lane per OBJECT instead of one per window
-  // cell.  Each visible object's position in the row is the token count of the visible objects that come
-  // earlier in Manhattan order, found by walking the few set lanes of a ballot.
-  const int nobj = w.E[MGEV_NEXT_OBJ] - 1;
-  if (nobj <= 32 && fmask == 0) {
-    const int rr = w.hdr[MGH_OBS_H] >> 1, cr = w.hdr[MGH_OBS_W] >> 1;
-    int n = 0, rank = 0xFF, loc = 0;
-    uint32_t* o = nullptr;
-    if (lane < nobj) {
-      o = objs + (size_t)(lane + 1) * OS;
-      if (o_alive(o)) {
-        const int dr = o_r(o) - r0 + rr, dc = o_c(o) - c0 + cr;
-        if (dr >= 0 && dc >= 0 && dr <= 2 * rr && dc <= 2 * cr) {
-          loc = (dr << 4) | dc;
-          rank = s.rank[loc];
+  const int fmask = (!PLAIN && d.NTERR > 0) ? hdr[MGH_FEAT_AOE_MASK] : 0;
+  const uint32_t* const me = objs + (size_t)me_in.w * OS;
+  const TokCtx tc{d.P, hdr, E, d.TW, d.B, d.ND, TOKOFF};
+  uint32_t pk[NP], slot[NP], nt[NP], t0[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const int k = 32 * p + lane;
+    pk[p] = k < NOFF ? offs[k] : 0u;
+    slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    nt[p] = t0[p] = 0;
+    if (slot[p]) {
+      const uint32_t* o = objs + (size_t)slot[p] * OS;
+      nt[p] = o[MGO_NTOK], t0[p] = o[TOKOFF];
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    if (32 * p >= NOFF) break;
+    const int loc = (int)((pk[p] >> 8) & 0xffu);
+    const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
+    int tmask = 0, n = 0;
+    if (fmask && 32 * p + lane < NOFF && r >= 0 && c >= 0 && r < d.H && c < d.W) {
+      // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens (ownership map: mg_world.cuh)
+      const uint8_t* own = d.owner_map + (size_t)env * d.NTERR * d.HW + r * d.W + c;
+      for (int ti = 0; ti < d.NTERR && !tmask; ti++) {
+        const int v = own[(size_t)ti * d.HW];
+        if (v) {
+          const int tag = __ldg(d.P + hdr[MGS_POOL] + __ldg(d.P + hdr[MGS_TERRITORIES] + ti * MG_TERR_WORDS) + v - 1);
+          tmask = o_has_tag(me, tag) ? 1 : 2;
         }
       }
     }
-    uint32_t m = __ballot_sync(MG_FULL, rank != 0xFF);
-    if (rank != 0xFF) {
-      const uint32_t vis = o[MGO_VISITED];
-      if (vis < step) {
-        stale_sum += step - vis;
-        o[MGO_VISITED] = step;
+    const uint32_t m_obj_any = __ballot_sync(MG_FULL, slot[p] != 0);
+    if ((m_obj_any | __ballot_sync(MG_FULL, tmask != 0)) == 0) continue;  // nothing visible in these 32 cells
+    if (m_obj_any) {
+      const bool earlier = seen_earlier(r, c);  // shuffles inside: every lane asks
+      const bool first = slot[p] != 0 && !earlier;
+      if (slot[p]) {
+        uint32_t* o = objs + (size_t)slot[p] * OS;
+        if (first) {  // cell staleness (:787-796): this agent is the first, in index order, to see the object
+          const uint32_t vis = o[MGO_VISITED];
+          if (vis < step) {
+            stale_sum += step - vis;
+            o[MGO_VISITED] = step;
+          }
+        }
+        n = (int)nt[p];
+        if ((uint32_t)n == MG_TOK_DIRTY) {
+          n = rebuild_token_cache(tc, o);
+          t0[p] = o[TOKOFF];
+        }
       }
-      n = (int)o[MGO_NTOK];
-      if ((uint32_t)n == MG_TOK_DIRTY) n = rebuild_token_cache(w, o);
     }
-    int before = 0, tot = 0;
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const int rb = __shfl_sync(MG_FULL, rank, b), nb = __shfl_sync(MG_FULL, n, b);
-      before += rb < rank ? nb : 0;
-      tot += nb;
+    const int cnt = n + (tmask != 0);
+    const uint32_t m_any = __ballot_sync(MG_FULL, cnt != 0);
+    uint32_t m_multi = __ballot_sync(MG_FULL, cnt > 1);
+    int pos = base + __popc(m_any & lt), tot = __popc(m_any);
+    while (m_multi) {
+      const int b = __ffs(m_multi) - 1;
+      m_multi &= m_multi - 1;
+      const int extra = __shfl_sync(MG_FULL, cnt, b) - 1;
+      pos += b < lane ? extra : 0;
+      tot += extra;
     }
-    if (rank != 0xFF) {
-      const uint16_t* tk = (const uint16_t*)(o + TOKOFF);
-      int pos = base + before;
-      for (int j = 0; j < n && pos < T; j++, pos++) {
-        const uint32_t e = tk[j];
-        out[pos * 3 + 0] = (uint8_t)loc;
-        out[pos * 3 + 1] = (uint8_t)e;
-        out[pos * 3 + 2] = (uint8_t)(e >> 8);
+    if (tmask) put_token(out, T, pos, loc, fmask, tmask);
+    pos += tmask != 0;
+    if (n == 1) put_token(out, T, pos, loc, (int)(t0[p] & 0xffu), (int)((t0[p] >> 8) & 0xffu));
+    uint32_t m_obj = __ballot_sync(MG_FULL, n > 1);
+    while (m_obj) {
+      uint32_t ev[4], sv[4];
+      int nv[4], pv[4], lv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        nv[q] = 0;
+        if (m_obj) {
+          const int b = __ffs(m_obj) - 1;
+          m_obj &= m_obj - 1;
+          nv[q] = __shfl_sync(MG_FULL, n, b), pv[q] = __shfl_sync(MG_FULL, pos, b), lv[q] = __shfl_sync(MG_FULL, loc, b);
+          sv[q] = __shfl_sync(MG_FULL, slot[p], b);
+          if (lane < nv[q]) ev[q] = ((const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF))[lane];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (lane < nv[q]) put_token(out, T, pv[q] + lane, lv[q], (int)(ev[q] & 0xffu), (int)(ev[q] >> 8));
+        if (nv[q] > 32) {  // longer lists than lanes: the rest straight from the record
+          const uint16_t* tk = (const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF);
+          for (int j = lane + 32; j < nv[q]; j += 32) {
+            const uint32_t e = tk[j];
+            put_token(out, T, pv[q] + j, lv[q], (int)(e & 0xffu), (int)(e >> 8));
+          }
+        }
       }
     }
     base += tot;
-  } else {
-    // Dense environments: one lane per window cell.  The loads of MG_OBS_GROUP passes -- cell ids, then the heads of
-    // the objects standing there (visited stamp, cached token count, first token pair) -- are issued back to back,
-    // so a group costs two memory round trips instead of two per pass.  Token positions come from two ballots (an
-    // object with one token -- every wall -- needs no scan); the few multi-token objects are copied by the whole
-    // warp, one token per lane.
-    const int W_ = w.W;
-    for (int k0 = 0; k0 < NOFF; k0 += 32 * MG_OBS_GROUP) {
-      uint32_t pk[MG_OBS_GROUP], slot[MG_OBS_GROUP], vis[MG_OBS_GROUP], nt[MG_OBS_GROUP], t0[MG_OBS_GROUP];
-#pragma unroll
-      for (int p = 0; p < MG_OBS_GROUP; p++) {
-        const int k = k0 + 32 * p + lane;
-        pk[p] = k < NOFF ? offs[k] : 0u;
-        slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
-      }
-#pragma unroll
-      for (int p = 0; p < MG_OBS_GROUP; p++) {
-        vis[p] = nt[p] = t0[p] = 0;
-        if (slot[p]) {
-          const uint32_t* o = objs + (size_t)slot[p] * OS;
-          vis[p] = o[MGO_VISITED], nt[p] = o[MGO_NTOK], t0[p] = o[TOKOFF];
-        }
-      }
-#pragma unroll
-      for (int p = 0; p < MG_OBS_GROUP; p++) {
-        if (k0 + 32 * p >= NOFF) break;
-        const int loc = (int)((pk[p] >> 8) & 0xffu);
-        int mask = 0, n = 0;
-        if (fmask && k0 + 32 * p + lane < NOFF) {  // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens
-          const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
-          if (valid_loc(w, r, c)) mask = territory_mask(w, r * W_ + c, me);
-        }
-        if (__ballot_sync(MG_FULL, (slot[p] | (uint32_t)mask) != 0) == 0) continue;  // nothing visible in these 32 cells
-        if (slot[p]) {
-          uint32_t* o = objs + (size_t)slot[p] * OS;
-          if (vis[p] < step) {  // cell staleness (:787-796): agents are visited in index order
-            stale_sum += step - vis[p];
-            o[MGO_VISITED] = step;
-          }
-          n = (int)nt[p];
-          if ((uint32_t)n == MG_TOK_DIRTY) {
-            n = rebuild_token_cache(w, o);
-            t0[p] = o[TOKOFF];
-          }
-        }
-        const int cnt = n + (mask != 0);
-        const uint32_t m_any = __ballot_sync(MG_FULL, cnt != 0);
-        uint32_t m_multi = __ballot_sync(MG_FULL, cnt > 1);
-        int pos = base + __popc(m_any & lt), tot = __popc(m_any);
-        while (m_multi) {
-          const int b = __ffs(m_multi) - 1;
-          m_multi &= m_multi - 1;
-          const int extra = __shfl_sync(MG_FULL, cnt, b) - 1;
-          pos += b < lane ? extra : 0;
-          tot += extra;
-        }
-        if (mask) put_token(out, T, pos, loc, fmask, mask);
-        pos += mask != 0;
-        if (n == 1) put_token(out, T, pos, loc, (int)(t0[p] & 0xffu), (int)((t0[p] >> 8) & 0xffu));
-        // multi-token objects (agents, chests ...): the whole warp copies each one's cached (feature, value) pairs behind
-        // its location byte, one lane per token; the loads of up to four objects are in flight together
-        uint32_t m_obj = __ballot_sync(MG_FULL, n > 1);
-        while (m_obj) {
-          uint32_t ev[4], sv[4];
-          int nv[4], pv[4], lv[4];
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            nv[q] = 0;
-            if (m_obj) {
-              const int b = __ffs(m_obj) - 1;
-              m_obj &= m_obj - 1;
-              nv[q] = __shfl_sync(MG_FULL, n, b), pv[q] = __shfl_sync(MG_FULL, pos, b), lv[q] = __shfl_sync(MG_FULL, loc, b);
-              sv[q] = __shfl_sync(MG_FULL, slot[p], b);
-              if (lane < nv[q]) ev[q] = ((const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF))[lane];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            if (lane < nv[q]) put_token(out, T, pv[q] + lane, lv[q], (int)(ev[q] & 0xffu), (int)(ev[q] >> 8));
-            if (nv[q] > 32) {  // longer lists than lanes: the rest straight from the record
-              const uint16_t* tk = (const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF);
-              for (int j = lane + 32; j < nv[q]; j += 32) {
-                const uint32_t e = tk[j];
-                put_token(out, T, pv[q] + j, lv[q], (int)(e & 0xffu), (int)(e >> 8));
-              }
-            }
-          }
-        }
-        base += tot;
-      }
-    }
   }
   stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
-  if (lane == 0 && stale_sum) astat_add(w, a, w.hdr[MGH_ST_CELL_VISITED], (float)stale_sum);
-
+  if (lane == 0) {
+    if (stale_sum) {  // this warp is the only writer of its agent's stats during the pass
+      const int id = hdr[MGH_ST_CELL_VISITED];
+      float* p = d.astats + ((size_t)env * A + a) * d.SA + id;
+      *p = __fadd_rn(*p, (float)stale_sum);
+      uint32_t* tp = d.atouched + ((size_t)env * A + a) * d.SAW + (id >> 5);
+      if (!(*tp & (1u << (id & 31)))) *tp |= 1u << (id & 31);
+    }
+    d.tok_attempted[(size_t)env * A + a] = base;  // k_finish adds the env's token stats in agent order (:659-661)
+  }
   // ---- stream out: token bytes come from the stage, the rest of the row is 0xFF (EmptyTokenByte, :940-942)
   __syncwarp();
-  flush_row(out, g, 3 * T, 3 * min(base, T), lane);
-  __syncwarp();
-  return base;
+  flush_row(out, g_row, 3 * T, 3 * min(base, T), lane);
 }
 
-// all agents' observations + token stats (:826-912, :640-642)
-__device__ __noinline__ void observe_all(const Wv& w, const Smem& s, int lane, bool initial) {
-  const bool plain = w.NTERR == 0 && w.hdr[MGH_NUM_OBS_VALUES] == 0;
-  // token stats: one float add per agent in agent order like the reference (:659-661), carried in registers
-  const int idw = w.hdr[MGH_GST_TOKENS_WRITTEN], idf = w.hdr[MGH_GST_TOKENS_FREE];
-  float tw = w.gstats[idw], tf = w.gstats[idf];
-  // agents are the objects whose tokens change most (inventory, vibe): rebuild their caches one lane per agent instead
-  // of lazily on whichever single lane meets them first
-  for (int a = lane; a < w.A; a += 32) {
-    uint32_t* o = objp(w, (int)s.a_slot[a]);
-    if (o[MGO_NTOK] == MG_TOK_DIRTY) rebuild_token_cache(w, o);
-  }
-  __syncwarp();
-  for (int a = 0; a < w.A; a++) {
-    int action = initial ? 0 : s.a_exec[a];
-    int attempted = plain ? observe_agent<true>(w, s, a, action, s.a_step[a], lane)
-                          : observe_agent<false>(w, s, a, action, s.a_step[a], lane);
-    if (attempted > w.T) {  // hard error in the reference (:364-375)
-      if (lane == 0) set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
-    } else {
-      tw = __fadd_rn(tw, (float)attempted);
-      tf = __fadd_rn(tf, (float)(w.T - attempted));
+// =================================================================================================
+// k_finish: what the reference does after the observation pass (:640-661,1062-1096), one warp per env: the env's
+// token stats in agent order, rewards (systems/reward.hpp:56-77), episode rewards, truncation / termination.
+// =================================================================================================
+// What k_world / k_init_buffers leave for the observation pass: per agent {executed action, start-of-tick location,
+// location, object slot}, the tokens of the configured global game values (:1207-1238, evaluated here because they need
+// the interpreter), fresh token caches for the agents, a fresh territory ownership map.
+__device__ __noinline__ void hand_over(const MgDev& d, const Wv& w, const Smem& s, int env, int lane, bool initial) {
+  const int A = w.A;
+  const TokCtx tc = tok_ctx(w);
+  const int nov = w.hdr[MGH_NUM_OBS_VALUES];
+  for (int a = lane; a < A; a += 32) {
+    const uint32_t slot = s.a_slot[a];
+    uint32_t* o = objp(w, (int)slot);
+    const uint32_t loc = o[MGO_LOC];
+    d.obs_in[(size_t)env * A + a] = make_uint4(initial ? 0u : (uint32_t)s.a_exec[a], initial ? loc : s.a_step[a], loc, slot);
+    if (o[MGO_NTOK] == MG_TOK_DIRTY) rebuild_token_cache(tc, o);
+    if (nov > 0) {
+      uint16_t* ov = d.obsval + ((size_t)env * A + a) * d.OVW;
+      const int32_t* cfg = sec(w, MGS_OBS_VALUES);
+      int n = 0;
+      for (int i = 0; i < nov; i++) {
+        Ctx vc = make_ctx();
+        vc.actor = vc.target = (uint16_t)slot;
+        uint32_t enc = (uint32_t)eval_value(w, MG_DEPTH, __ldg(cfg + 2 * i + 1), vc, (int)slot);
+        int f = __ldg(cfg + 2 * i);
+        do {  // systems/encoding_utils.hpp:16-35: base-B digits on consecutive feature ids, at least one token
+          if (1 + n < d.OVW) ov[1 + n] = (uint16_t)((f & 0xff) | ((enc % (uint32_t)w.B) << 8));
+          n++, f++;
+          enc /= (uint32_t)w.B;
+        } while (enc > 0);
+      }
+      ov[0] = (uint16_t)min(n, d.OVW - 1);
     }
   }
-  if (lane == 0) {
-    w.gstats[idw] = tw;
-    w.gstats[idf] = tf;
-    gstat_touch(w, idw);
-    gstat_touch(w, w.hdr[MGH_GST_TOKENS_DROPPED]);
-    gstat_touch(w, idf);
-  }
+  __syncwarp();
+  terr_refresh(w, lane);  // the aoe_mask tokens read the ownership map
 }
-
 
 // =================================================================================================
 // k_reset: the constructor.  Objects get ids 1.. in row-major map order, agents get ids in
@@ -698,7 +744,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
     if (w.hdr[MGH_NUM_MQ] > 0) {  // QuerySystem::compute_all (core/query_system.cpp:91-114)
       Ctx g = make_ctx();
       const int32_t* mq = sec(w, MGS_MQ);
-      for (int i = 0; i < w.hdr[MGH_NUM_MQ]; i++) recompute_mq<MG_DEPTH>(w, __ldg(mq + 2 * i), g, false);
+      for (int i = 0; i < w.hdr[MGH_NUM_MQ]; i++) recompute_mq(w, MG_DEPTH, __ldg(mq + 2 * i), g, false);
     }
   }
   __syncwarp();
@@ -761,12 +807,11 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
     d.rewards[gi] = 0.0f;
   }
   __syncwarp();
-  terr_refresh(w, lane);
-  observe_all(w, s, lane, true);
+  hand_over(d, w, s, env, lane, true);  // k_observe + k_finish follow in the same stream
 }
 
 // =================================================================================================
-// k_step: one tick for every environment
+// k_world: phases 1-12 of one tick for every environment
 // =================================================================================================
 #define MGR_ACTED_P 1u
 #define MGR_OK_P 2u
@@ -814,7 +859,7 @@ __device__ __noinline__ bool do_action(const Wv& w, int slot, int kind, int arg)
       ctx.tc = tc;
       ctx.distance = i;
       ctx.move_dir = arg;
-      if (handler_apply<MG_DEPTH>(w, mh.x, ctx)) return true;
+      if (handler_apply(w, MG_DEPTH, mh.x, ctx)) return true;
       break;
     }
   }
@@ -1032,12 +1077,12 @@ __device__ __forceinline__ void on_tick_one(const Wv& w, const Smem& s, int a) {
   if (h >= 0) {
     Ctx c = make_ctx();
     c.actor = c.target = slot;
-    handler_apply<MG_DEPTH>(w, h, c);
+    handler_apply(w, MG_DEPTH, h, c);
   }
 }
 
 template <bool PLAIN>
-__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_step(MgDev d) {
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_world(MgDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   MG_PHASE_BEGIN();
@@ -1192,7 +1237,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
       const int gh = w.hdr[MGH_GAME_ON_TICK];
       if (gh >= 0) {
         Ctx c = make_ctx();
-        handler_apply<MG_DEPTH>(w, gh, c);
+        handler_apply(w, MG_DEPTH, gh, c);
       }
     }
   }
@@ -1222,33 +1267,84 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
   }
   __syncwarp();
 
-  // phase 13: observations
-  if (!PLAIN) terr_refresh(w, lane);  // the aoe_mask tokens read the ownership map
   MG_PHASE(5);
-  observe_all(w, s, lane, false);
-  MG_PHASE(6);
+  // phases 13-15 (observations, rewards, truncation) run in k_observe (one warp per agent) and k_finish
+  rng_window_commit(w, lane);
+  if (lane == 0) w.E[MGEV_STEP] = (int32_t)w.step;
+  hand_over(d, w, s, env, lane, false);
+  MG_PHASE(7);
+}
 
-  // phase 14-15: rewards (systems/reward.hpp:56-77), episode rewards, truncation (:1070-1096)
+// =================================================================================================
+// k_finish: what the reference does after the observation pass (:640-661,1062-1096), one warp per env: the env's
+// token stats in agent order, rewards (systems/reward.hpp:56-77), episode rewards, truncation / termination.
+// =================================================================================================
+template <bool PLAIN>
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_finish(MgDev d, const uint8_t* __restrict__ mask, int initial) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (mask) {
+    const int e = blockIdx.x * MG_WARPS_PER_CTA + warp;
+    if (!__syncthreads_or(e < d.num_envs && mask[e])) return;
+  }
+  {
+    Smem cta;
+    carve(d, smem_raw, warp, cta);
+    load_cta_tables(d, cta);
+  }
+  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  if (env >= d.num_envs) return;
+  if (mask && !mask[env]) return;
+  Smem s0;
+  carve(d, smem_raw, warp, s0);
+  publish_warp(d, s0, env, lane);
+  Wv& w = *s0.wv;
+  const int A = w.A;
+  const size_t g0 = (size_t)env * A;
+  if (lane == 0) {
+    // token stats: one float add per agent in agent order like the reference (:659-661)
+    const int idw = w.hdr[MGH_GST_TOKENS_WRITTEN], idf = w.hdr[MGH_GST_TOKENS_FREE];
+    float tw = w.gstats[idw], tf = w.gstats[idf];
+    for (int a = 0; a < A; a++) {
+      const int attempted = d.tok_attempted[g0 + a];
+      if (attempted > w.T) {  // hard error in the reference (:364-375)
+        set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
+      } else {
+        tw = __fadd_rn(tw, (float)attempted);
+        tf = __fadd_rn(tf, (float)(w.T - attempted));
+      }
+    }
+    w.gstats[idw] = tw;
+    w.gstats[idf] = tf;
+    gstat_touch(w, idw);
+    gstat_touch(w, w.hdr[MGH_GST_TOKENS_DROPPED]);
+    gstat_touch(w, idf);
+  }
+  if (initial) return;
+  __syncwarp();
+  // rewards (systems/reward.hpp:56-77), episode rewards, truncation (:1070-1096), one lane per agent
   const int ms = w.hdr[MGH_MAX_STEPS];
   const bool done = ms > 0 && w.step >= (uint32_t)ms;
   for (int a = lane; a < A; a += 32) {
     uint32_t* ag = w.agents + a * w.AS;
-    const int slot = (int)s.a_slot[a];
-    const int32_t* tp = tmpl(w, o_tmpl(objp(w, slot)));
-    const int nr = PLAIN ? 0 : __ldg(tp + MGT_REWARDS_N);
     float reward = 0.0f;
-    if (nr > 0) {
-      const int32_t* rw = pool(w, __ldg(tp + MGT_REWARDS));
-      float total = 0.0f;
-      Ctx rc = make_ctx();
-      rc.actor = rc.target = slot;
-      for (int i = 0; i < nr; i++) {
-        const float v = eval_value<MG_DEPTH>(w, __ldg(rw + 2 * i), rc, slot);
-        const float prevv = __uint_as_float(ag[MGAG_REWARD_PREV + i]);
-        total = __ldg(rw + 2 * i + 1) ? __fadd_rn(total, v) : __fadd_rn(total, __fsub_rn(v, prevv));
-        ag[MGAG_REWARD_PREV + i] = __float_as_uint(v);
+    if (!PLAIN) {
+      const int slot = (int)ag[MGAG_OBJ];
+      const int32_t* tp = tmpl(w, o_tmpl(objp(w, slot)));
+      const int nr = __ldg(tp + MGT_REWARDS_N);
+      if (nr > 0) {
+        const int32_t* rw = pool(w, __ldg(tp + MGT_REWARDS));
+        float total = 0.0f;
+        Ctx rc = make_ctx();
+        rc.actor = rc.target = (uint16_t)slot;
+        for (int i = 0; i < nr; i++) {
+          const float v = eval_value(w, MG_DEPTH, __ldg(rw + 2 * i), rc, slot);
+          const float prevv = __uint_as_float(ag[MGAG_REWARD_PREV + i]);
+          total = __ldg(rw + 2 * i + 1) ? __fadd_rn(total, v) : __fadd_rn(total, __fsub_rn(v, prevv));
+          ag[MGAG_REWARD_PREV + i] = __float_as_uint(v);
+        }
+        if (total != 0.0f) reward = __fadd_rn(0.0f, total);
       }
-      if (total != 0.0f) reward = __fadd_rn(0.0f, total);
     }
     d.rewards[g0 + a] = reward;
     ag[MGAG_EPISODE_REWARD] = __float_as_uint(__fadd_rn(__uint_as_float(ag[MGAG_EPISODE_REWARD]), reward));
@@ -1259,9 +1355,6 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_s
         d.terminals[g0 + a] = 1;
     }
   }
-  rng_window_commit(w, lane);
-  if (lane == 0) w.E[MGEV_STEP] = (int32_t)w.step;
-  MG_PHASE(7);
 }
 
 // Agent::set_inventory (objects/agent.cpp:86-104) for one agent of one env: a single warp, lane 0 works
@@ -1283,10 +1376,10 @@ __global__ void k_set_inventory(MgDev d, int env, int agent, const int32_t* __re
   const uint64_t existing = o_order(o);
   for (int i = 0; i < ord_count(existing); i++) {
     const int it = ord_item(existing, i);
-    inv_update<2>(w, o, it, -(int)o_inv(w, o)[it]);
+    inv_update(w, 2, o, it, -(int)o_inv(w, o)[it]);
     astat_set(w, agent, __ldg(sec(w, MGS_RES_STATS) + it * 4 + 2), 0.0f);
   }
-  for (int i = 0; i < n; i++) inv_update<2>(w, o, items[i], amounts[i] - (int)o_inv(w, o)[items[i]]);
+  for (int i = 0; i < n; i++) inv_update(w, 2, o, items[i], amounts[i] - (int)o_inv(w, o)[items[i]]);
 }
 
 }  // namespace
@@ -1316,33 +1409,61 @@ cudaError_t mg_launch_clear_outputs(const MgDev& d, const uint8_t* mask, cudaStr
 // ---- host-side launchers (used by mg_capi.cu) --------------------------------------------------
 size_t mg_smem_bytes(const MgDev& d) { return smem_per_cta(d.NOFF) + (size_t)MG_WARPS_PER_CTA * smem_per_warp(d.stage_grid ? d.HWp : 0, d.T, d.A); }
 
+template <class K>
+static cudaError_t set_smem(K k, size_t bytes) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+
 cudaError_t mg_configure_kernels(const MgDev& d) {
-  size_t bytes = mg_smem_bytes(d);
+  const size_t bytes = mg_smem_bytes(d), obytes = obs_smem_bytes(d.NOFF, d.T);
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_init_buffers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_reset, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_init_buffers, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_world<false>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_world<true>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_finish<false>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_finish<true>, bytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_observe<false, 4>, obytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_observe<false, 8>, obytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_observe<true, 4>, obytes)) != cudaSuccess) return e;
+  if ((e = set_smem(k_observe<true, 8>, obytes)) != cudaSuccess) return e;
   // leave room for MG_MIN_CTAS_PER_SM CTAs' shared memory; the rest of the 256 KB stays L1
   int want_kb = (int)((bytes + 1024) * MG_MIN_CTAS_PER_SM / 1024) + 8;
   int pct = want_kb * 100 / 228 + 1;
   if (pct > 100) pct = 100;
-  if ((e = cudaFuncSetAttribute(k_step<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  if ((e = cudaFuncSetAttribute(k_world<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_world<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 static inline int mg_grid(const MgDev& d) { return (d.num_envs + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
+// the observation pass + what follows it, for a tick (initial = 0) or for _init_buffers (initial = 1)
+static cudaError_t launch_observe_finish(const MgDev& d, const uint8_t* mask, int initial, cudaStream_t st) {
+  const long long rows = (long long)d.num_envs * d.A;
+  const unsigned grid = (unsigned)((rows + MG_OBS_WARPS - 1) / MG_OBS_WARPS);
+  const size_t ob = obs_smem_bytes(d.NOFF, d.T);
+  const bool plain = d.plain || (d.NTERR == 0 && d.OVW == 0);
+  if (d.NOFF <= 128) {
+    if (plain) k_observe<true, 4><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
+    else k_observe<false, 4><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
+  } else {
+    if (plain) k_observe<true, 8><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
+    else k_observe<false, 8><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
+  }
+  if (d.plain)
+    k_finish<true><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask, initial);
+  else
+    k_finish<false><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask, initial);
+  return cudaGetLastError();
+}
 cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
   k_reset<<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask);
   return cudaGetLastError();
 }
 cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st) {
   k_init_buffers<<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask);
-  return cudaGetLastError();
+  return launch_observe_finish(d, mask, 1, st);
 }
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st) {
   if (d.plain)
-    k_step<true><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
+    k_world<true><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
   else
-    k_step<false><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
-  return cudaGetLastError();
+    k_world<false><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d);
+  return launch_observe_finish(d, nullptr, 0, st);
 }

@@ -46,6 +46,11 @@ struct MgDev {
   uint32_t* rng_seeded;       // [N][626] freshly seeded state of each env + the seed it came from + valid flag (k_reset)
   int32_t* env;               // [N][MGEV_WORDS]
   uint8_t* success;           // [N][A]
+  // hand-over from k_world / k_init_buffers to k_observe and k_finish (mg_kernels.cu)
+  uint4* obs_in;              // [N][A] executed action, start-of-tick location, location, object slot
+  int32_t* tok_attempted;     // [N][A] tokens each agent's row attempted (k_finish adds the env's token stats in order)
+  uint16_t* obsval;           // [N][A][OVW] word 0 = count, then (feature | value << 8) tokens of the configured global values
+  int OVW;                    // 0 when the program has no global observation values
   const float* logtab;        // logf(k + 1), k in [0, 65536), from the host libm
   // world systems (queries / AOE / territory / tags); sizes are 0 when the program does not use them
   uint16_t* arena;            // [N][ARENA] scratch for query result lists (stack discipline)

@@ -10,7 +10,7 @@ __device__ __noinline__ int event_execute(const Wv& w, int ev, int depth) {
   const int maxt = __ldg(e + 1), f0 = __ldg(e + 2), fn = __ldg(e + 3), m0 = __ldg(e + 4), mn = __ldg(e + 5);
   Ctx g = make_ctx();
   int mark = arena_top(w);
-  QList q = query_eval<MG_DEPTH>(w, __ldg(e), g);
+  QList q = query_eval(w, MG_DEPTH, __ldg(e), g);
   if (maxt >= 0 && q.n > maxt) rng_shuffle(w, q.p, q.n);
   int applied = 0;
   for (int i = 0; i < q.n; i++) {
@@ -20,8 +20,8 @@ __device__ __noinline__ int event_execute(const Wv& w, int ev, int depth) {
     c.actor = c.target = t;
     const uint32_t* o = objp(w, t);
     c.tr = o_r(o), c.tc = o_c(o);
-    if (!filters_pass<MG_DEPTH>(w, f0, fn, c)) continue;
-    for (int k = 0; k < mn; k++) mutate<MG_DEPTH>(w, m0 + k, c);
+    if (!filters_pass(w, MG_DEPTH, f0, fn, c)) continue;
+    for (int k = 0; k < mn; k++) mutate(w, MG_DEPTH, m0 + k, c);
     applied++;
   }
   arena_set(w, mark);
@@ -118,7 +118,7 @@ __device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag, const uint32_t
     Ctx c = base;
     c.actor = (int)s[0];
     const bool skip_self = !__ldg(a + 2) && (int)s[0] == target;
-    const bool now = !skip_self && filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c);
+    const bool now = !skip_self && filters_pass(w, MG_DEPTH, __ldg(a + 3), __ldg(a + 4), c);
     const bool was = aoe_inside(s, ag);
     if (now && !was) {
       aoe_set_inside(s, ag, true);
@@ -130,13 +130,13 @@ __device__ __noinline__ void aoe_apply_fixed(const Wv& w, int ag, const uint32_t
     if (now && mn > 0) {  // AOESource::try_apply re-checks the filters, then applies every mutation
       Ctx c2 = base;
       c2.actor = (int)s[0];
-      if (filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c2))
-        for (int i = 0; i < mn; i++) mutate<MG_DEPTH>(w, __ldg(a + 5) + i, c2);
+      if (filters_pass(w, MG_DEPTH, __ldg(a + 3), __ldg(a + 4), c2))
+        for (int i = 0; i < mn; i++) mutate(w, MG_DEPTH, __ldg(a + 5) + i, c2);
     }
   }
   for (int i = 0; i < df.n; i++) {
     int rid = df.order[i];
-    if (df.delta[rid] != 0) inv_update<2>(w, objp(w, target), rid, df.delta[rid]);
+    if (df.delta[rid] != 0) inv_update(w, 2, objp(w, target), rid, df.delta[rid]);
   }
 }
 // one mobile source against one agent (aoe_tracker.cpp:364-415)
@@ -158,7 +158,7 @@ __device__ __forceinline__ void aoe_mobile_one(const Wv& w, uint32_t* s, const i
   Ctx c = make_ctx();
   c.actor = so;
   c.target = t;
-  const bool now = filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c);
+  const bool now = filters_pass(w, MG_DEPTH, __ldg(a + 3), __ldg(a + 4), c);
   if (now) {
     if (!was) {
       aoe_set_inside(s, ag, true);
@@ -168,8 +168,8 @@ __device__ __forceinline__ void aoe_mobile_one(const Wv& w, uint32_t* s, const i
       Ctx c2 = make_ctx();
       c2.actor = so;
       c2.target = t;
-      if (filters_pass<MG_DEPTH>(w, __ldg(a + 3), __ldg(a + 4), c2))
-        for (int i = 0; i < mn; i++) mutate<MG_DEPTH>(w, __ldg(a + 5) + i, c2);
+      if (filters_pass(w, MG_DEPTH, __ldg(a + 3), __ldg(a + 4), c2))
+        for (int i = 0; i < mn; i++) mutate(w, MG_DEPTH, __ldg(a + 5) + i, c2);
     }
   } else if (was) {
     aoe_set_inside(s, ag, false);
@@ -360,8 +360,8 @@ __device__ __noinline__ void terr_run(const Wv& w, int ti, int list_off, int n, 
     Ctx c = make_ctx();
     c.actor = px;
     c.target = target;
-    if (filters_pass<MG_DEPTH>(w, __ldg(hd + 1), __ldg(hd + 2), c))
-      for (int k = 0; k < __ldg(hd + 4); k++) mutate<MG_DEPTH>(w, __ldg(hd + 3) + k, c);  // no mutation_failed check
+    if (filters_pass(w, MG_DEPTH, __ldg(hd + 1), __ldg(hd + 2), c))
+      for (int k = 0; k < __ldg(hd + 4); k++) mutate(w, MG_DEPTH, __ldg(hd + 3) + k, c);  // no mutation_failed check
   }
 }
 __device__ __noinline__ void terr_apply(const Wv& w, int ag) {

@@ -91,7 +91,65 @@ class _Lower:
             for v in gv.values:
                 c.add_value(self.value(v))
             return c
+        if kind == "QueryInventoryValue":
+            c = m.QueryInventoryValueConfig()
+            c.id = b.rid[gv.item]
+            c.set_query(self.query(gv.query))
+            return c
+        if kind == "QueryCountValue":
+            c = m.QueryCountValueConfig()
+            c.set_query(self.query(gv.query))
+            return c
         raise RefUnsupported(f"game value {kind}")
+
+    # -- queries (mettagrid_c_config.py:83-186) ------------------------------------------------------
+    def _max_items(self, q, cq):
+        mi = getattr(q, "max_items", None)
+        if mi is not None:
+            cq.max_items = self.value(float(mi) if isinstance(mi, int) else mi)
+        if getattr(q, "order_by", None) == "random":
+            cq.order_by = self.m.QueryOrderBy.random
+
+    def query(self, q):
+        m, b = self.m, self.b
+        if isinstance(q, str):
+            from mettagrid_b200.config import Query  # noqa: PLC0415
+
+            return self.query(Query(source=q))
+        qt = getattr(q, "query_type", "query")
+        if qt == "materialized":
+            from mettagrid_b200.config import Query  # noqa: PLC0415
+
+            return self.query(Query(source=q.tag))
+        if qt == "closure":
+            cq = m.ClosureQueryConfig()
+            cq.set_source(self.query(q.source))
+            cq.set_candidates(self.query(q.candidates))
+            self._max_items(q, cq)
+            self.add_filters(cq, q.edge_filters, prefix="edge_")
+            self.add_filters(cq, q.filters, prefix="result_")
+            return m.make_query_config(cq)
+        if qt == "raycast":
+            dirs = {"north": (-1, 0), "south": (1, 0), "east": (0, 1), "west": (0, -1)}
+            cq = m.RaycastQueryConfig()
+            cq.max_range = self.value(float(q.max_range) if isinstance(q.max_range, int) else q.max_range)
+            cq.include_blocker = bool(q.include_blocker)
+            cq.directions = [dirs[d] for d in q.directions]
+            self._max_items(q, cq)
+            cq.set_source(self.query(q.source))
+            self.add_filters(cq, q.blocker, prefix="blocker_")
+            return m.make_query_config(cq)
+        if not isinstance(q.source, str):
+            cq = m.FilteredQueryConfig()
+            cq.set_source(self.query(q.source))
+            self._max_items(q, cq)
+            self.add_filters(cq, q.filters)
+            return m.make_query_config(cq)
+        cq = m.TagQueryConfig()
+        cq.tag_id = b.tid[q.source]
+        self._max_items(q, cq)
+        self.add_filters(cq, q.filters)
+        return m.make_query_config(cq)
 
     # -- filters -----------------------------------------------------------------------------------
     def add_filters(self, target, filters, prefix=""):
@@ -136,11 +194,16 @@ class _Lower:
         if ft == "shared_tag_prefix":
             return [("shared_tag_prefix", m.SharedTagPrefixFilterConfig(tag_ids=b.prefix_tags(f.tag_prefix)))]
         if ft == "max_distance":
-            if f.query is not None:
-                raise RefUnsupported("max_distance with a query")
             c = m.MaxDistanceFilterConfig()
             c.entity, c.radius = self.ent(f.target), int(f.radius)
+            if f.query is not None:
+                c.set_source(self.query(f.query))
             return [("max_distance", c)]
+        if ft == "query_resource":
+            c = m.QueryResourceFilterConfig()
+            c.set_query(self.query(f.query))
+            c.requirements = [(b.rid[r], int(v)) for r, v in f.requirements.items()]
+            return [("query_resource", c)]
         if ft == "game_value":
             mn = f.min
             return [("game_value", m.GameValueFilterConfig(value=self.value(f.value),
@@ -196,8 +259,75 @@ class _Lower:
                 target.add_push_object_mutation(m.PushObjectMutationConfig())
             elif mt == "attack":
                 continue  # dropped by the reference's Python lowering
+            elif mt == "add_tag":
+                target.add_add_tag_mutation(m.AddTagMutationConfig(entity=self.ent(mu.target), tag_id=b.tid[mu.tag]))
+            elif mt == "remove_tag":
+                target.add_remove_tag_mutation(m.RemoveTagMutationConfig(entity=self.ent(mu.target), tag_id=b.tid[mu.tag]))
+            elif mt == "remove_tags_with_prefix":
+                target.add_remove_tags_with_prefix_mutation(
+                    m.RemoveTagsWithPrefixMutationConfig(entity=self.ent(mu.target), tag_ids=b.prefix_tags(mu.prefix)))
+            elif mt == "recompute_materialized_query":
+                for tg in b.prefix_tags(mu.tag_prefix):
+                    c = m.RecomputeMaterializedQueryMutationConfig()
+                    c.tag_id = tg
+                    target.add_recompute_materialized_query_mutation(c)
+            elif mt == "query_inventory":
+                c = m.QueryInventoryMutationConfig()
+                c.set_query(self.query(mu.query))
+                c.deltas = [(b.rid[r], int(d)) for r, d in mu.deltas.items()]
+                if mu.source is not None:
+                    c.source, c.has_source = self.ent(mu.source), True
+                if mu.transfer_stats:
+                    c.transfer_stat_names = [(b.rid[r], sname) for r, sname in mu.transfer_stats.items()]
+                target.add_query_inventory_mutation(c)
+            elif mt == "spawn_object":
+                c = m.SpawnObjectMutationConfig()
+                c.object_type = mu.object_type
+                target.add_spawn_object_mutation(c)
+            elif mt == "raycast_spawn":
+                dirs = {"north": (-1, 0), "south": (1, 0), "east": (0, 1), "west": (0, -1)}
+                c = m.RaycastSpawnMutationConfig()
+                c.object_type = mu.object_type
+                c.max_range = self.value(float(mu.max_range) if isinstance(mu.max_range, int) else mu.max_range)
+                c.directions = [dirs[d] for d in mu.directions]
+                self.add_filters(c, mu.blocker, prefix="blocker_")
+                target.add_raycast_spawn_mutation(c)
             else:
                 raise RefUnsupported(f"mutation {mt}")
+
+    # -- AOE / territory / tag handlers (mettagrid_c_config.py:452-545) ----------------------------------
+    def aoe_configs(self, aoes):
+        out = []
+        for a in (aoes or {}).values():
+            c = self.m.AOEConfig()
+            c.radius, c.is_static, c.effect_self = int(a.radius), bool(a.is_static), bool(a.effect_self)
+            self.add_filters(c, a.filters)
+            self.add_mutations(c, a.mutations)
+            c.presence_deltas = [self.m.ResourceDelta(self.b.rid[r], int(d)) for r, d in a.presence_deltas.items()]
+            out.append(c)
+        return out
+
+    def territory_controls(self, controls, index):
+        out = []
+        for tc in controls or []:
+            c = self.m.TerritoryControlConfig()
+            c.strength, c.decay, c.territory_index = int(tc.strength), int(tc.decay), index[tc.territory]
+            out.append(c)
+        return out
+
+    def tag_remove_handlers(self, cfg, handlers):
+        for prefix, h in (handlers or {}).items():
+            hc = self.handler_config(h, prefix)
+            for tg in self.b.prefix_tags(prefix):
+                cfg.add_on_tag_remove_handler(tg, hc)
+
+    def world_extras(self, cfg_obj, src, terr_index):
+        if src.aoes:
+            cfg_obj.aoe_configs = self.aoe_configs(src.aoes)
+        if src.territory_controls:
+            cfg_obj.territory_controls = self.territory_controls(src.territory_controls, terr_index)
+        if src.on_tag_remove:
+            self.tag_remove_handlers(cfg_obj, src.on_tag_remove)
 
     def handler_config(self, h, name):
         hc = self.m.HandlerConfig(name)
@@ -223,8 +353,7 @@ class _Lower:
     # -- the whole game ----------------------------------------------------------------------------
     def game_config(self):
         m, b, g = self.m, self.b, self.g
-        if g.territories or g.events or g.materialize_queries or g.obs.global_obs.obs:
-            raise RefUnsupported("territories / events / materialized queries / obs values")
+        terr_index = {name: i for i, name in enumerate(g.territories.keys())}
         objects = {}
         team_groups: dict[int, list] = {}
         for a in b.agent_cfgs:
@@ -235,8 +364,6 @@ class _Lower:
             canonical = f"agent.{gname}"
             per_agent = []
             for idx, a in enumerate(members):
-                if a.aoes or a.territory_controls or a.on_tag_remove:
-                    raise RefUnsupported("agent AOEs / territory controls / tag handlers")
                 defs, configured = [], set()
                 for lim in a.inventory.limits.values():
                     defs.append(([b.rid[n] for n in lim.resources], lim.base, lim.max,
@@ -261,6 +388,7 @@ class _Lower:
                 ac.on_tick = self.any_handler(a.on_tick)
                 ac.on_use_handler = self.any_handler(a.on_use_handler)
                 ac.on_after_use_handler = self.any_handler(a.on_after_use_handler)
+                self.world_extras(ac, a, terr_index)
                 cell = f"{canonical}.{idx}"
                 objects[cell] = ac
                 per_agent.append(cell)
@@ -281,8 +409,6 @@ class _Lower:
                 if canonical in renames:
                     renames[al] = renames[canonical]
         for _key, oc in g.objects.items():
-            if oc.aoes or oc.territory_controls or oc.on_tag_remove:
-                raise RefUnsupported("object AOEs / territory controls / tag handlers")
             tid = b.type_id[oc.name]
             if getattr(oc, "pydantic_type", "object") == "wall":
                 cc = m.WallConfig(type_id=tid, type_name=oc.name, initial_vibe=int(oc.vibe))
@@ -306,13 +432,14 @@ class _Lower:
                     cc.inventory_config = ic
             cc.tag_ids = [b.tid[n] for n in list(oc.tags) + [f"type:{oc.name}"]]
             cc.on_use_handler = self.any_handler(oc.on_use_handler)
+            self.world_extras(cc, oc, terr_index)
             objects[oc.map_name] = cc
 
         gobs = g.obs.global_obs
         global_obs = m.GlobalObsConfig(
             episode_completion_pct=gobs.episode_completion_pct, last_action=gobs.last_action,
             last_action_move=gobs.last_action_move, last_reward=gobs.last_reward, goal_obs=gobs.goal_obs,
-            local_position=gobs.local_position, obs=[])  # fmt: skip
+            local_position=gobs.local_position, obs=self.obs_values(gobs.obs))  # fmt: skip
         mv = g.actions.move
         move_kw = dict(allowed_directions=list(mv.allowed_directions), required_resources={}, consumed_resources={})
         if mv.handlers:
@@ -330,8 +457,52 @@ class _Lower:
             vibe_names=list(b.vibes), num_observation_tokens=int(g.obs.num_tokens), global_obs=global_obs,
             feature_ids=dict(b.feature_ids), actions=actions, objects=objects,
             tag_id_map={i: n for i, n in enumerate(b.tag_names)}, protocol_details_obs=bool(g.protocol_details_obs),
-            token_value_base=int(g.obs.token_value_base), on_tick=self.any_handler(g.on_tick))  # fmt: skip
+            token_value_base=int(g.obs.token_value_base), on_tick=self.any_handler(g.on_tick), **self.game_extras(terr_index))  # fmt: skip
         return cfg, renames
+
+    def obs_values(self, obs):
+        out = []
+        for fname, gv in (obs or {}).items():
+            c = self.m.ObsValueConfig()
+            c.value, c.feature_id = self.value(gv), self.b.feature_ids[fname]
+            out.append(c)
+        return out
+
+    def game_extras(self, terr_index):
+        """territories / events / materialized queries (mettagrid_c_config.py:428-445,503-525,983-1002)"""
+        m, b, g = self.m, self.b, self.g
+        kw = {}
+        if g.territories:
+            terrs = [m.TerritoryConfig() for _ in terr_index]
+            for name, tc in g.territories.items():
+                c = terrs[terr_index[name]]
+                c.tag_prefix_ids = b.prefix_tags(tc.tag_prefix)
+                ctx = f"territory '{name}'"
+                c.on_enter = [self.handler_config(h, f"{ctx}.on_enter.{k}") for k, h in tc.on_enter.items()]
+                c.on_exit = [self.handler_config(h, f"{ctx}.on_exit.{k}") for k, h in tc.on_exit.items()]
+                c.presence = [self.handler_config(h, f"{ctx}.presence.{k}") for k, h in tc.presence.items()]
+            kw["territories"] = terrs
+        if g.events:
+            evs = {}
+            for name, ev in g.events.items():
+                c = m.EventConfig(ev.name)
+                c.timesteps = [int(t) for t in ev.timesteps]
+                c.max_targets = -1 if ev.max_targets is None else int(ev.max_targets)
+                c.fallback = ev.fallback or ""
+                c.set_target_query(self.query(ev.target_query))
+                self.add_filters(c, ev.filters)
+                self.add_mutations(c, ev.mutations)
+                evs[name] = c
+            kw["events"] = evs
+        mqs = []
+        for mq in g.materialize_queries:
+            c = m.MaterializedQueryTag()
+            c.tag_id = b.tid[mq.tag]
+            c.set_query(self.query(mq.query))
+            mqs.append(c)
+        if mqs:
+            kw["materialized_queries"] = mqs
+        return kw
 
 
 def rename_agents(grid: np.ndarray, renames: dict[str, list[str]]) -> list[list[str]]:

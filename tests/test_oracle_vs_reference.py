@@ -100,3 +100,38 @@ def test_ref_driver_agrees_with_reference_lowering(reference_pkg):
         b.step(prim[t], vibe[t])
         assert np.array_equal(a.observations(), b.observations()) and np.array_equal(a.rewards(), b.rewards())
     assert a.get_episode_stats() == b.get_episode_stats()
+
+
+@pytest.mark.parametrize("game", ["world", "network", "beam_chain", "event_targets", "many_tagged"])
+def test_ref_driver_agrees_with_reference_lowering_on_world_systems(reference_pkg, game):
+    """The driver's pybind configs for AOE / territory / events / queries / tag handlers / spawn (what bench.py's C4
+    cpu_baseline runs on the GPU box) give the same trajectories as the reference's own Python lowering."""
+    from mettagrid.config.mettagrid_c_config import convert_to_cpp_game_config, rename_map_agents
+    from mettagrid.mettagrid_c import MettaGrid
+
+    from mettagrid_b200 import config as C
+    from oracle.ref_driver import RefEnv
+    from tests import edge_cases as ec, refns
+
+    ns = refns.reference_namespace()
+    mk, grid, nprim = {
+        "world": (lambda n: cases.world_config(n, 3), cases.world_map(3, seed=8), 9),
+        "network": (lambda n: cases.network_config(n, 4), cases.network_map(4, seed=8), 5),
+        "beam_chain": (lambda n: ec.beam_chain_config(n if n is not None else C), ec.beam_chain_map(8), 5),
+        "event_targets": (lambda n: ec.event_targets_config(n if n is not None else C), ec.event_targets_map(8), 5),
+        "many_tagged": (lambda n: ec.many_tagged_config(n if n is not None else C), ec.many_tagged_map(8), 5),
+    }[game]
+    c_cfg, renames = convert_to_cpp_game_config(mk(ns).game)
+    a = MettaGrid(c_cfg, rename_map_agents(grid.tolist(), renames), 8)
+    b = RefEnv(mk(None), grid, 8)
+    A = a.observations().shape[0]
+    na = len(compile_config(mk(None), *grid.shape).action_names)
+    prim, vibe = cases.random_actions(np.random.RandomState(8), 250, (A,), nprim, na, 0.2)
+    assert np.array_equal(a.observations(), b.observations())
+    for t in range(250):
+        a.actions()[:] = prim[t]
+        a.vibe_actions()[:] = vibe[t]
+        a.step()
+        b.step(prim[t], vibe[t])
+        assert np.array_equal(a.observations(), b.observations()) and np.array_equal(a.rewards(), b.rewards()), f"{game}: step {t}"
+    assert a.get_episode_stats() == b.get_episode_stats()
