@@ -104,6 +104,15 @@ int mg_vecenv_configure(mg_handle* h, int num_primary, const int32_t* vibe_actio
 int mg_vecenv_step(mg_handle* h, const void* actions, int is_int64, int ncols, int auto_reset, void* stream);
 int mg_vecenv_poll(mg_handle* h, int* episodes_finished, int* error_bits);
 
+/* step_info_keys (next row 8f-2): replaces MettaGridPufferEnv._build_step_info_payload --
+ * python/src/mettagrid/envs/mettagrid_puffer_env.py:132-282 -- whose per-step get_game_stat / get_agent_stat calls a
+ * batch cannot afford.  mg_info_configure fixes the stats to export: game stat ids (-1 = attributes/steps) and agent
+ * stat ids (-1 = reward_step, -2 = reward_episode); mg_info_gather writes, asynchronously on `stream`, float32
+ * [N][n_game] + uint8 presence and float32 [N][A][n_agent] + uint8 presence (all DEVICE; "present" = the reference's
+ * "value is not None": the stat was touched this episode). */
+int mg_info_configure(mg_handle* h, int n_game, const int32_t* game_stat_ids, int n_agent, const int32_t* agent_stat_ids);
+int mg_info_gather(mg_handle* h, void* game_values, void* game_present, void* agent_values, void* agent_present, void* stream);
+
 /* Dense grid observations (next row 8f-3): replaces GridObsWrapper._convert --
  * python/src/mettagrid/envs/grid_obs_wrapper.py:33-96.  mg_grid_obs_configure fixes the number of feature planes C
  * (max feature id + 1) and the per-feature normalisation (host float[256], entries < 1 are raised to 1 like the

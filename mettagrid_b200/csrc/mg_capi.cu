@@ -31,6 +31,9 @@ cudaError_t mg_launch_vecenv_prepare(const void* act, int is_int64, int ncols, i
                                      const int32_t* vibe_ids, int32_t* actions, int32_t* vibe_actions, const uint8_t* term,
                                      const uint8_t* trunc, uint8_t* done, int64_t* steps, int* counters, cudaStream_t st);
 cudaError_t mg_launch_vecenv_post(int num_envs, int A, int64_t* steps, int64_t* early, uint8_t* trunc, cudaStream_t st);
+cudaError_t mg_launch_gather_info(const MgDev& d, int packed, int G, int n_game, const int32_t* game_ids, int n_agent,
+                                  const int32_t* agent_ids, int idw, int idd, int idf, float* game_out, uint8_t* game_present,
+                                  float* agent_out, uint8_t* agent_present, cudaStream_t st);
 cudaError_t mg_launch_set_inventory(const MgDev& d, int env, int agent, const int32_t* items, const int32_t* amounts, int n,
                                     cudaStream_t st);
 
@@ -72,6 +75,9 @@ struct mg_handle {
   int64_t* ve_steps = nullptr;
   int64_t* ve_early = nullptr;
   int* ve_counters = nullptr;  // [0] episodes finished, [1] decoder error bits
+  int32_t* info_game_ids = nullptr;   // step_info_keys: configured game / agent stat ids on the device
+  int32_t* info_agent_ids = nullptr;
+  int info_ngame = 0, info_nagent = 0;
   float* grid_scale = nullptr;  // device float[256], per-feature normalisation of the dense grid observations
   int grid_features = 0;
   cudaStream_t own_stream = nullptr;
@@ -305,6 +311,29 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   TRY(dev_alloc(h, &d.env, N * MGEV_WORDS));
   TRY(dev_alloc(h, &d.success, N * d.A));
   TRY(dev_alloc(h, &d.obs_in, N * d.A));
+  TRY(dev_alloc(h, &d.claims, N * d.maxobj));
+  memcpy(h->fh.v, P, sizeof h->fh.v);
+  d.hdr_host = &h->fh;
+  {
+    // packed window offsets in the reference's Manhattan order (core/observation_shape.cpp:19-66) -- bits 0-7:
+    // dr + 8 | (dc + 8) << 4; bits 8-15: packed location (packed_coordinate.hpp:50-56); bits 16-31: cell delta in the
+    // padded grid
+    const int32_t* po = P + P[MGS_OFFSETS];
+    const int rr = P[MGH_OBS_H] >> 1, cr = P[MGH_OBS_W] >> 1;
+    std::vector<uint32_t> tab((size_t)d.NOFF);
+    for (int i = 0; i < d.NOFF; i++) {
+      const int dr = po[2 * i], dc = po[2 * i + 1];
+      const uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));
+      tab[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8) | ((uint32_t)((dr * d.WP + dc) & 0xffff) << 16);
+    }
+    uint32_t* dev;
+    TRY(dev_alloc(h, &dev, tab.size()));
+    if (cudaMemcpy(dev, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      h->err = "mg_create: upload failed";
+      return fail(MG_E_CUDA);
+    }
+    d.obs_offs = dev;
+  }
   TRY(dev_alloc(h, &d.tok_attempted, N * d.A));
   {
     // tokens a configured global observation value can take: the base-B digits of a 32-bit value (encoding_utils.hpp:16-35)
@@ -809,6 +838,42 @@ int mg_obs_to_grid(mg_handle* h, const void* observations, int rows, void* grid,
   CK(cudaSetDevice(h->device));
   CK(mg_launch_obs_to_grid(obs, (float*)grid, rows, h->d.T, h->grid_features, h->program[MGH_OBS_H], h->program[MGH_OBS_W],
                            h->grid_scale, (cudaStream_t)stream));
+  return MG_OK;
+}
+
+int mg_info_configure(mg_handle* h, int n_game, const int32_t* game_stat_ids, int n_agent, const int32_t* agent_stat_ids) {
+  if (!h || n_game < 0 || n_agent < 0 || (n_game && !game_stat_ids) || (n_agent && !agent_stat_ids)) return MG_E_INVALID;
+  for (int i = 0; i < n_game; i++)
+    if (game_stat_ids[i] < -1 || game_stat_ids[i] >= h->d.SG) return MG_E_INVALID;
+  for (int i = 0; i < n_agent; i++)
+    if (agent_stat_ids[i] < -2 || agent_stat_ids[i] >= h->d.SA) return MG_E_INVALID;
+  CK(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = dev_alloc(h, &h->info_game_ids, (size_t)(n_game ? n_game : 1))) || (rc = dev_alloc(h, &h->info_agent_ids, (size_t)(n_agent ? n_agent : 1))))
+    return rc;
+  if (n_game) CK(cudaMemcpy(h->info_game_ids, game_stat_ids, (size_t)n_game * 4, cudaMemcpyHostToDevice));
+  if (n_agent) CK(cudaMemcpy(h->info_agent_ids, agent_stat_ids, (size_t)n_agent * 4, cudaMemcpyHostToDevice));
+  h->info_ngame = n_game, h->info_nagent = n_agent;
+  return MG_OK;
+}
+
+int mg_info_gather(mg_handle* h, void* game_values, void* game_present, void* agent_values, void* agent_present, void* stream) {
+  if (!h) return MG_E_INVALID;
+  if ((h->info_ngame && (!game_values || !game_present)) || (h->info_nagent && (!agent_values || !agent_present))) {
+    h->err = "mg_info_gather: an output tensor is missing for the configured keys";
+    return MG_E_INVALID;
+  }
+  if (!h->buffers_set) {
+    h->err = "mg_info_gather: call mg_set_buffers first";
+    return MG_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  const int32_t* P = h->program.data();
+  h->last_stream = (cudaStream_t)stream;
+  CK(mg_launch_gather_info(h->d, h->fast && h->newest == mg_handle::PACKED, h->fl.G, h->info_ngame, h->info_game_ids, h->info_nagent,
+                           h->info_agent_ids, P[MGH_GST_TOKENS_WRITTEN], P[MGH_GST_TOKENS_DROPPED], P[MGH_GST_TOKENS_FREE],
+                           (float*)game_values, (uint8_t*)game_present, (float*)agent_values, (uint8_t*)agent_present,
+                           (cudaStream_t)stream));
   return MG_OK;
 }
 

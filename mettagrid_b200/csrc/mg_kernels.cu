@@ -294,73 +294,63 @@ __device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc,
 // in d.obs_in and the tokens of the configured global game values in d.obsval; from there on an agent's row depends
 // on nothing another agent's row computes -- with one exception, the reference's cell staleness (:787-796):
 // an object's `visited` stamp is advanced by the FIRST agent, in index order, that sees it this tick, and the ticks
-// since go to that agent's cell.visited stat.  "First" is decided without communication: agent a owns an object iff no
-// agent a' < a has it inside its own window, and the warp tests that against the positions of the (few) earlier agents
-// close enough to share cells with a.  Only the owner reads or writes the stamp.
+// since go to that agent's cell.visited stat.  Observers only CLAIM what they see -- one fire-and-forget
+// atomicMax(claim[object], step << 32 | ~agent) each, so the lowest agent of the latest tick wins -- and k_finish, which
+// runs when every row is written, advances the stamps of the objects claimed this tick and credits the winners.
+//
+// The program header travels as a kernel argument (constant bank) and the packed window offsets are a small
+// read-only table (L1-resident), so a CTA has no prologue; blockIdx.y is the environment.
 // =================================================================================================
-#define MG_OBS_WARPS 8
-#ifndef MG_OBS_MIN_CTAS
-#define MG_OBS_MIN_CTAS 3  // 80 registers: 24 resident warps per SM (A/B: profiles/README.md)
+#ifndef MG_OBS_MIN_WARPS
+#define MG_OBS_MIN_WARPS 32  // resident warps per SM the register budget is chosen for (64 registers; A/B: profiles/README.md)
 #endif
+#define MG_OBS_MAX_WARPS 8   // warps (agents) per CTA: the launcher picks a divisor of A when it can
 
-__host__ __device__ inline size_t obs_smem_bytes(int NOFF, int T) {
-  return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4) + 256 + (size_t)MG_OBS_WARPS * align16((size_t)3 * T + 32);
-}
+__host__ __device__ inline size_t obs_smem_bytes(int warps, int T) { return (size_t)warps * align16((size_t)3 * T + 32); }
 
 // NP = window passes of 32 cells whose loads are issued together: 4 (up to 11 x 11 windows) or 8 (up to 15 x 15)
 template <bool PLAIN, int NP>
-__global__ void __launch_bounds__(MG_OBS_WARPS * 32, MG_OBS_MIN_CTAS) k_observe(MgDev d, const uint8_t* __restrict__ mask) {
+__global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_OBS_MAX_WARPS)
+    k_observe(const MgDev d, const MgFastHdr HD, const uint8_t* __restrict__ mask) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* const hdr = (int32_t*)smem_raw;
-  uint32_t* const offs = (uint32_t*)(smem_raw + align16(MGH_HEADER_WORDS * 4));
-  uint8_t* const rank = (uint8_t*)offs + align16((size_t)d.NOFF * 4);
+  const int* const hdr = HD.v;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* const stage0 = rank + 256 + (size_t)warp * align16((size_t)3 * d.T + 32);
+  const int env = blockIdx.y, a = blockIdx.x * (blockDim.x >> 5) + warp;
   const int A = d.A, T = d.T;
-  {
-    const long long g_first = (long long)blockIdx.x * MG_OBS_WARPS, g_last = g_first + MG_OBS_WARPS - 1;
-    if (mask) {  // a masked launch usually selects few environments
-      const int e0 = (int)(g_first / A), e1 = (int)min(g_last / A, (long long)d.num_envs - 1);
-      bool any = false;
-      for (int e = e0; e <= e1; e++) any = any || mask[e];
-      if (!any) return;
-    }
-  }
-  for (int i = threadIdx.x; i < MGH_HEADER_WORDS; i += blockDim.x) hdr[i] = __ldg(d.P + i);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) rank[i] = 0xFF;
-  __syncthreads();
-  {
-    const int32_t* po = d.P + hdr[MGS_OFFSETS];
-    const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
-    for (int i = threadIdx.x; i < d.NOFF; i += blockDim.x) {
-      const int dr = __ldg(po + 2 * i), dc = __ldg(po + 2 * i + 1);
-      const uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));  // systems/packed_coordinate.hpp:50-56
-      // bits 0-7: dr + 8 | (dc + 8) << 4 ; bits 8-15: packed location ; bits 16-31: cell delta in the padded grid
-      offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8) | ((uint32_t)((dr * d.WP + dc) & 0xffff) << 16);
-      rank[loc] = (uint8_t)i;
-    }
-  }
-  __syncthreads();
-  const long long g = (long long)blockIdx.x * MG_OBS_WARPS + warp;
-  if (g >= (long long)d.num_envs * A) return;
-  const int env = (int)(g / A), a = (int)(g - (long long)env * A);
-  if (mask && !mask[env]) return;
+  if (a >= A || (mask && !mask[env])) return;
 
-  const uint4* const oin = d.obs_in + (size_t)env * A;
-  const uint4 me_in = oin[a];  // executed action, start-of-tick location, location, object slot
+  const uint4 me_in = d.obs_in[(size_t)env * A + a];  // executed action, start-of-tick location, location, object slot
   const int r0 = (int)(me_in.z >> 16), c0 = (int)(me_in.z & 0xffffu);
-  int32_t* const E = d.env + (size_t)env * MGEV_WORDS;
-  const uint32_t step = (uint32_t)E[MGEV_STEP];
+  const uint32_t step = (uint32_t)d.env[(size_t)env * MGEV_WORDS + MGEV_STEP];
   uint32_t* const objs = d.objs + (size_t)env * (d.maxobj + d.NPROXY) * d.OS;
   const uint16_t* const centre = d.cells + (size_t)env * d.HWp + (r0 + d.PAD) * d.WP + c0 + d.PAD;
   uint8_t* const g_row = d.obs + ((size_t)env * A + a) * (size_t)(3 * T);
-  uint8_t* const out = stage0 + ((uint32_t)(uintptr_t)g_row & 15u);
+  uint8_t* const out = smem_raw + (size_t)warp * align16((size_t)3 * T + 32) + ((uint32_t)(uintptr_t)g_row & 15u);
   const int OS = d.OS, NOFF = d.NOFF, TOKOFF = MG_TOKOFF(d.TW, d.R);
   const uint32_t lt = (1u << lane) - 1u;
-  const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
-  const int flags = hdr[MGH_GLOBAL_FLAGS];
+
+  // ---- window cells in Manhattan order, 32 per pass (:756-811).  The grid carries an empty frame as wide as the
+  // window radius, so a cell outside the map reads as empty and needs no bounds test.  All cell ids are loaded
+  // first, then the heads of the objects standing there (cached token count, first token pair): two memory round
+  // trips per agent, issued before anything else is computed.
+  uint32_t pk[NP], slot[NP], nt[NP], t0[NP];
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const int k = 32 * p + lane;
+    pk[p] = k < NOFF ? __ldg(d.obs_offs + k) : 0u;
+    slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    nt[p] = t0[p] = 0;
+    if (slot[p]) {
+      const uint32_t* o = objs + (size_t)slot[p] * OS;
+      nt[p] = o[MGO_NTOK], t0[p] = o[TOKOFF];
+    }
+  }
 
   // ---- global tokens (:700-742), one candidate per lane, compacted in order
+  const int flags = hdr[MGH_GLOBAL_FLAGS];
   int feat = 0, val = 0, have = 0;
   if (lane == 0 && (flags & MGG_EPISODE_PCT)) {
     const int ms = hdr[MGH_MAX_STEPS];
@@ -393,97 +383,39 @@ __global__ void __launch_bounds__(MG_OBS_WARPS * 32, MG_OBS_MIN_CTAS) k_observe(
     base += n;
   }
 
-  // ---- earlier agents that can share window cells with this one (cell staleness ownership, see above)
-  uint32_t near_loc = 0xffffffffu;  // lane j < min(a, 32): agent j's location when it is that close
-  if (lane < a) {
-    near_loc = oin[lane].z;
-    const int dr = (int)(near_loc >> 16) - r0, dc = (int)(near_loc & 0xffffu) - c0;
-    if (dr < -2 * rr || dr > 2 * rr || dc < -2 * cr || dc > 2 * cr) near_loc = 0xffffffffu;
-  }
-  const uint32_t near = __ballot_sync(MG_FULL, near_loc != 0xffffffffu);
-  // does an agent with a smaller index see the cell (r, c)?  (uniform loops: every lane asks about its own cell)
-  auto seen_earlier = [&](int r, int c) {
-    bool seen = false;
-    uint32_t m = near;
-    while (m) {
-      const int j = __ffs(m) - 1;
-      m &= m - 1;
-      const uint32_t lj = __shfl_sync(MG_FULL, near_loc, j);
-      const int dr = r - (int)(lj >> 16) + rr, dc = c - (int)(lj & 0xffffu) + cr;
-      if (dr >= 0 && dc >= 0 && dr <= 2 * rr && dc <= 2 * cr && rank[(dr << 4) | dc] != 0xFF) seen = true;
-    }
-    for (int j0 = 32; j0 < a; j0 += 32) {  // more than 32 agents per env: the rest, 32 at a time
-      uint32_t lj = 0xffffffffu;
-      if (j0 + lane < a) lj = oin[j0 + lane].z;
-      for (int j = 0; j < 32 && j0 + j < a; j++) {
-        const uint32_t l2 = __shfl_sync(MG_FULL, lj, j);
-        const int dr = r - (int)(l2 >> 16) + rr, dc = c - (int)(l2 & 0xffffu) + cr;
-        if (dr >= 0 && dc >= 0 && dr <= 2 * rr && dc <= 2 * cr && rank[(dr << 4) | dc] != 0xFF) seen = true;
-      }
-    }
-    return seen;
-  };
-
-  // ---- window cells in Manhattan order, 32 per pass (:756-811).  The grid carries an empty frame as wide as the
-  // window radius, so a cell outside the map reads as empty and needs no bounds test.  All cell ids are loaded
-  // first, then the heads of the objects standing there (visited stamp, cached token count, first token pair):
-  // two memory round trips per agent.  Token positions come from two ballots (an object with one token -- every
-  // wall -- needs no scan); multi-token objects are copied by the whole warp, one token per lane, four at a time.
-  uint32_t stale_sum = 0;
+  // ---- tokens.  Positions come from two ballots (an object with one token -- every wall -- needs no scan);
+  // multi-token objects are copied by the whole warp, one token per lane, four at a time.
   const int fmask = (!PLAIN && d.NTERR > 0) ? hdr[MGH_FEAT_AOE_MASK] : 0;
   const uint32_t* const me = objs + (size_t)me_in.w * OS;
-  const TokCtx tc{d.P, hdr, E, d.TW, d.B, d.ND, TOKOFF};
-  uint32_t pk[NP], slot[NP], nt[NP], t0[NP];
-#pragma unroll
-  for (int p = 0; p < NP; p++) {
-    const int k = 32 * p + lane;
-    pk[p] = k < NOFF ? offs[k] : 0u;
-    slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
-  }
-#pragma unroll
-  for (int p = 0; p < NP; p++) {
-    nt[p] = t0[p] = 0;
-    if (slot[p]) {
-      const uint32_t* o = objs + (size_t)slot[p] * OS;
-      nt[p] = o[MGO_NTOK], t0[p] = o[TOKOFF];
-    }
-  }
+  unsigned long long* const claims = d.claims + (size_t)env * d.maxobj;
+  const unsigned long long my_claim = ((unsigned long long)step << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     if (32 * p >= NOFF) break;
     const int loc = (int)((pk[p] >> 8) & 0xffu);
-    const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
     int tmask = 0, n = 0;
-    if (fmask && 32 * p + lane < NOFF && r >= 0 && c >= 0 && r < d.H && c < d.W) {
+    if (fmask && 32 * p + lane < NOFF) {
       // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens (ownership map: mg_world.cuh)
-      const uint8_t* own = d.owner_map + (size_t)env * d.NTERR * d.HW + r * d.W + c;
-      for (int ti = 0; ti < d.NTERR && !tmask; ti++) {
-        const int v = own[(size_t)ti * d.HW];
-        if (v) {
-          const int tag = __ldg(d.P + hdr[MGS_POOL] + __ldg(d.P + hdr[MGS_TERRITORIES] + ti * MG_TERR_WORDS) + v - 1);
-          tmask = o_has_tag(me, tag) ? 1 : 2;
+      const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
+      if (r >= 0 && c >= 0 && r < d.H && c < d.W) {
+        const uint8_t* own = d.owner_map + (size_t)env * d.NTERR * d.HW + r * d.W + c;
+        for (int ti = 0; ti < d.NTERR && !tmask; ti++) {
+          const int v = own[(size_t)ti * d.HW];
+          if (v) {
+            const int tag = __ldg(d.P + hdr[MGS_POOL] + __ldg(d.P + hdr[MGS_TERRITORIES] + ti * MG_TERR_WORDS) + v - 1);
+            tmask = o_has_tag(me, tag) ? 1 : 2;
+          }
         }
       }
     }
-    const uint32_t m_obj_any = __ballot_sync(MG_FULL, slot[p] != 0);
-    if ((m_obj_any | __ballot_sync(MG_FULL, tmask != 0)) == 0) continue;  // nothing visible in these 32 cells
-    if (m_obj_any) {
-      const bool earlier = seen_earlier(r, c);  // shuffles inside: every lane asks
-      const bool first = slot[p] != 0 && !earlier;
-      if (slot[p]) {
+    if (__ballot_sync(MG_FULL, (slot[p] | (uint32_t)tmask) != 0) == 0) continue;  // nothing visible in these 32 cells
+    if (slot[p]) {
+      atomicMax(claims + slot[p], my_claim);  // cell staleness (:787-796): settled by k_finish
+      n = (int)nt[p];
+      if ((uint32_t)n == MG_TOK_DIRTY) {
         uint32_t* o = objs + (size_t)slot[p] * OS;
-        if (first) {  // cell staleness (:787-796): this agent is the first, in index order, to see the object
-          const uint32_t vis = o[MGO_VISITED];
-          if (vis < step) {
-            stale_sum += step - vis;
-            o[MGO_VISITED] = step;
-          }
-        }
-        n = (int)nt[p];
-        if ((uint32_t)n == MG_TOK_DIRTY) {
-          n = rebuild_token_cache(tc, o);
-          t0[p] = o[TOKOFF];
-        }
+        n = rebuild_token_cache(TokCtx{d.P, d.P, d.env + (size_t)env * MGEV_WORDS, d.TW, d.B, d.ND, TOKOFF}, o);  // header = start of P
+        t0[p] = o[TOKOFF];
       }
     }
     const int cnt = n + (tmask != 0);
@@ -529,26 +461,12 @@ __global__ void __launch_bounds__(MG_OBS_WARPS * 32, MG_OBS_MIN_CTAS) k_observe(
     }
     base += tot;
   }
-  stale_sum = __reduce_add_sync(MG_FULL, stale_sum);
-  if (lane == 0) {
-    if (stale_sum) {  // this warp is the only writer of its agent's stats during the pass
-      const int id = hdr[MGH_ST_CELL_VISITED];
-      float* p = d.astats + ((size_t)env * A + a) * d.SA + id;
-      *p = __fadd_rn(*p, (float)stale_sum);
-      uint32_t* tp = d.atouched + ((size_t)env * A + a) * d.SAW + (id >> 5);
-      if (!(*tp & (1u << (id & 31)))) *tp |= 1u << (id & 31);
-    }
-    d.tok_attempted[(size_t)env * A + a] = base;  // k_finish adds the env's token stats in agent order (:659-661)
-  }
+  if (lane == 0) d.tok_attempted[(size_t)env * A + a] = base;  // k_finish adds the env's token stats in agent order (:659-661)
   // ---- stream out: token bytes come from the stage, the rest of the row is 0xFF (EmptyTokenByte, :940-942)
   __syncwarp();
   flush_row(out, g_row, 3 * T, 3 * min(base, T), lane);
 }
 
-// =================================================================================================
-// k_finish: what the reference does after the observation pass (:640-661,1062-1096), one warp per env: the env's
-// token stats in agent order, rewards (systems/reward.hpp:56-77), episode rewards, truncation / termination.
-// =================================================================================================
 // What k_world / k_init_buffers leave for the observation pass: per agent {executed action, start-of-tick location,
 // location, object slot}, the tokens of the configured global game values (:1207-1238, evaluated here because they need
 // the interpreter), fresh token caches for the agents, a fresh territory ownership map.
@@ -609,6 +527,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
   Wv& w = *s0.wv;
 
   for (int i = lane; i < d.HWp; i += 32) w.cells_g[i] = 0;
+  for (int i = lane; i < d.maxobj; i += 32) d.claims[(size_t)env * d.maxobj + i] = 0ull;
   for (int i = lane; i < d.A * d.SA; i += 32) w.astats[i] = 0.0f;
   for (int i = lane; i < d.A * d.SAW; i += 32) w.atouched[i] = 0;
   for (int i = lane; i < d.A * d.CW; i += 32) w.cover[i] = 0;
@@ -1299,8 +1218,32 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_finish(MgDev d, const
   carve(d, smem_raw, warp, s0);
   publish_warp(d, s0, env, lane);
   Wv& w = *s0.wv;
+  const Smem& s = *s0.self;
   const int A = w.A;
   const size_t g0 = (size_t)env * A;
+  if (!initial) {
+    // cell staleness (:787-796): every object some agent saw this tick was claimed by the lowest such agent
+    // (k_observe); advance its stamp and give the ticks since to that agent's cell.visited -- one float add per agent
+    for (int i = lane; i < A; i += 32) s.a_res[i] = 0;
+    __syncwarp();
+    const unsigned long long* claims = d.claims + (size_t)env * d.maxobj;
+    const int nobj = w.E[MGEV_NEXT_OBJ];
+    for (int sl = 1 + lane; sl < nobj; sl += 32) {
+      const unsigned long long c = claims[sl];
+      if ((uint32_t)(c >> 32) != w.step) continue;
+      uint32_t* o = objp(w, sl);
+      const uint32_t vis = o[MGO_VISITED];
+      if (vis < w.step) {
+        o[MGO_VISITED] = w.step;
+        const uint32_t ag = 0xffffffffu - (uint32_t)c;
+        if (ag < (uint32_t)A) atomicAdd(&s.a_res[ag], w.step - vis);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < A; i += 32)
+      if (s.a_res[i]) astat_add(w, i, w.hdr[MGH_ST_CELL_VISITED], (float)s.a_res[i]);
+    __syncwarp();
+  }
   if (lane == 0) {
     // token stats: one float add per agent in agent order like the reference (:659-661)
     const int idw = w.hdr[MGH_GST_TOKENS_WRITTEN], idf = w.hdr[MGH_GST_TOKENS_FREE];
@@ -1413,7 +1356,7 @@ template <class K>
 static cudaError_t set_smem(K k, size_t bytes) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
 cudaError_t mg_configure_kernels(const MgDev& d) {
-  const size_t bytes = mg_smem_bytes(d), obytes = obs_smem_bytes(d.NOFF, d.T);
+  const size_t bytes = mg_smem_bytes(d), obytes = obs_smem_bytes(MG_OBS_MAX_WARPS, d.T);
   cudaError_t e;
   if ((e = set_smem(k_reset, bytes)) != cudaSuccess) return e;
   if ((e = set_smem(k_init_buffers, bytes)) != cudaSuccess) return e;
@@ -1434,17 +1377,24 @@ cudaError_t mg_configure_kernels(const MgDev& d) {
 }
 static inline int mg_grid(const MgDev& d) { return (d.num_envs + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
 // the observation pass + what follows it, for a tick (initial = 0) or for _init_buffers (initial = 1)
+static int obs_warps(int A) {  // agents per CTA: all of them, or the largest divisor of A that fits, so no warp idles
+  if (A <= MG_OBS_MAX_WARPS) return A;
+  for (int wpc = MG_OBS_MAX_WARPS; wpc >= 4; wpc--)
+    if (A % wpc == 0) return wpc;
+  return MG_OBS_MAX_WARPS;
+}
 static cudaError_t launch_observe_finish(const MgDev& d, const uint8_t* mask, int initial, cudaStream_t st) {
-  const long long rows = (long long)d.num_envs * d.A;
-  const unsigned grid = (unsigned)((rows + MG_OBS_WARPS - 1) / MG_OBS_WARPS);
-  const size_t ob = obs_smem_bytes(d.NOFF, d.T);
+  const int wpc = obs_warps(d.A);
+  const dim3 grid((unsigned)((d.A + wpc - 1) / wpc), (unsigned)d.num_envs);
+  const size_t ob = obs_smem_bytes(wpc, d.T);
   const bool plain = d.plain || (d.NTERR == 0 && d.OVW == 0);
+  const MgFastHdr& H = *d.hdr_host;
   if (d.NOFF <= 128) {
-    if (plain) k_observe<true, 4><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
-    else k_observe<false, 4><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
+    if (plain) k_observe<true, 4><<<grid, wpc * 32, ob, st>>>(d, H, mask);
+    else k_observe<false, 4><<<grid, wpc * 32, ob, st>>>(d, H, mask);
   } else {
-    if (plain) k_observe<true, 8><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
-    else k_observe<false, 8><<<grid, MG_OBS_WARPS * 32, ob, st>>>(d, mask);
+    if (plain) k_observe<true, 8><<<grid, wpc * 32, ob, st>>>(d, H, mask);
+    else k_observe<false, 8><<<grid, wpc * 32, ob, st>>>(d, H, mask);
   }
   if (d.plain)
     k_finish<true><<<mg_grid(d), MG_WARPS_PER_CTA * 32, mg_smem_bytes(d), st>>>(d, mask, initial);

@@ -17,6 +17,11 @@
 #define MG_RNG_WINDOW 32
 #define MG_TAG_LIST_CAP 64
 
+// the program header as a kernel argument (constant bank)
+struct MgFastHdr {
+  int v[MGH_HEADER_WORDS];
+};
+
 // Everything a kernel needs, passed by value.
 struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
@@ -51,6 +56,9 @@ struct MgDev {
   int32_t* tok_attempted;     // [N][A] tokens each agent's row attempted (k_finish adds the env's token stats in order)
   uint16_t* obsval;           // [N][A][OVW] word 0 = count, then (feature | value << 8) tokens of the configured global values
   int OVW;                    // 0 when the program has no global observation values
+  unsigned long long* claims; // [N][maxobj] step << 32 | ~agent of the lowest agent that saw the object in the latest tick
+  const uint32_t* obs_offs;   // [NOFF] packed window offsets in Manhattan order (mg_capi.cu), read-only
+  const struct MgFastHdr* hdr_host;  // HOST copy of the program header, passed to kernels by value
   const float* logtab;        // logf(k + 1), k in [0, 65536), from the host libm
   // world systems (queries / AOE / territory / tags); sizes are 0 when the program does not use them
   uint16_t* arena;            // [N][ARENA] scratch for query result lists (stack discipline)
@@ -80,10 +88,6 @@ struct MgFastLayout {
   int rank_off, cta_bytes;
   int tok_off, tok_stride, oloc_off, key_off, group_bytes;
   size_t smem_bytes;
-};
-// the program header as a kernel argument (constant bank)
-struct MgFastHdr {
-  int v[MGH_HEADER_WORDS];
 };
 
 // ---- packed hot state of k_step_fast: one contiguous block per env, G = lanes per env -------------------

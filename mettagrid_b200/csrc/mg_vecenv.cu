@@ -103,3 +103,72 @@ cudaError_t mg_launch_vecenv_post(int num_envs, int A, int64_t* steps, int64_t* 
   k_vecenv_post<<<(num_envs + 255) / 256, 256, 0, st>>>(num_envs, A, steps, early, trunc);
   return cudaGetLastError();
 }
+
+// ---- step_info_keys (mettagrid_puffer_env.py:132-282): the per-step stat export trainers read ---------------------
+// One thread per (env, key) for the game keys and per (env, agent, key) for the agent keys gathers the configured stats
+// into dense device tensors, so a training loop reads them without per-env host getters.  `present` mirrors the
+// reference's "value is not None": a stat exists once it was touched.  A fast handle keeps the agent stats with ids
+// below MGFB_STATS (and the token game stats) in its packed block while that is the newest copy.
+namespace {
+__global__ void k_gather_info(MgDev d, int packed, int G, int n_game, const int32_t* __restrict__ game_ids, int n_agent,
+                              const int32_t* __restrict__ agent_ids, int idw, int idd, int idf, float* __restrict__ game_out,
+                              uint8_t* __restrict__ game_present, float* __restrict__ agent_out, uint8_t* __restrict__ agent_present) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ng = (long long)d.num_envs * n_game, na = (long long)d.num_envs * d.A * n_agent;
+  if (i < ng) {
+    const int env = (int)(i / n_game), id = game_ids[i % n_game];
+    const uint32_t* blk = packed ? d.fast_blk + (size_t)env * d.fast_stride : nullptr;
+    float v = 0.0f;
+    int have = 0;
+    if (id == -1) {  // attributes/steps
+      v = (float)(packed ? (int)blk[MGFB_STEP] : d.env[(size_t)env * MGEV_WORDS + MGEV_STEP]);
+      have = 1;
+    } else if (id >= 0 && id < d.SG) {
+      if (packed && (id == idw || id == idd || id == idf)) {
+        v = id == idw ? __uint_as_float(blk[MGFB_TOKENS_WRITTEN]) : id == idf ? __uint_as_float(blk[MGFB_TOKENS_FREE]) : 0.0f;
+        have = (blk[MGFB_GTOUCHED] >> (id == idw ? 0 : id == idd ? 1 : 2)) & 1u;
+      } else {
+        v = d.gstats[(size_t)env * d.SG + id];
+        have = (d.gtouched[(size_t)env * d.SGW + (id >> 5)] >> (id & 31)) & 1u;
+      }
+    }
+    game_out[i] = have ? v : 0.0f;
+    game_present[i] = (uint8_t)have;
+    return;
+  }
+  const long long j = i - ng;
+  if (j >= na) return;
+  const int key = (int)(j % n_agent), id = agent_ids[key];
+  const long long ga = j / n_agent;  // env * A + agent
+  const int env = (int)(ga / d.A), a = (int)(ga % d.A);
+  float v = 0.0f;
+  int have = 0;
+  if (id == -1) {  // reward_step
+    v = d.rewards[ga], have = 1;
+  } else if (id == -2) {  // reward_episode
+    v = __uint_as_float(d.agents[(size_t)ga * d.AS + MGAG_EPISODE_REWARD]), have = 1;
+  } else if (id >= 0 && id < d.SA) {
+    if (packed && id < MGFB_STATS) {
+      const uint32_t* blk = d.fast_blk + (size_t)env * d.fast_stride;
+      v = __uint_as_float(blk[MGFB_STAT(G, id, a)]);
+      have = (blk[MGFB_AGENT(G, a) + 6] >> id) & 1u;
+    } else {
+      v = d.astats[(size_t)ga * d.SA + id];
+      have = (d.atouched[(size_t)ga * d.SAW + (id >> 5)] >> (id & 31)) & 1u;
+    }
+  }
+  agent_out[j] = have ? v : 0.0f;
+  agent_present[j] = (uint8_t)have;
+}
+}  // namespace
+
+cudaError_t mg_launch_gather_info(const MgDev& d, int packed, int G, int n_game, const int32_t* game_ids, int n_agent,
+                                  const int32_t* agent_ids, int idw, int idd, int idf, float* game_out, uint8_t* game_present,
+                                  float* agent_out, uint8_t* agent_present, cudaStream_t st) {
+  const long long n = (long long)d.num_envs * n_game + (long long)d.num_envs * d.A * n_agent;
+  if (n <= 0) return cudaSuccess;
+  k_gather_info<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d, packed, G, n_game, game_ids, n_agent, agent_ids, idw, idd, idf, game_out,
+                                                              game_present, agent_out, agent_present);
+  return cudaGetLastError();
+}
+

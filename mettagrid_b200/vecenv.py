@@ -13,7 +13,7 @@ episode of every environment is truncated at a step drawn from ``numpy.random.de
 
 from __future__ import annotations
 
-from typing import Any
+from typing import Any, Sequence
 
 import numpy as np
 import torch
@@ -69,7 +69,8 @@ class MettaGridVecEnv:
     With ``validate=True`` (default, the reference's behaviour) out-of-range actions raise ``ValueError`` at
     once, which costs one host synchronisation per step; ``validate=False`` defers the check to ``poll()``."""
 
-    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, desync_episodes: bool = False, validate: bool = True, **kw):
+    def __init__(self, cfg: Any, num_envs: int, seed: int = 0, desync_episodes: bool = False, validate: bool = True,
+                 step_info_keys: Sequence[str] | None = None, **kw):  # fmt: skip
         self.sim = BatchedSimulation(cfg, num_envs, seeds=seed, **kw)
         s = self.sim
         game = getattr(cfg, "game", cfg)
@@ -87,6 +88,7 @@ class MettaGridVecEnv:
         self._desync = bool(desync_episodes) and self._max_steps > 0
         self._vibe_ids_host = np.asarray(vibe_ids, dtype=np.int32)
         self._configure()
+        self._configure_step_info_keys(step_info_keys)
 
     def _configure(self):
         early = None
@@ -96,6 +98,93 @@ class MettaGridVecEnv:
         v = self._vibe_ids_host
         self.sim._check(self.sim._L.mg_vecenv_configure(self.sim._h, self.num_primary, v.ctypes.data if v.size else None, int(v.size),
                                                         None if early is None else early.ctypes.data))  # fmt: skip
+
+    # ---- step_info_keys (mettagrid_puffer_env.py:132-184): same key grammar, gathered on the device -----------------
+    def _configure_step_info_keys(self, keys: Sequence[str] | None) -> None:
+        """'game/<stat>', 'team/<team>/<stat>', 'attributes/{seed,map_w,map_h,steps,max_steps}' (an 'env_' prefix is
+        accepted and dropped like the reference does) and 'agent/<stat>' incl. reward_step / reward_episode."""
+        self._info_game: list[tuple[str, int]] = []  # (payload key, game stat id | -1 steps)
+        self._info_attr: list[tuple[str, str]] = []
+        self._info_agent: list[tuple[str, int]] = []
+        P = self.sim.program
+        for key in dict.fromkeys(str(k) for k in (keys or [])):
+            if key.startswith("agent/"):
+                name = key[len("agent/"):]
+                if not name:
+                    raise ValueError("step_info_keys contains invalid entry 'agent/' (missing key suffix)")
+                sid = {"reward_step": -1, "reward_episode": -2}.get(name)
+                if sid is None:
+                    sid = P.agent_stat_names.index(name) if name in P.agent_stat_names else None
+                if sid is not None:  # a stat the program never writes is never present: the reference omits it too
+                    self._info_agent.append((name, sid))
+                continue
+            raw = key[len("env_"):] if key.startswith("env_") else key
+            if raw.startswith("game/") or raw.startswith("team/"):
+                if raw.startswith("game/"):
+                    stat = raw[len("game/"):]
+                    if not stat:
+                        raise ValueError("step_info_keys contains invalid entry 'game/' (missing key suffix)")
+                else:
+                    rest = raw[len("team/"):]
+                    cut = rest.find("/")
+                    if cut <= 0:
+                        raise ValueError(f"step_info_keys entry {key!r}: expected 'team/{{team}}/{{stat}}'")
+                    if not rest[cut + 1:]:
+                        raise ValueError(f"step_info_keys entry {key!r}: missing stat key after team name")
+                    stat = rest
+                if stat in P.game_stat_names:
+                    self._info_game.append((raw, P.game_stat_names.index(stat)))
+                continue
+            if raw.startswith("attributes/"):
+                attr = raw[len("attributes/"):]
+                if not attr:
+                    raise ValueError("step_info_keys contains invalid entry 'attributes/' (missing key suffix)")
+                if attr not in ("seed", "map_w", "map_h", "steps", "max_steps"):
+                    raise ValueError(f"Unsupported step_info_keys attribute {raw!r}. Supported: seed, map_w, map_h, steps, max_steps.")
+                if attr == "steps":
+                    self._info_game.append((raw, -1))
+                else:
+                    self._info_attr.append((raw, attr))
+                continue
+            raise ValueError(f"Unsupported step_info_keys entry {key!r}; expected 'game/...', 'attributes/...', 'team/...', or 'agent/...'.")
+        s = self.sim
+        g = np.asarray([i for _, i in self._info_game], dtype=np.int32)
+        a = np.asarray([i for _, i in self._info_agent], dtype=np.int32)
+        s._check(s._L.mg_info_configure(s._h, int(g.size), g.ctypes.data if g.size else None, int(a.size), a.ctypes.data if a.size else None))
+        N, A = self.num_envs, self.agents_per_env
+        self.info_game = torch.zeros((N, max(len(self._info_game), 1)), dtype=torch.float32, device=s.device)
+        self.info_game_present = torch.zeros((N, max(len(self._info_game), 1)), dtype=torch.uint8, device=s.device)
+        self.info_agent = torch.zeros((N, A, max(len(self._info_agent), 1)), dtype=torch.float32, device=s.device)
+        self.info_agent_present = torch.zeros((N, A, max(len(self._info_agent), 1)), dtype=torch.uint8, device=s.device)
+
+    @property
+    def has_step_info(self) -> bool:
+        return bool(self._info_game or self._info_agent or self._info_attr)
+
+    def gather_step_info(self) -> dict:
+        """Device tensors of the configured stats after the latest step (asynchronous; no host synchronisation):
+        {'game': [N, Kg], 'game_present', 'game_keys', 'agent': [N, A, Ka], 'agent_present', 'agent_keys'}."""
+        s = self.sim
+        s._check(s._L.mg_info_gather(s._h, self.info_game.data_ptr(), self.info_game_present.data_ptr(), self.info_agent.data_ptr(),
+                                     self.info_agent_present.data_ptr(), s._stream()))  # fmt: skip
+        return {"game": self.info_game, "game_present": self.info_game_present, "game_keys": [k for k, _ in self._info_game],
+                "agent": self.info_agent, "agent_present": self.info_agent_present, "agent_keys": [k for k, _ in self._info_agent]}  # fmt: skip
+
+    def step_info_payload(self, env: int) -> dict:
+        """The reference's info payload for ONE env as a host dict (_build_step_info_payload, :230-282) -- for tests
+        and debugging; training loops read gather_step_info()'s tensors."""
+        t = self.gather_step_info()
+        torch.cuda.current_stream(self.sim.device).synchronize()
+        P = self.sim.program
+        gv, gp = t["game"][env].cpu().numpy(), t["game_present"][env].cpu().numpy()
+        out: dict = {k: float(gv[i]) for i, (k, _) in enumerate(self._info_game) if gp[i]}
+        for raw, attr in self._info_attr:
+            out[raw] = float({"seed": int(self.sim.seeds[env]), "map_w": P.width, "map_h": P.height, "max_steps": self._max_steps}[attr])
+        if self._info_agent:
+            av, ap = t["agent"][env].cpu().numpy(), t["agent_present"][env].cpu().numpy()
+            out["_per_agent_infos"] = {a: {k: float(av[a, i]) for i, (k, _) in enumerate(self._info_agent) if ap[a, i]}
+                                       for a in range(self.agents_per_env)}  # fmt: skip
+        return out
 
     # flat zero-copy views, the layout PufferLib hands to policies
     @property
@@ -149,7 +238,8 @@ class MettaGridVecEnv:
         if self.validate and self.poll():
             decode_actions(a, self.num_primary, self._vibe_ids)  # raises the reference's ValueError for this tensor
             raise ValueError("invalid actions")
-        return self.observations, self.rewards, self.terminals, self.truncations, {}
+        info = self.gather_step_info() if self.has_step_info else {}
+        return self.observations, self.rewards, self.terminals, self.truncations, info
 
     def close(self):
         self.sim.close()

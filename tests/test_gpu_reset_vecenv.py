@@ -319,3 +319,51 @@ def test_masked_reset_with_new_seeds_then_autoreset_uses_the_new_seeds():
         for e, o in enumerate(orc):
             assert np.array_equal(ob[e], o.observations()), f"step {t} env {e}"
     env.close()
+
+
+@pytest.mark.parametrize("game", ["benchmark", "combat"])
+def test_step_info_keys_match_the_reference_payload(game):
+    """mettagrid_puffer_env.py:230-282: game / attributes / agent keys, present only once the stat exists."""
+    from mettagrid_b200.vecenv import MettaGridVecEnv
+
+    keys = ["game/tokens_written", "env_game/objects.agent.red", "game/never.written", "attributes/steps", "attributes/seed",
+            "attributes/map_w", "attributes/max_steps", "agent/action.move.success", "agent/action.failed", "agent/reward_step",
+            "agent/reward_episode", "agent/cell.visited", "agent/not.a.stat"]  # fmt: skip
+    if game == "combat":
+        cfg, kw, nprim = cases.combat_config(None, 2, max_steps=40), {"maps": [cases.combat_map(2, seed=s) for s in range(3)]}, 9
+        keys += ["game/attack.hits", "agent/hp.amount", "agent/loot.gained", "agent/attack.landed"]
+    else:
+        cfg, kw, nprim = cases.benchmark_config(4, max_steps=40), {}, 5
+    env = MettaGridVecEnv(cfg, 3, seed=5, step_info_keys=keys, **kw)
+    orc = _oracles(env.sim)
+    P = env.sim.program
+    A = P.num_agents
+    rng = np.random.RandomState(3)
+    with pytest.raises(ValueError, match="Unsupported step_info_keys"):
+        MettaGridVecEnv(cfg, 1, seed=5, step_info_keys=["bogus/key"], **kw)
+    for t in range(30):
+        a = rng.randint(0, nprim, size=3 * A)
+        _, _, _, _, info = env.step(torch.from_numpy(a).cuda())
+        assert info["game"].is_cuda and info["agent"].shape == (3, A, len(info["agent_keys"]))
+        for e, o in enumerate(orc):
+            o.step(a.reshape(3, A)[e], np.zeros(A, np.int32))
+        if t % 7 == 0 or t == 29:
+            for e, o in enumerate(orc):
+                st = o.get_episode_stats()
+                want = {}
+                for k in keys:
+                    raw = k[len("env_"):] if k.startswith("env_") else k
+                    if raw.startswith("game/") and raw[5:] in st["game"]:
+                        want[raw] = st["game"][raw[5:]]
+                want.update({"attributes/steps": float(t + 1), "attributes/seed": float(env.sim.seeds[e]), "attributes/map_w": float(P.width),
+                             "attributes/max_steps": 40.0})  # fmt: skip
+                per_agent = {}
+                for ag in range(A):
+                    row = {"reward_step": float(o.rewards()[ag]), "reward_episode": float(o.episode_rewards()[ag])}
+                    for k in keys:
+                        if k.startswith("agent/") and k[6:] in st["agent"][ag]:
+                            row[k[6:]] = st["agent"][ag][k[6:]]
+                    per_agent[ag] = row
+                want["_per_agent_infos"] = per_agent
+                assert env.step_info_payload(e) == want, f"tick {t} env {e}"
+    env.close()
