@@ -494,12 +494,27 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
     CK(cudaDeviceSynchronize());
     h->foreign_pending = false;
   }
-  const MgDev run = host_dev(h);
+  MgDev run = host_dev(h);
+  // Observation rows are the bulk of the traffic (3T bytes per agent, 20 MB per step at C2) and the step kernels only
+  // WRITE them, in whole 16-byte vectors.  When the caller's buffer is pinned host memory (cudaHostAlloc /
+  // cudaHostRegister, what PufferLib-style numpy buffers are once pinned), the kernels store the rows straight into it
+  // over PCIe: the transfer overlaps the tick instead of following it and the staging copy disappears.  Pageable memory
+  // takes the staged path.  METTAGRID_B200_STAGED_OBS=1 forces staging (A/B).
+  bool direct_obs = false;
+  if (observations && !getenv("METTAGRID_B200_STAGED_OBS")) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, observations) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+      run.obs = (uint8_t*)at.devicePointer;
+      direct_obs = true;
+    } else {
+      cudaGetLastError();
+    }
+  }
   if (!h->buffers_set && !h->host_inited) {
     // a caller that only ever uses host buffers: _init_buffers (coverage, flags) against the staging set.  A handle
     // whose buffers were set keeps its episode state untouched -- mg_set_buffers already ran _init_buffers.
     if (int rc = sync_generic(h, st)) return rc;
-    CK(mg_launch_init_buffers(run, nullptr, st));
+    CK(mg_launch_init_buffers(host_dev(h), nullptr, st));
     if (h->fast) h->newest = mg_handle::GENERIC;
     h->host_inited = true;
   }
@@ -512,7 +527,7 @@ int mg_step_host(mg_handle* h, const int32_t* actions, const int32_t* vibe_actio
     const int rc = launch_step(h, run, st);
     if (rc) return rc;
   }
-  if (observations) CK(cudaMemcpyAsync(observations, h->h_obs, NA * d.T * 3, cudaMemcpyDeviceToHost, st));
+  if (observations && !direct_obs) CK(cudaMemcpyAsync(observations, h->h_obs, NA * d.T * 3, cudaMemcpyDeviceToHost, st));
   if (rewards) CK(cudaMemcpyAsync(rewards, h->h_rew, NA * 4, cudaMemcpyDeviceToHost, st));
   if (terminals) CK(cudaMemcpyAsync(terminals, h->h_term, NA, cudaMemcpyDeviceToHost, st));
   if (truncations) CK(cudaMemcpyAsync(truncations, h->h_trunc, NA, cudaMemcpyDeviceToHost, st));

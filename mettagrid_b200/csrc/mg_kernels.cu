@@ -1199,7 +1199,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_w
 // token stats in agent order, rewards (systems/reward.hpp:56-77), episode rewards, truncation / termination.
 // =================================================================================================
 template <bool PLAIN>
-__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_finish(MgDev d, const uint8_t* __restrict__ mask, int initial) {
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_finish(MgDev d, const uint8_t* __restrict__ mask, int initial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mask) {
@@ -1228,15 +1228,27 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_finish(MgDev d, const
     __syncwarp();
     const unsigned long long* claims = d.claims + (size_t)env * d.maxobj;
     const int nobj = w.E[MGEV_NEXT_OBJ];
-    for (int sl = 1 + lane; sl < nobj; sl += 32) {
-      const unsigned long long c = claims[sl];
-      if ((uint32_t)(c >> 32) != w.step) continue;
-      uint32_t* o = objp(w, sl);
-      const uint32_t vis = o[MGO_VISITED];
-      if (vis < w.step) {
-        o[MGO_VISITED] = w.step;
-        const uint32_t ag = 0xffffffffu - (uint32_t)c;
-        if (ag < (uint32_t)A) atomicAdd(&s.a_res[ag], w.step - vis);
+    const uint32_t step = w.step;
+    for (int s0_ = 1; s0_ < nobj; s0_ += 128) {  // four independent claim loads per lane in flight
+      unsigned long long c[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int sl = s0_ + 32 * q + lane;
+        c[q] = sl < nobj ? claims[sl] : 0ull;
+      }
+      uint32_t vis[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        vis[q] = step;
+        if ((uint32_t)(c[q] >> 32) == step) vis[q] = objp(w, s0_ + 32 * q + lane)[MGO_VISITED];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        if (vis[q] < step) {
+          objp(w, s0_ + 32 * q + lane)[MGO_VISITED] = step;
+          const uint32_t ag = 0xffffffffu - (uint32_t)c[q];
+          if (ag < (uint32_t)A) atomicAdd(&s.a_res[ag], step - vis[q]);
+        }
       }
     }
     __syncwarp();

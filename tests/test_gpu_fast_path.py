@@ -291,8 +291,9 @@ def test_set_buffers_mid_episode_on_a_fast_handle_sees_the_moved_agents():
     sim.close()
 
 
+@pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("game", ["benchmark", "walled", "combat"])
-def test_step_host_leaves_the_callers_buffers_bound(game):
+def test_step_host_leaves_the_callers_buffers_bound(game, pinned):
     """mg_step_host steps on the handle's own staging set and must not rebind the handle: device steps, host steps and
     resets interleave on one handle, and the caller's tensors keep receiving the device steps' results."""
     from mettagrid_b200.sim import BatchedSimulation
@@ -311,6 +312,9 @@ def test_step_host_leaves_the_callers_buffers_bound(game):
     orc = mk()
     prim, vibe = cases.random_actions(np.random.RandomState(6), 50, (3, A), nprim, len(P.action_names), 0.2)
     h_obs = np.zeros((3, A, T, 3), np.uint8)
+    if pinned:  # pinned rows are written by the step kernels directly (no staging copy): same bytes
+        keep = torch.zeros((3, A, T, 3), dtype=torch.uint8).pin_memory()
+        h_obs = keep.numpy()
     h_rew, h_term, h_trunc = np.zeros((3, A), np.float32), np.zeros((3, A), np.uint8), np.zeros((3, A), np.uint8)
     for t in range(50):
         if t == 30:
