@@ -293,7 +293,7 @@ def test_set_buffers_mid_episode_on_a_fast_handle_sees_the_moved_agents():
 
 @pytest.mark.parametrize("pinned", [False, True])
 @pytest.mark.parametrize("game", ["benchmark", "walled", "combat"])
-def test_step_host_leaves_the_callers_buffers_bound(game, pinned):
+def test_step_host_leaves_the_callers_buffers_bound(game, pinned, monkeypatch):
     """mg_step_host steps on the handle's own staging set and must not rebind the handle: device steps, host steps and
     resets interleave on one handle, and the caller's tensors keep receiving the device steps' results."""
     from mettagrid_b200.sim import BatchedSimulation
@@ -312,7 +312,8 @@ def test_step_host_leaves_the_callers_buffers_bound(game, pinned):
     orc = mk()
     prim, vibe = cases.random_actions(np.random.RandomState(6), 50, (3, A), nprim, len(P.action_names), 0.2)
     h_obs = np.zeros((3, A, T, 3), np.uint8)
-    if pinned:  # pinned rows are written by the step kernels directly (no staging copy): same bytes
+    if pinned:  # opt-in: pinned rows are written by the step kernels directly (no staging copy): same bytes
+        monkeypatch.setenv("METTAGRID_B200_DIRECT_OBS", "1")
         keep = torch.zeros((3, A, T, 3), dtype=torch.uint8).pin_memory()
         h_obs = keep.numpy()
     h_rew, h_term, h_trunc = np.zeros((3, A), np.float32), np.zeros((3, A), np.uint8), np.zeros((3, A), np.uint8)

@@ -340,7 +340,7 @@ def test_step_info_keys_match_the_reference_payload(game):
     A = P.num_agents
     rng = np.random.RandomState(3)
     with pytest.raises(ValueError, match="Unsupported step_info_keys"):
-        MettaGridVecEnv(cfg, 1, seed=5, step_info_keys=["bogus/key"], **kw)
+        MettaGridVecEnv(cfg, 3, seed=5, step_info_keys=["bogus/key"], **kw)
     for t in range(30):
         a = rng.randint(0, nprim, size=3 * A)
         _, _, _, _, info = env.step(torch.from_numpy(a).cuda())
