@@ -24,6 +24,10 @@
 
 #include "mg_state.h"
 
+#ifndef MG_FAST_NO_BULK
+#define MG_FAST_NO_BULK 0  // 1: always stream the observation block with vector stores (A/B against cp.async.bulk)
+#endif
+
 namespace {
 
 #define FAST_INVALID 0xFFFFFFFFu
@@ -621,8 +625,20 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   __syncwarp();
 
-  // ---- stream the env's observation block out
-  {
+  // ---- stream the env's observation block out.  The block [A][T][3] is contiguous in the stage and in HBM: when both
+  // ends are 16-byte aligned one elected lane hands the whole block to the bulk-copy engine (cp.async.bulk, shared ->
+  // global; UBLKCP in the SASS) and the group goes on with its write-back while the copy drains; the wait sits at the
+  // end of the kernel.  Unaligned blocks (odd T * A) take the vector loop.
+  const bool bulk = (((uint32_t)(uintptr_t)gobs | (uint32_t)nbytes) & 15u) == 0 && !MG_FAST_NO_BULK;
+  if (bulk) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written through the generic proxy
+    __syncwarp();
+    if (gl == 0 && live) {
+      const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stage);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gobs), "r"(saddr), "r"(nbytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else {
     const int head = min(nbytes, (int)((16u - ((uint32_t)(uintptr_t)gobs & 15u)) & 15u));
     if (live) {
 #pragma unroll 1
@@ -735,6 +751,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     if (o_ntok != ntok_raw || o_meta != o_meta0) *(uint4*)(bob + 4) = make_uint4(tw0, tw1, tw2, tw3);
   }
   if (gl == 0 && live) blk[MGFB_STEP] = step;
+  if (bulk && gl == 0 && live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage must outlive the copy
 }
 
 
