@@ -336,6 +336,7 @@ enum {
 #define MGERR_TOKEN_OVERFLOW 1
 #define MGERR_POOL_EXHAUSTED 2
 #define MGERR_UNSUPPORTED 4
+#define MGERR_BOUNDS 8 /* checked builds only (MG_CHECKED): a state accessor was handed an index outside its array */
 
 #define MG_RNG_WORDS 624
 

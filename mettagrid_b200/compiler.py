@@ -1192,7 +1192,9 @@ def compile_config(cfg: Any, map_height: int | None = None, map_width: int | Non
     max_static_tags = max([sum(bin(b.pool[t[K["MGT_TAGS"]] + k] & 0xFFFFFFFF).count("1") for k in range(TW)) for t in templates] + [0])
     tok_cap = max_static_tags + len(b.dyn_tags) + 1 + R * b.inv_digits + 2
     tok_off = (K["MGO_TAGS"] + TW + (R + 1) // 2 + 3) // 4 * 4  # the token cache starts 16-byte aligned (one vector load)
-    obj_stride = (tok_off + (tok_cap + 1) // 2 + 3) // 4 * 4
+    # at least four token words per record: the fast path and its pack / unpack kernels move the first eight cached
+    # tokens as one 16-byte vector, whatever the count
+    obj_stride = (tok_off + max((tok_cap + 1) // 2, 4) + 3) // 4 * 4
     agent_stride = K["MGAG_REWARD_PREV"] + max_rewards
     dyn = sorted(b.dyn_tags)
     dyn_slot = [-1] * len(b.tag_names)

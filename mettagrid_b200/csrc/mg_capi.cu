@@ -257,7 +257,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   if (init_gstats) TRY(dev_alloc(h, &ig, N * d.SG));
   TRY(dev_alloc(h, &h->seeds_dev, N));
   TRY(dev_alloc(h, &d.cells, N * d.HWp));
-  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NPROXY) * d.OS + 64));  // slack: k_step_fast reads 4 token words blind
+  TRY(dev_alloc(h, &d.objs, N * (d.maxobj + d.NPROXY) * d.OS));  // records hold >= 4 token words (compiler.py: obj_stride)
   {
     // capacities of the world-system tables, from the program and the initial maps
     const int32_t* TP = P + P[MGS_TEMPLATES];

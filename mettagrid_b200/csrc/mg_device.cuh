@@ -86,13 +86,31 @@ __device__ __forceinline__ Ctx make_ctx() {
   return c;
 }
 
+// MG_CHECKED=1 (python -m mettagrid_b200.build --variant checked -DMG_CHECKED=1): every state accessor verifies its
+// index and reports MGERR_BOUNDS through the env's error word, which the Python wrapper raises -- the pool's
+// compute-sanitizer is closed, so the whole GPU test suite is run once against this build instead (profiles/README.md).
+#ifndef MG_CHECKED
+#define MG_CHECKED 0
+#endif
+#define MG_CHECK(w, cond, info)                                                   \
+  do {                                                                            \
+    if (MG_CHECKED && !(cond)) {                                                  \
+      if (!((w).E[MGEV_ERROR] & MGERR_BOUNDS)) (w).E[MGEV_ERR_INFO] = (info);     \
+      atomicOr(&(w).E[MGEV_ERROR], MGERR_BOUNDS);                                 \
+    }                                                                             \
+  } while (0)
+
 // ---- program access -------------------------------------------------------------------------
 __device__ __forceinline__ const int32_t* sec(const Wv& w, int k) { return w.P + w.hdr[k]; }
 __device__ __forceinline__ const int32_t* pool(const Wv& w, int off) { return w.P + w.hdr[MGS_POOL] + off; }
 __device__ __forceinline__ const int32_t* tmpl(const Wv& w, int t) { return sec(w, MGS_TEMPLATES) + t * MG_TEMPLATE_WORDS; }
 
 // ---- object records ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t* objp(const Wv& w, int s) { return w.objs + (size_t)s * w.OS; }
+__device__ __forceinline__ uint32_t* objp(const Wv& w, int s) {
+  MG_CHECK(w, (unsigned)s < (unsigned)(w.maxobj + w.NPROXY), 1000);
+  if (MG_CHECKED && (unsigned)s >= (unsigned)(w.maxobj + w.NPROXY)) s = 0;
+  return w.objs + (size_t)s * w.OS;
+}
 __device__ __forceinline__ int o_r(const uint32_t* o) { return (int)(o[MGO_LOC] >> 16); }
 __device__ __forceinline__ int o_c(const uint32_t* o) { return (int)(o[MGO_LOC] & 0xffffu); }
 __device__ __forceinline__ int o_tmpl(const uint32_t* o) { return (int)(o[MGO_META] & 0xffffu); }
@@ -135,21 +153,29 @@ __device__ __forceinline__ uint64_t ord_erase(uint64_t v, int item) {
 
 // ---- stats (systems/stats_tracker.hpp:57-98); lane-exclusive per (agent) or serial ----------
 __device__ __forceinline__ void astat_touch(const Wv& w, int a, int id) {
+  MG_CHECK(w, (unsigned)a < (unsigned)w.A && (unsigned)id < (unsigned)w.SA, 1001);
+  if (MG_CHECKED && !((unsigned)a < (unsigned)w.A && (unsigned)id < (unsigned)w.SA)) return;
   uint32_t* p = w.atouched + a * w.SAW + (id >> 5);
   const uint32_t bit = 1u << (id & 31);
   if (!(*p & bit)) *p |= bit;
 }
 __device__ __forceinline__ void astat_add(const Wv& w, int a, int id, float v) {
+  MG_CHECK(w, (unsigned)a < (unsigned)w.A && (unsigned)id < (unsigned)w.SA, 1002);
+  if (MG_CHECKED && !((unsigned)a < (unsigned)w.A && (unsigned)id < (unsigned)w.SA)) return;
   float* p = w.astats + a * w.SA + id;
   *p = __fadd_rn(*p, v);
   astat_touch(w, a, id);
 }
 __device__ __forceinline__ void astat_set(const Wv& w, int a, int id, float v) {
+  MG_CHECK(w, (unsigned)a < (unsigned)w.A && (unsigned)id < (unsigned)w.SA, 1003);
+  if (MG_CHECKED && !((unsigned)a < (unsigned)w.A && (unsigned)id < (unsigned)w.SA)) return;
   w.astats[a * w.SA + id] = v;
   astat_touch(w, a, id);
 }
 __device__ __forceinline__ float astat_get(const Wv& w, int a, int id) { return w.astats[a * w.SA + id]; }
 __device__ __forceinline__ void gstat_touch(const Wv& w, int id) {
+  MG_CHECK(w, id >= 0, 1005);
+  if (MG_CHECKED && id < 0) return;
   uint32_t* p = w.gtouched + (id >> 5);
   const uint32_t bit = 1u << (id & 31);
   if (!(*p & bit)) atomicOr(p, bit);  // agents of one env may report from different lanes
@@ -379,7 +405,11 @@ __device__ __noinline__ int transfer(const Wv& w, uint32_t* src, uint32_t* dst, 
 
 // ---- grid (core/grid.hpp:31-130) -----------------------------------------------------------------
 __device__ __forceinline__ bool valid_loc(const Wv& w, int r, int c) { return r >= 0 && c >= 0 && r < w.H && c < w.W; }
-__device__ __forceinline__ int cidx(const Wv& w, int r, int c) { return (r + w.PAD) * w.WP + c + w.PAD; }
+__device__ __forceinline__ int cidx(const Wv& w, int r, int c) {
+  const int i = (r + w.PAD) * w.WP + c + w.PAD;
+  MG_CHECK(w, (unsigned)i < (unsigned)((w.H + 2 * w.PAD) * w.WP), 1004);
+  return (MG_CHECKED && (unsigned)i >= (unsigned)((w.H + 2 * w.PAD) * w.WP)) ? 0 : i;
+}
 __device__ __forceinline__ int cell_at(const Wv& w, int r, int c) { return w.cells[cidx(w, r, c)]; }
 __device__ __forceinline__ void set_cell(const Wv& w, int r, int c, int s) {
   int i = cidx(w, r, c);

@@ -339,6 +339,10 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
     const int k = 32 * p + lane;
     pk[p] = k < NOFF ? __ldg(d.obs_offs + k) : 0u;
     slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
+    if (MG_CHECKED && slot[p] >= (uint32_t)d.maxobj) {  // checked builds: a cell must name a slot of this env's pool
+      atomicOr(&d.env[(size_t)env * MGEV_WORDS + MGEV_ERROR], MGERR_BOUNDS);
+      slot[p] = 0;
+    }
   }
 #pragma unroll
   for (int p = 0; p < NP; p++) {
