@@ -281,7 +281,7 @@ enum {
 /* object record words (stride = MGH_OBJ_STRIDE, multiple of 4 words) */
 enum {
   MGO_LOC = 0,  /* r << 16 | c */
-  MGO_VISITED,  /* GridObject::visited */
+  MGO_VISITED,  /* unused: GridObject::visited lives in a compact per-env array (mg_state.h: visited) */
   MGO_META,     /* template (16) | vibe (8) << 16 | flags (8) << 24 */
   MGO_AGENT,    /* agent index or -1 */
   MGO_INVORD_LO,/* inventory iteration order: 4-bit resource ids, most recent first */

@@ -312,6 +312,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   TRY(dev_alloc(h, &d.success, N * d.A));
   TRY(dev_alloc(h, &d.obs_in, N * d.A));
   TRY(dev_alloc(h, &d.claims, N * d.maxobj));
+  TRY(dev_alloc(h, &d.visited, N * d.maxobj));
   memcpy(h->fh.v, P, sizeof h->fh.v);
   d.hdr_host = &h->fh;
   {

@@ -795,7 +795,7 @@ __global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, cons
     const int TOKOFF = MG_TOKOFF(d.TW, d.R);
     const uint32_t ntok = o[MGO_NTOK];
     const uint32_t w3 = (((uint32_t)((int)o[MGO_AGENT] + 1)) & 0xffu) | (ntok == MG_TOK_DIRTY ? MGFB_DIRTY : ((ntok & 0xffu) << 8));
-    o0 = make_uint4(o[MGO_LOC], o[MGO_VISITED], o[MGO_META], w3);
+    o0 = make_uint4(o[MGO_LOC], d.visited[(size_t)env * d.maxobj + gl + 1], o[MGO_META], w3);  // the generic kernels keep the stamps apart
     const int nw = min(4, (hdr[MGH_TOK_CAP] + 1) / 2);
     uint32_t tk[4] = {0, 0, 0, 0};
     for (int k = 0; k < nw; k++) tk[k] = o[TOKOFF + k];
@@ -838,7 +838,7 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
     uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)(gl + 1)) * d.OS;
     const int TOKOFF = MG_TOKOFF(d.TW, d.R);
     const uint4 o0 = *(const uint4*)(blk + MGFB_OBJECT(G, gl)), o1 = *(const uint4*)(blk + MGFB_OBJECT(G, gl) + 4);
-    o[MGO_LOC] = o0.x, o[MGO_VISITED] = o0.y, o[MGO_META] = o0.z;
+    o[MGO_LOC] = o0.x, d.visited[(size_t)env * d.maxobj + gl + 1] = o0.y, o[MGO_META] = o0.z;
     if (o0.w & MGFB_DIRTY) {
       o[MGO_NTOK] = MG_TOK_DIRTY;
     } else {

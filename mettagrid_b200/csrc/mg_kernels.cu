@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
   Wv& w = *s0.wv;
 
   for (int i = lane; i < d.HWp; i += 32) w.cells_g[i] = 0;
-  for (int i = lane; i < d.maxobj; i += 32) d.claims[(size_t)env * d.maxobj + i] = 0ull;
+  for (int i = lane; i < d.maxobj; i += 32) d.claims[(size_t)env * d.maxobj + i] = 0ull, d.visited[(size_t)env * d.maxobj + i] = 0u;
   for (int i = lane; i < d.A * d.SA; i += 32) w.astats[i] = 0.0f;
   for (int i = lane; i < d.A * d.SAW; i += 32) w.atouched[i] = 0;
   for (int i = lane; i < d.A * d.CW; i += 32) w.cover[i] = 0;
@@ -1231,6 +1231,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_f
     for (int i = lane; i < A; i += 32) s.a_res[i] = 0;
     __syncwarp();
     const unsigned long long* claims = d.claims + (size_t)env * d.maxobj;
+    uint32_t* visited = d.visited + (size_t)env * d.maxobj;  // GridObject::visited, kept apart from the records: this scan is coalesced
     const int nobj = w.E[MGEV_NEXT_OBJ];
     const uint32_t step = w.step;
     for (int s0_ = 1; s0_ < nobj; s0_ += 128) {  // four independent claim loads per lane in flight
@@ -1244,12 +1245,12 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_f
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         vis[q] = step;
-        if ((uint32_t)(c[q] >> 32) == step) vis[q] = objp(w, s0_ + 32 * q + lane)[MGO_VISITED];
+        if ((uint32_t)(c[q] >> 32) == step) vis[q] = visited[s0_ + 32 * q + lane];
       }
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         if (vis[q] < step) {
-          objp(w, s0_ + 32 * q + lane)[MGO_VISITED] = step;
+          visited[s0_ + 32 * q + lane] = step;
           const uint32_t ag = 0xffffffffu - (uint32_t)c[q];
           if (ag < (uint32_t)A) atomicAdd(&s.a_res[ag], step - vis[q]);
         }

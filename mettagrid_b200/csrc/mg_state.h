@@ -57,6 +57,7 @@ struct MgDev {
   uint16_t* obsval;           // [N][A][OVW] word 0 = count, then (feature | value << 8) tokens of the configured global values
   int OVW;                    // 0 when the program has no global observation values
   unsigned long long* claims; // [N][maxobj] step << 32 | ~agent of the lowest agent that saw the object in the latest tick
+  uint32_t* visited;          // [N][maxobj] GridObject::visited (the step an object was last observed); MGO_VISITED in the record is unused
   const uint32_t* obs_offs;   // [NOFF] packed window offsets in Manhattan order (mg_capi.cu), read-only
   const struct MgFastHdr* hdr_host;  // HOST copy of the program header, passed to kernels by value
   const float* logtab;        // logf(k + 1), k in [0, 65536), from the host libm
