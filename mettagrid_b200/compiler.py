@@ -623,6 +623,12 @@ class _Builder:
             elif mt == "attack":
                 # The reference's Python lowering has no AttackMutation branch: dropped.
                 continue
+            elif mt == "cpp_attack":  # the C++ op itself (attack_mutation.hpp:20-38), reachable only through pybind
+                for r in (m.weapon, m.armor, m.health):
+                    if r not in self.rid:
+                        raise CompileError(f"AttackMutation references unknown resource '{r}'.")
+                node(K["MGM_ATTACK"], 0, 0, self.rid[m.weapon], self.rid[m.armor], self.rid[m.health], int(m.damage_multiplier_pct))
+                self.features.add("inventory")
             else:
                 raise CompileError(f"Unknown mutation type: {type(m)}")
         first = len(self.mutations)

@@ -487,6 +487,20 @@ class SwapMutation:
 
 
 @dataclass
+class CppAttackMutation:
+    """The C++ engine's AttackMutation (cpp/include/mettagrid/handler/mutations/attack_mutation.hpp:20-38): damage =
+    max(0, actor[weapon] * pct / 100 - target[armor]) taken from target[health].  The reference's Python lowering never
+    emits it (its own `AttackMutation` config class is dropped), so it has no counterpart there: a handler
+    holding one can only be built for the reference through the pybind `add_attack_mutation` (oracle/ref_driver.py)."""
+
+    weapon: str
+    armor: str
+    health: str
+    damage_multiplier_pct: int = 100
+    mutation_type: str = "cpp_attack"
+
+
+@dataclass
 class UseTargetMutation:
     mutation_type: str = "use_target"
 

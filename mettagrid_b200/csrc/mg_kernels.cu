@@ -299,7 +299,7 @@ __device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc,
 // runs when every row is written, advances the stamps of the objects claimed this tick and credits the winners.
 //
 // The program header travels as a kernel argument (constant bank) and the packed window offsets are a small
-// read-only table (L1-resident), so a CTA has no prologue; blockIdx.y is the environment.
+// read-only table (L1-resident), so a CTA has no prologue; blockIdx.x is the environment.
 // =================================================================================================
 #ifndef MG_OBS_MIN_WARPS
 #define MG_OBS_MIN_WARPS 32  // resident warps per SM the register budget is chosen for (64 registers; A/B: profiles/README.md)
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int* const hdr = HD.v;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.y, a = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int env = blockIdx.x, a = blockIdx.y * (blockDim.x >> 5) + warp;  // grid.x = environments (no 65535 limit)
   const int A = d.A, T = d.T;
   if (a >= A || (mask && !mask[env])) return;
 
@@ -1402,7 +1402,7 @@ static int obs_warps(int A) {  // agents per CTA: all of them, or the largest di
 }
 static cudaError_t launch_observe_finish(const MgDev& d, const uint8_t* mask, int initial, cudaStream_t st) {
   const int wpc = obs_warps(d.A);
-  const dim3 grid((unsigned)((d.A + wpc - 1) / wpc), (unsigned)d.num_envs);
+  const dim3 grid((unsigned)d.num_envs, (unsigned)((d.A + wpc - 1) / wpc));
   const size_t ob = obs_smem_bytes(wpc, d.T);
   const bool plain = d.plain || (d.NTERR == 0 && d.OVW == 0);
   const MgFastHdr& H = *d.hdr_host;

@@ -259,6 +259,10 @@ class _Lower:
                 target.add_push_object_mutation(m.PushObjectMutationConfig())
             elif mt == "attack":
                 continue  # dropped by the reference's Python lowering
+            elif mt == "cpp_attack":  # handler_bindings.hpp:335-355,543-546: the only way to reach the C++ AttackMutation
+                target.add_attack_mutation(m.AttackMutationConfig(
+                    weapon_resource=b.rid[mu.weapon], armor_resource=b.rid[mu.armor], health_resource=b.rid[mu.health],
+                    damage_multiplier_pct=int(mu.damage_multiplier_pct)))  # fmt: skip
             elif mt == "add_tag":
                 target.add_add_tag_mutation(m.AddTagMutationConfig(entity=self.ent(mu.target), tag_id=b.tid[mu.tag]))
             elif mt == "remove_tag":

@@ -222,6 +222,48 @@ def many_tagged_map(seed: int = 0, num_agents: int = 4):
                                       objects={"pillar": 90, "shrine": 6, "wall": 4}))  # fmt: skip
 
 
+# ---------------------------------------------------------------------------------------------------------------
+def attack_mutation_config(ns, agents_per_team: int = 3):
+    """The C++ AttackMutation (attack_mutation.hpp:20-38: damage = max(0, weapon * pct / 100 - armor) off the target's
+    health).  No Python config of the reference lowers to it, so `ns` must be our mirror classes; the
+    reference side is built through pybind's add_attack_mutation (oracle/ref_driver.py), which is how its golden
+    fixture is recorded."""
+    H = ns.Handler
+    strike = H(name="strike", filters=[ns.isA("agent"), ns.actorHas({"weapon": 1}), ns.isNot(ns.sharedTagPrefix("team:"))],
+               mutations=[ns.CppAttackMutation(weapon="weapon", armor="armor", health="hp", damage_multiplier_pct=150),
+                          ns.updateActor({"energy": -1}), ns.logStat("strikes")])  # fmt: skip
+    heavy = H(name="heavy", filters=[ns.isA("agent"), ns.actorVibe("swords"), ns.actorHas({"weapon": 3})],
+              mutations=[ns.CppAttackMutation(weapon="weapon", armor="armor", health="hp", damage_multiplier_pct=333)])  # fmt: skip
+
+    def agent(team, tag, weapon, armor):
+        return ns.AgentConfig(team_id=team, tags=[tag], inventory=ns.InventoryConfig(
+            default_limit=40, initial={"hp": 30, "weapon": weapon, "armor": armor, "energy": 9}),
+            on_tick=H(name="mend", filters=[ns.PeriodicFilter(period=6)], mutations=[ns.updateTarget({"hp": 2, "energy": 1})]))  # fmt: skip
+
+    armory = ns.GridObjectConfig(name="armory", inventory=ns.InventoryConfig(initial={"weapon": 9, "armor": 9}),
+                                 on_use_handler=ns.firstMatch([
+                                     H(name="arm", filters=[ns.actorVibe("swords")], mutations=[ns.withdraw({"weapon": 1})]),
+                                     H(name="plate", mutations=[ns.withdraw({"armor": 1})])]))  # fmt: skip
+    agents = [agent(0, "team:red", 1 + i, i % 3) for i in range(agents_per_team)] + \
+             [agent(1, "team:blue", 3 - i % 3, 2 - i % 2) for i in range(agents_per_team)]  # fmt: skip
+    game = ns.GameConfig(
+        resource_names=["hp", "weapon", "armor", "energy"],
+        num_agents=2 * agents_per_team,
+        max_steps=0,
+        obs=ns.ObsConfig(width=9, height=9, num_tokens=160),
+        agents=agents,
+        actions=ns.ActionsConfig(noop=ns.NoopActionConfig(), move=ns.MoveActionConfig(handlers=[heavy, strike]),
+                                 change_vibe=ns.ChangeVibeActionConfig(vibes=_vibes(ns, ["default", "swords"]))),
+        objects={"wall": ns.WallConfig(), "armory": armory},
+    )  # fmt: skip
+    return ns.MettaGridConfig(game=game)
+
+
+def attack_mutation_map(seed: int = 0, agents_per_team: int = 3):
+    return random_map(RandomMapConfig(width=9, height=8, border_width=1, seed=seed, agents={"red": agents_per_team, "blue": agents_per_team},
+                                      objects={"armory": 3, "wall": 2}))  # fmt: skip
+
+
 def wrong_stream_actions(rng: np.random.RandomState, steps: int, agents: int, num_primary: int, num_actions: int):
     """The reference benchmark's verbatim sampling (uniform over ALL ids into the primary buffer) plus valid
     ids on the wrong stream in the vibe buffer (cpp/bindings/mettagrid_c.cpp:975-978: silently ignored, not failures)."""

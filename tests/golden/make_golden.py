@@ -30,10 +30,17 @@ from tests import refns  # noqa: E402
 ns = refns.reference_namespace()
 out_dir = Path(__file__).resolve().parent
 for name, (mk_cfg, mk_map, seed, steps, _pv, _pi) in gc.CASES.items():
-    cfg = mk_cfg(ns)
     grid = mk_map()
-    c_cfg, renames = convert_to_cpp_game_config(cfg.game)
-    env = MettaGrid(c_cfg, rename_map_agents(grid.tolist(), renames), seed)
+    if name in gc.VIA_DRIVER:  # e.g. the C++ AttackMutation: unreachable from the reference's Python configs
+        from mettagrid_b200 import config as C  # noqa: E402
+        from oracle.ref_driver import RefEnv  # noqa: E402
+
+        cfg = mk_cfg(C)
+        env = RefEnv(cfg, grid, seed).env
+    else:
+        cfg = mk_cfg(ns)
+        c_cfg, renames = convert_to_cpp_game_config(cfg.game)
+        env = MettaGrid(c_cfg, rename_map_agents(grid.tolist(), renames), seed)
     prog = compile_config(cfg, *grid.shape)  # only for action-space sizes
     prim, vibe = gc.case_actions(name, prog)
     steps = len(prim)

@@ -67,9 +67,15 @@ CASES = {
     "dyn_limits": (lambda ns: ec.dyn_limits_config(ns), lambda: ec.dyn_limits_map(5), 5, 500, 0.3, 0.0),
     "event_targets": (lambda ns: ec.event_targets_config(ns), lambda: ec.event_targets_map(6), 6, 300, 0.0, 0.0),
     "many_tagged": (lambda ns: ec.many_tagged_config(ns), lambda: ec.many_tagged_map(7), 7, 200, 0.0, 0.0),
+    "attack_mutation": (lambda ns: ec.attack_mutation_config(ns), lambda: ec.attack_mutation_map(8), 8, 500, 0.3, 0.0),
     "world_2v2_nospawn_trunc": (lambda ns: cases.world_config(ns, 2, spawn=False, max_steps=120, num_tokens=160),
                                 lambda: cases.world_map(2, width=15, height=12, seed=9), 9, 150, 0.25, 0.01),  # fmt: skip
 }
+
+
+# cases no Python config of the reference can express: recorded through oracle/ref_driver.py (pybind configs built
+# directly, checked against the reference's own lowering in tests/test_oracle_vs_reference.py) from our mirror classes
+VIA_DRIVER = {"attack_mutation"}
 
 
 def case_actions(name, prog):
