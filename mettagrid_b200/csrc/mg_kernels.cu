@@ -46,8 +46,6 @@ namespace {
 
 struct Smem {
   int32_t* hdr;
-  uint32_t* offs;
-  uint8_t* rank;      // [(dr + rr) * 16 + (dc + cr)] -> position of the offset in Manhattan order, 0xFF = outside the shape
   // per warp
   uint16_t* cells;
   int* rs;
@@ -87,15 +85,11 @@ __host__ __device__ inline size_t smem_per_warp(int HWp, int T, int A) {  // HWp
   n += align16(sizeof(Wv)) + align16(sizeof(Smem));
   return n;
 }
-__host__ __device__ inline size_t smem_per_cta(int NOFF) { return align16(MGH_HEADER_WORDS * 4) + align16((size_t)NOFF * 4) + 256; }
+__host__ __device__ inline size_t smem_per_cta(int) { return align16(MGH_HEADER_WORDS * 4); }
 
 __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int warp, Smem& s) {
   s.hdr = (int32_t*)base;
   base += align16(MGH_HEADER_WORDS * 4);
-  s.offs = (uint32_t*)base;
-  base += align16((size_t)d.NOFF * 4);
-  s.rank = (uint8_t*)base;
-  base += 256;
   base += (size_t)warp * smem_per_warp(d.stage_grid ? d.HWp : 0, d.T, d.A);
   s.cells = (uint16_t*)base;
   base += align16((size_t)(d.stage_grid ? d.HWp : 0) * 2);
@@ -119,21 +113,9 @@ __device__ __forceinline__ void carve(const MgDev& d, unsigned char* base, int w
   s.self = (Smem*)base;
 }
 
-// CTA prologue: header + packed observation offsets into shared memory
+// CTA prologue: the program header into shared memory (the interpreter reads it through the env view)
 __device__ __forceinline__ void load_cta_tables(const MgDev& d, Smem& s) {
   for (int i = threadIdx.x; i < MGH_HEADER_WORDS; i += blockDim.x) s.hdr[i] = __ldg(d.P + i);
-  __syncthreads();
-  const int32_t* offs = d.P + s.hdr[MGS_OFFSETS];
-  int rr = s.hdr[MGH_OBS_H] >> 1, cr = s.hdr[MGH_OBS_W] >> 1;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s.rank[i] = 0xFF;
-  __syncthreads();
-  for (int i = threadIdx.x; i < d.NOFF; i += blockDim.x) {
-    int dr = __ldg(offs + 2 * i), dc = __ldg(offs + 2 * i + 1);
-    uint32_t loc = (uint32_t)(((dr + rr) << 4) | ((dc + cr) & 15));  // systems/packed_coordinate.hpp:50-56
-    // bits 0-7: dr + 8 | (dc + 8) << 4 ; bits 8-15: packed location ; bits 16-31: cell delta in the padded grid
-    s.offs[i] = (uint32_t)(dr + 8) | ((uint32_t)(dc + 8) << 4) | (loc << 8) | ((uint32_t)((dr * d.WP + dc) & 0xffff) << 16);
-    s.rank[loc] = (uint8_t)i;  // loc = (dr + rr) << 4 | (dc + cr); NOFF <= 225
-  }
   __syncthreads();
 }
 
