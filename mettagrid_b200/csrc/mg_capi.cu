@@ -81,6 +81,12 @@ struct mg_handle {
   float* grid_scale = nullptr;  // device float[256], per-feature normalisation of the dense grid observations
   int grid_features = 0;
   cudaStream_t own_stream = nullptr;
+  // mg_step of a generic handle splits the batch into chunks on these streams so that one chunk's latency-bound
+  // k_world overlaps another chunk's issue-bound k_observe (launch_step)
+  enum { MAX_CHUNKS = 8 };
+  int chunks = 1;
+  cudaStream_t chunk_stream[MAX_CHUNKS] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_CHUNKS] = {};
 };
 
 static std::string g_create_error;
@@ -107,7 +113,24 @@ static int sync_generic(mg_handle* h, cudaStream_t st) {
 }
 static int launch_step(mg_handle* h, const MgDev& dev, cudaStream_t st) {
   if (!h->fast) {
-    CK(mg_launch_step(dev, st));
+    if (h->chunks <= 1) {
+      CK(mg_launch_step(dev, st));
+      return MG_OK;
+    }
+    // k_world -> k_observe -> k_finish per chunk of envs, every chunk on its own stream, forked from and joined back
+    // into the caller's stream: envs are independent, and the tick's three kernels stress different parts of an SM
+    CK(cudaEventRecord(h->ev_fork, st));
+    const int n = dev.num_envs, per = ((n + h->chunks - 1) / h->chunks + 3) & ~3;
+    for (int c = 0; c < h->chunks; c++) {
+      MgDev part = dev;
+      part.env0 = c * per;
+      part.num_envs = (c + 1) * per < n ? (c + 1) * per : n;
+      if (part.env0 >= part.num_envs) break;
+      CK(cudaStreamWaitEvent(h->chunk_stream[c], h->ev_fork, 0));
+      CK(mg_launch_step(part, h->chunk_stream[c]));
+      CK(cudaEventRecord(h->ev_join[c], h->chunk_stream[c]));
+      CK(cudaStreamWaitEvent(st, h->ev_join[c], 0));
+    }
     return MG_OK;
   }
   if (h->newest == mg_handle::GENERIC) {
@@ -417,6 +440,23 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     h->err = "mg_create: stream creation failed";
     return fail(MG_E_CUDA);
   }
+  if (!h->fast) {
+    // chunks per tick: METTAGRID_B200_CHUNKS, default 4 once the batch is large enough to fill the GPU several times
+    const char* f = getenv("METTAGRID_B200_CHUNKS");
+    int want = f ? atoi(f) : ((long long)num_envs * d.A >= 131072 ? 4 : 1);
+    if (want > mg_handle::MAX_CHUNKS) want = mg_handle::MAX_CHUNKS;
+    if (want > 1) {
+      bool ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int c = 0; c < want && ok; c++)
+        ok = cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) {
+        h->err = "mg_create: stream creation failed";
+        return fail(MG_E_CUDA);
+      }
+      h->chunks = want;
+    }
+  }
   e = cudaDeviceSynchronize();  // the zero fills above ran on the legacy stream, own_stream does not wait for it
   if (e == cudaSuccess) e = mg_launch_reset(d, nullptr, h->own_stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->own_stream);
@@ -434,6 +474,11 @@ void mg_destroy(mg_handle* h) {
   cudaSetDevice(h->device);
   for (void* p : h->allocs) cudaFree(p);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int c = 0; c < mg_handle::MAX_CHUNKS; c++) {
+    if (h->chunk_stream[c]) cudaStreamDestroy(h->chunk_stream[c]);
+    if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 

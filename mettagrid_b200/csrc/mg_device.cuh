@@ -69,19 +69,19 @@ struct Deferred {
 // Packed into 24 bytes: contexts live in local memory (they are passed by reference through the non-inlined
 // interpreter) and one is built per handler invocation.  Object slots are < 65536 (mg_create), coordinates fit
 // int16 (a line scan may step one cell outside the map).
-struct Ctx {
+struct alignas(8) Ctx {
   uint16_t actor, target, source;
   int16_t distance, tr, tc;
   int8_t move_dir;
   bool skip_trigger, failed;
+  uint8_t pad_;
   Deferred* deferred;
 };
-__device__ __forceinline__ Ctx make_ctx() {
+static_assert(sizeof(Ctx) == 24, "Ctx is built and copied as three 8-byte words");
+__device__ __forceinline__ Ctx make_ctx() {  // two 8-byte zero stores + the pointer instead of one store per field
   Ctx c;
-  c.actor = c.target = c.source = 0;
-  c.distance = c.tr = c.tc = 0;
-  c.move_dir = 0;
-  c.skip_trigger = c.failed = false;
+  unsigned long long* q = reinterpret_cast<unsigned long long*>(&c);
+  q[0] = 0ull, q[1] = 0ull;
   c.deferred = nullptr;
   return c;
 }

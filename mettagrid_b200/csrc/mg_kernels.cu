@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int* const hdr = HD.v;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x, a = blockIdx.y * (blockDim.x >> 5) + warp;  // grid.x = environments (no 65535 limit)
+  const int env = d.env0 + blockIdx.x, a = blockIdx.y * (blockDim.x >> 5) + warp;  // grid.x = environments (no 65535 limit)
   const int A = d.A, T = d.T;
   if (a >= A || (mask && !mask[env])) return;
 
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mask) {  // a masked launch usually selects few environments: a CTA without any leaves before loading tables
-    const int e = blockIdx.x * MG_WARPS_PER_CTA + warp;
+    const int e = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
     if (!__syncthreads_or(e < d.num_envs && mask[e])) return;
   }
   {
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_reset(MgDev d, const 
     carve(d, smem_raw, warp, cta);
     load_cta_tables(d, cta);
   }
-  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  const int env = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
   if (mask && !mask[env]) return;
   Smem s0;
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mask) {  // a masked launch usually selects few environments: a CTA without any leaves before loading tables
-    const int e = blockIdx.x * MG_WARPS_PER_CTA + warp;
+    const int e = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
     if (!__syncthreads_or(e < d.num_envs && mask[e])) return;
   }
   {
@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32) k_init_buffers(MgDev d,
     carve(d, smem_raw, warp, cta);
     load_cta_tables(d, cta);
   }
-  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  const int env = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
   if (mask && !mask[env]) return;
   Smem s0;
@@ -996,7 +996,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_w
     carve(d, smem_raw, warp, cta);
     load_cta_tables(d, cta);
   }
-  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  const int env = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
   Smem s0;
   carve(d, smem_raw, warp, s0);
@@ -1189,7 +1189,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mask) {
-    const int e = blockIdx.x * MG_WARPS_PER_CTA + warp;
+    const int e = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
     if (!__syncthreads_or(e < d.num_envs && mask[e])) return;
   }
   {
@@ -1197,7 +1197,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_f
     carve(d, smem_raw, warp, cta);
     load_cta_tables(d, cta);
   }
-  const int env = blockIdx.x * MG_WARPS_PER_CTA + warp;
+  const int env = d.env0 + blockIdx.x * MG_WARPS_PER_CTA + warp;
   if (env >= d.num_envs) return;
   if (mask && !mask[env]) return;
   Smem s0;
@@ -1374,7 +1374,8 @@ cudaError_t mg_configure_kernels(const MgDev& d) {
   if ((e = cudaFuncSetAttribute(k_world<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_world<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
-static inline int mg_grid(const MgDev& d) { return (d.num_envs + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
+// a launch covers the envs [d.env0, d.num_envs): the whole handle, or one chunk of it (mg_capi.cu: launch_step)
+static inline int mg_grid(const MgDev& d) { return (d.num_envs - d.env0 + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
 // the observation pass + what follows it, for a tick (initial = 0) or for _init_buffers (initial = 1)
 static int obs_warps(int A) {  // agents per CTA: all of them, or the largest divisor of A that fits, so no warp idles
   if (A <= MG_OBS_MAX_WARPS) return A;
@@ -1384,7 +1385,7 @@ static int obs_warps(int A) {  // agents per CTA: all of them, or the largest di
 }
 static cudaError_t launch_observe_finish(const MgDev& d, const uint8_t* mask, int initial, cudaStream_t st) {
   const int wpc = obs_warps(d.A);
-  const dim3 grid((unsigned)d.num_envs, (unsigned)((d.A + wpc - 1) / wpc));
+  const dim3 grid((unsigned)(d.num_envs - d.env0), (unsigned)((d.A + wpc - 1) / wpc));
   const size_t ob = obs_smem_bytes(wpc, d.T);
   const bool plain = d.plain || (d.NTERR == 0 && d.OVW == 0);
   const MgFastHdr& H = *d.hdr_host;

@@ -26,6 +26,7 @@ struct MgFastHdr {
 struct MgDev {
   const int32_t* P;  // compiled program (global, read-only)
   int num_envs;
+  int env0;  // first env of this launch (0 unless mg_step splits the batch into chunks on several streams)
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
   int NPROXY;  // territory proxy objects behind the object pool: one per territory and agent
   uint32_t* fast_blk;    // [N][fast_stride] packed hot state of k_step_fast (layout below), or null

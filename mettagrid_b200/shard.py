@@ -41,16 +41,45 @@ def reduce_agent_stats(values: torch.Tensor, counts: torch.Tensor, group=None) -
     return (total / n.clamp(min=1)).to(torch.float32)
 
 
+def gpu_cpu_affinity(device_index: int) -> set[int]:
+    """CPUs NVML recommends for a GPU (the cores of its NUMA node); empty when NVML cannot say."""
+    try:
+        import os
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = [int(x) for x in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if x.strip().isdigit()]
+        h = pynvml.nvmlDeviceGetHandleByIndex(vis[device_index] if device_index < len(vis) else device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() or 64 + 63) // 64 + 1)
+        return {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+    except Exception:
+        return set()
+
+
 def gpu_numa_node(device_index: int) -> int | None:
-    """NUMA node of a GPU, from its PCI address in sysfs (None when the platform does not say)."""
+    """NUMA node of a GPU: from its PCI address in sysfs, else the node that holds the CPUs NVML recommends."""
     try:
         p = torch.cuda.get_device_properties(device_index)
         addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
         with open(f"/sys/bus/pci/devices/{addr}/numa_node") as f:
             node = int(f.read().strip())
-        return node if node >= 0 else None
+        if node >= 0:
+            return node
     except Exception:
-        return None
+        pass
+    try:
+        import glob
+
+        cpus = gpu_cpu_affinity(device_index)
+        if cpus:
+            for path in sorted(glob.glob("/sys/devices/system/node/node[0-9]*/cpulist")):
+                with open(path) as f:
+                    if min(cpus) in _cpulist(f.read()):
+                        return int(path.split("/node")[-1].split("/")[0])
+    except Exception:
+        pass
+    return None
 
 
 def _cpulist(text: str) -> set[int]:
@@ -73,16 +102,19 @@ def bind_to_gpu_numa(device_index: int) -> dict:
 
     node = gpu_numa_node(device_index)
     info: dict = {"gpu": device_index, "numa_node": node, "cpus": None, "mempolicy": False}
-    if node is None:
-        return info
     try:
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            cpus = _cpulist(f.read()) & os.sched_getaffinity(0)
-        if cpus:
+        cpus = gpu_cpu_affinity(device_index)
+        if not cpus and node is not None:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = _cpulist(f.read())
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
             os.sched_setaffinity(0, cpus)
             info["cpus"] = len(cpus)
     except Exception:
         pass
+    if node is None:
+        return info
     try:  # set_mempolicy(MPOL_PREFERRED, {node}): x86-64 syscall 238
         mask = ctypes.c_ulong(1 << node)
         rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
