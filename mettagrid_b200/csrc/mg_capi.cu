@@ -441,9 +441,10 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     return fail(MG_E_CUDA);
   }
   if (!h->fast) {
-    // chunks per tick: METTAGRID_B200_CHUNKS, default 4 once the batch is large enough to fill the GPU several times
+    // chunks per tick: METTAGRID_B200_CHUNKS, default 2 once the batch is large enough to fill the GPU several times
+    // (C4 8192 envs: 1292 -> 1228 us per tick, C3 16 384 envs: 2126 -> 2097 us; profiles/README.md)
     const char* f = getenv("METTAGRID_B200_CHUNKS");
-    int want = f ? atoi(f) : ((long long)num_envs * d.A >= 131072 ? 4 : 1);
+    int want = f ? atoi(f) : ((long long)num_envs * d.A >= 131072 ? 2 : 1);  // measured: 2 / 4 / 8 chunks within 1 % of each other
     if (want > mg_handle::MAX_CHUNKS) want = mg_handle::MAX_CHUNKS;
     if (want > 1) {
       bool ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
