@@ -121,6 +121,14 @@ int mg_info_gather(mg_handle* h, void* game_values, void* game_present, void* ag
 int mg_grid_obs_configure(mg_handle* h, int num_features, const float* scale);
 int mg_obs_to_grid(mg_handle* h, const void* observations, int rows, void* grid, void* stream);
 
+/* Token-policy front end (next row 8f-3): replaces TokenPolicyNet._encode_tokens up to the pooled summary --
+ * python/src/mettagrid/policy/token_encoder.py:89-113.  observations: uint8 [rows][T][3] (DEVICE; NULL = the handle's
+ * buffer); pos_x / pos_y: float32 [>=16][hidden] (nn.Embedding weights; a nibble selects rows 0-15), feat: float32
+ * [num_feat][hidden], scale: float32 [num_feat] (the module's _feature_scale), out: float32 [rows][hidden]; all DEVICE,
+ * hidden <= 256; asynchronous.  Forward only: the token_mlp / heads behind it stay torch modules. */
+int mg_token_summary(mg_handle* h, const void* observations, int rows, const void* pos_x, const void* pos_y, const void* feat,
+                     const void* scale, int hidden, int num_feat, void* out, void* stream);
+
 /* sizes */
 int mg_num_envs(const mg_handle* h);
 int mg_num_agents(const mg_handle* h);

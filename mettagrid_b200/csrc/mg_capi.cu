@@ -27,6 +27,8 @@ cudaError_t mg_launch_fast_restore(const MgDev& d, const MgFastLayout& L, const 
 cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_obs_to_grid(const uint8_t* obs, float* grid, int rows, int T, int C, int H, int W, const float* scale,
                                   cudaStream_t st);
+cudaError_t mg_launch_token_summary(const uint8_t* obs, int rows, int T, int hidden, int num_feat, const float* pos_x,
+                                    const float* pos_y, const float* feat, const float* scale, float* out, cudaStream_t st);
 cudaError_t mg_launch_vecenv_prepare(const void* act, int is_int64, int ncols, int num_envs, int A, int P, int V,
                                      const int32_t* vibe_ids, int32_t* actions, int32_t* vibe_actions, const uint8_t* term,
                                      const uint8_t* trunc, uint8_t* done, int64_t* steps, int* counters, cudaStream_t st);
@@ -902,6 +904,24 @@ int mg_obs_to_grid(mg_handle* h, const void* observations, int rows, void* grid,
   CK(cudaSetDevice(h->device));
   CK(mg_launch_obs_to_grid(obs, (float*)grid, rows, h->d.T, h->grid_features, h->program[MGH_OBS_H], h->program[MGH_OBS_W],
                            h->grid_scale, (cudaStream_t)stream));
+  return MG_OK;
+}
+
+int mg_token_summary(mg_handle* h, const void* observations, int rows, const void* pos_x, const void* pos_y, const void* feat,
+                     const void* scale, int hidden, int num_feat, void* out, void* stream) {
+  if (!h || !pos_x || !pos_y || !feat || !scale || !out || rows <= 0 || num_feat <= 0) return MG_E_INVALID;
+  if (hidden <= 0 || hidden > 256) {
+    h->err = "mg_token_summary: hidden must be in [1, 256]";
+    return MG_E_INVALID;
+  }
+  const uint8_t* obs = observations ? (const uint8_t*)observations : h->d.obs;
+  if (!obs) {
+    h->err = "mg_token_summary: no observation buffer (pass one or call mg_set_buffers)";
+    return MG_E_INVALID;
+  }
+  CK(cudaSetDevice(h->device));
+  CK(mg_launch_token_summary(obs, rows, h->d.T, hidden, num_feat, (const float*)pos_x, (const float*)pos_y, (const float*)feat,
+                             (const float*)scale, (float*)out, (cudaStream_t)stream));
   return MG_OK;
 }
 

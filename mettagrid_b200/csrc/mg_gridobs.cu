@@ -69,3 +69,74 @@ cudaError_t mg_launch_obs_to_grid(const uint8_t* obs, float* grid, int rows, int
   k_obs_to_grid<<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(obs, grid, rows, T, C, H, W, scale);
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_token_summary: the front end of the reference's token policy, TokenPolicyNet._encode_tokens up to the pooled
+// summary (python/src/mettagrid/policy/token_encoder.py:89-113), fused over the observation rows where they lie:
+//   summary[row, h] = sum over valid tokens of (pos_x[x][h] + pos_y[y][h] + feat[f][h]) * (value / (scale[f] + 1e-6))
+//                     / sqrt(max(#valid, 1)),     valid = coord byte != 0xFF, x = low nibble, y = high nibble.
+// The torch version materialises a [rows, T, hidden] float tensor (7.5 GB at C2) before pooling it; here a warp owns a
+// row, lanes own hidden columns, the row's tokens are staged in shared memory, and only [rows, hidden] leaves the SM.
+// The 16 rows of each position table a nibble can select are staged per CTA; the feature table is read through L1.
+// Sums run in token order in fp32 (torch reduces the token axis in its own order: parity is a tolerance, 1e-5 relative).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+#define MG_TS_WARPS 8
+#define MG_TS_MAXH 8  // hidden columns per lane: hidden <= 256
+__global__ void __launch_bounds__(MG_TS_WARPS * 32) k_token_summary(const uint8_t* __restrict__ obs, int rows, int T, int hidden,
+                                                                   int num_feat, const float* __restrict__ pos_x,
+                                                                   const float* __restrict__ pos_y, const float* __restrict__ feat,
+                                                                   const float* __restrict__ scale, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char ts_smem[];
+  float* spx = (float*)ts_smem;           // [16][hidden]
+  float* spy = spx + 16 * hidden;         // [16][hidden]
+  uint8_t* stok = (uint8_t*)(spy + 16 * hidden);  // [warps][3T rounded up to 16]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 16 * hidden; i += blockDim.x) spx[i] = pos_x[i], spy[i] = pos_y[i];
+  __syncthreads();
+  const int row = blockIdx.x * MG_TS_WARPS + warp;
+  if (row >= rows) return;
+  const int nb = 3 * T;
+  uint8_t* tk = stok + (size_t)warp * ((nb + 15) & ~15);
+  const uint8_t* src = obs + (size_t)row * nb;
+  for (int i = lane; i < nb; i += 32) tk[i] = src[i];
+  __syncwarp();
+  float acc[MG_TS_MAXH];
+#pragma unroll
+  for (int j = 0; j < MG_TS_MAXH; j++) acc[j] = 0.0f;
+  int count = 0;
+  for (int t = 0; t < T; t++) {
+    const int coord = tk[3 * t];
+    if (coord == 0xFF) continue;  // warp-uniform: every lane reads the same token
+    count++;
+    const int x = coord & 15, y = coord >> 4;
+    const int f = min((int)tk[3 * t + 1], num_feat - 1);
+    const float sv = __fdiv_rn((float)tk[3 * t + 2], __fadd_rn(__ldg(scale + f), 1e-6f));
+    const float* fr = feat + (size_t)f * hidden;
+#pragma unroll
+    for (int j = 0; j < MG_TS_MAXH; j++) {
+      const int h = lane + 32 * j;
+      if (h < hidden) {
+        const float e = __fadd_rn(__fadd_rn(spx[x * hidden + h], spy[y * hidden + h]), __ldg(fr + h));
+        acc[j] = __fadd_rn(acc[j], __fmul_rn(e, sv));
+      }
+    }
+  }
+  const float norm = sqrtf((float)max(count, 1));
+#pragma unroll
+  for (int j = 0; j < MG_TS_MAXH; j++) {
+    const int h = lane + 32 * j;
+    if (h < hidden) out[(size_t)row * hidden + h] = __fdiv_rn(acc[j], norm);
+  }
+}
+}  // namespace
+
+cudaError_t mg_launch_token_summary(const uint8_t* obs, int rows, int T, int hidden, int num_feat, const float* pos_x,
+                                    const float* pos_y, const float* feat, const float* scale, float* out, cudaStream_t st) {
+  const size_t smem = (size_t)32 * hidden * sizeof(float) + (size_t)MG_TS_WARPS * ((3 * T + 15) & ~15);
+  cudaError_t e = cudaFuncSetAttribute(k_token_summary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_token_summary<<<(rows + MG_TS_WARPS - 1) / MG_TS_WARPS, MG_TS_WARPS * 32, smem, st>>>(obs, rows, T, hidden, num_feat, pos_x, pos_y,
+                                                                                         feat, scale, out);
+  return cudaGetLastError();
+}

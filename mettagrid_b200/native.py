@@ -40,6 +40,7 @@ SYMBOLS = {
     "mg_vecenv_configure": (_i, [_vp, _i, _vp, _i, _vp]),
     "mg_vecenv_step": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "mg_vecenv_poll": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "mg_token_summary": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "mg_info_configure": (_i, [_vp, _i, _vp, _i, _vp]),
     "mg_info_gather": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mg_grid_obs_configure": (_i, [_vp, _i, _vp]),
