@@ -105,20 +105,25 @@ __global__ void __launch_bounds__(MG_TS_WARPS * 32) k_token_summary(const uint8_
 #pragma unroll
   for (int j = 0; j < MG_TS_MAXH; j++) acc[j] = 0.0f;
   int count = 0;
-  for (int t = 0; t < T; t++) {
-    const int coord = tk[3 * t];
-    if (coord == 0xFF) continue;  // warp-uniform: every lane reads the same token
-    count++;
-    const int x = coord & 15, y = coord >> 4;
-    const int f = min((int)tk[3 * t + 1], num_feat - 1);
-    const float sv = __fdiv_rn((float)tk[3 * t + 2], __fadd_rn(__ldg(scale + f), 1e-6f));
-    const float* fr = feat + (size_t)f * hidden;
+  for (int t0 = 0; t0 < T; t0 += 32) {  // 32 coordinate bytes per ballot: only valid tokens are visited
+    const int tl = t0 + lane;
+    uint32_t m = __ballot_sync(0xffffffffu, tl < T && tk[3 * tl] != 0xFF);
+    count += __popc(m);
+    while (m) {
+      const int t = t0 + __ffs(m) - 1;
+      m &= m - 1;
+      const int coord = tk[3 * t];
+      const int x = coord & 15, y = coord >> 4;
+      const int f = min((int)tk[3 * t + 1], num_feat - 1);
+      const float sv = __fdiv_rn((float)tk[3 * t + 2], __fadd_rn(__ldg(scale + f), 1e-6f));
+      const float* fr = feat + (size_t)f * hidden;
 #pragma unroll
-    for (int j = 0; j < MG_TS_MAXH; j++) {
-      const int h = lane + 32 * j;
-      if (h < hidden) {
-        const float e = __fadd_rn(__fadd_rn(spx[x * hidden + h], spy[y * hidden + h]), __ldg(fr + h));
-        acc[j] = __fadd_rn(acc[j], __fmul_rn(e, sv));
+      for (int j = 0; j < MG_TS_MAXH; j++) {
+        const int h = lane + 32 * j;
+        if (h < hidden) {
+          const float e = __fadd_rn(__fadd_rn(spx[x * hidden + h], spy[y * hidden + h]), __ldg(fr + h));
+          acc[j] = __fadd_rn(acc[j], __fmul_rn(e, sv));
+        }
       }
     }
   }
