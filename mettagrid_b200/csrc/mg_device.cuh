@@ -505,9 +505,71 @@ __device__ __noinline__ QList query_eval(const Wv& w, int D, int qi, const Ctx& 
 __device__ __noinline__ void mutate(const Wv& w, int D, int mi, Ctx& ctx);
 __device__ __noinline__ bool handler_apply(const Wv& w, int D, int h, Ctx& ctx);
 
-__device__ __forceinline__ bool filters_pass(const Wv& w, int D, int f0, int n, const Ctx& ctx) {
-  for (int i = 0; i < n; i++)
-    if (!filter_pass(w, D, f0 + i, ctx)) return false;
+// AND of a handler's filters (handler/handler.cpp:76-103).  Most filters are leaves -- a compare against the actor's or
+// the target's record -- and most NOT / OR filters wrap leaves: those are evaluated right here from one row load each,
+// so a typical filter list costs ONE call instead of one per filter (calls spill and reload registers through local
+// memory, which the profile shows as the interpreter's main latency).  Anything else goes through filter_pass.
+__device__ __forceinline__ int filter_leaf(const Wv& w, const int32_t* f, const Ctx& ctx) {  // 1 / 0, or -1: not a leaf
+  const int2 r0 = __ldg((const int2*)f), r1 = __ldg((const int2*)f + 1);  // op, entity, a, b (rows are 8-byte aligned)
+  const int op = r0.x, a = r1.x, b = r1.y;
+  const int e = r0.y == MGE_ACTOR ? ctx.actor : r0.y == MGE_TARGET ? ctx.target : ctx.source;
+  switch (op) {
+    case MGF_VIBE:
+      return e && o_vibe(objp(w, e)) == a;
+    case MGF_RESOURCE:
+      return e && (int)o_inv(w, objp(w, e))[a] >= b;
+    case MGF_TAG_PREFIX: {
+      if (!e) return 0;
+      const uint32_t* x = objp(w, e);
+      const int32_t* m = pool(w, a);
+      for (int k = 0; k < w.TW; k++)
+        if (x[MGO_TAGS + k] & (uint32_t)__ldg(m + k)) return 1;
+      return 0;
+    }
+    case MGF_SHARED_TAG_PREFIX: {
+      if (!ctx.actor || !ctx.target) return 0;
+      const uint32_t *x = objp(w, ctx.actor), *y = objp(w, ctx.target);
+      const int32_t* m = pool(w, a);
+      for (int k = 0; k < w.TW; k++)
+        if (x[MGO_TAGS + k] & y[MGO_TAGS + k] & (uint32_t)__ldg(m + k)) return 1;
+      return 0;
+    }
+    case MGF_TARGET_LOC_EMPTY:
+      return ctx.target == 0;
+    case MGF_TARGET_IS_USABLE:
+      return ctx.target != 0;
+    case MGF_PERIODIC:
+      return w.step >= (uint32_t)b && (w.step - (uint32_t)b) % (uint32_t)a == 0;
+    default:
+      return -1;
+  }
+}
+__device__ __noinline__ bool filters_pass(const Wv& w, int D, int f0, int n, const Ctx& ctx) {
+  const int32_t* f = sec(w, MGS_FILTERS) + f0 * MG_FILTER_WORDS;
+  for (int i = 0; i < n; i++, f += MG_FILTER_WORDS) {
+    int r = filter_leaf(w, f, ctx);
+    if (r < 0) {
+      const int op = __ldg(f);
+      if ((op == MGF_NEG || op == MGF_OR) && D > 0) {  // one level of NOT(AND(leaves)) / OR(leaves) inline
+        const int c0 = __ldg(f + 2), cn = __ldg(f + 3);
+        const int32_t* cf = sec(w, MGS_FILTERS) + c0 * MG_FILTER_WORDS;
+        bool all = true, any = false, flat = true;
+        for (int k = 0; k < cn && flat; k++, cf += MG_FILTER_WORDS) {
+          const int cr = filter_leaf(w, cf, ctx);
+          if (cr < 0) {
+            flat = false;
+          } else {
+            all = all && cr;
+            any = any || cr;
+            if (op == MGF_NEG ? !cr : cr) break;  // the reference stops at the first failing (NOT) / passing (OR) child
+          }
+        }
+        if (flat) r = op == MGF_NEG ? !all : any;
+      }
+      if (r < 0) r = filter_pass(w, D, f0 + i, ctx);
+    }
+    if (!r) return false;
+  }
   return true;
 }
 __device__ __forceinline__ int resolve_entity(const Ctx& c, int e) { return e == MGE_ACTOR ? c.actor : e == MGE_TARGET ? c.target : c.source; }
