@@ -316,11 +316,18 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   // first, then the heads of the objects standing there (cached token count, first token pair): two memory round
   // trips per agent, issued before anything else is computed.
   uint32_t pk[NP], slot[NP], nt[NP], t0[NP];
+  uint8_t own0[NP];  // territory 0's winner at the cell (aoe_mask tokens), loaded with the cell ids
+  const int fmask = (!PLAIN && d.NTERR > 0) ? hdr[MGH_FEAT_AOE_MASK] : 0;
 #pragma unroll
   for (int p = 0; p < NP; p++) {
     const int k = 32 * p + lane;
     pk[p] = k < NOFF ? __ldg(d.obs_offs + k) : 0u;
     slot[p] = k < NOFF ? (uint32_t)centre[(int)(short)(pk[p] >> 16)] : 0u;
+    own0[p] = 0xFF;  // 0xFF: outside the map (no token)
+    if (!PLAIN && fmask && k < NOFF) {
+      const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
+      if (r >= 0 && c >= 0 && r < d.H && c < d.W) own0[p] = d.owner_map[(size_t)env * d.NTERR * d.HW + r * d.W + c];
+    }
     if (MG_CHECKED && slot[p] >= (uint32_t)d.maxobj) {  // checked builds: a cell must name a slot of this env's pool
       atomicOr(&d.env[(size_t)env * MGEV_WORDS + MGEV_ERROR], MGERR_BOUNDS);
       slot[p] = 0;
@@ -371,7 +378,6 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
 
   // ---- tokens.  Positions come from two ballots (an object with one token -- every wall -- needs no scan);
   // multi-token objects are copied by the whole warp, one token per lane, four at a time.
-  const int fmask = (!PLAIN && d.NTERR > 0) ? hdr[MGH_FEAT_AOE_MASK] : 0;
   const uint32_t* const me = objs + (size_t)me_in.w * OS;
   unsigned long long* const claims = d.claims + (size_t)env * d.maxobj;
   const unsigned long long my_claim = ((unsigned long long)step << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
@@ -380,17 +386,15 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
     if (32 * p >= NOFF) break;
     const int loc = (int)((pk[p] >> 8) & 0xffu);
     int tmask = 0, n = 0;
-    if (fmask && 32 * p + lane < NOFF) {
+    if (!PLAIN && fmask && own0[p] != 0xFF) {
       // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens (ownership map: mg_world.cuh)
       const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
-      if (r >= 0 && c >= 0 && r < d.H && c < d.W) {
-        const uint8_t* own = d.owner_map + (size_t)env * d.NTERR * d.HW + r * d.W + c;
-        for (int ti = 0; ti < d.NTERR && !tmask; ti++) {
-          const int v = own[(size_t)ti * d.HW];
-          if (v) {
-            const int tag = __ldg(d.P + hdr[MGS_POOL] + __ldg(d.P + hdr[MGS_TERRITORIES] + ti * MG_TERR_WORDS) + v - 1);
-            tmask = o_has_tag(me, tag) ? 1 : 2;
-          }
+      const uint8_t* own = d.owner_map + (size_t)env * d.NTERR * d.HW + r * d.W + c;
+      for (int ti = 0; ti < d.NTERR && !tmask; ti++) {
+        const int v = ti == 0 ? (int)own0[p] : (int)own[(size_t)ti * d.HW];
+        if (v) {
+          const int tag = __ldg(d.P + hdr[MGS_POOL] + __ldg(d.P + hdr[MGS_TERRITORIES] + ti * MG_TERR_WORDS) + v - 1);
+          tmask = o_has_tag(me, tag) ? 1 : 2;
         }
       }
     }
