@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B timing of kernel build variants on ONE box (scratch; variant libraries are built into variants/)
+shopt -s nullglob
 for lib in mettagrid_b200/libmettagrid_b200.so variants/lib_*.so; do
   echo "== $lib"
   for rep in 1 2; do

@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B timing of generic-kernel build variants on ONE box (libraries built into variants/ by
 # python -m mettagrid_b200.build --variant NAME -DFLAG...)
+shopt -s nullglob
 for lib in mettagrid_b200/libmettagrid_b200.so variants/lib_*.so; do
   case $lib in *prof*) continue;; esac
   echo "== $lib"
