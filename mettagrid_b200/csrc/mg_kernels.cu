@@ -288,7 +288,10 @@ __device__ __forceinline__ void put_token(uint8_t* out, int T, int pos, int loc,
 #endif
 #define MG_OBS_MAX_WARPS 8   // warps (agents) per CTA: the launcher picks a divisor of A when it can
 
-__host__ __device__ inline size_t obs_smem_bytes(int warps, int T) { return (size_t)warps * align16((size_t)3 * T + 32); }
+#define MG_OBS_MULTI 24      // multi-token objects per window listed in shared memory (more: copied lane-serially)
+__host__ __device__ inline size_t obs_smem_bytes(int warps, int T) {  // per warp: the row's stage + the multi-token list
+  return (size_t)warps * (align16((size_t)3 * T + 32) + (size_t)16 * MG_OBS_MULTI);
+}
 
 // NP = window passes of 32 cells whose loads are issued together: 4 (up to 11 x 11 windows) or 8 (up to 15 x 15)
 template <bool PLAIN, int NP>
@@ -376,81 +379,127 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
     base += n;
   }
 
-  // ---- tokens.  Positions come from two ballots (an object with one token -- every wall -- needs no scan);
-  // multi-token objects are copied by the whole warp, one token per lane, four at a time.
+  // ---- tokens.  The whole window is settled at once: lane l holds the cells of rank l, l + 32, ... (Manhattan order),
+  // so "tokens before mine" = the cells of earlier passes + the lower lanes of my pass: one ballot and two popcounts
+  // per pass for the cells that emit one token (every wall), plus a short loop over the few cells that emit more.
   const uint32_t* const me = objs + (size_t)me_in.w * OS;
   unsigned long long* const claims = d.claims + (size_t)env * d.maxobj;
   const unsigned long long my_claim = ((unsigned long long)step << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
+  int n[NP], tm[NP], cnt[NP], pos[NP];
+  uint32_t m_any[NP], m_multi[NP];
+  bool dirty = false;
 #pragma unroll
   for (int p = 0; p < NP; p++) {
-    if (32 * p >= NOFF) break;
-    const int loc = (int)((pk[p] >> 8) & 0xffu);
-    int tmask = 0, n = 0;
+    tm[p] = 0;
     if (!PLAIN && fmask && own0[p] != 0xFF) {
       // :337-362, one aoe_mask token per in-map cell, before the cell's object tokens (ownership map: mg_world.cuh)
       const int r = r0 + (int)(pk[p] & 15u) - 8, c = c0 + (int)((pk[p] >> 4) & 15u) - 8;
       const uint8_t* own = d.owner_map + (size_t)env * d.NTERR * d.HW + r * d.W + c;
-      for (int ti = 0; ti < d.NTERR && !tmask; ti++) {
+      for (int ti = 0; ti < d.NTERR && !tm[p]; ti++) {
         const int v = ti == 0 ? (int)own0[p] : (int)own[(size_t)ti * d.HW];
         if (v) {
           const int tag = __ldg(d.P + hdr[MGS_POOL] + __ldg(d.P + hdr[MGS_TERRITORIES] + ti * MG_TERR_WORDS) + v - 1);
-          tmask = o_has_tag(me, tag) ? 1 : 2;
+          tm[p] = o_has_tag(me, tag) ? 1 : 2;
         }
       }
     }
-    if (__ballot_sync(MG_FULL, (slot[p] | (uint32_t)tmask) != 0) == 0) continue;  // nothing visible in these 32 cells
+    n[p] = 0;
     if (slot[p]) {
       atomicMax(claims + slot[p], my_claim);  // cell staleness (:787-796): settled by k_finish
-      n = (int)nt[p];
-      if ((uint32_t)n == MG_TOK_DIRTY) {
+      n[p] = (int)nt[p];
+      dirty = dirty || nt[p] == MG_TOK_DIRTY;
+    }
+  }
+  if (__any_sync(MG_FULL, dirty)) {  // a non-agent object changed since it was last seen: rebuild its cached tokens
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+      if (slot[p] && nt[p] == MG_TOK_DIRTY) {
         uint32_t* o = objs + (size_t)slot[p] * OS;
-        n = rebuild_token_cache(TokCtx{d.P, d.P, d.env + (size_t)env * MGEV_WORDS, d.TW, d.B, d.ND, TOKOFF}, o);  // header = start of P
+        n[p] = rebuild_token_cache(TokCtx{d.P, d.P, d.env + (size_t)env * MGEV_WORDS, d.TW, d.B, d.ND, TOKOFF}, o);  // header = start of P
         t0[p] = o[TOKOFF];
       }
-    }
-    const int cnt = n + (tmask != 0);
-    const uint32_t m_any = __ballot_sync(MG_FULL, cnt != 0);
-    uint32_t m_multi = __ballot_sync(MG_FULL, cnt > 1);
-    int pos = base + __popc(m_any & lt), tot = __popc(m_any);
-    while (m_multi) {
-      const int b = __ffs(m_multi) - 1;
-      m_multi &= m_multi - 1;
-      const int extra = __shfl_sync(MG_FULL, cnt, b) - 1;
-      pos += b < lane ? extra : 0;
-      tot += extra;
-    }
-    if (tmask) put_token(out, T, pos, loc, fmask, tmask);
-    pos += tmask != 0;
-    if (n == 1) put_token(out, T, pos, loc, (int)(t0[p] & 0xffu), (int)((t0[p] >> 8) & 0xffu));
-    uint32_t m_obj = __ballot_sync(MG_FULL, n > 1);
-    while (m_obj) {
-      uint32_t ev[4], sv[4];
-      int nv[4], pv[4], lv[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        nv[q] = 0;
-        if (m_obj) {
-          const int b = __ffs(m_obj) - 1;
-          m_obj &= m_obj - 1;
-          nv[q] = __shfl_sync(MG_FULL, n, b), pv[q] = __shfl_sync(MG_FULL, pos, b), lv[q] = __shfl_sync(MG_FULL, loc, b);
-          sv[q] = __shfl_sync(MG_FULL, slot[p], b);
-          if (lane < nv[q]) ev[q] = ((const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF))[lane];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        if (lane < nv[q]) put_token(out, T, pv[q] + lane, lv[q], (int)(ev[q] & 0xffu), (int)(ev[q] >> 8));
-        if (nv[q] > 32) {  // longer lists than lanes: the rest straight from the record
-          const uint16_t* tk = (const uint16_t*)(objs + (size_t)sv[q] * OS + TOKOFF);
-          for (int j = lane + 32; j < nv[q]; j += 32) {
-            const uint32_t e = tk[j];
-            put_token(out, T, pv[q] + j, lv[q], (int)(e & 0xffu), (int)(e >> 8));
-          }
-        }
-      }
-    }
-    base += tot;
   }
+  int run = base;
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    cnt[p] = n[p] + (tm[p] != 0);
+    m_any[p] = __ballot_sync(MG_FULL, cnt[p] != 0);
+    m_multi[p] = __ballot_sync(MG_FULL, cnt[p] > 1);
+    pos[p] = run + __popc(m_any[p] & lt);
+    run += __popc(m_any[p]);
+  }
+#pragma unroll
+  for (int p = 0; p < NP; p++) {  // cells with more than one token push everything behind them
+    uint32_t m = m_multi[p];
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int extra = __shfl_sync(MG_FULL, cnt[p], b) - 1;
+#pragma unroll
+      for (int q = p; q < NP; q++) pos[q] += (q > p || lane > b) ? extra : 0;
+      run += extra;
+    }
+  }
+  // single tokens straight from registers; multi-token objects go through a list in shared memory
+  uint32_t* const mlist = (uint32_t*)(smem_raw + (size_t)(blockDim.x >> 5) * align16((size_t)3 * T + 32)) + warp * (4 * MG_OBS_MULTI);
+  int nmulti = 0;
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const int loc = (int)((pk[p] >> 8) & 0xffu);
+    if (tm[p]) put_token(out, T, pos[p], loc, fmask, tm[p]);
+    const int tpos = pos[p] + (tm[p] != 0);
+    if (n[p] == 1) put_token(out, T, tpos, loc, (int)(t0[p] & 0xffu), (int)((t0[p] >> 8) & 0xffu));
+    const uint32_t mo = __ballot_sync(MG_FULL, n[p] > 1);
+    if (n[p] > 1) {
+      const int i = nmulti + __popc(mo & lt);
+      if (i < MG_OBS_MULTI) {
+        uint32_t* e = mlist + 4 * i;
+        e[0] = slot[p], e[1] = (uint32_t)tpos, e[2] = (uint32_t)loc, e[3] = (uint32_t)n[p];
+      }
+    }
+    nmulti += __popc(mo);
+  }
+  __syncwarp();
+  // the whole warp copies each listed object's cached (feature, value) pairs behind its location byte, one lane per
+  // token, the loads of four objects in flight together; anything beyond the list's capacity is copied by its own lane
+  const int listed = min(nmulti, MG_OBS_MULTI);
+  for (int i0 = 0; i0 < listed; i0 += 4) {
+    uint32_t ev[4];
+    uint4 en[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      en[q] = make_uint4(0, 0, 0, 0);
+      if (i0 + q < listed) {
+        en[q] = *(const uint4*)(mlist + 4 * (i0 + q));
+        if (lane < (int)en[q].w) ev[q] = ((const uint16_t*)(objs + (size_t)en[q].x * OS + TOKOFF))[lane];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (lane < (int)en[q].w) put_token(out, T, (int)en[q].y + lane, (int)en[q].z, (int)(ev[q] & 0xffu), (int)(ev[q] >> 8));
+      if ((int)en[q].w > 32) {  // longer lists than lanes: the rest straight from the record
+        const uint16_t* tk = (const uint16_t*)(objs + (size_t)en[q].x * OS + TOKOFF);
+        for (int j = lane + 32; j < (int)en[q].w; j += 32) {
+          const uint32_t e = tk[j];
+          put_token(out, T, (int)en[q].y + j, (int)en[q].z, (int)(e & 0xffu), (int)(e >> 8));
+        }
+      }
+    }
+  }
+  if (nmulti > MG_OBS_MULTI) {  // more multi-token objects in one window than the list holds (rare): each by its own lane
+    int seen = 0;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const uint32_t mo = __ballot_sync(MG_FULL, n[p] > 1);
+      if (n[p] > 1 && seen + __popc(mo & lt) >= MG_OBS_MULTI) {
+        const uint16_t* tk = (const uint16_t*)(objs + (size_t)slot[p] * OS + TOKOFF);
+        const int tpos = pos[p] + (tm[p] != 0), loc = (int)((pk[p] >> 8) & 0xffu);
+        for (int j = 0; j < n[p]; j++) put_token(out, T, tpos + j, loc, (int)(tk[j] & 0xffu), (int)(tk[j] >> 8));
+      }
+      seen += __popc(mo);
+    }
+  }
+  base = run;
   if (lane == 0) d.tok_attempted[(size_t)env * A + a] = base;  // k_finish adds the env's token stats in agent order (:659-661)
   // ---- stream out: token bytes come from the stage, the rest of the row is 0xFF (EmptyTokenByte, :940-942)
   __syncwarp();
