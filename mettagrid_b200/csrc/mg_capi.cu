@@ -259,6 +259,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   d.SG = P[MGH_NUM_GAME_STATS], d.SGW = (d.SG + 31) / 32, d.CW = P[MGH_COVER_WORDS], d.maxobj = P[MGH_MAX_OBJECTS];
   d.NOFF = P[MGH_NUM_OFFSETS], d.B = P[MGH_TOKEN_BASE], d.ND = P[MGH_INV_DIGITS], d.NTERR = P[MGH_NUM_TERRITORIES];
   d.NPROXY = d.NTERR * d.A;
+  d.objs_stride = (uint32_t)(d.maxobj + d.NPROXY) * (uint32_t)d.OS;
   d.plain = program_is_plain(P);
   if (d.R > 13 || d.maxobj > 65535 || d.A > 4096) {
     h->err = "mg_create: program exceeds engine limits (R<=13, objects<=65535, agents<=4096)";

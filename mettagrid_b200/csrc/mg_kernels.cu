@@ -193,7 +193,9 @@ __device__ __forceinline__ void flush_row(uint8_t* src, uint8_t* g, int n, int u
   const uint4* s4 = (const uint4*)(src + head);
   uint4* g4 = (uint4*)(g + head);
   const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-  for (int i = lane; i < body; i += 32) __stcs(g4 + i, head + 16 * i < pad_to - 15 ? s4[i] : ff);
+  const int tv = min(body, max(0, (pad_to - head) >> 4));  // vectors that lie entirely inside the staged (token + pad) bytes
+  for (int i = lane; i < tv; i += 32) __stcs(g4 + i, s4[i]);
+  for (int i = tv + lane; i < body; i += 32) __stcs(g4 + i, ff);
   const int done = head + (body << 4);
   if (lane < n - done) g[done + lane] = done + lane < pad_to ? src[done + lane] : (uint8_t)0xFF;
 }
@@ -304,13 +306,16 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   const int A = d.A, T = d.T;
   if (a >= A || (mask && !mask[env])) return;
 
-  const uint4 me_in = d.obs_in[(size_t)env * A + a];  // executed action, start-of-tick location, location, object slot
+  // 32-bit index arithmetic throughout (one widening multiply per base pointer): rows, slots and strides all fit
+  const uint32_t row = (uint32_t)env * (uint32_t)A + (uint32_t)a;
+  const uint4 me_in = d.obs_in[row];  // executed action, start-of-tick location, location, object slot
   const int r0 = (int)(me_in.z >> 16), c0 = (int)(me_in.z & 0xffffu);
-  const uint32_t step = (uint32_t)d.env[(size_t)env * MGEV_WORDS + MGEV_STEP];
-  uint32_t* const objs = d.objs + (size_t)env * (d.maxobj + d.NPROXY) * d.OS;
-  const uint16_t* const centre = d.cells + (size_t)env * d.HWp + (r0 + d.PAD) * d.WP + c0 + d.PAD;
-  uint8_t* const g_row = d.obs + ((size_t)env * A + a) * (size_t)(3 * T);
-  uint8_t* const out = smem_raw + (size_t)warp * align16((size_t)3 * T + 32) + ((uint32_t)(uintptr_t)g_row & 15u);
+  const uint32_t step = (uint32_t)d.env[(uint32_t)env * (uint32_t)MGEV_WORDS + MGEV_STEP];
+  uint32_t* const objs = d.objs + (size_t)(uint32_t)env * (size_t)d.objs_stride;
+  const uint16_t* const centre = d.cells + (size_t)(uint32_t)env * (size_t)(uint32_t)d.HWp + (uint32_t)((r0 + d.PAD) * d.WP + c0 + d.PAD);
+  uint8_t* const g_row = d.obs + (size_t)row * (size_t)(uint32_t)(3 * T);
+  const uint32_t stage_bytes = ((uint32_t)(3 * T + 32) + 15u) & ~15u;
+  uint8_t* const out = smem_raw + (uint32_t)warp * stage_bytes + ((uint32_t)(uintptr_t)g_row & 15u);
   const int OS = d.OS, NOFF = d.NOFF, TOKOFF = MG_TOKOFF(d.TW, d.R);
   const uint32_t lt = (1u << lane) - 1u;
 
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   for (int p = 0; p < NP; p++) {
     nt[p] = t0[p] = 0;
     if (slot[p]) {
-      const uint32_t* o = objs + (size_t)slot[p] * OS;
+      const uint32_t* o = objs + slot[p] * (uint32_t)OS;
       nt[p] = o[MGO_NTOK], t0[p] = o[TOKOFF];
     }
   }
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
     // rewards are zeroed before and written after the observation pass (:937-938,1062,1070): always 0
     have = 1, feat = hdr[MGH_FEAT_LAST_REWARD], val = 0;
   } else if ((lane == 4 || lane == 5) && (flags & MGG_LOCAL_POSITION)) {
-    const uint32_t sp = d.agents[((size_t)env * A + a) * d.AS + MGAG_SPAWN];
+    const uint32_t sp = d.agents[(size_t)row * (size_t)(uint32_t)d.AS + MGAG_SPAWN];
     const int dd = lane == 4 ? c0 - (int)(sp & 0xffffu) : (int)(sp >> 16) - r0;
     if (dd != 0) {
       have = 1;
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   int base = __popc(gm);
   // ---- configured global game values (:1207-1238): evaluated by k_world, one (feature | value << 8) pair per token
   if (!PLAIN && d.OVW > 0) {
-    const uint16_t* ov = d.obsval + ((size_t)env * A + a) * d.OVW;
+    const uint16_t* ov = d.obsval + (size_t)row * (size_t)(uint32_t)d.OVW;
     const int n = ov[0];
     for (int j = lane; j < n; j += 32) put_token(out, T, base + j, 0xFE, ov[1 + j] & 0xff, ov[1 + j] >> 8);
     base += n;
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
   // so "tokens before mine" = the cells of earlier passes + the lower lanes of my pass: one ballot and two popcounts
   // per pass for the cells that emit one token (every wall), plus a short loop over the few cells that emit more.
   const uint32_t* const me = objs + (size_t)me_in.w * OS;
-  unsigned long long* const claims = d.claims + (size_t)env * d.maxobj;
+  unsigned long long* const claims = d.claims + (size_t)(uint32_t)env * (size_t)(uint32_t)d.maxobj;
   const unsigned long long my_claim = ((unsigned long long)step << 32) | (unsigned long long)(0xffffffffu - (uint32_t)a);
   int n[NP], tm[NP], cnt[NP], pos[NP];
   uint32_t m_any[NP], m_multi[NP];
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
     }
   }
   // single tokens straight from registers; multi-token objects go through a list in shared memory
-  uint32_t* const mlist = (uint32_t*)(smem_raw + (size_t)(blockDim.x >> 5) * align16((size_t)3 * T + 32)) + warp * (4 * MG_OBS_MULTI);
+  uint32_t* const mlist = (uint32_t*)(smem_raw + (blockDim.x >> 5) * stage_bytes) + warp * (4 * MG_OBS_MULTI);
   int nmulti = 0;
 #pragma unroll
   for (int p = 0; p < NP; p++) {
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
       en[q] = make_uint4(0, 0, 0, 0);
       if (i0 + q < listed) {
         en[q] = *(const uint4*)(mlist + 4 * (i0 + q));
-        if (lane < (int)en[q].w) ev[q] = ((const uint16_t*)(objs + (size_t)en[q].x * OS + TOKOFF))[lane];
+        if (lane < (int)en[q].w) ev[q] = ((const uint16_t*)(objs + en[q].x * (uint32_t)OS + TOKOFF))[lane];
       }
     }
 #pragma unroll
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(MG_OBS_MAX_WARPS * 32, MG_OBS_MIN_WARPS / MG_O
     }
   }
   base = run;
-  if (lane == 0) d.tok_attempted[(size_t)env * A + a] = base;  // k_finish adds the env's token stats in agent order (:659-661)
+  if (lane == 0) d.tok_attempted[row] = base;  // k_finish adds the env's token stats in agent order (:659-661)
   // ---- stream out: token bytes come from the stage, the rest of the row is 0xFF (EmptyTokenByte, :940-942)
   __syncwarp();
   flush_row(out, g_row, 3 * T, 3 * min(base, T), lane);

@@ -29,6 +29,7 @@ struct MgDev {
   int env0;  // first env of this launch (0 unless mg_step splits the batch into chunks on several streams)
   int H, W, HW, HWp, A, T, R, TW, OS, AS, SA, SAW, SG, SGW, CW, maxobj, NOFF, B, ND, NTERR;
   int NPROXY;  // territory proxy objects behind the object pool: one per territory and agent
+  uint32_t objs_stride;  // words of object records per env = (maxobj + NPROXY) * OS
   uint32_t* fast_blk;    // [N][fast_stride] packed hot state of k_step_fast (layout below), or null
   int fast_stride;       // words per env
   const uint32_t* rank_lut;  // [256] packed window offset (dr + rr) << 4 | (dc + cr) -> rank << 24 | offset << 16, where rank is

@@ -1,4 +1,4 @@
-"""Per-phase cycle split of the generic step kernel (needs the -DMG_PHASE_TIMING variant):
+"""Per-phase cycle split of k_world, the first kernel of the generic tick, (needs the -DMG_PHASE_TIMING variant):
     python -m mettagrid_b200.build --variant prof -DMG_PHASE_TIMING
     METTAGRID_B200_LIB=$PWD/variants/lib_prof.so python tools/phase_timing.py c3 16384
 """
@@ -35,7 +35,7 @@ for i in range(K):
     sim.actions.copy_(prim[i % 16]); sim.vibe_actions.copy_(vibe[i % 16]); sim.step()
 e1.record(); torch.cuda.synchronize()
 L.mg_debug_phase_cycles(out, 0)
-names = sys.argv[3].split(",") if len(sys.argv) > 3 else ["prologue", "shuffle+actions", "bookkeeping", "events+on_tick", "aoe+territory+game_on_tick", "coverage+terr_table", "observations", "rewards+tail"]
+names = sys.argv[3].split(",") if len(sys.argv) > 3 else ["prologue", "shuffle+actions", "bookkeeping", "events+on_tick", "aoe+territory+game_on_tick", "coverage (+ hand-over follows)"]
 tot = sum(out)
 print(f"{wl} N={N}: {e0.elapsed_time(e1) / K * 1000:.0f} us/tick (kernel {sim.step_kernel})")
 for n, c in zip(names, out):
