@@ -190,6 +190,8 @@ class ClockSampler(threading.Thread):
 
 def kernel_name(sk: int) -> str:
     """What mg_step launches per tick (include/mettagrid_b200.h: mg_step_kernel)."""
+    if sk >= 64:
+        return f"k_step_fast<{sk - 64},static>"
     return f"k_step_fast<{sk}>" if sk >= 8 else ("k_world<true>+k_observe+k_finish<true>" if sk == 1 else "k_world<false>+k_observe+k_finish<false>")
 
 

@@ -135,7 +135,8 @@ int mg_num_agents(const mg_handle* h);
 int mg_num_tokens(const mg_handle* h);
 size_t mg_state_bytes(const mg_handle* h); /* HBM held by the handle */
 /* which step kernel mg_step launches for this handle: 0 = generic (handler interpreter), 1 = plain (handler-free
- * program), 8 / 16 / 32 = the sparse fast path with that many lanes per environment */
+ * program), 8 / 16 / 32 = the sparse fast path with that many lanes per environment, 64 + lanes = the same with the
+ * static layer (walls kept as a bitmap outside the lanes) */
 int mg_step_kernel(const mg_handle* h);
 
 #ifdef __cplusplus

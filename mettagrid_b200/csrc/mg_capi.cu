@@ -18,7 +18,7 @@ cudaError_t mg_launch_reset(const MgDev& d, const uint8_t* mask, cudaStream_t st
 cudaError_t mg_launch_init_buffers(const MgDev& d, const uint8_t* mask, cudaStream_t st);
 cudaError_t mg_launch_step(const MgDev& d, cudaStream_t st);
 cudaError_t mg_launch_clear_outputs(const MgDev& d, const uint8_t* mask, cudaStream_t st);
-MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap);
+MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics);
 cudaError_t mg_fast_configure(const MgFastLayout& L);
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st);
 cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st);
@@ -48,6 +48,7 @@ struct mg_handle {
   std::string err;
   bool buffers_set = false;
   bool fast = false;  // k_step_fast applies (mg_fast.cu): plain program, sparse environments
+  int static_template = -1;  // static-layer variant: the one template every non-agent object is made from
   MgFastLayout fl{};
   MgFastHdr fh{};
   // which copy of the hot state is current on a fast handle: the generic arrays, the packed block, or both
@@ -196,7 +197,8 @@ static int program_is_plain(const int32_t* P) {
 
 // k_step_fast (mg_fast.cu) needs: a plain program, agents and objects that fit one warp, primary-stream actions
 // that are noop / move and vibe-stream actions that are change_vibe, well-known stat ids below 64, a window of at
-// most 15 x 15 cells.  Returns the lanes per environment (8, 16, 32) or 0.
+// most 15 x 15 cells.  Returns the lanes per environment (8, 16, 32) or 0.  `max_objects_per_env` counts what has to
+// sit in the object lanes: every object, or -- static-layer variant -- the agents only.
 static int fast_group_size(const int32_t* P, const MgDev& d, int max_objects_per_env) {
   if (!d.plain || getenv("METTAGRID_B200_NO_FAST")) return 0;
   if ((d.AS & 3) || (d.OS & 3)) return 0;  // vector loads of the records
@@ -210,6 +212,27 @@ static int fast_group_size(const int32_t* P, const MgDev& d, int max_objects_per
   }
   const int need = d.A > max_objects_per_env ? d.A : max_objects_per_env;
   return need <= 8 ? 8 : need <= 16 ? 16 : 32;
+}
+
+// The static-layer variant applies when every non-agent object of every map comes from ONE template whose token list
+// is short: then walls (or blocks) are a bitmap plus one shared token list.  Returns that template, -1 if the maps
+// hold no non-agent object or none qualifies (-2).
+static int static_layer_template(const int32_t* P, const MgDev& d, const int16_t* init_cells, size_t n_cells) {
+  if (getenv("METTAGRID_B200_NO_FAST_STATIC")) return -2;
+  const int32_t* TP = P + P[MGS_TEMPLATES];
+  int tmpl = -1;
+  for (size_t i = 0; i < n_cells; i++) {
+    const int t = init_cells[i];
+    if (t < 0 || TP[t * MG_TEMPLATE_WORDS + MGT_KIND] == 1) continue;
+    if (tmpl >= 0 && t != tmpl) return -2;
+    tmpl = t;
+  }
+  if (tmpl < 0) return -1;
+  const int32_t* tp = TP + tmpl * MG_TEMPLATE_WORDS;
+  int tokens = tp[MGT_VIBE] ? 1 : 0;
+  for (int k = 0; k < d.TW; k++) tokens += __builtin_popcount((uint32_t)P[P[MGS_POOL] + tp[MGT_TAGS] + k]);
+  tokens += tp[MGT_INIT_INV_N] * d.ND;  // upper bound: every digit of every held resource
+  return tokens <= MGFS_MAX_TOKENS ? tmpl : -2;
 }
 
 static const char* unsupported_reason(const int32_t* P) {
@@ -267,6 +290,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   }
   int rc;
   int max_objs = 0;  // most objects any env starts with
+  int max_static = 0;  // ... most non-agent objects
 #define TRY(x) \
   if ((rc = (x)) != MG_OK) return fail(rc)
   if (cudaSetDevice(device) != cudaSuccess) {
@@ -290,7 +314,7 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
     size_t max_aoe = 0, max_terr = 0;
     for (size_t e = 0; e < N; e++) {
       size_t na = 0, nt = 0;
-      int no = 0;
+      int no = 0, ns = 0;
       const int16_t* cells = init_cells + e * d.HW;
       for (int i = 0; i < d.HW; i++)
         if (cells[i] >= 0) {
@@ -299,10 +323,12 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
             return fail(MG_E_INVALID);
           }
           no++;
+          ns += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_KIND] != 1;
           na += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_AOES_N];
           nt += TP[cells[i] * MG_TEMPLATE_WORDS + MGT_TERR_N];
         }
       max_objs = no > max_objs ? no : max_objs;
+      max_static = ns > max_static ? ns : max_static;
       max_aoe = na > max_aoe ? na : max_aoe;
       max_terr = nt > max_terr ? nt : max_terr;
     }
@@ -427,16 +453,56 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
              " (shared memory per CTA = " + std::to_string(mg_smem_bytes(d)) + " bytes)";
     return fail(MG_E_CUDA);
   }
-  if (const int G = fast_group_size(P, d, max_objs)) {
-    h->fl = mg_fast_layout(d, G, P[MGH_TOK_CAP]);
+  // Sparse maps put every object into a lane; maps with more objects than lanes keep the agents there and carry the
+  // rest as the static layer, when one template makes all of it (walls).
+  int statics = 0;
+  if (d.plain && max_objs > 32) {
+    h->static_template = static_layer_template(P, d, init_cells, N * d.HW);
+    statics = h->static_template >= 0;
+  }
+  if (const int G = fast_group_size(P, d, statics ? d.A : max_objs)) {
+    if (statics) {
+      d.fast_sbw = (d.W + 2 * d.PAD + 31) / 32 + 1;  // + 1: a window row is a funnel shift over two adjacent words
+      d.fast_sstride = (MGFS_HDR_WORDS + (d.H + 2 * d.PAD) * d.fast_sbw + 3) & ~3;
+      d.fast_ns_cap = (max_static + 31) & ~31;
+    }
+    h->fl = mg_fast_layout(d, G, P[MGH_TOK_CAP], statics);
     memcpy(h->fh.v, P, sizeof h->fh.v);
     if (h->fl.smem_bytes <= 200 * 1024 && mg_fast_configure(h->fl) == cudaSuccess) {
       d.fast_stride = MGFB_WORDS(G);
       TRY(dev_alloc(h, &d.fast_blk, N * d.fast_stride));
       TRY(dev_alloc(h, &h->snapshot, N * d.fast_stride));
+      if (statics) {
+        uint32_t *sb, *sl, *less;
+        uint16_t* ss;
+        TRY(dev_alloc(h, &sb, N * d.fast_sstride));
+        TRY(dev_alloc(h, &sl, N * d.fast_ns_cap));
+        TRY(dev_alloc(h, &ss, N * d.fast_ns_cap));
+        TRY(dev_alloc(h, &d.fast_svis, N * d.fast_ns_cap));
+        TRY(dev_alloc(h, &less, 257 * 8));
+        // per packed window offset: the offsets that come earlier in the reference's Manhattan order
+        // (core/observation_shape.cpp:52-66); row 256: every offset of the shape
+        std::vector<uint32_t> tab(257 * 8, 0u);
+        const int32_t* offs = P + P[MGS_OFFSETS];
+        const int rr = P[MGH_OBS_H] >> 1, cr = P[MGH_OBS_W] >> 1;
+        uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < d.NOFF; i++) {
+          const uint32_t loc = (uint32_t)(((offs[2 * i] + rr) << 4) | ((offs[2 * i + 1] + cr) & 15));
+          memcpy(&tab[loc * 8], acc, sizeof acc);
+          acc[loc >> 5] |= 1u << (loc & 31);
+        }
+        memcpy(&tab[256 * 8], acc, sizeof acc);
+        if (cudaMemcpy(less, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+          h->err = "mg_create: upload failed";
+          return fail(MG_E_CUDA);
+        }
+        d.fast_static = sb, d.fast_slist = sl, d.fast_sslot = ss, d.fast_less = less;
+      }
       h->fast = true;
     } else {
       cudaGetLastError();  // too large for shared memory: the generic kernel runs instead
+      d.fast_sbw = d.fast_sstride = d.fast_ns_cap = 0;
+      h->fl.statics = 0;
     }
   }
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -620,16 +686,22 @@ int mg_set_map(mg_handle* h, int env, const int16_t* init_cells, const float* in
   if (!h || !init_cells || env < 0 || env >= h->d.num_envs) return MG_E_INVALID;
   const MgDev& d = h->d;
   const int32_t* P = h->program.data();
-  int nobj = 0;
+  int nobj = 0, nstatic = 0;
+  bool foreign = false;  // a non-agent object made from another template than the handle's static layer
   for (int i = 0; i < d.HW; i++) {
     if (init_cells[i] >= P[MGH_NUM_TEMPLATES]) {
       h->err = "mg_set_map: init_cells holds a template index outside the program";
       return MG_E_INVALID;
     }
     nobj += init_cells[i] >= 0;
+    if (init_cells[i] >= 0 && P[P[MGS_TEMPLATES] + init_cells[i] * MG_TEMPLATE_WORDS + MGT_KIND] != 1) {
+      nstatic++;
+      foreign |= init_cells[i] != h->static_template;
+    }
   }
-  if (nobj >= d.maxobj || (h->fast && nobj > h->fl.G)) {
-    h->err = "mg_set_map: the map holds more objects than this handle was created for";
+  const bool fits = !h->fast || (h->fl.statics ? nstatic <= d.fast_ns_cap && !foreign : nobj <= h->fl.G);
+  if (nobj >= d.maxobj || !fits) {
+    h->err = "mg_set_map: the map holds more objects (or other static objects) than this handle was created for";
     return MG_E_INVALID;
   }
   if (init_gstats && !d.init_gstats) {
@@ -963,6 +1035,8 @@ int mg_info_gather(mg_handle* h, void* game_values, void* game_present, void* ag
 }
 
 size_t mg_state_bytes(const mg_handle* h) { return h ? h->bytes : 0; }
-int mg_step_kernel(const mg_handle* h) { return !h ? MG_E_INVALID : h->fast ? h->fl.G : h->d.plain ? 1 : 0; }
+int mg_step_kernel(const mg_handle* h) {
+  return !h ? MG_E_INVALID : h->fast ? h->fl.G + (h->fl.statics ? 64 : 0) : h->d.plain ? 1 : 0;
+}
 
 }  // extern "C"

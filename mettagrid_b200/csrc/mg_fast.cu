@@ -20,6 +20,17 @@
 //   * `cell.visited` (:787-796) goes to the lowest agent index that sees an object (one ballot per object);
 //   * stat updates are decided in registers and written back once, in the reference's float-add order.
 // k_fast_pack / k_fast_unpack move the packed block from / to the generic arrays (mg_capi.cu decides when).
+//
+// k_step_fast<G, true> -- the static layer.  In a handler-free game nothing ever changes a non-agent object (walls,
+// blocks): no handler, event or AOE exists that could move, re-tag or refill it.  Maps with hundreds of them stay on
+// this kernel by keeping them OUT of the object lanes: the lanes hold the agents only, and the env carries
+//   * an occupancy bitmap of the padded grid (move test: one bit; observation: each window row is one funnel shift),
+//   * the list of static cells with one `visited` stamp each (:787-796).
+// An observer's window becomes a 256-bit mask indexed by the packed window offset; the position of any token is
+// (global tokens) + (tokens of dynamic objects earlier in Manhattan order) + (static tokens) x popcount(mask & the
+// precomputed set of offsets that come earlier).  The STATIC OBJECTS are then spread over all lanes: each finds its
+// observers from per-row / per-column agent masks, stamps `visited` for the lowest one and writes its token(s) into
+// every observer's row -- balanced over the lanes however unevenly the walls are spread over the windows.
 #include <cuda_runtime.h>
 
 #include "mg_state.h"
@@ -192,7 +203,7 @@ __device__ __forceinline__ void sort_net(uint32_t (&key)[32]) {
   }
 }
 
-template <int G>
+template <int G, bool S>
 __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_fast(const MgDev d, const MgFastLayout L, const MgFastHdr HD) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int GPW = 32 / G;  // environments per warp
@@ -224,7 +235,15 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   uint32_t* bag = blk + MGFB_AGENT(G, gl);
   uint32_t* bob = blk + MGFB_OBJECT(G, gl);
   float* bst = (float*)(blk + MGFB_STAT(G, 0, gl));  // stat id at bst[id * G]
-  uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)min(gl + 1, d.maxobj - 1)) * d.OS;
+  uint32_t* const sb = (uint32_t*)(gb + L.sb_off);  // static variant: the env's static block (header + bitmap)
+  if (S) {  // fire-and-forget copy of the block into shared memory; waited for before the moves
+    const uint32_t* src = d.fast_static + (size_t)env * d.fast_sstride;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sb);
+#pragma unroll 1
+    for (int v = gl; v < (L.sb_words >> 2); v += G)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * v), "l"(src + 4 * v) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   uint32_t* cvrow = d.cover + ga * d.CW;
   const int TOKOFF = MG_TOKOFF(d.TW, d.R);
   const int tokw = L.tok_stride;  // words per object in the shared token table
@@ -254,6 +273,15 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     }
   }
 
+  const uint32_t* slist = d.fast_slist + (size_t)env * d.fast_ns_cap;
+  uint32_t* svis = d.fast_svis + (size_t)env * d.fast_ns_cap;
+  if (S) {  // the static cells and their stamps are read late: pull their lines towards L2 now
+#pragma unroll 1
+    for (int i = gl * 32; i < d.fast_ns_cap; i += G * 32) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(slist + i));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(svis + i));
+    }
+  }
   uint8_t* gobs = d.obs + g0 * (size_t)(3 * T);
   const int nbytes = A * 3 * T;
 #pragma unroll
@@ -265,6 +293,9 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   int idx0 = (int)bh0.y;
   const int nobj = (int)bh0.z;
   const int ia = isA ? ia_raw : -1, iv = isA ? iv_raw : -1;
+  // the generic record behind this lane's object (long token tails, cache rebuilds): slot l + 1, or -- static variant,
+  // where the lanes hold the agents' objects -- the agent's own slot
+  uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)min(S ? (int)ag0.x : gl + 1, d.maxobj - 1)) * d.OS;
   const uint32_t a_slot = isA ? ag0.x : 1u, a_spawn = ag0.y, a_prev = ag0.z, a_swm = ag0.w, a_maxd = ag1.x;
   uint32_t a_unique = ag1.y;
   const bool isO = gl < nobj;
@@ -315,6 +346,12 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     for (; v < nv; v += G) s4[v] = ff;
   }
   stale[gl] = 0;
+  uint32_t* const rowm = (uint32_t*)(gb + L.rc_off);  // static variant: agents whose window covers row r / column c
+  uint32_t* const colm = rowm + d.H;
+  if (S) {
+#pragma unroll 1
+    for (int i = gl; i < d.H + d.W; i += G) rowm[i] = 0;
+  }
   const bool act_p = isA && !inv_p && ap.w == 0;  // executed in the primary stream (:966-999)
   const bool act_v = isA && !inv_v && av.w == 1;  // executed in the vibe stream
 
@@ -359,12 +396,15 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   if (!rej && live && gl < ndraws) rng[idx0 + gl] = nw;
   if (!rej && live && gl == 0 && ndraws > 0) blk[MGFB_RNG_IDX] = (uint32_t)(idx0 + ndraws);
-  __syncthreads();  // the window table (per CTA)
+  if (S) asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();  // the window table (per CTA), the static block (per group)
 
   // ---- moves in shuffled order, highest priority first (actions/move.hpp:81-115 with the two default
   // handlers: relocate into an empty in-map cell, else fail).  Lane i first fetches what the agent acting at
   // step i wants; the loop then only carries the object locations from step to step.
-  const int my_ol = (int)a_slot - 1;  // lane that plays this agent's object
+  const int my_ol = S ? gl : (int)a_slot - 1;  // lane that plays this agent's object
+  const uint32_t* const sbm = sb + MGFS_HDR_WORDS;  // static occupancy: bit c + PAD of row r + PAD
+  const int SBW = d.fast_sbw;
   const uint32_t my_loc0 = __shfl_sync(MG_FULL, o_loc, my_ol, G);
   if (isA && my_loc0 != FAST_INVALID)  // the coverage word this agent most likely needs (it moves at most one cell)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(cvrow + (((my_loc0 >> 16) * d.W + (my_loc0 & 0xffffu)) >> 5)));
@@ -375,7 +415,13 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     const int dr = (arg == 0 || arg == 4 || arg == 5) ? -1 : (arg == 1 || arg == 6 || arg == 7) ? 1 : 0;
     const int dc = (arg == 2 || arg == 4 || arg == 6) ? -1 : (arg == 3 || arg == 5 || arg == 7) ? 1 : 0;
     const int tr = (int)(my_loc0 >> 16) + dr, tc = (int)(my_loc0 & 0xffffu) + dc;
-    if (my_loc0 != FAST_INVALID && tr >= 0 && tr < d.H && tc >= 0 && tc < d.W) my_tgt = ((uint32_t)tr << 16) | (uint32_t)tc;
+    if (my_loc0 != FAST_INVALID && tr >= 0 && tr < d.H && tc >= 0 && tc < d.W) {
+      my_tgt = ((uint32_t)tr << 16) | (uint32_t)tc;
+      if (S) {  // a static object in the way: TargetLocEmpty fails, and nothing there has an on_use handler
+        const int cb = tc + d.PAD;
+        if ((sbm[(tr + d.PAD) * SBW + (cb >> 5)] >> (cb & 31)) & 1u) my_tgt = FAST_INVALID;
+      }
+    }
   }
   {
     // the step at which each agent acts (inverse of the shuffled order), handed to the lane that plays its object
@@ -580,12 +626,72 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // window tokens in Manhattan order (:756-811).  The observer walks its sorted keys once to give every visible
   // object its first token position; the object lanes then write their own tokens into each observer's row.
   uint32_t* tab = (uint32_t*)(gb + L.key_off);  // [observer][object] -> first token position | packed offset << 16
+  // static variant: this observer's window as a 256-bit set of packed offsets (row << 4 | column) holding a static object
+  uint32_t M[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t* const wm = (uint32_t*)(gb + L.wm_off);   // [agent][9] window masks
+  uint32_t* const dl = (uint32_t*)(gb + L.dl_off);   // [k][agent] sorted keys of the visible dynamic objects
+  uint32_t* const agw = (uint32_t*)(gb + L.ag_off);  // [agent] location, global-token count, visible dynamic objects
+  uint32_t* const ngw = agw + G;
+  uint32_t* const nvw = ngw + G;
+  const int s_ntok = S ? (int)sb[MGFS_NTOK] : 0;
+  if (S) {
+    const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W];
+    const int rtop = r0 - (OH >> 1) + d.PAD, cbit = c0 - (OW >> 1) + d.PAD;  // >= 0: the bitmap has a PAD-wide frame
+    const int kw = cbit >> 5, sh = cbit & 31;
+    const uint32_t wmask = (1u << OW) - 1u;
+#pragma unroll
+    for (int wr = 0; wr < 15; wr++) {
+      uint32_t bits = 0;
+      if (wr < OH && isA) {
+        const uint32_t* rw = sbm + (rtop + wr) * SBW + kw;
+        bits = __funnelshift_r(rw[0], rw[1], sh) & wmask;
+      }
+      if (wr & 1)
+        M[wr >> 1] |= bits << 16;
+      else
+        M[wr >> 1] = bits;
+    }
+    const uint4 sa = __ldg((const uint4*)(d.fast_less + 256 * 8)), sc = __ldg((const uint4*)(d.fast_less + 256 * 8) + 1);
+    M[0] &= sa.x, M[1] &= sa.y, M[2] &= sa.z, M[3] &= sa.w, M[4] &= sc.x, M[5] &= sc.y, M[6] &= sc.z, M[7] &= sc.w;
+#pragma unroll
+    for (int k = 0; k < 8; k++) wm[gl * 9 + k] = M[k];
+    agw[gl] = isA ? my_loc : FAST_INVALID;
+    ngw[gl] = (uint32_t)pos;
+  }
+  // static objects that come before packed offset `loc` in Manhattan order
+  auto statics_before = [&](uint32_t loc) {
+    const uint4* lp = (const uint4*)(d.fast_less + loc * 8);
+    const uint4 a = __ldg(lp), b = __ldg(lp + 1);
+    return __popc(M[0] & a.x) + __popc(M[1] & a.y) + __popc(M[2] & a.z) + __popc(M[3] & a.w) + __popc(M[4] & b.x) +
+           __popc(M[5] & b.y) + __popc(M[6] & b.z) + __popc(M[7] & b.w);
+  };
+  int nvis = 0;
 #pragma unroll
   for (int k = 0; k < G; k++) {
     const uint32_t kk = key[k];
     if (kk != FAST_INVALID) {
-      tab[gl * G + (int)(kk & 0xffu)] = (uint32_t)pos | (kk & 0x00ff0000u);
+      int p = pos;
+      if (S) {
+        p += s_ntok * statics_before((kk >> 16) & 0xffu);
+        dl[k * G + gl] = kk;
+        nvis++;
+      }
+      tab[gl * G + (int)(kk & 0xffu)] = (uint32_t)p | (kk & 0x00ff0000u);
       pos += (int)((kk >> 8) & 0xffu);
+    }
+  }
+  if (S) {
+    nvw[gl] = (uint32_t)nvis;
+    pos += s_ntok * (__popc(M[0]) + __popc(M[1]) + __popc(M[2]) + __popc(M[3]) + __popc(M[4]) + __popc(M[5]) + __popc(M[6]) +
+                     __popc(M[7]));
+    // which agents' windows cover each row and each column (the bounding box of the observation shape)
+    if (isA) {
+      const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W];
+      const uint32_t me = 1u << gl;
+#pragma unroll 1
+      for (int r = max(r0 - (OH >> 1), 0); r <= min(r0 + (OH >> 1), d.H - 1); r++) atomicOr(&rowm[r], me);
+#pragma unroll 1
+      for (int c = max(c0 - (OW >> 1), 0); c <= min(c0 + (OW >> 1), d.W - 1); c++) atomicOr(&colm[c], me);
     }
   }
   const int attempted = pos;
@@ -620,6 +726,55 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       for (int t = 8; t < m; t++) {
         const uint32_t x = tk[t];
         p[3 * t] = (uint8_t)loc, p[3 * t + 1] = (uint8_t)x, p[3 * t + 2] = (uint8_t)(x >> 8);
+      }
+    }
+  }
+  if (S) {
+    // ---- the static objects, spread over all lanes: observers from the row / column masks, `visited` (:787-796) for
+    // the lowest-index observer, and the object's token(s) into every observer's row
+    const int NS = (int)sb[MGFS_COUNT];
+    const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
+    const uint16_t* stok = (const uint16_t*)(sb + MGFS_TOKENS);
+#pragma unroll 1
+    for (int idx = gl; idx < NS; idx += G) {
+      const uint32_t e = __ldg(slist + idx);
+      const int r = (int)(e >> 16), c = (int)(e & 0xffffu);
+      uint32_t cand = rowm[r] & colm[c];
+      bool first = true;
+      while (cand) {
+        const int a = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const uint32_t la = agw[a];
+        const uint32_t loc = (uint32_t)(((r - (int)(la >> 16) + rr) << 4) | (c - (int)(la & 0xffffu) + cr));
+        const uint32_t lk = lut[loc];
+        if (lk >= 0xff000000u) continue;  // inside the bounding box but outside the shape
+        if (first) {
+          first = false;
+          const uint32_t v = svis[idx];
+          if (v < step) {
+            atomicAdd(&stale[a], step - v);
+            if (live) svis[idx] = step;
+          }
+        }
+        const uint32_t rank = lk >> 24;
+        const uint4* lp = (const uint4*)(d.fast_less + loc * 8);
+        const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
+        const uint32_t* w = wm + a * 9;
+        int p = (int)ngw[a] + s_ntok * (__popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
+                                        __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y) + __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w));
+        const int nva = (int)nvw[a];
+#pragma unroll 1
+        for (int k = 0; k < nva; k++) {  // dynamic objects earlier in the order (the observer itself is always first)
+          const uint32_t kk = dl[k * G + a];
+          if ((kk >> 24) >= rank) break;
+          p += (int)((kk >> 8) & 0xffu);
+        }
+        uint8_t* q = stage + a * 3 * T + p * 3;
+#pragma unroll 1
+        for (int t = 0; t < s_ntok && p + t < T; t++) {
+          const uint32_t x = stok[t];
+          q[3 * t] = (uint8_t)loc, q[3 * t + 1] = (uint8_t)x, q[3 * t + 2] = (uint8_t)(x >> 8);
+        }
       }
     }
   }
@@ -756,14 +911,14 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
 
 
 // ---- generic arrays <-> packed hot state (layout in mg_state.h); one thread per (env, lane) --------------
-__global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, const uint8_t* __restrict__ mask) {
+__global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, const int S, const uint8_t* __restrict__ mask) {
   const int* const hdr = HD.v;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int env = (int)(t / G), gl = (int)(t % G);
   if (env >= d.num_envs || (mask && !mask[env])) return;
   uint32_t* blk = d.fast_blk + (size_t)env * d.fast_stride;
   const int32_t* E = d.env + (size_t)env * MGEV_WORDS;
-  const int nobj = E[MGEV_NEXT_OBJ] - 1;
+  const int nobj = S ? d.A : E[MGEV_NEXT_OBJ] - 1;  // static variant: the lanes hold the agents' objects
   if (gl == 0) {
     const float* gs = d.gstats + (size_t)env * d.SG;
     const uint32_t* gt = d.gtouched + (size_t)env * d.SGW;
@@ -790,12 +945,13 @@ __global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, cons
   *(uint4*)(blk + MGFB_AGENT(G, gl)) = a0;
   *(uint4*)(blk + MGFB_AGENT(G, gl) + 4) = a1;
   uint4 o0 = make_uint4(0, 0, 0, 0), o1 = make_uint4(0, 0, 0, 0);
-  if (gl < nobj && gl + 1 < d.maxobj) {
-    const uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)(gl + 1)) * d.OS;
+  const int slot = S ? (int)a0.x : gl + 1;
+  if (gl < nobj && slot < d.maxobj) {
+    const uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)slot) * d.OS;
     const int TOKOFF = MG_TOKOFF(d.TW, d.R);
     const uint32_t ntok = o[MGO_NTOK];
     const uint32_t w3 = (((uint32_t)((int)o[MGO_AGENT] + 1)) & 0xffu) | (ntok == MG_TOK_DIRTY ? MGFB_DIRTY : ((ntok & 0xffu) << 8));
-    o0 = make_uint4(o[MGO_LOC], d.visited[(size_t)env * d.maxobj + gl + 1], o[MGO_META], w3);  // the generic kernels keep the stamps apart
+    o0 = make_uint4(o[MGO_LOC], d.visited[(size_t)env * d.maxobj + slot], o[MGO_META], w3);  // the generic kernels keep the stamps apart
     const int nw = min(4, (hdr[MGH_TOK_CAP] + 1) / 2);
     uint32_t tk[4] = {0, 0, 0, 0};
     for (int k = 0; k < nw; k++) tk[k] = o[TOKOFF + k];
@@ -805,7 +961,66 @@ __global__ void k_fast_pack(const MgDev d, const MgFastHdr HD, const int G, cons
   *(uint4*)(blk + MGFB_OBJECT(G, gl) + 4) = o1;
 }
 
-__global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
+// Static layer of an env (k_step_fast<G, true>): bitmap, cell list, slots and stamps of the non-agent objects, in slot
+// order; one warp per env.  All of them share one template (mg_capi.cu checks the maps), so one token list serves all.
+__global__ void k_fast_pack_static(const MgDev d, const MgFastHdr HD, const uint8_t* __restrict__ mask) {
+  const int* const hdr = HD.v;
+  const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (env >= d.num_envs || (mask && !mask[env])) return;
+  int32_t* E = d.env + (size_t)env * MGEV_WORDS;
+  uint32_t* sblk = (uint32_t*)d.fast_static + (size_t)env * d.fast_sstride;
+  uint32_t* slist = (uint32_t*)d.fast_slist + (size_t)env * d.fast_ns_cap;
+  uint16_t* sslot = (uint16_t*)d.fast_sslot + (size_t)env * d.fast_ns_cap;
+  uint32_t* svis = d.fast_svis + (size_t)env * d.fast_ns_cap;
+  for (int i = lane; i < d.fast_sstride; i += 32) sblk[i] = 0;
+  __syncwarp();
+  const int nall = min(E[MGEV_NEXT_OBJ] - 1, d.maxobj - 1);
+  uint32_t* bm = sblk + MGFS_HDR_WORDS;
+  int count = 0, first_slot = 0;
+  uint32_t first_meta = 0;
+  bool mixed = false;
+  for (int base = 1; base <= nall; base += 32) {
+    const int slot = base + lane;
+    uint32_t loc = 0, meta = 0;
+    bool st = false;
+    if (slot <= nall) {
+      const uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)slot) * d.OS;
+      loc = o[MGO_LOC], meta = o[MGO_META];
+      st = ((meta >> 24) & MGOF_ALIVE) && !((meta >> 24) & MGOF_AGENT);
+    }
+    const uint32_t b = __ballot_sync(MG_FULL, st);
+    if (b && !first_slot) {
+      const int src = __ffs(b) - 1;
+      first_slot = base + src;
+      first_meta = __shfl_sync(MG_FULL, meta, src);
+    }
+    if (st && (meta & 0x00ffffffu) != (first_meta & 0x00ffffffu)) mixed = true;  // template and vibe
+    const int idx = count + __popc(b & ((1u << lane) - 1u));
+    if (st && idx < d.fast_ns_cap) {
+      const int r = (int)(loc >> 16), c = (int)(loc & 0xffffu), cb = c + d.PAD;
+      slist[idx] = loc, sslot[idx] = (uint16_t)slot, svis[idx] = d.visited[(size_t)env * d.maxobj + slot];
+      atomicOr(&bm[(r + d.PAD) * d.fast_sbw + (cb >> 5)], 1u << (cb & 31));
+    }
+    count += __popc(b);
+  }
+  mixed = __any_sync(MG_FULL, mixed);
+  if (lane == 0) {
+    int n = 0;
+    if (first_slot) {
+      const TokDims td = {d.P, d.TW, d.ND, d.B, hdr[MGH_TOK_CAP], hdr[MGH_FEAT_TAG], hdr[MGH_FEAT_VIBE], hdr[MGH_FEAT_GROUP],
+                          hdr[MGH_FEAT_AGENT_ID], hdr[MGS_INV_FEATS], hdr[MGS_TEMPLATES]};
+      uint16_t tk[128];  // MGH_TOK_CAP <= 126 on this path
+      const uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)first_slot) * d.OS;
+      n = build_tokens(td, o, first_meta, tk, E, true);
+      for (int t = 0; t < n && t < MGFS_MAX_TOKENS; t++) ((uint16_t*)(sblk + MGFS_TOKENS))[t] = tk[t];
+    }
+    if (count > d.fast_ns_cap || n > MGFS_MAX_TOKENS || mixed) set_error(E, MGERR_POOL_EXHAUSTED, 20);
+    sblk[MGFS_COUNT] = (uint32_t)min(count, d.fast_ns_cap);
+    sblk[MGFS_NTOK] = (uint32_t)min(n, MGFS_MAX_TOKENS);
+  }
+}
+
+__global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G, const int S) {
   const int* const hdr = HD.v;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int env = (int)(t / G), gl = (int)(t % G);
@@ -834,11 +1049,12 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
     d.atouched[ga * d.SAW] = (d.atouched[ga * d.SAW] & ~0xffffu) | (a1.z & 0xffffu);  // the block owns stat ids < 16
     for (int id = 0; id < MGFB_STATS && id < d.SA; id++) d.astats[ga * d.SA + id] = __uint_as_float(blk[MGFB_STAT(G, id, gl)]);
   }
-  if (gl < nobj && gl + 1 < d.maxobj) {
-    uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)(gl + 1)) * d.OS;
+  const int slot = S ? (int)blk[MGFB_AGENT(G, gl < d.A ? gl : 0)] : gl + 1;  // static variant: lane l holds agent l's object
+  if (gl < nobj && slot < d.maxobj) {
+    uint32_t* o = d.objs + ((size_t)env * (d.maxobj + d.NPROXY) + (size_t)slot) * d.OS;
     const int TOKOFF = MG_TOKOFF(d.TW, d.R);
     const uint4 o0 = *(const uint4*)(blk + MGFB_OBJECT(G, gl)), o1 = *(const uint4*)(blk + MGFB_OBJECT(G, gl) + 4);
-    o[MGO_LOC] = o0.x, d.visited[(size_t)env * d.maxobj + gl + 1] = o0.y, o[MGO_META] = o0.z;
+    o[MGO_LOC] = o0.x, d.visited[(size_t)env * d.maxobj + slot] = o0.y, o[MGO_META] = o0.z;
     if (o0.w & MGFB_DIRTY) {
       o[MGO_NTOK] = MG_TOK_DIRTY;
     } else {
@@ -854,9 +1070,20 @@ __global__ void k_fast_unpack(const MgDev d, const MgFastHdr HD, const int G) {
   uint16_t* cells = d.cells + (size_t)env * d.HWp;
   for (int i = gl; i < d.HWp; i += G) cells[i] = 0;
   __syncwarp();
-  if (gl < nobj && gl + 1 < d.maxobj) {
+  if (gl < nobj && slot < d.maxobj) {
     const uint32_t loc = blk[MGFB_OBJECT(G, gl)];
-    cells[((int)(loc >> 16) + d.PAD) * d.WP + (int)(loc & 0xffffu) + d.PAD] = (uint16_t)(gl + 1);
+    cells[((int)(loc >> 16) + d.PAD) * d.WP + (int)(loc & 0xffffu) + d.PAD] = (uint16_t)slot;
+  }
+  if (S) {  // the static objects: their cells and their stamps
+    const int NS = (int)d.fast_static[(size_t)env * d.fast_sstride + MGFS_COUNT];
+    const uint32_t* slist = d.fast_slist + (size_t)env * d.fast_ns_cap;
+    const uint16_t* sslot = d.fast_sslot + (size_t)env * d.fast_ns_cap;
+    const uint32_t* svis = d.fast_svis + (size_t)env * d.fast_ns_cap;
+    for (int i = gl; i < NS; i += G) {
+      const uint32_t loc = slist[i];
+      cells[((int)(loc >> 16) + d.PAD) * d.WP + (int)(loc & 0xffffu) + d.PAD] = sslot[i];
+      d.visited[(size_t)env * d.maxobj + sslot[i]] = svis[i];
+    }
   }
 }
 
@@ -883,6 +1110,8 @@ __global__ void k_fast_restore(const MgDev d, const int G, const uint32_t* __res
     const int cell = (int)(spawn >> 16) * d.W + (int)(spawn & 0xffffu);
     cover[i] = (cell >> 5) == wd ? 1u << (cell & 31) : 0u;
   }
+  if (d.fast_svis)  // static variant: nothing has been observed yet
+    for (int i = t; i < d.fast_ns_cap; i += nt) d.fast_svis[(size_t)env * d.fast_ns_cap + i] = 0;
   for (int a = t; a < d.A; a += nt) {  // _init_buffers (:294-319)
     const size_t gi = (size_t)env * d.A + a;
     d.terminals[gi] = 0, d.truncations[gi] = 0, d.rewards[gi] = 0.0f, d.success[gi] = 0;
@@ -898,9 +1127,10 @@ __global__ void k_fast_restore(const MgDev d, const int G, const uint32_t* __res
 // ---- host side -------------------------------------------------------------------------------------
 static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap) {
-  MgFastLayout L;
+MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
+  MgFastLayout L{};
   L.G = G;
+  L.statics = statics;
   L.rank_off = 0;
   L.cta_bytes = 1024;  // the window table
   size_t n = al16((size_t)d.A * 3 * d.T + 16) + 16;  // stage (+ phase slack)
@@ -912,47 +1142,70 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap) {
   n += al16((size_t)G * 4 * 4 + G);  // oloc, ontok, stale, draw, order
   L.key_off = (int)n;
   n += (size_t)G * G * 4;  // sorted window keys, one column per lane
-  L.group_bytes = (int)n;
+  if (statics) {
+    L.sb_words = (d.fast_sstride + 3) & ~3;
+    L.sb_off = (int)n;
+    n += (size_t)L.sb_words * 4;
+    L.rc_off = (int)n;
+    n += al16((size_t)(d.H + d.W) * 4);
+    L.wm_off = (int)n;
+    n += al16((size_t)G * 9 * 4);
+    L.dl_off = (int)n;
+    n += (size_t)G * G * 4;
+    L.ag_off = (int)n;
+    n += (size_t)G * 3 * 4;
+  }
+  L.group_bytes = (int)al16(n);
   L.smem_bytes = L.cta_bytes + (size_t)MG_FAST_WARPS * (32 / G) * L.group_bytes;
   return L;
 }
 
-template <int G>
+template <int G, bool S>
 static cudaError_t launch_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
   const int envs_per_cta = MG_FAST_WARPS * (32 / G);
   const int grid = (d.num_envs + envs_per_cta - 1) / envs_per_cta;
-  k_step_fast<G><<<grid, MG_FAST_WARPS * 32, L.smem_bytes, st>>>(d, L, H);
+  k_step_fast<G, S><<<grid, MG_FAST_WARPS * 32, L.smem_bytes, st>>>(d, L, H);
   return cudaGetLastError();
 }
 
+template <int G, bool S>
+static cudaError_t configure_one(int bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k_step_fast<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  // prefer shared memory: the working set lives there, L1 only serves the program tables
+  return cudaFuncSetAttribute(k_step_fast<G, S>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+}
+
 cudaError_t mg_fast_configure(const MgFastLayout& L) {
-  cudaError_t e;
   const int bytes = (int)L.smem_bytes;
-  if ((e = cudaFuncSetAttribute(k_step_fast<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_step_fast<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_step_fast<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  const int c = 100;  // prefer shared memory: the working set lives there, L1 only serves the program tables
-  if ((e = cudaFuncSetAttribute(k_step_fast<8>, cudaFuncAttributePreferredSharedMemoryCarveout, c)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_step_fast<16>, cudaFuncAttributePreferredSharedMemoryCarveout, c)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_step_fast<32>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+  if (L.statics) return L.G == 8 ? configure_one<8, true>(bytes) : L.G == 16 ? configure_one<16, true>(bytes) : configure_one<32, true>(bytes);
+  return L.G == 8 ? configure_one<8, false>(bytes) : L.G == 16 ? configure_one<16, false>(bytes) : configure_one<32, false>(bytes);
 }
 
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
+  if (L.statics) {
+    switch (L.G) {
+      case 8: return launch_fast<8, true>(d, L, H, st);
+      case 16: return launch_fast<16, true>(d, L, H, st);
+      default: return launch_fast<32, true>(d, L, H, st);
+    }
+  }
   switch (L.G) {
-    case 8: return launch_fast<8>(d, L, H, st);
-    case 16: return launch_fast<16>(d, L, H, st);
-    default: return launch_fast<32>(d, L, H, st);
+    case 8: return launch_fast<8, false>(d, L, H, st);
+    case 16: return launch_fast<16, false>(d, L, H, st);
+    default: return launch_fast<32, false>(d, L, H, st);
   }
 }
 
 cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st) {
   const size_t threads = (size_t)d.num_envs * L.G;
-  k_fast_pack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G, mask);
+  k_fast_pack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G, L.statics, mask);
+  if (L.statics) k_fast_pack_static<<<(d.num_envs + 3) / 4, 128, 0, st>>>(d, H, mask);
   return cudaGetLastError();
 }
 cudaError_t mg_launch_fast_unpack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
   const size_t threads = (size_t)d.num_envs * L.G;
-  k_fast_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G);
+  k_fast_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d, H, L.G, L.statics);
   return cudaGetLastError();
 }
 

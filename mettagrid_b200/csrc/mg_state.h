@@ -32,6 +32,14 @@ struct MgDev {
   uint32_t objs_stride;  // words of object records per env = (maxobj + NPROXY) * OS
   uint32_t* fast_blk;    // [N][fast_stride] packed hot state of k_step_fast (layout below), or null
   int fast_stride;       // words per env
+  // static layer of k_step_fast<G, true> (mg_fast.cu): every non-agent object of a handler-free game is immutable
+  const uint32_t* fast_static;  // [N][fast_sstride] header (MGFS_*) + occupancy bitmap of the padded grid, bit c + PAD of row r + PAD
+  const uint32_t* fast_slist;   // [N][fast_ns_cap] r << 16 | c of static object i
+  const uint16_t* fast_sslot;   // [N][fast_ns_cap] its object slot (pack / unpack only)
+  uint32_t* fast_svis;          // [N][fast_ns_cap] GridObject::visited of static object i
+  const uint32_t* fast_less;    // [257][8] per packed window offset: the 256-bit set of offsets that come earlier in the
+                                // reference's Manhattan order; row 256 = every offset inside the observation shape
+  int fast_sstride, fast_ns_cap, fast_sbw;  // words per env, static objects per env (capacity), bitmap words per row
   const uint32_t* rank_lut;  // [256] packed window offset (dr + rr) << 4 | (dc + cr) -> rank << 24 | offset << 16, where rank is
                              // the position in Manhattan order; 0xFFFFFF00 outside the shape
   int plain;    // 1: the program has no handlers / rewards / world systems (k_step<PLAIN> applies)
@@ -88,10 +96,17 @@ struct MgDev {
 // shared-memory layout of k_step_fast (mg_fast.cu), computed on the host
 struct MgFastLayout {
   int G;           // lanes per environment: 8, 16 or 32
+  int statics;     // 1: the static-layer variant (walls and other immutable objects outside the object lanes)
   int rank_off, cta_bytes;
   int tok_off, tok_stride, oloc_off, key_off, group_bytes;
+  int sb_off, sb_words, rc_off, wm_off, dl_off, ag_off;  // static variant: bitmap block, row / column observer masks,
+                                                         // window masks [G][9], sorted dynamic keys [G][G], per-agent words
   size_t smem_bytes;
 };
+
+// per-env header of the static block (MgDev::fast_static); the bitmap follows at word MGFS_HDR_WORDS
+enum { MGFS_COUNT = 0, MGFS_NTOK, MGFS_TOKENS /* 4 words: up to eight (feature | value << 8) tokens */, MGFS_HDR_WORDS = 8 };
+#define MGFS_MAX_TOKENS 8
 
 // ---- packed hot state of k_step_fast: one contiguous block per env, G = lanes per env -------------------
 // words [0, 8)                      : header (MGFB_*)

@@ -37,25 +37,25 @@ def _sparse_config(num_agents, walls, width, height, obs_w, obs_h, num_tokens=12
     )
 
 
-def _make(cfg, num_envs, seed0, fast):
+def _make(cfg, num_envs, seed0, fast, maps=None):
     from mettagrid_b200.sim import BatchedSimulation
 
     old = os.environ.pop("METTAGRID_B200_NO_FAST", None)
     try:
         if not fast:
             os.environ["METTAGRID_B200_NO_FAST"] = "1"
-        return BatchedSimulation(cfg, num_envs, seeds=seed0)
+        return BatchedSimulation(cfg, num_envs, seeds=seed0, maps=maps)
     finally:
         os.environ.pop("METTAGRID_B200_NO_FAST", None)
         if old is not None:
             os.environ["METTAGRID_B200_NO_FAST"] = old
 
 
-def _triple(cfg, num_envs, steps, expect_lanes, seed0=7, p_vibe=0.2, p_invalid=0.02, check_every=1):
+def _triple(cfg, num_envs, steps, expect_lanes, seed0=7, p_vibe=0.2, p_invalid=0.02, check_every=1, maps=None):
     from oracle.oracle import OracleEnv
 
-    fast = _make(cfg, num_envs, seed0, True)
-    slow = _make(cfg, num_envs, seed0, False)
+    fast = _make(cfg, num_envs, seed0, True, maps)
+    slow = _make(cfg, num_envs, seed0, False, maps)
     assert fast.step_kernel == expect_lanes, f"fast path not selected: kernel {fast.step_kernel}"
     assert slow.step_kernel == 1
     P = fast.program
