@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       const uint32_t tgt_o = __shfl_sync(MG_FULL, tgt_a, oa, G);        // target of this lane's object
 #pragma unroll
       for (int i = 0; i < G; i++) {  // steps beyond the agent count carry no target and change nothing
+        if (S && i >= A) break;
         const uint32_t tgt = __shfl_sync(MG_FULL, tgt_s, i, G);
         const uint32_t occ = __ballot_sync(MG_FULL, o_loc == tgt) & gmask;
         if (o_step == i && tgt_o != FAST_INVALID && occ == 0) o_loc = tgt_o;  // TargetLocEmpty -> Relocate
@@ -568,33 +569,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
                                   ((uint32_t)my_n << 8) | (uint32_t)gl);
   __syncwarp();
 
-  // ---- observations: sort keys for the objects in this agent's window
-  // key = Manhattan rank << 24 | packed offset << 16 | token count << 8 | object lane
-  uint32_t key[G];
-  uint32_t col = 0;  // which agents see this lane's object
-  {
-    const uint32_t bias = (((uint32_t)(hdr[MGH_OBS_H] >> 1) << 16) | (uint32_t)(hdr[MGH_OBS_W] >> 1)) - my_loc;
-#pragma unroll
-    for (int j = 0; j < G; j++) {
-      // both offsets in one subtraction; a negative column borrows into the row field but then fails the test
-      const uint2 oi = ((const uint2*)oloc)[j];
-      const uint32_t df = oi.x + bias;
-      const uint32_t kk = lut[((df >> 12) & 0xf0u) | (df & 0xfu)] | oi.y;
-      const bool vis = isA && (df & 0xfff0fff0u) == 0 && kk < 0xff000000u;
-      key[j] = vis ? kk : FAST_INVALID;
-      const uint32_t b = __ballot_sync(MG_FULL, vis);
-      if (gl == j) col = b;
-    }
-    col = (col & gmask) >> gshift;
-  }
-  // cell staleness (:787-796) goes to the lowest agent index among the observers
-  if (o_alive && col != 0 && o_vis < step) {
-    atomicAdd(&stale[__ffs(col) - 1], step - o_vis);
-    o_vis = step;
-  }
-  sort_net(key);
-
-  // global tokens (:700-742)
+  // ---- observations (:665-824)
   uint8_t* row = stage + gl * 3 * T;
   int pos = 0;
   auto put = [&](uint32_t loc, uint32_t feat, uint32_t val) {
@@ -605,7 +580,8 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     }
     pos++;
   };
-  if (isA) {
+  auto global_tokens = [&]() {  // :700-742
+    if (!isA) return;
     const int flags = hdr[MGH_GLOBAL_FLAGS];
     if (flags & MGG_EPISODE_PCT) {
       const int ms = hdr[MGH_MAX_STEPS];
@@ -622,123 +598,138 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       if (de != 0) put(0xFE, de > 0 ? hdr[MGH_FEAT_LP_EAST] : hdr[MGH_FEAT_LP_WEST], min(abs(de), 255));
       if (dn != 0) put(0xFE, dn > 0 ? hdr[MGH_FEAT_LP_NORTH] : hdr[MGH_FEAT_LP_SOUTH], min(abs(dn), 255));
     }
-  }
-  // window tokens in Manhattan order (:756-811).  The observer walks its sorted keys once to give every visible
-  // object its first token position; the object lanes then write their own tokens into each observer's row.
-  uint32_t* tab = (uint32_t*)(gb + L.key_off);  // [observer][object] -> first token position | packed offset << 16
-  // static variant: this observer's window as a 256-bit set of packed offsets (row << 4 | column) holding a static object
-  uint32_t M[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint32_t* const wm = (uint32_t*)(gb + L.wm_off);   // [agent][9] window masks
-  uint32_t* const dl = (uint32_t*)(gb + L.dl_off);   // [k][agent] sorted keys of the visible dynamic objects
-  uint32_t* const agw = (uint32_t*)(gb + L.ag_off);  // [agent] location, global-token count, visible dynamic objects
-  uint32_t* const ngw = agw + G;
-  uint32_t* const nvw = ngw + G;
-  const int s_ntok = S ? (int)sb[MGFS_NTOK] : 0;
-  if (S) {
-    const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W];
-    const int rtop = r0 - (OH >> 1) + d.PAD, cbit = c0 - (OW >> 1) + d.PAD;  // >= 0: the bitmap has a PAD-wide frame
-    const int kw = cbit >> 5, sh = cbit & 31;
-    const uint32_t wmask = (1u << OW) - 1u;
+  };
+  uint32_t* tab = (uint32_t*)(gb + L.key_off);
+  if constexpr (!S) {
+    // sort keys for the objects in this agent's window:
+    // key = Manhattan rank << 24 | packed offset << 16 | token count << 8 | object lane
+    uint32_t key[G];
+    uint32_t col = 0;  // which agents see this lane's object
+    {
+      const uint32_t bias = (((uint32_t)(hdr[MGH_OBS_H] >> 1) << 16) | (uint32_t)(hdr[MGH_OBS_W] >> 1)) - my_loc;
 #pragma unroll
-    for (int wr = 0; wr < 15; wr++) {
-      uint32_t bits = 0;
-      if (wr < OH && isA) {
-        const uint32_t* rw = sbm + (rtop + wr) * SBW + kw;
-        bits = __funnelshift_r(rw[0], rw[1], sh) & wmask;
+      for (int j = 0; j < G; j++) {
+        // both offsets in one subtraction; a negative column borrows into the row field but then fails the test
+        const uint2 oi = ((const uint2*)oloc)[j];
+        const uint32_t df = oi.x + bias;
+        const uint32_t kk = lut[((df >> 12) & 0xf0u) | (df & 0xfu)] | oi.y;
+        const bool vis = isA && (df & 0xfff0fff0u) == 0 && kk < 0xff000000u;
+        key[j] = vis ? kk : FAST_INVALID;
+        const uint32_t b = __ballot_sync(MG_FULL, vis);
+        if (gl == j) col = b;
       }
-      if (wr & 1)
-        M[wr >> 1] |= bits << 16;
-      else
-        M[wr >> 1] = bits;
+      col = (col & gmask) >> gshift;
     }
-    const uint4 sa = __ldg((const uint4*)(d.fast_less + 256 * 8)), sc = __ldg((const uint4*)(d.fast_less + 256 * 8) + 1);
-    M[0] &= sa.x, M[1] &= sa.y, M[2] &= sa.z, M[3] &= sa.w, M[4] &= sc.x, M[5] &= sc.y, M[6] &= sc.z, M[7] &= sc.w;
+    // cell staleness (:787-796) goes to the lowest agent index among the observers
+    if (o_alive && col != 0 && o_vis < step) {
+      atomicAdd(&stale[__ffs(col) - 1], step - o_vis);
+      o_vis = step;
+    }
+    sort_net(key);
+    global_tokens();
+    // window tokens in Manhattan order (:756-811).  The observer walks its sorted keys once to give every visible
+    // object its first token position; the object lanes then write their own tokens into each observer's row.
+    // tab: [observer][object] -> first token position | packed offset << 16
 #pragma unroll
-    for (int k = 0; k < 8; k++) wm[gl * 9 + k] = M[k];
+    for (int k = 0; k < G; k++) {
+      const uint32_t kk = key[k];
+      if (kk != FAST_INVALID) {
+        tab[gl * G + (int)(kk & 0xffu)] = (uint32_t)pos | (kk & 0x00ff0000u);
+        pos += (int)((kk >> 8) & 0xffu);
+      }
+    }
+    __syncwarp();
+    while (col) {
+      const int a = __ffs(col) - 1;
+      col &= col - 1;
+      const uint32_t e = tab[a * G + gl];
+      const int start = (int)(e & 0xffffu);
+      const uint32_t loc = e >> 16;
+      const int m = min(my_n, T - start);  // tokens that fit the budget
+      uint8_t* p = stage + a * 3 * T + start * 3;
+      if (m > 0) {
+        p[0] = (uint8_t)loc, p[1] = (uint8_t)tw0, p[2] = (uint8_t)(tw0 >> 8);
+        if (m > 1) p[3] = (uint8_t)loc, p[4] = (uint8_t)(tw0 >> 16), p[5] = (uint8_t)(tw0 >> 24);
+      }
+      if (m > 2) {
+        p[6] = (uint8_t)loc, p[7] = (uint8_t)tw1, p[8] = (uint8_t)(tw1 >> 8);
+        if (m > 3) p[9] = (uint8_t)loc, p[10] = (uint8_t)(tw1 >> 16), p[11] = (uint8_t)(tw1 >> 24);
+      }
+      if (m > 4) {
+        p[12] = (uint8_t)loc, p[13] = (uint8_t)tw2, p[14] = (uint8_t)(tw2 >> 8);
+        if (m > 5) p[15] = (uint8_t)loc, p[16] = (uint8_t)(tw2 >> 16), p[17] = (uint8_t)(tw2 >> 24);
+      }
+      if (m > 6) {
+        p[18] = (uint8_t)loc, p[19] = (uint8_t)tw3, p[20] = (uint8_t)(tw3 >> 8);
+        if (m > 7) p[21] = (uint8_t)loc, p[22] = (uint8_t)(tw3 >> 16), p[23] = (uint8_t)(tw3 >> 24);
+      }
+      if (m > 8) {  // long token lists continue from the shared table
+        const uint16_t* tk = (const uint16_t*)(toks + gl * tokw);
+#pragma unroll 1
+        for (int t = 8; t < m; t++) {
+          const uint32_t x = tk[t];
+          p[3 * t] = (uint8_t)loc, p[3 * t + 1] = (uint8_t)x, p[3 * t + 2] = (uint8_t)(x >> 8);
+        }
+      }
+    }
+  } else {
+    // Static-layer variant.  No sort: an object at packed window offset `loc` of observer a starts at
+    //   (a's global tokens) + s_ntok * popcount(a's static window set & offsets earlier than loc)
+    //                       + (tokens of the dynamic objects a sees at an earlier rank),
+    // so every (object, observer) pair can be placed on its own.  The pairs -- of the agents' objects first, then of the
+    // static objects -- go to a work list that all lanes drain together, however unevenly they are spread over windows.
+    global_tokens();
+    uint32_t* const wm = (uint32_t*)(gb + L.wm_off);   // [agent][9] static window set, 256 bits by packed offset
+    uint32_t* const dl = (uint32_t*)(gb + L.dl_off);   // [k][agent] dynamic objects the agent sees: rank << 24 | offset << 16 | tokens << 8
+    uint32_t* const agw = (uint32_t*)(gb + L.ag_off);  // [agent] location
+    uint32_t* const ngw = agw + G;                     // [agent] global tokens
+    uint32_t* const nvw = ngw + G;                     // [agent] entries in its dl column
+    uint32_t* const wl_count = nvw + G;
+    uint32_t* const wl = tab;                          // work list: offset | observer << 8 | source << 16 (0xFF: static)
+    const int s_ntok = (int)sb[MGFS_NTOK];
+    const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W], rr = OH >> 1, cr = OW >> 1;
+    int n_static = 0;  // static objects in this agent's window
+    {
+      uint32_t M[8];
+      const int rtop = r0 - rr + d.PAD, cbit = c0 - cr + d.PAD;  // >= 0: the bitmap has a PAD-wide frame
+      const int kw = cbit >> 5, sh = cbit & 31;
+      const uint32_t wmask = (1u << OW) - 1u;
+#pragma unroll
+      for (int wr = 0; wr < 15; wr++) {  // a window row = OW bits of a bitmap row; rows sit 16 bits apart like packed offsets
+        uint32_t bits = 0;
+        if (wr < OH && isA) {
+          const uint32_t* rw = sbm + (rtop + wr) * SBW + kw;
+          bits = __funnelshift_r(rw[0], rw[1], sh) & wmask;
+        }
+        if (wr & 1)
+          M[wr >> 1] |= bits << 16;
+        else
+          M[wr >> 1] = bits;
+      }
+      const uint4* shape = (const uint4*)(d.fast_less + 256 * 8);  // offsets inside the observation shape
+      const uint4 sa = __ldg(shape), sc = __ldg(shape + 1);
+      M[0] &= sa.x, M[1] &= sa.y, M[2] &= sa.z, M[3] &= sa.w, M[4] &= sc.x, M[5] &= sc.y, M[6] &= sc.z, M[7] &= sc.w;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        wm[gl * 9 + k] = M[k];
+        n_static += __popc(M[k]);
+      }
+    }
     agw[gl] = isA ? my_loc : FAST_INVALID;
     ngw[gl] = (uint32_t)pos;
-  }
-  // static objects that come before packed offset `loc` in Manhattan order
-  auto statics_before = [&](uint32_t loc) {
-    const uint4* lp = (const uint4*)(d.fast_less + loc * 8);
-    const uint4 a = __ldg(lp), b = __ldg(lp + 1);
-    return __popc(M[0] & a.x) + __popc(M[1] & a.y) + __popc(M[2] & a.z) + __popc(M[3] & a.w) + __popc(M[4] & b.x) +
-           __popc(M[5] & b.y) + __popc(M[6] & b.z) + __popc(M[7] & b.w);
-  };
-  int nvis = 0;
-#pragma unroll
-  for (int k = 0; k < G; k++) {
-    const uint32_t kk = key[k];
-    if (kk != FAST_INVALID) {
-      int p = pos;
-      if (S) {
-        p += s_ntok * statics_before((kk >> 16) & 0xffu);
-        dl[k * G + gl] = kk;
-        nvis++;
-      }
-      tab[gl * G + (int)(kk & 0xffu)] = (uint32_t)p | (kk & 0x00ff0000u);
-      pos += (int)((kk >> 8) & 0xffu);
-    }
-  }
-  if (S) {
-    nvw[gl] = (uint32_t)nvis;
-    pos += s_ntok * (__popc(M[0]) + __popc(M[1]) + __popc(M[2]) + __popc(M[3]) + __popc(M[4]) + __popc(M[5]) + __popc(M[6]) +
-                     __popc(M[7]));
-    // which agents' windows cover each row and each column (the bounding box of the observation shape)
-    if (isA) {
-      const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W];
+    nvw[gl] = 0;
+    if (gl == 0) *wl_count = 0;
+    if (isA) {  // which agents' windows cover each row and each column (the bounding box of the observation shape)
       const uint32_t me = 1u << gl;
 #pragma unroll 1
-      for (int r = max(r0 - (OH >> 1), 0); r <= min(r0 + (OH >> 1), d.H - 1); r++) atomicOr(&rowm[r], me);
+      for (int r = max(r0 - rr, 0); r <= min(r0 + rr, d.H - 1); r++) atomicOr(&rowm[r], me);
 #pragma unroll 1
-      for (int c = max(c0 - (OW >> 1), 0); c <= min(c0 + (OW >> 1), d.W - 1); c++) atomicOr(&colm[c], me);
+      for (int c = max(c0 - cr, 0); c <= min(c0 + cr, d.W - 1); c++) atomicOr(&colm[c], me);
     }
-  }
-  const int attempted = pos;
-  __syncwarp();
-  while (col) {
-    const int a = __ffs(col) - 1;
-    col &= col - 1;
-    const uint32_t e = tab[a * G + gl];
-    const int start = (int)(e & 0xffffu);
-    const uint32_t loc = e >> 16;
-    const int m = min(my_n, T - start);  // tokens that fit the budget
-    uint8_t* p = stage + a * 3 * T + start * 3;
-    if (m > 0) {
-      p[0] = (uint8_t)loc, p[1] = (uint8_t)tw0, p[2] = (uint8_t)(tw0 >> 8);
-      if (m > 1) p[3] = (uint8_t)loc, p[4] = (uint8_t)(tw0 >> 16), p[5] = (uint8_t)(tw0 >> 24);
-    }
-    if (m > 2) {
-      p[6] = (uint8_t)loc, p[7] = (uint8_t)tw1, p[8] = (uint8_t)(tw1 >> 8);
-      if (m > 3) p[9] = (uint8_t)loc, p[10] = (uint8_t)(tw1 >> 16), p[11] = (uint8_t)(tw1 >> 24);
-    }
-    if (m > 4) {
-      p[12] = (uint8_t)loc, p[13] = (uint8_t)tw2, p[14] = (uint8_t)(tw2 >> 8);
-      if (m > 5) p[15] = (uint8_t)loc, p[16] = (uint8_t)(tw2 >> 16), p[17] = (uint8_t)(tw2 >> 24);
-    }
-    if (m > 6) {
-      p[18] = (uint8_t)loc, p[19] = (uint8_t)tw3, p[20] = (uint8_t)(tw3 >> 8);
-      if (m > 7) p[21] = (uint8_t)loc, p[22] = (uint8_t)(tw3 >> 16), p[23] = (uint8_t)(tw3 >> 24);
-    }
-    if (m > 8) {  // long token lists continue from the shared table
-      const uint16_t* tk = (const uint16_t*)(toks + gl * tokw);
-#pragma unroll 1
-      for (int t = 8; t < m; t++) {
-        const uint32_t x = tk[t];
-        p[3 * t] = (uint8_t)loc, p[3 * t + 1] = (uint8_t)x, p[3 * t + 2] = (uint8_t)(x >> 8);
-      }
-    }
-  }
-  if (S) {
-    // ---- the static objects, spread over all lanes: observers from the row / column masks, `visited` (:787-796) for
-    // the lowest-index observer, and the object's token(s) into every observer's row
-    const int NS = (int)sb[MGFS_COUNT];
-    const int rr = hdr[MGH_OBS_H] >> 1, cr = hdr[MGH_OBS_W] >> 1;
-    const uint16_t* stok = (const uint16_t*)(sb + MGFS_TOKENS);
-#pragma unroll 1
-    for (int idx = gl; idx < NS; idx += G) {
-      const uint32_t e = __ldg(slist + idx);
-      const int r = (int)(e >> 16), c = (int)(e & 0xffffu);
+    __syncwarp();
+    // the agents' objects: observers, `visited` (:787-796) for the lowest one, one work-list entry per observer
+    if (o_alive) {
+      const int r = (int)(o_loc >> 16), c = (int)(o_loc & 0xffffu);
       uint32_t cand = rowm[r] & colm[c];
       bool first = true;
       while (cand) {
@@ -750,34 +741,92 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
         if (lk >= 0xff000000u) continue;  // inside the bounding box but outside the shape
         if (first) {
           first = false;
-          const uint32_t v = svis[idx];
-          if (v < step) {
-            atomicAdd(&stale[a], step - v);
-            if (live) svis[idx] = step;
+          if (o_vis < step) {
+            atomicAdd(&stale[a], step - o_vis);
+            o_vis = step;
           }
         }
-        const uint32_t rank = lk >> 24;
-        const uint4* lp = (const uint4*)(d.fast_less + loc * 8);
-        const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
-        const uint32_t* w = wm + a * 9;
-        int p = (int)ngw[a] + s_ntok * (__popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
-                                        __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y) + __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w));
-        const int nva = (int)nvw[a];
+        dl[atomicAdd(&nvw[a], 1u) * G + a] = lk | ((uint32_t)my_n << 8);
+        wl[atomicAdd(wl_count, 1u)] = loc | ((uint32_t)a << 8) | ((uint32_t)gl << 16);
+      }
+    }
+    __syncwarp();
+    if (isA) {  // every token this row attempts (:640-661)
+      const int nva = (int)nvw[gl];
+      pos += s_ntok * n_static;
 #pragma unroll 1
-        for (int k = 0; k < nva; k++) {  // dynamic objects earlier in the order (the observer itself is always first)
-          const uint32_t kk = dl[k * G + a];
-          if ((kk >> 24) >= rank) break;
-          p += (int)((kk >> 8) & 0xffu);
+      for (int k = 0; k < nva; k++) pos += (int)((dl[k * G + gl] >> 8) & 0xffu);
+    }
+    // the static objects, G at a time: observers from the row / column masks, `visited` for the lowest one, entries
+    const int NS = (int)sb[MGFS_COUNT];
+    const int wl_cap = G * G, per_round = G * A;
+    const uint16_t* stok = (const uint16_t*)(sb + MGFS_TOKENS);
+#pragma unroll 1
+    for (int base = 0;; base += G) {
+      __syncwarp(gmask);
+      const int cnt = (int)*wl_count;
+      const bool last = base >= NS;
+      __syncwarp(gmask);  // everyone has read the count before anyone appends again
+      if (last || cnt + per_round > wl_cap) {  // drain the list: one pair per lane and turn
+#pragma unroll 1
+        for (int i = gl; i < cnt; i += G) {
+          const uint32_t e = wl[i];
+          const uint32_t loc = e & 0xffu;
+          const int a = (int)((e >> 8) & 0xffu), src = (int)(e >> 16);
+          const uint32_t rank = lut[loc] >> 24;
+          const uint4* lp = (const uint4*)(d.fast_less + loc * 8);  // offsets earlier in Manhattan order
+          const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
+          const uint32_t* w = wm + a * 9;
+          int p = (int)ngw[a] + s_ntok * (__popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
+                                          __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y) + __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w));
+          const int nva = (int)nvw[a];
+#pragma unroll 1
+          for (int k = 0; k < nva; k++) {
+            const uint32_t kk = dl[k * G + a];
+            if ((kk >> 24) < rank) p += (int)((kk >> 8) & 0xffu);
+          }
+          const uint16_t* tk = stok;
+          int nt = s_ntok;
+          if (src != 0xff) tk = (const uint16_t*)(toks + src * tokw), nt = (int)(((const uint2*)oloc)[src].y >> 8);
+          nt = min(nt, T - p);  // tokens that fit the budget
+          uint8_t* q = stage + a * 3 * T + p * 3;
+#pragma unroll 1
+          for (int t = 0; t < nt; t++) {
+            const uint32_t x = tk[t];
+            q[3 * t] = (uint8_t)loc, q[3 * t + 1] = (uint8_t)x, q[3 * t + 2] = (uint8_t)(x >> 8);
+          }
         }
-        uint8_t* q = stage + a * 3 * T + p * 3;
-#pragma unroll 1
-        for (int t = 0; t < s_ntok && p + t < T; t++) {
-          const uint32_t x = stok[t];
-          q[3 * t] = (uint8_t)loc, q[3 * t + 1] = (uint8_t)x, q[3 * t + 2] = (uint8_t)(x >> 8);
+        __syncwarp(gmask);
+        if (gl == 0) *wl_count = 0;
+        __syncwarp(gmask);
+      }
+      if (last) break;
+      const int idx = base + gl;
+      if (idx < NS) {
+        const uint32_t e = __ldg(slist + idx);
+        const int r = (int)(e >> 16), c = (int)(e & 0xffffu);
+        uint32_t cand = rowm[r] & colm[c];
+        bool first = true;
+        while (cand) {
+          const int a = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const uint32_t la = agw[a];
+          const uint32_t loc = (uint32_t)(((r - (int)(la >> 16) + rr) << 4) | (c - (int)(la & 0xffffu) + cr));
+          if (lut[loc] >= 0xff000000u) continue;
+          if (first) {
+            first = false;
+            const uint32_t v = svis[idx];
+            if (v < step) {
+              atomicAdd(&stale[a], step - v);
+              if (live) svis[idx] = step;
+            }
+          }
+          wl[atomicAdd(wl_count, 1u)] = loc | ((uint32_t)a << 8) | 0xff0000u;
         }
       }
     }
   }
+  const int attempted = pos;
   __syncwarp();
 
   // ---- stream the env's observation block out.  The block [A][T][3] is contiguous in the stage and in HBM: when both
@@ -1153,7 +1202,7 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
     L.dl_off = (int)n;
     n += (size_t)G * G * 4;
     L.ag_off = (int)n;
-    n += (size_t)G * 3 * 4;
+    n += (size_t)(G * 3 + 4) * 4;  // + the work-list counter
   }
   L.group_bytes = (int)al16(n);
   L.smem_bytes = L.cta_bytes + (size_t)MG_FAST_WARPS * (32 / G) * L.group_bytes;
