@@ -334,8 +334,12 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   }
   // independent work while wave 2 is in flight: the observation stage starts as all EmptyTokenByte (:940-942);
   // it shares the destination's 16-byte phase so that whole vectors can be streamed out
-  uint8_t* stage = gb + ((uint32_t)(uintptr_t)gobs & 15u);
-  {
+  // Static variant: only the first L.stage_tokens tokens of a row are staged (rows are mostly padding; the padding is
+  // stored straight from registers and the rare longer row writes its tail to HBM directly), which keeps four times as
+  // many environments resident per SM.
+  uint8_t* stage = S ? gb : gb + ((uint32_t)(uintptr_t)gobs & 15u);
+  const int SC = L.stage_tokens, RS = 3 * SC;  // static variant: staged tokens / bytes per row
+  if (!S) {
     uint4* s4 = (uint4*)gb;
     const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     const int nv = (nbytes + 15 + 16) >> 4;
@@ -572,8 +576,20 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // ---- observations (:665-824)
   uint8_t* row = stage + gl * 3 * T;
   int pos = 0;
+  // static variant: token p of agent a's row -- staged, or written in place when the row outgrows its stage
+  auto emit = [&](int a, int p, uint32_t loc, uint32_t x) {
+    if (p < SC) {
+      uint8_t* q = stage + a * RS + p * 3;
+      q[0] = (uint8_t)loc, q[1] = (uint8_t)x, q[2] = (uint8_t)(x >> 8);
+    } else if (p < T && live) {
+      uint8_t* q = gobs + (size_t)a * (3 * T) + p * 3;
+      q[0] = (uint8_t)loc, q[1] = (uint8_t)x, q[2] = (uint8_t)(x >> 8);
+    }
+  };
   auto put = [&](uint32_t loc, uint32_t feat, uint32_t val) {
-    if (pos < T) {
+    if (S) {
+      emit(gl, pos, loc, (feat & 0xffu) | ((val & 0xffu) << 8));
+    } else if (pos < T) {
       row[pos * 3 + 0] = (uint8_t)loc;
       row[pos * 3 + 1] = (uint8_t)feat;
       row[pos * 3 + 2] = (uint8_t)val;
@@ -680,11 +696,12 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     // static objects -- go to a work list that all lanes drain together, however unevenly they are spread over windows.
     global_tokens();
     uint32_t* const wm = (uint32_t*)(gb + L.wm_off);   // [agent][9] static window set, 256 bits by packed offset
-    uint32_t* const dl = (uint32_t*)(gb + L.dl_off);   // [k][agent] dynamic objects the agent sees: rank << 24 | offset << 16 | tokens << 8
+    uint16_t* const dl = (uint16_t*)(gb + L.dl_off);   // [k][agent] dynamic objects the agent sees: rank << 8 | tokens
     uint32_t* const agw = (uint32_t*)(gb + L.ag_off);  // [agent] location
     uint32_t* const ngw = agw + G;                     // [agent] global tokens
     uint32_t* const nvw = ngw + G;                     // [agent] entries in its dl column
     uint32_t* const wl_count = nvw + G;
+    uint32_t* const nvb = wl_count + 4;                // [agent] valid bytes of its row
     uint32_t* const wl = tab;                          // work list: offset | observer << 8 | source << 16 (0xFF: static)
     const int s_ntok = (int)sb[MGFS_NTOK];
     const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W], rr = OH >> 1, cr = OW >> 1;
@@ -726,102 +743,117 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
 #pragma unroll 1
       for (int c = max(c0 - cr, 0); c <= min(c0 + cr, d.W - 1); c++) atomicOr(&colm[c], me);
     }
+    // the first round of static cells and stamps: in flight while the agents' objects are handled
+    const int NS = (int)sb[MGFS_COUNT];
+    uint32_t e_nxt = 0, v_nxt = 0;
+    if (gl < NS) e_nxt = __ldg(slist + gl), v_nxt = svis[gl];
     __syncwarp();
-    // the agents' objects: observers, `visited` (:787-796) for the lowest one, one work-list entry per observer
+    // packed window offset of cell (r, c) for observer a, or 0xFFFFFFFF outside the observation shape
+    auto offset_for = [&](int a, int r, int c) {
+      const uint32_t la = agw[a];
+      const uint32_t loc = (uint32_t)(((r - (int)(la >> 16) + rr) << 4) | (c - (int)(la & 0xffffu) + cr));
+      return lut[loc] >= 0xff000000u ? FAST_INVALID : loc;
+    };
+    // one (object, observer) pair: where the object's tokens start in the observer's row, then the tokens
+    const uint16_t* stok = (const uint16_t*)(sb + MGFS_TOKENS);
+    auto place = [&](uint32_t e) {
+      const uint32_t loc = e & 0xffu;
+      const int a = (int)((e >> 8) & 0xffu), src = (int)(e >> 16);
+      const uint32_t rank = lut[loc] >> 24;
+      const uint4* lp = (const uint4*)(d.fast_less + loc * 8);  // offsets earlier in Manhattan order
+      const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
+      const uint32_t* w = wm + a * 9;
+      int p = (int)ngw[a] + s_ntok * (__popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
+                                      __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y) + __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w));
+      const int nva = (int)nvw[a];
+#pragma unroll 1
+      for (int k = 0; k < nva; k++) {
+        const uint32_t kk = dl[k * G + a];
+        if ((kk >> 8) < rank) p += (int)(kk & 0xffu);
+      }
+      const uint16_t* tk = stok;
+      int nt = s_ntok;
+      if (src != 0xff) tk = (const uint16_t*)(toks + src * tokw), nt = (int)(((const uint2*)oloc)[src].y >> 8);
+#pragma unroll 1
+      for (int t = 0; t < nt; t++) emit(a, p + t, loc, tk[t]);
+    };
+    // append to the work list; a full list places the pair at once instead
+    auto push = [&](uint32_t e) {
+      const uint32_t slot = atomicAdd(wl_count, 1u);
+      if (slot < (uint32_t)L.wl_cap)
+        wl[slot] = e;
+      else
+        place(e);
+    };
+    // the agents' objects: observers, `visited` (:787-796) for the lowest one
+    uint32_t seen = 0;
     if (o_alive) {
       const int r = (int)(o_loc >> 16), c = (int)(o_loc & 0xffffu);
       uint32_t cand = rowm[r] & colm[c];
-      bool first = true;
       while (cand) {
         const int a = __ffs(cand) - 1;
         cand &= cand - 1;
-        const uint32_t la = agw[a];
-        const uint32_t loc = (uint32_t)(((r - (int)(la >> 16) + rr) << 4) | (c - (int)(la & 0xffffu) + cr));
-        const uint32_t lk = lut[loc];
-        if (lk >= 0xff000000u) continue;  // inside the bounding box but outside the shape
-        if (first) {
-          first = false;
-          if (o_vis < step) {
-            atomicAdd(&stale[a], step - o_vis);
-            o_vis = step;
-          }
-        }
-        dl[atomicAdd(&nvw[a], 1u) * G + a] = lk | ((uint32_t)my_n << 8);
-        wl[atomicAdd(wl_count, 1u)] = loc | ((uint32_t)a << 8) | ((uint32_t)gl << 16);
+        const uint32_t loc = offset_for(a, r, c);
+        if (loc == FAST_INVALID) continue;  // inside the bounding box but outside the shape
+        seen |= 1u << a;
+        dl[atomicAdd(&nvw[a], 1u) * G + a] = (uint16_t)(((lut[loc] >> 24) << 8) | (uint32_t)my_n);  // rank << 8 | tokens
+      }
+      if (seen && o_vis < step) {
+        atomicAdd(&stale[__ffs(seen) - 1], step - o_vis);
+        o_vis = step;
       }
     }
-    __syncwarp();
-    if (isA) {  // every token this row attempts (:640-661)
+    __syncwarp();  // every agent's list of dynamic objects is complete
+    if (isA) {     // every token this row attempts (:640-661)
       const int nva = (int)nvw[gl];
       pos += s_ntok * n_static;
 #pragma unroll 1
-      for (int k = 0; k < nva; k++) pos += (int)((dl[k * G + gl] >> 8) & 0xffu);
+      for (int k = 0; k < nva; k++) pos += (int)(dl[k * G + gl] & 0xffu);
+    }
+    nvb[gl] = (uint32_t)(3 * min(pos, T));  // valid bytes of the row, for the stream-out below
+    if (o_alive) {
+      const int r = (int)(o_loc >> 16), c = (int)(o_loc & 0xffffu);
+      while (seen) {
+        const int a = __ffs(seen) - 1;
+        seen &= seen - 1;
+        push(offset_for(a, r, c) | ((uint32_t)a << 8) | ((uint32_t)gl << 16));
+      }
     }
     // the static objects, G at a time: observers from the row / column masks, `visited` for the lowest one, entries
-    const int NS = (int)sb[MGFS_COUNT];
-    const int wl_cap = G * G, per_round = G * A;
-    const uint16_t* stok = (const uint16_t*)(sb + MGFS_TOKENS);
 #pragma unroll 1
     for (int base = 0;; base += G) {
       __syncwarp(gmask);
-      const int cnt = (int)*wl_count;
+      const int cnt = min((int)*wl_count, L.wl_cap);
       const bool last = base >= NS;
       __syncwarp(gmask);  // everyone has read the count before anyone appends again
-      if (last || cnt + per_round > wl_cap) {  // drain the list: one pair per lane and turn
+      if (last || cnt > L.wl_cap - 2 * G) {  // drain the list: one pair per lane and turn
 #pragma unroll 1
-        for (int i = gl; i < cnt; i += G) {
-          const uint32_t e = wl[i];
-          const uint32_t loc = e & 0xffu;
-          const int a = (int)((e >> 8) & 0xffu), src = (int)(e >> 16);
-          const uint32_t rank = lut[loc] >> 24;
-          const uint4* lp = (const uint4*)(d.fast_less + loc * 8);  // offsets earlier in Manhattan order
-          const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
-          const uint32_t* w = wm + a * 9;
-          int p = (int)ngw[a] + s_ntok * (__popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
-                                          __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y) + __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w));
-          const int nva = (int)nvw[a];
-#pragma unroll 1
-          for (int k = 0; k < nva; k++) {
-            const uint32_t kk = dl[k * G + a];
-            if ((kk >> 24) < rank) p += (int)((kk >> 8) & 0xffu);
-          }
-          const uint16_t* tk = stok;
-          int nt = s_ntok;
-          if (src != 0xff) tk = (const uint16_t*)(toks + src * tokw), nt = (int)(((const uint2*)oloc)[src].y >> 8);
-          nt = min(nt, T - p);  // tokens that fit the budget
-          uint8_t* q = stage + a * 3 * T + p * 3;
-#pragma unroll 1
-          for (int t = 0; t < nt; t++) {
-            const uint32_t x = tk[t];
-            q[3 * t] = (uint8_t)loc, q[3 * t + 1] = (uint8_t)x, q[3 * t + 2] = (uint8_t)(x >> 8);
-          }
-        }
+        for (int i = gl; i < cnt; i += G) place(wl[i]);
         __syncwarp(gmask);
         if (gl == 0) *wl_count = 0;
         __syncwarp(gmask);
       }
       if (last) break;
       const int idx = base + gl;
+      const uint32_t e = e_nxt, v = v_nxt;
+      if (idx + G < NS) e_nxt = __ldg(slist + idx + G), v_nxt = svis[idx + G];
       if (idx < NS) {
-        const uint32_t e = __ldg(slist + idx);
         const int r = (int)(e >> 16), c = (int)(e & 0xffffu);
         uint32_t cand = rowm[r] & colm[c];
         bool first = true;
         while (cand) {
           const int a = __ffs(cand) - 1;
           cand &= cand - 1;
-          const uint32_t la = agw[a];
-          const uint32_t loc = (uint32_t)(((r - (int)(la >> 16) + rr) << 4) | (c - (int)(la & 0xffffu) + cr));
-          if (lut[loc] >= 0xff000000u) continue;
+          const uint32_t loc = offset_for(a, r, c);
+          if (loc == FAST_INVALID) continue;
           if (first) {
             first = false;
-            const uint32_t v = svis[idx];
             if (v < step) {
               atomicAdd(&stale[a], step - v);
               if (live) svis[idx] = step;
             }
           }
-          wl[atomicAdd(wl_count, 1u)] = loc | ((uint32_t)a << 8) | 0xff0000u;
+          push(loc | ((uint32_t)a << 8) | 0xff0000u);
         }
       }
     }
@@ -833,8 +865,76 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // ends are 16-byte aligned one elected lane hands the whole block to the bulk-copy engine (cp.async.bulk, shared ->
   // global; UBLKCP in the SASS) and the group goes on with its write-back while the copy drains; the wait sits at the
   // end of the kernel.  Unaligned blocks (odd T * A) take the vector loop.
-  const bool bulk = (((uint32_t)(uintptr_t)gobs | (uint32_t)nbytes) & 15u) == 0 && !MG_FAST_NO_BULK;
-  if (bulk) {
+  const bool bulk = !S && (((uint32_t)(uintptr_t)gobs | (uint32_t)nbytes) & 15u) == 0 && !MG_FAST_NO_BULK;
+  if (S) {
+    // Static variant: a row is its staged prefix, the tail it wrote in place (rare) and EmptyTokenByte padding
+    // (:940-942).  The block goes out as 16-byte vectors; a vector is padding, staged bytes, or -- where two kinds meet
+    // -- settled byte by byte.  Rows are whole 8-byte units when 3T is a multiple of 8, so half a vector never spans rows.
+    const uint32_t* nvb = (const uint32_t*)(gb + L.ag_off) + 3 * G + 4;
+    const int RB = 3 * T;
+    auto byte_at = [&](int a, int off, uint8_t* dst) {  // one byte of row a; bytes the row wrote in place are left alone
+      const int nv = (int)nvb[a];
+      if (off >= nv)
+        *dst = 0xff;
+      else if (off < RS)
+        *dst = stage[a * RS + off];
+    };
+    if (live && ((uint32_t)(uintptr_t)gobs & 15u) == 0 && (RB & 7) == 0) {
+      const int nvec = nbytes >> 4;
+      int o = 16 * gl;
+      int a = o / RB, rem = o - a * RB;
+#pragma unroll 1
+      for (int v = gl; v < nvec; v += G) {
+        uint2 h[2];
+        int kind[2];  // 0: store h, 1: the row wrote these bytes in place, 2: in-place bytes meet padding
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          int ak = a, rk = rem + 8 * k;
+          if (rk >= RB) ak++, rk -= RB;
+          const int nv = (int)nvb[ak];
+          h[k] = make_uint2(0xffffffffu, 0xffffffffu);
+          kind[k] = 0;
+          if (rk < nv) {
+            if (rk < RS) {  // staged (RS is a multiple of 8); the row may end inside this unit
+              h[k] = *(const uint2*)(stage + ak * RS + rk);
+              const int n = nv - rk;
+              if (n < 4)
+                h[k].x |= 0xffffffffu << (8 * n), h[k].y = 0xffffffffu;
+              else if (n < 8)
+                h[k].y |= 0xffffffffu << (8 * (n - 4));
+            } else {
+              kind[k] = rk + 8 <= nv ? 1 : 2;
+            }
+          }
+        }
+        uint8_t* dst = gobs + 16 * (size_t)v;
+        if ((kind[0] | kind[1]) == 0) {
+          __stcs((uint4*)dst, make_uint4(h[0].x, h[0].y, h[1].x, h[1].y));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            if (kind[k] == 0) {
+              *(uint2*)(dst + 8 * k) = h[k];
+            } else if (kind[k] == 2) {
+              int ak = a, rk = rem + 8 * k;
+              if (rk >= RB) ak++, rk -= RB;
+              const int nv = (int)nvb[ak];
+#pragma unroll 1
+              for (int b = 0; b < 8; b++)
+                if (rk + b >= nv) dst[8 * k + b] = 0xff;
+            }
+          }
+        }
+        rem += 16 * G;
+        while (rem >= RB) rem -= RB, a++;
+      }
+#pragma unroll 1
+      for (int i = (nvec << 4) + gl; i < nbytes; i += G) byte_at(i / RB, i % RB, gobs + i);
+    } else if (live) {
+#pragma unroll 1
+      for (int i = gl; i < nbytes; i += G) byte_at(i / RB, i % RB, gobs + i);
+    }
+  } else if (bulk) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written through the generic proxy
     __syncwarp();
     if (gl == 0 && live) {
@@ -1183,6 +1283,10 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
   L.rank_off = 0;
   L.cta_bytes = 1024;  // the window table
   size_t n = al16((size_t)d.A * 3 * d.T + 16) + 16;  // stage (+ phase slack)
+  if (statics) {  // only a prefix of every row is staged
+    L.stage_tokens = d.T < 64 ? (d.T + 15) & ~15 : 64;
+    n = (size_t)d.A * 3 * L.stage_tokens;  // a multiple of 16
+  }
   L.tok_stride = ((tok_cap + 1) / 2) | 1;               // odd word stride: conflict-free columns
   if (L.tok_stride < 5) L.tok_stride = 5;               // the first four words are always staged
   L.tok_off = (int)n;
@@ -1190,7 +1294,8 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
   L.oloc_off = (int)n;
   n += al16((size_t)G * 4 * 4 + G);  // oloc, ontok, stale, draw, order
   L.key_off = (int)n;
-  n += (size_t)G * G * 4;  // sorted window keys, one column per lane
+  L.wl_cap = 16 * G;
+  n += statics ? (size_t)L.wl_cap * 4 : (size_t)G * G * 4;  // first token positions [observer][object] / the work list
   if (statics) {
     L.sb_words = (d.fast_sstride + 3) & ~3;
     L.sb_off = (int)n;
@@ -1200,9 +1305,9 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
     L.wm_off = (int)n;
     n += al16((size_t)G * 9 * 4);
     L.dl_off = (int)n;
-    n += (size_t)G * G * 4;
+    n += (size_t)G * G * 2;
     L.ag_off = (int)n;
-    n += (size_t)(G * 3 + 4) * 4;  // + the work-list counter
+    n += (size_t)(G * 4 + 4) * 4;  // location, global tokens, list length, valid bytes per agent + the work-list counter
   }
   L.group_bytes = (int)al16(n);
   L.smem_bytes = L.cta_bytes + (size_t)MG_FAST_WARPS * (32 / G) * L.group_bytes;

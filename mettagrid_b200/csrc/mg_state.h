@@ -100,7 +100,8 @@ struct MgFastLayout {
   int rank_off, cta_bytes;
   int tok_off, tok_stride, oloc_off, key_off, group_bytes;
   int sb_off, sb_words, rc_off, wm_off, dl_off, ag_off;  // static variant: bitmap block, row / column observer masks,
-                                                         // window masks [G][9], sorted dynamic keys [G][G], per-agent words
+                                                         // window sets [G][9], dynamic objects per observer [G][G], per-agent words
+  int stage_tokens, wl_cap;  // static variant: tokens of a row that are staged; entries of the work list
   size_t smem_bytes;
 };
 

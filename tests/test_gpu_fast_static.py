@@ -32,18 +32,22 @@ def test_toy_preset_selects_the_static_fast_kernel():
 
 
 @pytest.mark.parametrize(
-    "agents,lanes,walls,width,height,obs_w,obs_h",
+    "agents,lanes,walls,width,height,obs_w,obs_h,tokens",
     [
-        (6, 8, 60, 16, 12, 7, 5),     # elliptical window, 8 lanes: 4 envs per warp with different wall counts
-        (12, 16, 90, 20, 20, 11, 11),  # 16 lanes
-        (3, 8, 40, 9, 9, 15, 15),      # the widest window: it always hangs over the map's edge
-        (5, 8, 50, 70, 6, 3, 3),       # a map row spans three bitmap words; the smallest window
-        (32, 32, 100, 24, 24, 9, 13),  # every lane an agent
-        (2, 8, 330, 20, 20, 5, 5),     # almost everything is wall: most moves are blocked
+        (6, 8, 60, 16, 12, 7, 5, 200),      # elliptical window, 8 lanes: 4 envs per warp with different wall counts
+        (12, 16, 90, 20, 20, 11, 11, 200),  # 16 lanes
+        (3, 8, 40, 9, 9, 15, 15, 200),      # the widest window: it always hangs over the map's edge
+        (5, 8, 50, 70, 6, 3, 3, 200),       # a map row spans three bitmap words; the smallest window
+        (32, 32, 100, 24, 24, 9, 13, 200),  # every lane an agent
+        (2, 8, 330, 20, 20, 5, 5, 200),     # almost everything is wall: most moves are blocked
+        (4, 8, 260, 20, 20, 15, 15, 200),   # ~100 tokens per row: past the staged prefix, work list overflows
+        (5, 8, 60, 14, 14, 9, 9, 201),      # 3T not a multiple of 8: the byte-wise stream-out
+        (3, 8, 45, 12, 10, 7, 7, 36),       # T below the staged prefix; rows are 108 bytes (not a multiple of 8)
+        (20, 32, 300, 30, 30, 13, 13, 252),  # crowded and walled: long lists of dynamic objects per observer
     ],
 )
-def test_walled_maps_static_layer(agents, lanes, walls, width, height, obs_w, obs_h):
-    cfg = _sparse_config(agents, walls=walls, width=width, height=height, obs_w=obs_w, obs_h=obs_h, num_tokens=200,
+def test_walled_maps_static_layer(agents, lanes, walls, width, height, obs_w, obs_h, tokens):
+    cfg = _sparse_config(agents, walls=walls, width=width, height=height, obs_w=obs_w, obs_h=obs_h, num_tokens=tokens,
                          max_steps=50, directions=EIGHT, local_position=True, last_action_move=True)  # fmt: skip
     n = 9
     _triple(cfg, num_envs=n, steps=70, expect_lanes=64 + lanes, check_every=2, p_vibe=0.3, maps=_maps(cfg, n))
