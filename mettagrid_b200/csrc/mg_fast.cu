@@ -339,6 +339,11 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // many environments resident per SM.
   uint8_t* stage = S ? gb : gb + ((uint32_t)(uintptr_t)gobs & 15u);
   const int SC = L.stage_tokens, RS = 3 * SC;  // static variant: staged tokens / bytes per row
+  if (S) {  // the CTA's constant 0xFF buffer, source of every row's padding (read by the bulk-copy engine)
+    uint4* f4 = (uint4*)(smem + 1024);
+    for (int v = tid; v < ((3 * T + 15) >> 4); v += MG_FAST_WARPS * 32) f4[v] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (!S) {
     uint4* s4 = (uint4*)gb;
     const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -866,73 +871,63 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   // global; UBLKCP in the SASS) and the group goes on with its write-back while the copy drains; the wait sits at the
   // end of the kernel.  Unaligned blocks (odd T * A) take the vector loop.
   const bool bulk = !S && (((uint32_t)(uintptr_t)gobs | (uint32_t)nbytes) & 15u) == 0 && !MG_FAST_NO_BULK;
+  const bool sbulk = S && (((uint32_t)(uintptr_t)gobs | (uint32_t)(3 * T)) & 7u) == 0;  // rows of whole 8-byte units
   if (S) {
     // Static variant: a row is its staged prefix, the tail it wrote in place (rare) and EmptyTokenByte padding
-    // (:940-942).  The block goes out as 16-byte vectors; a vector is padding, staged bytes, or -- where two kinds meet
-    // -- settled byte by byte.  Rows are whole 8-byte units when 3T is a multiple of 8, so half a vector never spans rows.
+    // (:940-942).  Rows are whole 8-byte units when 3T is a multiple of 8.  Lane a stores row a's staged units; the
+    // padding -- nine tenths of the block -- is handed to the bulk-copy engine row by row (cp.async.bulk from a constant
+    // 0xFF buffer, 16-byte aligned on both ends; the odd 8-byte unit at either end is a plain store).
     const uint32_t* nvb = (const uint32_t*)(gb + L.ag_off) + 3 * G + 4;
     const int RB = 3 * T;
-    auto byte_at = [&](int a, int off, uint8_t* dst) {  // one byte of row a; bytes the row wrote in place are left alone
-      const int nv = (int)nvb[a];
-      if (off >= nv)
-        *dst = 0xff;
-      else if (off < RS)
-        *dst = stage[a * RS + off];
-    };
-    if (live && ((uint32_t)(uintptr_t)gobs & 15u) == 0 && (RB & 7) == 0) {
-      const int nvec = nbytes >> 4;
-      int o = 16 * gl;
-      int a = o / RB, rem = o - a * RB;
+    if (sbulk) {
+      if (isA && live) {
+        uint8_t* grow = gobs + (size_t)gl * RB;
+        const uint8_t* srow = stage + gl * RS;
+        const int nv = (int)nvb[gl];
+        const int fd = min(nv, RS) >> 3;
 #pragma unroll 1
-      for (int v = gl; v < nvec; v += G) {
-        uint2 h[2];
-        int kind[2];  // 0: store h, 1: the row wrote these bytes in place, 2: in-place bytes meet padding
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-          int ak = a, rk = rem + 8 * k;
-          if (rk >= RB) ak++, rk -= RB;
-          const int nv = (int)nvb[ak];
-          h[k] = make_uint2(0xffffffffu, 0xffffffffu);
-          kind[k] = 0;
-          if (rk < nv) {
-            if (rk < RS) {  // staged (RS is a multiple of 8); the row may end inside this unit
-              h[k] = *(const uint2*)(stage + ak * RS + rk);
-              const int n = nv - rk;
-              if (n < 4)
-                h[k].x |= 0xffffffffu << (8 * n), h[k].y = 0xffffffffu;
-              else if (n < 8)
-                h[k].y |= 0xffffffffu << (8 * (n - 4));
-            } else {
-              kind[k] = rk + 8 <= nv ? 1 : 2;
-            }
+        for (int k = 0; k < fd; k++) *(uint2*)(grow + 8 * k) = *(const uint2*)(srow + 8 * k);
+        if (nv & 7) {  // the unit where the row's tokens end
+          const int kb = nv >> 3, n = nv & 7;
+          if (nv <= RS) {
+            uint2 h = *(const uint2*)(srow + 8 * kb);
+            if (n < 4)
+              h.x |= 0xffffffffu << (8 * n), h.y = 0xffffffffu;
+            else
+              h.y |= 0xffffffffu << (8 * (n - 4));
+            *(uint2*)(grow + 8 * kb) = h;
+          } else {
+#pragma unroll 1
+            for (int b = n; b < 8; b++) grow[8 * kb + b] = 0xff;
           }
         }
-        uint8_t* dst = gobs + 16 * (size_t)v;
-        if ((kind[0] | kind[1]) == 0) {
-          __stcs((uint4*)dst, make_uint4(h[0].x, h[0].y, h[1].x, h[1].y));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 2; k++) {
-            if (kind[k] == 0) {
-              *(uint2*)(dst + 8 * k) = h[k];
-            } else if (kind[k] == 2) {
-              int ak = a, rk = rem + 8 * k;
-              if (rk >= RB) ak++, rk -= RB;
-              const int nv = (int)nvb[ak];
-#pragma unroll 1
-              for (int b = 0; b < 8; b++)
-                if (rk + b >= nv) dst[8 * k + b] = 0xff;
-            }
-          }
-        }
-        rem += 16 * G;
-        while (rem >= RB) rem -= RB, a++;
+        int p0 = (nv + 7) & ~7, end = RB;
+        const uint2 ff = make_uint2(0xffffffffu, 0xffffffffu);
+        if (p0 < end && ((uint32_t)(uintptr_t)(grow + p0) & 8u)) *(uint2*)(grow + p0) = ff, p0 += 8;
+        if (p0 < end && ((uint32_t)(uintptr_t)(grow + end) & 8u)) end -= 8, *(uint2*)(grow + end) = ff;
       }
+      if (gl == 0 && live) {
+        const uint32_t fsrc = (uint32_t)__cvta_generic_to_shared(smem + 1024);  // the CTA's 0xFF buffer
 #pragma unroll 1
-      for (int i = (nvec << 4) + gl; i < nbytes; i += G) byte_at(i / RB, i % RB, gobs + i);
-    } else if (live) {
+        for (int a = 0; a < A; a++) {
+          uint8_t* grow = gobs + (size_t)a * RB;
+          int p0 = ((int)nvb[a] + 7) & ~7, end = RB;
+          if (p0 < end && ((uint32_t)(uintptr_t)(grow + p0) & 8u)) p0 += 8;
+          if (p0 < end && ((uint32_t)(uintptr_t)(grow + end) & 8u)) end -= 8;
+          if (end > p0)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grow + p0), "r"(fsrc), "r"(end - p0) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    } else if (live) {  // odd shapes: byte by byte; bytes a row wrote in place are left alone
 #pragma unroll 1
-      for (int i = gl; i < nbytes; i += G) byte_at(i / RB, i % RB, gobs + i);
+      for (int i = gl; i < nbytes; i += G) {
+        const int a = i / RB, off = i - a * RB;
+        if (off >= (int)nvb[a])
+          gobs[i] = 0xff;
+        else if (off < RS)
+          gobs[i] = stage[a * RS + off];
+      }
     }
   } else if (bulk) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was written through the generic proxy
@@ -1055,7 +1050,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     if (o_ntok != ntok_raw || o_meta != o_meta0) *(uint4*)(bob + 4) = make_uint4(tw0, tw1, tw2, tw3);
   }
   if (gl == 0 && live) blk[MGFB_STEP] = step;
-  if (bulk && gl == 0 && live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage must outlive the copy
+  if ((bulk || sbulk) && gl == 0 && live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage must outlive the copy
 }
 
 
@@ -1281,7 +1276,7 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
   L.G = G;
   L.statics = statics;
   L.rank_off = 0;
-  L.cta_bytes = 1024;  // the window table
+  L.cta_bytes = 1024 + (statics ? (int)al16((size_t)3 * d.T) : 0);  // the window table; static variant: + a row of 0xFF
   size_t n = al16((size_t)d.A * 3 * d.T + 16) + 16;  // stage (+ phase slack)
   if (statics) {  // only a prefix of every row is staged
     L.stage_tokens = d.T < 64 ? (d.T + 15) & ~15 : 64;
