@@ -456,9 +456,9 @@ int mg_create(const int32_t* program, size_t nwords, int num_envs, const int16_t
   // Sparse maps put every object into a lane; maps with more objects than lanes keep the agents there and carry the
   // rest as the static layer, when one template makes all of it (walls).
   int statics = 0;
-  if (d.plain && max_objs > 32) {
+  if (d.plain && (max_objs > 32 || getenv("METTAGRID_B200_FORCE_FAST_STATIC"))) {  // (the switch: A/B runs on sparse maps)
     h->static_template = static_layer_template(P, d, init_cells, N * d.HW);
-    statics = h->static_template >= 0;
+    statics = h->static_template >= 0 || (h->static_template == -1 && getenv("METTAGRID_B200_FORCE_FAST_STATIC"));
   }
   if (const int G = fast_group_size(P, d, statics ? d.A : max_objs)) {
     if (statics) {

@@ -905,17 +905,9 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
         const uint2 ff = make_uint2(0xffffffffu, 0xffffffffu);
         if (p0 < end && ((uint32_t)(uintptr_t)(grow + p0) & 8u)) *(uint2*)(grow + p0) = ff, p0 += 8;
         if (p0 < end && ((uint32_t)(uintptr_t)(grow + end) & 8u)) end -= 8, *(uint2*)(grow + end) = ff;
-      }
-      if (gl == 0 && live) {
-        const uint32_t fsrc = (uint32_t)__cvta_generic_to_shared(smem + 1024);  // the CTA's 0xFF buffer
-#pragma unroll 1
-        for (int a = 0; a < A; a++) {
-          uint8_t* grow = gobs + (size_t)a * RB;
-          int p0 = ((int)nvb[a] + 7) & ~7, end = RB;
-          if (p0 < end && ((uint32_t)(uintptr_t)(grow + p0) & 8u)) p0 += 8;
-          if (p0 < end && ((uint32_t)(uintptr_t)(grow + end) & 8u)) end -= 8;
-          if (end > p0)
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grow + p0), "r"(fsrc), "r"(end - p0) : "memory");
+        if (end > p0) {  // every row's lane queues its own copy
+          const uint32_t fsrc = (uint32_t)__cvta_generic_to_shared(smem + 1024);  // the CTA's 0xFF buffer
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grow + p0), "r"(fsrc), "r"(end - p0) : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -1050,7 +1042,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
     if (o_ntok != ntok_raw || o_meta != o_meta0) *(uint4*)(bob + 4) = make_uint4(tw0, tw1, tw2, tw3);
   }
   if (gl == 0 && live) blk[MGFB_STEP] = step;
-  if ((bulk || sbulk) && gl == 0 && live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage must outlive the copy
+  if (((bulk && gl == 0) || (sbulk && isA)) && live) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the stage must outlive the copy
 }
 
 
