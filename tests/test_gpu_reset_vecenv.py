@@ -227,9 +227,12 @@ def test_vecenv_action_validation_on_device():
     lazy.close()
 
 
-def test_vecenv_fast_path_autoreset_matches_oracle():
+@pytest.mark.parametrize("persistent", [False, True])
+def test_vecenv_fast_path_autoreset_matches_oracle(persistent):
     """Auto-reset on a fast handle restores finished envs from the post-reset snapshot of the packed block; the
-    trajectories must be those of freshly constructed environments, also after the snapshot was invalidated."""
+    trajectories must be those of freshly constructed environments, also after the snapshot was invalidated.
+    `persistent`: the caller reuses one action tensor, so the steady-state step runs as one captured CUDA graph
+    (mg_vecenv_step); a fresh tensor per step makes the handle rebuild the graph and then fall back to plain launches."""
     from mettagrid_b200.vecenv import MettaGridVecEnv
 
     cfg = cases.benchmark_config(4, max_steps=9)
@@ -249,7 +252,13 @@ def test_vecenv_fast_path_autoreset_matches_oracle():
         if t == 20:  # an inventory edit drops the snapshot: the generic reset path takes over
             env.sim.set_inventory(5, 2, {"heart": 4})
             orc[5].set_inventory(2, {"heart": 4})
-        obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
+        if persistent:
+            if t == 0:
+                held = torch.zeros(28, dtype=torch.int64, device="cuda")
+            held.copy_(torch.from_numpy(a))
+            obs, rew, term, trunc, _ = env.step(held)
+        else:
+            obs, rew, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
         for e, o in enumerate(orc):
             o.step(core[e], vib[e])
         torch.cuda.synchronize()
