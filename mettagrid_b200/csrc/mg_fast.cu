@@ -35,6 +35,9 @@
 
 #include "mg_state.h"
 
+#ifndef MG_FS_UNROLL
+#define MG_FS_UNROLL 1  // static variant: pairs a lane places per turn of the drain loop
+#endif
 #ifndef MG_FAST_NO_BULK
 #define MG_FAST_NO_BULK 0  // 1: always stream the observation block with vector stores (A/B against cp.async.bulk)
 #endif
@@ -42,6 +45,7 @@
 namespace {
 
 #define FAST_INVALID 0xFFFFFFFFu
+constexpr int kFsUnroll = MG_FS_UNROLL;
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 11;
@@ -203,8 +207,13 @@ __device__ __forceinline__ void sort_net(uint32_t (&key)[32]) {
   }
 }
 
-template <int G, bool S>
-__global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_fast(const MgDev d, const MgFastLayout L, const MgFastHdr HD) {
+// WPC = warps per CTA.  One-warp CTAs retire and refill SM slots env by env: 17.0 vs 18.4 us per tick at the headline
+// 4096 envs x 16 agents (less than one wave) and within 1 % of four-warp CTAs at 32 768 and 262 144 envs, so the
+// sorted-key variant always runs them; the static variant, whose CTAs share a 0xFF row besides the window table,
+// gains a few per cent from four-warp CTAs once the grid is many waves deep (toy 16 384 envs: 175 vs 183 us).
+// mg_fast_layout picks.
+template <int G, bool S, int WPC>
+__global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d, const MgFastLayout L, const MgFastHdr HD) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int GPW = 32 / G;  // environments per warp
   const int* const hdr = HD.v;  // the program header travels as a kernel argument: constant-bank reads, no load
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const uint32_t gmask = G == 32 ? MG_FULL : (((1u << (G & 31)) - 1u) << (grp * G));
   const int gshift = grp * G;
 
-  int env = (blockIdx.x * MG_FAST_WARPS + warp) * GPW + grp;
+  int env = (blockIdx.x * WPC + warp) * GPW + grp;
   const bool live = env < d.num_envs;  // a dead group mirrors the last env but stores nothing
   if (!live) env = d.num_envs - 1;
   uint32_t* lut = (uint32_t*)smem;  // window table: packed offset -> rank << 24 | offset << 16 (0xFFFFFF00 outside)
@@ -257,11 +266,11 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const uint4 orec = *(const uint4*)bob;       // loc, visited, meta, agent + 1 | ntok << 8 | dirty << 16
   const uint4 otok = *(const uint4*)(bob + 4); // first eight cached tokens
   const float s_cv0 = bst[hdr[MGH_ST_CELL_VISITED] * G];
-  constexpr int LV = (64 + MG_FAST_WARPS * 32 - 1) / (MG_FAST_WARPS * 32);  // window-table vectors per thread
+  constexpr int LV = (64 + WPC * 32 - 1) / (WPC * 32);  // window-table vectors per thread
   uint4 lutv[LV];
 #pragma unroll
   for (int k = 0; k < LV; k++) {
-    const int i = tid + k * MG_FAST_WARPS * 32;
+    const int i = tid + k * WPC * 32;
     lutv[k] = i < 64 ? __ldg((const uint4*)d.rank_lut + i) : make_uint4(0, 0, 0, 0);
   }
   if (gl < MGFB_STATS / 2) {  // the stat rows the end of the tick may update: pull them towards L2 now
@@ -286,7 +295,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const int nbytes = A * 3 * T;
 #pragma unroll
   for (int k = 0; k < LV; k++) {
-    const int i = tid + k * MG_FAST_WARPS * 32;
+    const int i = tid + k * WPC * 32;
     if (i < 64) ((uint4*)lut)[i] = lutv[k];
   }
   const uint32_t step = bh0.x + 1u;  // :951
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
   const int SC = L.stage_tokens, RS = 3 * SC;  // static variant: staged tokens / bytes per row
   if (S) {  // the CTA's constant 0xFF buffer, source of every row's padding (read by the bulk-copy engine)
     uint4* f4 = (uint4*)(smem + 1024);
-    for (int v = tid; v < ((3 * T + 15) >> 4); v += MG_FAST_WARPS * 32) f4[v] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int v = tid; v < ((3 * T + 15) >> 4); v += WPC * 32) f4[v] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (!S) {
@@ -768,8 +777,10 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       const uint4* lp = (const uint4*)(d.fast_less + loc * 8);  // offsets earlier in Manhattan order
       const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
       const uint32_t* w = wm + a * 9;
-      int p = (int)ngw[a] + s_ntok * (__popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
-                                      __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y) + __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w));
+      int before = __popc(w[0] & la4.x) + __popc(w[1] & la4.y) + __popc(w[2] & la4.z) + __popc(w[3] & la4.w) +
+                   __popc(w[4] & lb4.x) + __popc(w[5] & lb4.y);
+      if (OH > 12) before += __popc(w[6] & lb4.z) + __popc(w[7] & lb4.w);  // window rows 12-14
+      int p = (int)ngw[a] + s_ntok * before;
       const int nva = (int)nvw[a];
 #pragma unroll 1
       for (int k = 0; k < nva; k++) {
@@ -832,7 +843,7 @@ __global__ void __launch_bounds__(MG_FAST_WARPS * 32, MG_FAST_MIN_CTAS) k_step_f
       const bool last = base >= NS;
       __syncwarp(gmask);  // everyone has read the count before anyone appends again
       if (last || cnt > L.wl_cap - 2 * G) {  // drain the list: one pair per lane and turn
-#pragma unroll 1
+#pragma unroll kFsUnroll
         for (int i = gl; i < cnt; i += G) place(wl[i]);
         __syncwarp(gmask);
         if (gl == 0) *wl_count = 0;
@@ -1297,45 +1308,53 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
     n += (size_t)(G * 4 + 4) * 4;  // location, global tokens, list length, valid bytes per agent + the work-list counter
   }
   L.group_bytes = (int)al16(n);
-  L.smem_bytes = L.cta_bytes + (size_t)MG_FAST_WARPS * (32 / G) * L.group_bytes;
+  // warps per CTA: one while the grid is a few waves at most, four beyond (measured; see k_step_fast)
+  const long long warps = ((long long)d.num_envs + 32 / G - 1) / (32 / G);
+  L.warps = MG_FAST_WARPS ? MG_FAST_WARPS : (!statics || warps <= 8192) ? 1 : 4;
+  L.smem_bytes = L.cta_bytes + (size_t)L.warps * (32 / G) * L.group_bytes;
   return L;
 }
 
-template <int G, bool S>
+template <int G, bool S, int WPC>
 static cudaError_t launch_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
-  const int envs_per_cta = MG_FAST_WARPS * (32 / G);
+  const int envs_per_cta = WPC * (32 / G);
   const int grid = (d.num_envs + envs_per_cta - 1) / envs_per_cta;
-  k_step_fast<G, S><<<grid, MG_FAST_WARPS * 32, L.smem_bytes, st>>>(d, L, H);
+  k_step_fast<G, S, WPC><<<grid, WPC * 32, L.smem_bytes, st>>>(d, L, H);
   return cudaGetLastError();
 }
 
-template <int G, bool S>
+template <int G, bool S, int WPC>
 static cudaError_t configure_one(int bytes) {
-  cudaError_t e = cudaFuncSetAttribute(k_step_fast<G, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaError_t e = cudaFuncSetAttribute(k_step_fast<G, S, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   // prefer shared memory: the working set lives there, L1 only serves the program tables
-  return cudaFuncSetAttribute(k_step_fast<G, S>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return cudaFuncSetAttribute(k_step_fast<G, S, WPC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
 }
 
-cudaError_t mg_fast_configure(const MgFastLayout& L) {
-  const int bytes = (int)L.smem_bytes;
-  if (L.statics) return L.G == 8 ? configure_one<8, true>(bytes) : L.G == 16 ? configure_one<16, true>(bytes) : configure_one<32, true>(bytes);
-  return L.G == 8 ? configure_one<8, false>(bytes) : L.G == 16 ? configure_one<16, false>(bytes) : configure_one<32, false>(bytes);
-}
+// the instantiation for (lanes per env, static layer, warps per CTA)
+#define MG_FAST_DISPATCH(fn, L, ...)                                                             \
+  do {                                                                                           \
+    const int key_ = (L.G == 8 ? 0 : L.G == 16 ? 1 : 2) * 4 + (L.statics ? 2 : 0) + (L.warps == 1 ? 0 : 1); \
+    switch (key_) {                                                                              \
+      case 0: return fn<8, false, 1>(__VA_ARGS__);                                               \
+      case 1: return fn<8, false, 4>(__VA_ARGS__);                                               \
+      case 2: return fn<8, true, 1>(__VA_ARGS__);                                                \
+      case 3: return fn<8, true, 4>(__VA_ARGS__);                                                \
+      case 4: return fn<16, false, 1>(__VA_ARGS__);                                              \
+      case 5: return fn<16, false, 4>(__VA_ARGS__);                                              \
+      case 6: return fn<16, true, 1>(__VA_ARGS__);                                               \
+      case 7: return fn<16, true, 4>(__VA_ARGS__);                                               \
+      case 8: return fn<32, false, 1>(__VA_ARGS__);                                              \
+      case 9: return fn<32, false, 4>(__VA_ARGS__);                                              \
+      case 10: return fn<32, true, 1>(__VA_ARGS__);                                              \
+      default: return fn<32, true, 4>(__VA_ARGS__);                                              \
+    }                                                                                            \
+  } while (0)
+
+cudaError_t mg_fast_configure(const MgFastLayout& L) { MG_FAST_DISPATCH(configure_one, L, (int)L.smem_bytes); }
 
 cudaError_t mg_launch_step_fast(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, cudaStream_t st) {
-  if (L.statics) {
-    switch (L.G) {
-      case 8: return launch_fast<8, true>(d, L, H, st);
-      case 16: return launch_fast<16, true>(d, L, H, st);
-      default: return launch_fast<32, true>(d, L, H, st);
-    }
-  }
-  switch (L.G) {
-    case 8: return launch_fast<8, false>(d, L, H, st);
-    case 16: return launch_fast<16, false>(d, L, H, st);
-    default: return launch_fast<32, false>(d, L, H, st);
-  }
+  MG_FAST_DISPATCH(launch_fast, L, d, L, H, st);
 }
 
 cudaError_t mg_launch_fast_pack(const MgDev& d, const MgFastLayout& L, const MgFastHdr& H, const uint8_t* mask, cudaStream_t st) {

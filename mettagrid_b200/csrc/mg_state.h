@@ -9,10 +9,7 @@
 #define MG_WARPS_PER_CTA 4
 #endif
 #ifndef MG_FAST_WARPS
-#define MG_FAST_WARPS 4  // warps per CTA of k_step_fast (mg_fast.cu); 1 / 2 / 4 measured equal at 4096 envs, 4 best at 32768
-#endif
-#ifndef MG_FAST_MIN_CTAS
-#define MG_FAST_MIN_CTAS 4  // <= 128 registers: 16 resident warps per SM, one wave for 4096 envs x 16 agents
+#define MG_FAST_WARPS 0  // warps per CTA of k_step_fast (mg_fast.cu): 0 = chosen by grid size (1 or 4), 1 / 4 = forced (A/B builds)
 #endif
 #define MG_RNG_WINDOW 32
 #define MG_TAG_LIST_CAP 64
@@ -96,6 +93,7 @@ struct MgDev {
 // shared-memory layout of k_step_fast (mg_fast.cu), computed on the host
 struct MgFastLayout {
   int G;           // lanes per environment: 8, 16 or 32
+  int warps;       // warps per CTA: 1 or 4
   int statics;     // 1: the static-layer variant (walls and other immutable objects outside the object lanes)
   int rank_off, cta_bytes;
   int tok_off, tok_stride, oloc_off, key_off, group_bytes;
