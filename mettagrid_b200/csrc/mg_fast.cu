@@ -711,12 +711,12 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
     global_tokens();
     uint32_t* const wm = (uint32_t*)(gb + L.wm_off);   // [agent][9] static window set, 256 bits by packed offset
     uint16_t* const dl = (uint16_t*)(gb + L.dl_off);   // [k][agent] dynamic objects the agent sees: rank << 8 | tokens
-    uint32_t* const agw = (uint32_t*)(gb + L.ag_off);  // [agent] location
+    uint32_t* const agw = (uint32_t*)(gb + L.ag_off);  // [agent] bias that turns a cell into its packed window offset
     uint32_t* const ngw = agw + G;                     // [agent] global tokens
     uint32_t* const nvw = ngw + G;                     // [agent] entries in its dl column
     uint32_t* const wl_count = nvw + G;
     uint32_t* const nvb = wl_count + 4;                // [agent] valid bytes of its row
-    uint32_t* const wl = tab;                          // work list: offset | observer << 8 | source << 16 (0xFF: static)
+    uint32_t* const wl = tab;                          // work list of (object, observer) pairs, see place()
     const int s_ntok = (int)sb[MGFS_NTOK];
     const int OH = hdr[MGH_OBS_H], OW = hdr[MGH_OBS_W], rr = OH >> 1, cr = OW >> 1;
     int n_static = 0;  // static objects in this agent's window
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
         n_static += __popc(M[k]);
       }
     }
-    agw[gl] = isA ? my_loc : FAST_INVALID;
+    agw[gl] = (uint32_t)(((rr - r0) << 4) + (cr - c0));  // + (r << 4) + c = packed window offset of cell (r, c)
     ngw[gl] = (uint32_t)pos;
     nvw[gl] = 0;
     if (gl == 0) *wl_count = 0;
@@ -762,18 +762,17 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
     uint32_t e_nxt = 0, v_nxt = 0;
     if (gl < NS) e_nxt = __ldg(slist + gl), v_nxt = svis[gl];
     __syncwarp();
-    // packed window offset of cell (r, c) for observer a, or 0xFFFFFFFF outside the observation shape
-    auto offset_for = [&](int a, int r, int c) {
-      const uint32_t la = agw[a];
-      const uint32_t loc = (uint32_t)(((r - (int)(la >> 16) + rr) << 4) | (c - (int)(la & 0xffffu) + cr));
-      return lut[loc] >= 0xff000000u ? FAST_INVALID : loc;
+    // window-table entry (rank << 24 | packed offset << 16) of cell rc = (r << 4) + c for an observer whose bounding box
+    // holds it, or 0xFFFFFFFF outside the observation shape
+    auto entry_for = [&](int a, int rc) {
+      const uint32_t lk = lut[(uint32_t)(rc + (int)agw[a]) & 0xffu];
+      return lk >= 0xff000000u ? FAST_INVALID : lk;
     };
     // one (object, observer) pair: where the object's tokens start in the observer's row, then the tokens
     const uint16_t* stok = (const uint16_t*)(sb + MGFS_TOKENS);
-    auto place = [&](uint32_t e) {
-      const uint32_t loc = e & 0xffu;
-      const int a = (int)((e >> 8) & 0xffu), src = (int)(e >> 16);
-      const uint32_t rank = lut[loc] >> 24;
+    auto place = [&](uint32_t e) {  // e = rank << 24 | offset << 16 | observer << 8 | source lane (0xFF: static)
+      const uint32_t loc = (e >> 16) & 0xffu, rank = e >> 24;
+      const int a = (int)((e >> 8) & 0xffu), src = (int)(e & 0xffu);
       const uint4* lp = (const uint4*)(d.fast_less + loc * 8);  // offsets earlier in Manhattan order
       const uint4 la4 = __ldg(lp), lb4 = __ldg(lp + 1);
       const uint32_t* w = wm + a * 9;
@@ -809,10 +808,10 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
       while (cand) {
         const int a = __ffs(cand) - 1;
         cand &= cand - 1;
-        const uint32_t loc = offset_for(a, r, c);
-        if (loc == FAST_INVALID) continue;  // inside the bounding box but outside the shape
+        const uint32_t lk = entry_for(a, (r << 4) + c);
+        if (lk == FAST_INVALID) continue;  // inside the bounding box but outside the shape
         seen |= 1u << a;
-        dl[atomicAdd(&nvw[a], 1u) * G + a] = (uint16_t)(((lut[loc] >> 24) << 8) | (uint32_t)my_n);  // rank << 8 | tokens
+        dl[atomicAdd(&nvw[a], 1u) * G + a] = (uint16_t)(((lk >> 24) << 8) | (uint32_t)my_n);  // rank << 8 | tokens
       }
       if (seen && o_vis < step) {
         atomicAdd(&stale[__ffs(seen) - 1], step - o_vis);
@@ -832,7 +831,7 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
       while (seen) {
         const int a = __ffs(seen) - 1;
         seen &= seen - 1;
-        push(offset_for(a, r, c) | ((uint32_t)a << 8) | ((uint32_t)gl << 16));
+        push(entry_for(a, (r << 4) + c) | ((uint32_t)a << 8) | (uint32_t)gl);
       }
     }
     // the static objects, G at a time: observers from the row / column masks, `visited` for the lowest one, entries
@@ -854,14 +853,14 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
       const uint32_t e = e_nxt, v = v_nxt;
       if (idx + G < NS) e_nxt = __ldg(slist + idx + G), v_nxt = svis[idx + G];
       if (idx < NS) {
-        const int r = (int)(e >> 16), c = (int)(e & 0xffffu);
+        const int r = (int)(e >> 16), c = (int)(e & 0xffffu), rc = (r << 4) + c;
         uint32_t cand = rowm[r] & colm[c];
         bool first = true;
         while (cand) {
           const int a = __ffs(cand) - 1;
           cand &= cand - 1;
-          const uint32_t loc = offset_for(a, r, c);
-          if (loc == FAST_INVALID) continue;
+          const uint32_t lk = entry_for(a, rc);
+          if (lk == FAST_INVALID) continue;
           if (first) {
             first = false;
             if (v < step) {
@@ -869,7 +868,7 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
               if (live) svis[idx] = step;
             }
           }
-          push(loc | ((uint32_t)a << 8) | 0xff0000u);
+          push(lk | ((uint32_t)a << 8) | 0xffu);
         }
       }
     }
