@@ -38,6 +38,9 @@
 #ifndef MG_FS_UNROLL
 #define MG_FS_UNROLL 1  // static variant: pairs a lane places per turn of the drain loop
 #endif
+#ifndef MG_FS_WL
+#define MG_FS_WL 16  // static variant: work-list entries per lane
+#endif
 #ifndef MG_FAST_NO_BULK
 #define MG_FAST_NO_BULK 0  // 1: always stream the observation block with vector stores (A/B against cp.async.bulk)
 #endif
@@ -794,6 +797,8 @@ __global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d,
     };
     // append to the work list; a full list places the pair at once instead
     auto push = [&](uint32_t e) {
+      // (one atomic per lane: aggregating the lanes that arrive together -- ballot, leader, shuffle -- measured slower,
+      // 59 vs 55 us per tick on the toy preset)
       const uint32_t slot = atomicAdd(wl_count, 1u);
       if (slot < (uint32_t)L.wl_cap)
         wl[slot] = e;
@@ -1291,7 +1296,7 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
   L.oloc_off = (int)n;
   n += al16((size_t)G * 4 * 4 + G);  // oloc, ontok, stale, draw, order
   L.key_off = (int)n;
-  L.wl_cap = 16 * G;
+  L.wl_cap = MG_FS_WL * G;
   n += statics ? (size_t)L.wl_cap * 4 : (size_t)G * G * 4;  // first token positions [observer][object] / the work list
   if (statics) {
     L.sb_words = (d.fast_sstride + 3) & ~3;
