@@ -39,7 +39,7 @@
 #define MG_FS_UNROLL 1  // static variant: pairs a lane places per turn of the drain loop
 #endif
 #ifndef MG_FS_WL
-#define MG_FS_WL 16  // static variant: work-list entries per lane
+#define MG_FS_WL 8  // static variant: work-list entries per lane (16 measured equal; 8 lets a 16th one-warp CTA fit an SM on toy)
 #endif
 #ifndef MG_FAST_NO_BULK
 #define MG_FAST_NO_BULK 0  // 1: always stream the observation block with vector stores (A/B against cp.async.bulk)
@@ -1307,7 +1307,7 @@ MgFastLayout mg_fast_layout(const MgDev& d, int G, int tok_cap, int statics) {
     L.wm_off = (int)n;
     n += al16((size_t)G * 9 * 4);
     L.dl_off = (int)n;
-    n += (size_t)G * G * 2;
+    n += al16((size_t)d.A * G * 2);  // an observer sees at most the A agents' objects
     L.ag_off = (int)n;
     n += (size_t)(G * 4 + 4) * 4;  // location, global tokens, list length, valid bytes per agent + the work-list counter
   }
