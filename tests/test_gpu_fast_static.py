@@ -206,3 +206,49 @@ def test_vecenv_autoreset_on_a_static_handle():
         assert sim.get_episode_stats(e) == o.get_episode_stats(), f"stats differ in env {e}"
         assert np.array_equal(sim.dump_objects(e), o.dump_objects())
     env.close()
+
+
+def test_long_token_lists_with_vibe_edits_on_a_static_handle():
+    # every agent carries 9 resources: 12-13 cached tokens, more than the eight kept in the packed block -- the tail
+    # lives in the agent's object record, which the static variant finds through the agent's slot, and vibe edits shift it
+    cfg = _sparse_config(7, walls=60, width=15, height=13, obs_w=9, obs_h=9, num_tokens=200, directions=EIGHT)
+    cfg.game.agent.inventory.initial = {"ore_red": 3, "ore_blue": 300, "ore_green": 1, "battery_red": 9, "battery_blue": 2,
+                                        "heart": 70000 % 65536, "armor": 5, "laser": 1, "blueprint": 8}  # fmt: skip
+    n = 8
+    _triple(cfg, num_envs=n, steps=80, expect_lanes=64 + 8, p_vibe=0.6, check_every=2, maps=_maps(cfg, n))
+
+
+def test_set_inventory_and_reset_on_a_static_handle():
+    from oracle.oracle import OracleEnv
+
+    cfg = _sparse_config(4, walls=55, width=14, height=12, obs_w=7, obs_h=7, num_tokens=200)
+    N = 5
+    sim = _make(cfg, N, 21, True, _maps(cfg, N))
+    assert sim.step_kernel == 64 + 8
+    P = sim.program
+    A = P.num_agents
+    rs = np.random.RandomState(5)
+    acts = rs.randint(0, 5, size=(40, N, A)).astype(np.int32)
+    zeros = np.zeros((N, A), np.int32)
+    for t in range(10):
+        sim.step(acts[t], zeros)
+    sim.set_inventory(2, 1, {"heart": 3, "ore_red": 7})  # mid-episode: the agent's token cache is rebuilt from its record
+    sim.reset()
+    orc = [OracleEnv(P, sim._init_cells[e], int(sim.seeds[e]), sim._init_gstats[e]) for e in range(N)]
+    sim.set_inventory(2, 1, {"heart": 3, "ore_red": 7})
+    orc[2].set_inventory(1, {"heart": 3, "ore_red": 7})
+    for t in range(10, 40):
+        sim.step(acts[t], zeros)
+        for e, o in enumerate(orc):
+            o.step(acts[t, e], zeros[e])
+        if t == 25:
+            sim.set_inventory(4, 3, {"laser": 2})
+            orc[4].set_inventory(3, {"laser": 2})
+    torch.cuda.synchronize()
+    obs = sim.observations.cpu().numpy()
+    for e, o in enumerate(orc):
+        assert np.array_equal(obs[e], o.observations()), f"obs differ in env {e}"
+        assert sim.get_episode_stats(e) == o.get_episode_stats()
+        assert np.array_equal(sim.dump_objects(e), o.dump_objects())
+    sim.check_errors()
+    sim.close()
