@@ -71,6 +71,9 @@ struct Smem {
 #define MG_MIN_CTAS_PER_SM 8  // 64 registers per thread -> 32 resident warps per SM (measured best once the grid stopped
                               // occupying shared memory: profiles/README.md; 7 was best before)
 #endif
+#ifndef MG_FINISH_CTAS_PER_SM
+#define MG_FINISH_CTAS_PER_SM MG_MIN_CTAS_PER_SM  // k_finish's own register budget (it mostly waits on dependent loads)
+#endif
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -1243,7 +1246,7 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_w
 // token stats in agent order, rewards (systems/reward.hpp:56-77), episode rewards, truncation / termination.
 // =================================================================================================
 template <bool PLAIN>
-__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_finish(MgDev d, const uint8_t* __restrict__ mask, int initial) {
+__global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_FINISH_CTAS_PER_SM) k_finish(MgDev d, const uint8_t* __restrict__ mask, int initial) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mask) {
@@ -1301,24 +1304,33 @@ __global__ void __launch_bounds__(MG_WARPS_PER_CTA * 32, MG_MIN_CTAS_PER_SM) k_f
       if (s.a_res[i]) astat_add(w, i, w.hdr[MGH_ST_CELL_VISITED], (float)s.a_res[i]);
     __syncwarp();
   }
-  if (lane == 0) {
-    // token stats: one float add per agent in agent order like the reference (:659-661)
+  {
+    // token stats: one float add per agent in agent order like the reference (:659-661).  The counts are loaded 32 at a
+    // time, one per lane, and handed to lane 0 by shuffles -- not one dependent load per agent.
     const int idw = w.hdr[MGH_GST_TOKENS_WRITTEN], idf = w.hdr[MGH_GST_TOKENS_FREE];
-    float tw = w.gstats[idw], tf = w.gstats[idf];
-    for (int a = 0; a < A; a++) {
-      const int attempted = d.tok_attempted[g0 + a];
-      if (attempted > w.T) {  // hard error in the reference (:364-375)
-        set_error(w, MGERR_TOKEN_OVERFLOW, a | (min(attempted, 65535) << 16));
-      } else {
-        tw = __fadd_rn(tw, (float)attempted);
-        tf = __fadd_rn(tf, (float)(w.T - attempted));
+    float tw = 0.0f, tf = 0.0f;
+    if (lane == 0) tw = w.gstats[idw], tf = w.gstats[idf];
+    for (int base = 0; base < A; base += 32) {
+      const int mine = base + lane < A ? d.tok_attempted[g0 + base + lane] : 0;
+      const int n = min(32, A - base);
+      for (int j = 0; j < n; j++) {
+        const int attempted = __shfl_sync(MG_FULL, mine, j);
+        if (lane != 0) continue;
+        if (attempted > w.T) {  // hard error in the reference (:364-375)
+          set_error(w, MGERR_TOKEN_OVERFLOW, (base + j) | (min(attempted, 65535) << 16));
+        } else {
+          tw = __fadd_rn(tw, (float)attempted);
+          tf = __fadd_rn(tf, (float)(w.T - attempted));
+        }
       }
     }
-    w.gstats[idw] = tw;
-    w.gstats[idf] = tf;
-    gstat_touch(w, idw);
-    gstat_touch(w, w.hdr[MGH_GST_TOKENS_DROPPED]);
-    gstat_touch(w, idf);
+    if (lane == 0) {
+      w.gstats[idw] = tw;
+      w.gstats[idf] = tf;
+      gstat_touch(w, idw);
+      gstat_touch(w, w.hdr[MGH_GST_TOKENS_DROPPED]);
+      gstat_touch(w, idf);
+    }
   }
   if (initial) return;
   __syncwarp();
@@ -1430,7 +1442,12 @@ cudaError_t mg_configure_kernels(const MgDev& d) {
   int pct = want_kb * 100 / 228 + 1;
   if (pct > 100) pct = 100;
   if ((e = cudaFuncSetAttribute(k_world<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_world<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  if ((e = cudaFuncSetAttribute(k_world<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+  want_kb = (int)((bytes + 1024) * MG_FINISH_CTAS_PER_SM / 1024) + 8;
+  pct = want_kb * 100 / 228 + 1;
+  if (pct > 100) pct = 100;
+  if ((e = cudaFuncSetAttribute(k_finish<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_finish<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 // a launch covers the envs [d.env0, d.num_envs): the whole handle, or one chunk of it (mg_capi.cu: launch_step)
 static inline int mg_grid(const MgDev& d) { return (d.num_envs - d.env0 + MG_WARPS_PER_CTA - 1) / MG_WARPS_PER_CTA; }
