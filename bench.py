@@ -276,11 +276,13 @@ class Workload:
         self.torch.cuda.empty_cache()
 
 
-def measured_traffic(kernel: str, wl: str):
+def measured_traffic(kernel: str, wl: str, envs: int):
+    """DRAM bytes per launch from the committed ncu capture of this kernel at this shape, else None."""
     tpath = ROOT / "profiles" / "traffic.json"
     if not tpath.exists():
         return None
-    return json.loads(tpath.read_text()).get(f"{wl}:{kernel}", {}).get("dram_bytes_per_launch")
+    rec = json.loads(tpath.read_text()).get(f"{wl}:{kernel}", {})
+    return rec.get("dram_bytes_per_launch") if rec.get("envs") == envs else None
 
 
 def time_extra(wl: str, envs: int, agents: int, env0: int, world: int, rank: int, local_rank: int, ticks: int, flush, args,
@@ -310,7 +312,7 @@ def time_extra(wl: str, envs: int, agents: int, env0: int, world: int, rank: int
     out = {
         "workload": WORKLOADS[wl][0].format(A=agents) + f", {envs} envs/GPU", "value": world * envs * agents * ticks / (ms * 1e-3),
         "unit": UNIT, "ticks": ticks, "ms_per_tick": per_tick, "envs_per_gpu": envs, "total_envs": world * envs, "scaling": scaling,
-        "roofline": w.roofline(per_tick, measured_traffic(kernel_name(w.sim.step_kernel), wl)),
+        "roofline": w.roofline(per_tick, measured_traffic(kernel_name(w.sim.step_kernel), wl, envs)),
         "gpu_launches": ticks * launches_per_tick(w.sim.step_kernel),
     }  # fmt: skip
     w.close()
@@ -392,7 +394,7 @@ def run_ours(args):
     value = world * envs * A * steps * tps / (total_ms * 1e-3)
     e2e_value = world * envs * A * e2e_ticks / (e2e_ms * 1e-3)
     per_tick_ms = total_ms / (steps * tps)
-    roof = w.roofline(per_tick_ms, measured_traffic(kernel_name(sim.step_kernel), wl))
+    roof = w.roofline(per_tick_ms, measured_traffic(kernel_name(sim.step_kernel), wl, envs))
 
     # ---- the reference benchmark's verbatim action sampling on the same handle (report both)
     other = "verbatim" if ACTION_MODE == "effective" else "effective"
