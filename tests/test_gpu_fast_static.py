@@ -44,6 +44,7 @@ def test_toy_preset_selects_the_static_fast_kernel():
         (5, 8, 60, 14, 14, 9, 9, 201),      # 3T not a multiple of 8: the byte-wise stream-out
         (3, 8, 45, 12, 10, 7, 7, 36),       # T below the staged prefix; rows are 108 bytes (not a multiple of 8)
         (20, 32, 300, 30, 30, 13, 13, 252),  # crowded and walled: long lists of dynamic objects per observer
+        (1, 8, 45, 12, 40, 11, 11, 200),     # a single agent (no shuffle draws) on a tall map
     ],
 )
 def test_walled_maps_static_layer(agents, lanes, walls, width, height, obs_w, obs_h, tokens):
