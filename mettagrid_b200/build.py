@@ -58,6 +58,8 @@ def build_native(force: bool = False, verbose: bool = False, out: Path | None = 
     target = LIB if out is None else Path(out)
     target.parent.mkdir(parents=True, exist_ok=True)
     subprocess.check_call([nvcc, "-shared", "-o", str(target), *objs])
+    if out is not None:  # a variant's objects are of no further use (and would travel to the GPU box with every snapshot)
+        shutil.rmtree(build_dir, ignore_errors=True)
     return target
 
 
