@@ -38,6 +38,9 @@
 #ifndef MG_FS_UNROLL
 #define MG_FS_UNROLL 1  // static variant: pairs a lane places per turn of the drain loop
 #endif
+#ifndef MG_FAST_CTAS_PER_SM
+#define MG_FAST_CTAS_PER_SM 16  // one-warp CTAs per SM the register budget allows (128 registers)
+#endif
 #ifndef MG_FS_WL
 #define MG_FS_WL 8  // static variant: work-list entries per lane (16 measured equal; 8 lets a 16th one-warp CTA fit an SM on toy)
 #endif
@@ -216,7 +219,7 @@ __device__ __forceinline__ void sort_net(uint32_t (&key)[32]) {
 // gains a few per cent from four-warp CTAs once the grid is many waves deep (toy 16 384 envs: 175 vs 183 us).
 // mg_fast_layout picks.
 template <int G, bool S, int WPC>
-__global__ void __launch_bounds__(WPC * 32, 16 / WPC) k_step_fast(const MgDev d, const MgFastLayout L, const MgFastHdr HD) {
+__global__ void __launch_bounds__(WPC * 32, MG_FAST_CTAS_PER_SM / WPC) k_step_fast(const MgDev d, const MgFastLayout L, const MgFastHdr HD) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int GPW = 32 / G;  // environments per warp
   const int* const hdr = HD.v;  // the program header travels as a kernel argument: constant-bank reads, no load
