@@ -167,3 +167,9 @@ def test_c4_world_at_bench_shape():
 def test_toy_preset_at_bench_shape():
     """The reference's perf_benchmark.py toy preset: 4096 envs x 20 agents, 40 x 40 walled maps, 8-way moves."""
     _full_shape("toy", 4096, 32, (0, 15, 31), 600, 101)
+
+
+def test_toy_preset_many_waves():
+    """12 288 envs of the toy preset: past 8192 warps mg_fast_layout switches the static variant to four-warp CTAs
+    (k_step_fast<32, static, 4>), the instantiation the large-batch numbers in DESIGN.md come from."""
+    _full_shape("toy", 12288, 8, (0, 7), 120, 37)
