@@ -35,9 +35,6 @@
 
 #include "mg_state.h"
 
-#ifndef MG_FS_UNROLL
-#define MG_FS_UNROLL 1  // static variant: pairs a lane places per turn of the drain loop
-#endif
 #ifndef MG_FAST_CTAS_PER_SM
 #define MG_FAST_CTAS_PER_SM 16  // one-warp CTAs per SM the register budget allows (128 registers)
 #endif
@@ -51,7 +48,6 @@
 namespace {
 
 #define FAST_INVALID 0xFFFFFFFFu
-constexpr int kFsUnroll = MG_FS_UNROLL;
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   y ^= y >> 11;
@@ -850,7 +846,7 @@ __global__ void __launch_bounds__(WPC * 32, MG_FAST_CTAS_PER_SM / WPC) k_step_fa
       const bool last = base >= NS;
       __syncwarp(gmask);  // everyone has read the count before anyone appends again
       if (last || cnt > L.wl_cap - 2 * G) {  // drain the list: one pair per lane and turn
-#pragma unroll kFsUnroll
+#pragma unroll 1
         for (int i = gl; i < cnt; i += G) place(wl[i]);
         __syncwarp(gmask);
         if (gl == 0) *wl_count = 0;
