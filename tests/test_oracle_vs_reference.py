@@ -135,3 +135,27 @@ def test_ref_driver_agrees_with_reference_lowering_on_world_systems(reference_pk
         b.step(prim[t], vibe[t])
         assert np.array_equal(a.observations(), b.observations()) and np.array_equal(a.rewards(), b.rewards()), f"{game}: step {t}"
     assert a.get_episode_stats() == b.get_episode_stats()
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_toy_preset_fresh_seeds(reference_pkg, seed):
+    """The reference's perf_benchmark.py "toy" preset (benchmarks/perf/perf_benchmark.py:35-77): 40 x 40 map with a wall
+    border and 4 % walls, 20 agents, noop + 8-way moves, 11 x 11 window, 200 tokens -- the workload the static layer of
+    the fast path is measured on."""
+    from mettagrid_b200 import workloads as W
+    from mettagrid_b200.mapgen import random_map
+    from tests import refns
+
+    ns = refns.reference_namespace()
+    mirror = W.toy_config(max_steps=150)
+    ref = ns.MettaGridConfig(
+        game=ns.GameConfig(
+            num_agents=20,
+            max_steps=150,
+            obs=ns.ObsConfig(width=11, height=11, num_tokens=200),
+            actions=ns.ActionsConfig(noop=ns.NoopActionConfig(), move=ns.MoveActionConfig(allowed_directions=list(W.EIGHT_WAY))),
+            objects={"wall": ns.WallConfig()},
+        )
+    )
+    grid = random_map(mirror.game.map_builder, seed=seed)
+    _compare(ref, mirror, grid, seed, 220, p_vibe=0.0, p_invalid=0.03)
