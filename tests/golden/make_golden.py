@@ -1,6 +1,6 @@
 """Generate tests/golden/*.npz with the REAL reference (build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 
 For every case in tests/golden_cases.py the reference's own Python lowering
 (convert_to_cpp_game_config) and C++ step (oracle/_ref) are run; stored per case: the map, the action
@@ -29,7 +29,10 @@ from tests import refns  # noqa: E402
 
 ns = refns.reference_namespace()
 out_dir = Path(__file__).resolve().parent
+only = set(sys.argv[1:])  # optional: names of the cases to (re)record
 for name, (mk_cfg, mk_map, seed, steps, _pv, _pi) in gc.CASES.items():
+    if only and name not in only:
+        continue
     grid = mk_map()
     if name in gc.VIA_DRIVER:  # e.g. the C++ AttackMutation: unreachable from the reference's Python configs
         from mettagrid_b200 import config as C  # noqa: E402
