@@ -62,6 +62,12 @@ def _toy_map(agents, seed):
     return random_map(RandomMapConfig(width=40, height=40, agents=agents, border_width=1, seed=seed, objects={"wall": 64}))
 
 
+def _walled_big_map(agents, seed):
+    from mettagrid_b200.mapgen import RandomMapConfig, random_map
+
+    return random_map(RandomMapConfig(agents=agents, width=22, height=17, seed=seed, border_width=1, objects={"wall": 30}))
+
+
 def _walled_map(agents, seed):
     from mettagrid_b200.mapgen import RandomMapConfig, random_map
 
@@ -76,6 +82,7 @@ CASES = {
     "c1_a5_invalid": (lambda ns: _bench(ns, 5), lambda: _bench_map(5, 7), 9, 300, 0.4, 0.1),
     "walled_8way": (lambda ns: _walled(ns, 6), lambda: _walled_map(6, 3), 5, 90, 0.1, 0.02),
     "toy_a20": (lambda ns: _toy(ns), lambda: _toy_map(20, 42), 42, 300, 0.0, 0.02),  # 240 objects: the fast path's static layer
+    "walled_8way_big": (lambda ns: _walled(ns, 6, max_steps=100), lambda: _walled_big_map(6, 4), 6, 140, 0.1, 0.02),  # 7 x 9 elliptical window, static layer
     "combat_3v3": (lambda ns: cases.combat_config(ns, 3), lambda: cases.combat_map(3, seed=1), 1, 500, 0.3, 0.0),
     "combat_4v4_base16": (lambda ns: cases.combat_config(ns, 4, token_value_base=16, max_steps=250),
                           lambda: cases.combat_map(4, seed=5), 5, 300, 0.3, 0.01),  # fmt: skip
