@@ -23,6 +23,15 @@ def _bench(ns, agents, **kw):
     )
 
 
+def _bench_trunc(ns, agents):
+    """Benchmark game with a step limit that truncates, base-10 inventory digits and agents that start with inventory."""
+    cfg = _bench(ns, agents, num_tokens=220, max_steps=60)
+    cfg.game.episode_truncates = True
+    cfg.game.obs.token_value_base = 10
+    cfg.game.agent.inventory.initial = {"ore_red": 7, "heart": 345, "laser": 12}
+    return cfg
+
+
 def _bench_map(agents, seed):
     from mettagrid_b200.mapgen import RandomMapConfig, random_map
 
@@ -80,6 +89,7 @@ CASES = {
     "c1_a4": (lambda ns: _bench(ns, 4), lambda: _bench_map(4, 42), 42, 1000, 0.0, 0.0),
     "c1_a16": (lambda ns: _bench(ns, 16), lambda: _bench_map(16, 42), 42, 400, 0.1, 0.0),
     "c1_a5_invalid": (lambda ns: _bench(ns, 5), lambda: _bench_map(5, 7), 9, 300, 0.4, 0.1),
+    "c1_a5_trunc_base10": (lambda ns: _bench_trunc(ns, 5), lambda: _bench_map(5, 21), 21, 90, 0.4, 0.02),
     "walled_8way": (lambda ns: _walled(ns, 6), lambda: _walled_map(6, 3), 5, 90, 0.1, 0.02),
     "toy_a20": (lambda ns: _toy(ns), lambda: _toy_map(20, 42), 42, 300, 0.0, 0.02),  # 240 objects: the fast path's static layer
     "walled_8way_big": (lambda ns: _walled(ns, 6, max_steps=100), lambda: _walled_big_map(6, 4), 6, 140, 0.1, 0.02),  # 7 x 9 elliptical window, static layer
