@@ -32,6 +32,14 @@ def _bench_trunc(ns, agents):
     return cfg
 
 
+def _bench_rich(ns, agents):
+    """Benchmark game whose agents start with nine resources: 12-13 tokens per agent, initial inventory order."""
+    cfg = _bench(ns, agents, num_tokens=200)
+    cfg.game.agent.inventory.initial = {"ore_red": 3, "ore_blue": 300, "ore_green": 1, "battery_red": 9, "battery_blue": 2,
+                                        "heart": 70000 % 65536, "armor": 5, "laser": 1, "blueprint": 8}  # fmt: skip
+    return cfg
+
+
 def _bench_map(agents, seed):
     from mettagrid_b200.mapgen import RandomMapConfig, random_map
 
@@ -90,6 +98,7 @@ CASES = {
     "c1_a16": (lambda ns: _bench(ns, 16), lambda: _bench_map(16, 42), 42, 400, 0.1, 0.0),
     "c1_a5_invalid": (lambda ns: _bench(ns, 5), lambda: _bench_map(5, 7), 9, 300, 0.4, 0.1),
     "c1_a5_trunc_base10": (lambda ns: _bench_trunc(ns, 5), lambda: _bench_map(5, 21), 21, 90, 0.4, 0.02),
+    "c1_a7_nine_resources": (lambda ns: _bench_rich(ns, 7), lambda: _bench_map(7, 31), 31, 120, 0.6, 0.0),
     "walled_8way": (lambda ns: _walled(ns, 6), lambda: _walled_map(6, 3), 5, 90, 0.1, 0.02),
     "toy_a20": (lambda ns: _toy(ns), lambda: _toy_map(20, 42), 42, 300, 0.0, 0.02),  # 240 objects: the fast path's static layer
     "walled_8way_big": (lambda ns: _walled(ns, 6, max_steps=100), lambda: _walled_big_map(6, 4), 6, 140, 0.1, 0.02),  # 7 x 9 elliptical window, static layer
